@@ -1,0 +1,369 @@
+// extern "C" boundary: see include/amrex_b200_fi.h for the contract and the reference citations.
+#include "../mlmg/AMReX_MLMG.H"
+#include "amrex_b200_fi.h"
+
+#include <cstring>
+#include <limits>
+#include <string>
+
+using namespace amrex;
+
+namespace amrex { void clear_comm_caches (); }
+
+namespace {
+std::string g_err;
+bool g_has_err = false;
+void set_err (const char* where, const char* what) { g_err = std::string(where) + ": " + what; g_has_err = true; }
+constexpr double kNaN = std::numeric_limits<double>::quiet_NaN();
+}
+
+#define FI_TRY try {
+#define FI_CATCH(ret) } catch (std::exception const& e) { set_err(__func__, e.what()); ret; } catch (...) { set_err(__func__, "unknown exception"); ret; }
+#define FI_VOID(body) FI_TRY body FI_CATCH(return)
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------ runtime
+int amrex_b200_init (int device_id) { FI_TRY Gpu::Initialize(device_id); return 0; FI_CATCH(return 1) }
+void amrex_b200_finalize (void)
+{
+    FI_VOID( clear_comm_caches(); LevelLayout::clearCache(); ParallelDescriptor::FinalizeComm(); Gpu::Finalize(); )
+}
+int amrex_b200_initialized (void) { return Gpu::Initialized() ? 1 : 0; }
+int amrex_b200_nccl_unique_id_bytes (void) { return ParallelDescriptor::NcclUniqueIdBytes(); }
+int amrex_b200_nccl_get_unique_id (void* out) { FI_TRY ParallelDescriptor::NcclGetUniqueId(out); return 0; FI_CATCH(return 1) }
+int amrex_b200_comm_init (int rank, int nranks, const void* uid) { FI_TRY ParallelDescriptor::InitComm(rank, nranks, uid); return 0; FI_CATCH(return 1) }
+void amrex_b200_comm_finalize (void) { FI_VOID( ParallelDescriptor::FinalizeComm(); ) }
+int amrex_b200_myproc (void) { return ParallelDescriptor::MyProc(); }
+int amrex_b200_nprocs (void) { return ParallelDescriptor::NProcs(); }
+const char* amrex_b200_last_error (void) { return g_has_err ? g_err.c_str() : nullptr; }
+void amrex_b200_clear_error (void) { g_has_err = false; g_err.clear(); }
+void amrex_b200_synchronize (void) { FI_VOID( Gpu::streamSynchronize(); ) }
+long long amrex_b200_launch_count (void) { return Gpu::launchCount(); }
+void amrex_b200_reset_launch_count (void) { Gpu::resetLaunchCount(); }
+void* amrex_b200_stream (void) { return Gpu::gpuStream(); }
+
+// ----------------------------------------------------------------------------------------- Geometry
+void amrex_b200_geometry_setup (const Real problo[3], const Real probhi[3], const int is_periodic[3])
+{
+    RealBox rb({problo[0], problo[1], problo[2]}, {probhi[0], probhi[1], probhi[2]});
+    Geometry::Setup(&rb, 0, is_periodic);
+}
+void amrex_fi_new_geometry (Geometry** geom, int lo[3], int hi[3])
+{
+    FI_VOID( *geom = new Geometry(Box(IntVect(lo[0], lo[1], lo[2]), IntVect(hi[0], hi[1], hi[2]))); )
+}
+void amrex_fi_delete_geometry (Geometry* geom) { delete geom; }
+void amrex_fi_geometry_get_intdomain (const Geometry* geom, int lo[3], int hi[3])
+{
+    for (int d = 0; d < 3; ++d) { lo[d] = geom->Domain().smallEnd(d); hi[d] = geom->Domain().bigEnd(d); }
+}
+
+// ----------------------------------------------------------------------------------------- BoxArray
+void amrex_fi_new_boxarray (BoxArray** ba, int lo[3], int hi[3])
+{
+    FI_VOID( *ba = new BoxArray(Box(IntVect(lo[0], lo[1], lo[2]), IntVect(hi[0], hi[1], hi[2]))); )
+}
+void amrex_fi_new_boxarray_from_bxfarr (BoxArray** ba, const int* bxs, const int nsides, const int ndims, const int nbxs)
+{
+    FI_VOID(
+        AMREX_ALWAYS_ASSERT(nsides == 2 && ndims >= 3);
+        BoxList bl;
+        for (int i = 0; i < nbxs; ++i) {
+            bl.push_back(Box(IntVect(bxs[0], bxs[2], bxs[4]), IntVect(bxs[1], bxs[3], bxs[5])));
+            bxs += 2 * ndims;
+        }
+        *ba = new BoxArray(bl); )
+}
+void amrex_fi_delete_boxarray (BoxArray* ba) { delete ba; }
+void amrex_fi_clone_boxarray (BoxArray** bao, const BoxArray* bai) { FI_VOID( *bao = new BoxArray(*bai); ) }
+void amrex_fi_boxarray_maxsize (BoxArray* ba, int sz[]) { FI_VOID( ba->maxSize(IntVect(sz[0], sz[1], sz[2])); ) }
+long long amrex_fi_boxarray_nboxes (const BoxArray* ba) { return ba->size(); }
+void amrex_fi_boxarray_get_box (const BoxArray* ba, int i, int lo[3], int hi[3])
+{
+    Box const& b = (*ba)[i];
+    for (int d = 0; d < 3; ++d) { lo[d] = b.smallEnd(d); hi[d] = b.bigEnd(d); }
+}
+void amrex_fi_boxarray_nodal_type (const BoxArray* ba, int inodal[3]) { for (int d = 0; d < 3; ++d) { inodal[d] = ba->ixType()[d]; } }
+long long amrex_fi_boxarray_numpts (const BoxArray* ba) { return ba->numPts(); }
+int amrex_fi_boxarray_issame (const BoxArray* a, const BoxArray* b) { return *a == *b; }
+void amrex_b200_boxarray_coarsen (BoxArray* ba, int ratio) { FI_VOID( ba->coarsen(ratio); ) }
+void amrex_b200_boxarray_refine (BoxArray* ba, int ratio) { FI_VOID( ba->refine(ratio); ) }
+
+// ------------------------------------------------------------------------------ DistributionMapping
+void amrex_fi_new_distromap (DistributionMapping** dm, const BoxArray* ba) { FI_VOID( *dm = new DistributionMapping(*ba); ) }
+void amrex_fi_new_distromap_from_pmap (DistributionMapping** dm, const int* pmap, const int plen)
+{
+    FI_VOID( *dm = new DistributionMapping(Vector<int>(pmap, pmap + plen)); )
+}
+void amrex_fi_delete_distromap (DistributionMapping* dm) { delete dm; }
+void amrex_fi_distromap_get_pmap (const DistributionMapping* dm, int* pmap, const int plen)
+{
+    auto const& p = dm->ProcessorMap();
+    for (int i = 0; i < plen && i < int(p.size()); ++i) { pmap[i] = p[i]; }
+}
+void amrex_b200_new_distromap_sfc (DistributionMapping** dm, const BoxArray* ba, int nprocs) { FI_VOID( *dm = new DistributionMapping(*ba, nprocs); ) }
+
+// ----------------------------------------------------------------------------------------- MultiFab
+void amrex_fi_new_multifab (MultiFab** mf, const BoxArray** ba, const DistributionMapping** dm, int nc, const int* ng, const int* nodal)
+{
+    FI_VOID(
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(ng[0] == ng[1] && ng[1] == ng[2], "uniform ghost width required");
+        *mf = new MultiFab(amrex::convert(**ba, IntVect(nodal[0], nodal[1], nodal[2])), **dm, nc, ng[0]);
+        *ba = &((*mf)->boxArray()); *dm = &((*mf)->DistributionMap()); )
+}
+void amrex_fi_delete_multifab (MultiFab* mf) { FI_VOID( delete mf; ) }
+int amrex_fi_multifab_ncomp (const MultiFab* mf) { return mf->nComp(); }
+void amrex_fi_multifab_ngrow (const MultiFab* mf, int* ngv) { for (int d = 0; d < 3; ++d) { ngv[d] = mf->nGrow(); } }
+const BoxArray* amrex_fi_multifab_boxarray (const MultiFab* mf) { return &mf->boxArray(); }
+const DistributionMapping* amrex_fi_multifab_distromap (const MultiFab* mf) { return &mf->DistributionMap(); }
+void amrex_fi_multifab_dataptr_int (MultiFab* mf, int igrd, Real** dp, int lo[3], int hi[3])
+{
+    FI_VOID(
+        const int li = mf->layout().localIndex(igrd);
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(li >= 0, "grid is not local to this rank");
+        auto const& d = mf->desc(li);
+        *dp = d.p; for (int a = 0; a < 3; ++a) { lo[a] = d.lo[a]; hi[a] = d.hi[a]; } )
+}
+void amrex_b200_multifab_strides (const MultiFab* mf, int igrd, long long strides[3])
+{
+    FI_VOID( const int li = mf->layout().localIndex(igrd); AMREX_ALWAYS_ASSERT(li >= 0);
+             auto const& d = mf->desc(li); strides[0] = d.jstride; strides[1] = d.kstride; strides[2] = d.nstride; )
+}
+Real amrex_fi_multifab_sum (const MultiFab* mf, int comp) { FI_TRY AMREX_ALWAYS_ASSERT(comp == 0); return mf->sum(); FI_CATCH(return kNaN) }
+Real amrex_fi_multifab_norm0 (const MultiFab* mf, int comp) { FI_TRY AMREX_ALWAYS_ASSERT(comp == 0); return mf->norminf(); FI_CATCH(return kNaN) }
+void amrex_fi_multifab_setval (MultiFab* mf, Real val, int ic, int nc, const int* ng) { FI_VOID( AMREX_ALWAYS_ASSERT(ic == 0 && nc == 1); mf->setVal(val, ng[0]); ) }
+void amrex_fi_multifab_plus (MultiFab* mf, Real val, int ic, int nc, int ng) { FI_VOID( AMREX_ALWAYS_ASSERT(ic == 0 && nc == 1); mf->plus(val, ng); ) }
+void amrex_fi_multifab_mult (MultiFab* mf, Real val, int ic, int nc, int ng) { FI_VOID( AMREX_ALWAYS_ASSERT(ic == 0 && nc == 1); mf->mult(val, ng); ) }
+void amrex_fi_multifab_add (MultiFab* d, const MultiFab* s, int sc, int dc, int nc, const int* ng) { FI_VOID( MultiFab::Add(*d, *s, sc, dc, nc, ng[0]); ) }
+void amrex_fi_multifab_subtract (MultiFab* d, const MultiFab* s, int sc, int dc, int nc, const int* ng) { FI_VOID( MultiFab::Subtract(*d, *s, sc, dc, nc, ng[0]); ) }
+void amrex_fi_multifab_saxpy (MultiFab* d, Real a, const MultiFab* s, int sc, int dc, int nc, const int* ng) { FI_VOID( MultiFab::Saxpy(*d, a, *s, sc, dc, nc, ng[0]); ) }
+void amrex_fi_multifab_copy (MultiFab* d, const MultiFab* s, int sc, int dc, int nc, const int* ng) { FI_VOID( MultiFab::Copy(*d, *s, sc, dc, nc, ng[0]); ) }
+void amrex_fi_multifab_parallelcopy (MultiFab* d, const MultiFab* s, int sc, int dc, int nc, int srcng, int dstng, const Geometry* geom)
+{
+    FI_VOID( d->ParallelCopy(*s, sc, dc, nc, srcng, dstng, geom->periodicity()); )
+}
+void amrex_fi_multifab_fill_boundary (MultiFab* mf, const Geometry* geom, int c, int nc, int cross)
+{
+    FI_VOID( mf->FillBoundary(c, nc, geom->periodicity(), cross != 0); )
+}
+Real amrex_b200_multifab_dot (const MultiFab* x, const MultiFab* y) { FI_TRY return MultiFab::Dot(*x, *y); FI_CATCH(return kNaN) }
+void amrex_b200_multifab_upload (MultiFab* mf, const Real* h, const int lo[3], const int hi[3], int comp, int ng)
+{
+    FI_VOID( mf->copyFromHost(h, Box(IntVect(lo[0], lo[1], lo[2]), IntVect(hi[0], hi[1], hi[2]), mf->ixType()), comp, ng); )
+}
+void amrex_b200_multifab_download (const MultiFab* mf, Real* h, const int lo[3], const int hi[3], int comp, int ng)
+{
+    FI_VOID( mf->copyToHost(h, Box(IntVect(lo[0], lo[1], lo[2]), IntVect(hi[0], hi[1], hi[2]), mf->ixType()), comp, ng); )
+}
+void amrex_b200_average_cellcenter_to_face (MultiFab* fx, MultiFab* fy, MultiFab* fz, const MultiFab* cc, const Geometry* geom)
+{
+    FI_VOID( average_cellcenter_to_face({fx, fy, fz}, *cc, *geom); )
+}
+
+// --------------------------------------------------------------------------------- linear operators
+namespace {
+MLLinOp* make_linop (int kind, int nlevels, const Geometry* geom[], const BoxArray* ba[], const DistributionMapping* dm[], LPInfo const& info)
+{
+    Vector<Geometry> g; Vector<BoxArray> b; Vector<DistributionMapping> d;
+    for (int i = 0; i < nlevels; ++i) { g.push_back(*geom[i]); b.push_back(*ba[i]); d.push_back(*dm[i]); }
+    if (kind == 0) { return new MLABecLaplacian(g, b, d, info); }
+    return new MLPoisson(g, b, d, info);
+}
+LPInfo make_info (int agglomeration, int consolidation, int max_coarsening_level)
+{
+    LPInfo info;
+    if (agglomeration >= 0) { info.setAgglomeration(agglomeration); }
+    if (consolidation >= 0) { info.setConsolidation(consolidation); }
+    info.setMaxCoarseningLevel(max_coarsening_level);
+    return info;
+}
+}
+
+void amrex_fi_new_abeclaplacian (MLLinOp** linop, int nlevels, const Geometry* geom[], const BoxArray* ba[], const DistributionMapping* dm[],
+                                 int, int agglomeration, int consolidation, int max_coarsening_level)
+{
+    FI_VOID( *linop = make_linop(0, nlevels, geom, ba, dm, make_info(agglomeration, consolidation, max_coarsening_level)); )
+}
+void amrex_fi_new_poisson (MLLinOp** linop, int nlevels, const Geometry* geom[], const BoxArray* ba[], const DistributionMapping* dm[],
+                           int, int agglomeration, int consolidation, int max_coarsening_level)
+{
+    FI_VOID( *linop = make_linop(1, nlevels, geom, ba, dm, make_info(agglomeration, consolidation, max_coarsening_level)); )
+}
+void amrex_b200_new_linop (MLLinOp** linop, int kind, int nlevels, const Geometry* geom[], const BoxArray* ba[], const DistributionMapping* dm[],
+                           int agglomeration, int consolidation, int max_coarsening_level, int agg_grid_size, int con_grid_size)
+{
+    FI_VOID( LPInfo info = make_info(agglomeration, consolidation, max_coarsening_level);
+             info.setAgglomerationGridSize(agg_grid_size); info.setConsolidationGridSize(con_grid_size);
+             *linop = make_linop(kind, nlevels, geom, ba, dm, info); )
+}
+void amrex_fi_delete_linop (MLLinOp* linop) { FI_VOID( delete linop; ) }
+void amrex_fi_linop_set_maxorder (MLLinOp* linop, int ord) { linop->setMaxOrder(ord); }
+void amrex_fi_linop_set_domain_bc (MLLinOp* linop, const int* ilobc, const int* ihibc)
+{
+    FI_VOID( linop->setDomainBC({LinOpBCType(ilobc[0]), LinOpBCType(ilobc[1]), LinOpBCType(ilobc[2])},
+                                {LinOpBCType(ihibc[0]), LinOpBCType(ihibc[1]), LinOpBCType(ihibc[2])}); )
+}
+void amrex_fi_linop_set_coarse_fine_bc (MLLinOp* linop, const MultiFab* crse, int crse_ratio) { FI_VOID( linop->setCoarseFineBC(crse, crse_ratio); ) }
+void amrex_fi_linop_set_level_bc (MLLinOp* linop, int amrlev, const MultiFab* levelbcdata) { FI_VOID( linop->setLevelBC(amrlev, levelbcdata); ) }
+void amrex_fi_abeclap_set_scalars (MLLinOp* linop, Real a, Real b) { FI_VOID( dynamic_cast<MLABecLaplacian&>(*linop).setScalars(a, b); ) }
+void amrex_fi_abeclap_set_acoeffs (MLLinOp* linop, int amrlev, const MultiFab* alpha) { FI_VOID( dynamic_cast<MLABecLaplacian&>(*linop).setACoeffs(amrlev, *alpha); ) }
+void amrex_fi_abeclap_set_bcoeffs (MLLinOp* linop, int amrlev, const MultiFab* beta[])
+{
+    FI_VOID( dynamic_cast<MLABecLaplacian&>(*linop).setBCoeffs(amrlev, {beta[0], beta[1], beta[2]}); )
+}
+void amrex_b200_linop_set_smoother_fusion (MLLinOp* linop, int fuse) { linop->setSmootherFusion(fuse); }
+int amrex_b200_linop_num_mg_levels (const MLLinOp* linop, int amrlev) { return linop->NMGLevels(amrlev); }
+void amrex_b200_linop_prepare (MLLinOp* linop) { FI_VOID( linop->prepareForSolve(); ) }
+void amrex_b200_linop_make (MLLinOp* linop, MultiFab** mf, int amrlev, int mglev, int ng) { FI_VOID( *mf = new MultiFab(linop->make(amrlev, mglev, ng)); ) }
+void amrex_b200_linop_smooth (MLLinOp* linop, int amrlev, int mglev, MultiFab* sol, const MultiFab* rhs, int skip)
+{
+    FI_VOID( linop->smooth(amrlev, mglev, *sol, *rhs, skip != 0); )
+}
+void amrex_b200_linop_apply (MLLinOp* linop, int amrlev, int mglev, MultiFab* out, MultiFab* in, int inhomog)
+{
+    FI_VOID(
+        if (inhomog) { Abort("use amrex_b200_linop_residual for inhomogeneous apply"); }
+        linop->apply(amrlev, mglev, *out, *in, MLLinOp::BCMode::Homogeneous, MLLinOp::StateMode::Correction); )
+}
+void amrex_b200_linop_residual (MLLinOp* linop, int amrlev, int mglev, MultiFab* resid, MultiFab* x, const MultiFab* b, int inhomog)
+{
+    FI_VOID(
+        if (inhomog) { AMREX_ALWAYS_ASSERT(mglev == 0); linop->solutionResidual(amrlev, *resid, *x, *b, nullptr); }
+        else { linop->correctionResidual(amrlev, mglev, *resid, *x, *b, MLLinOp::BCMode::Homogeneous); } )
+}
+void amrex_b200_linop_restriction (MLLinOp* linop, int amrlev, int cmglev, MultiFab* crse, MultiFab* fine) { FI_VOID( linop->restriction(amrlev, cmglev, *crse, *fine); ) }
+void amrex_b200_linop_interp_add (MLLinOp* linop, int amrlev, int fmglev, MultiFab* fine, const MultiFab* crse)
+{
+    FI_VOID(
+        if (linop->isMFIterSafe(amrlev, fmglev, fmglev + 1)) { linop->interpolation(amrlev, fmglev, *fine, *crse); }
+        else {
+            MultiFab cfine(amrex::coarsen(fine->boxArray(), 2), fine->DistributionMap(), 1, 0);
+            cfine.ParallelCopy(*crse, 0, 0, 1);
+            linop->interpolation(amrlev, fmglev, *fine, cfine);
+            Gpu::streamSynchronize();
+        } )
+}
+void amrex_b200_linop_get_coeff (MLLinOp* linop, int amrlev, int mglev, int which, const MultiFab** mf)
+{
+    FI_VOID( auto& ab = dynamic_cast<MLABecLaplacian&>(*linop);
+             *mf = (which == 0) ? &ab.getACoeffs(amrlev, mglev) : &ab.getBCoeffs(amrlev, mglev, which - 1); )
+}
+
+namespace {
+void level_out (MGHierarchy const& H, int a, int m, int* boxes6, int* pmap, int* domain6)
+{
+    BoxArray const& ba = H.grids[a][m];
+    for (int i = 0, N = int(ba.size()); i < N; ++i) {
+        for (int d = 0; d < 3; ++d) { boxes6[6 * i + d] = ba[i].smallEnd(d); boxes6[6 * i + 3 + d] = ba[i].bigEnd(d); }
+        if (pmap) { pmap[i] = H.dmap[a][m][i]; }
+    }
+    if (domain6) { Box const& dom = H.geom[a][m].Domain(); for (int d = 0; d < 3; ++d) { domain6[d] = dom.smallEnd(d); domain6[3 + d] = dom.bigEnd(d); } }
+}
+}
+int amrex_b200_linop_level_nboxes (const MLLinOp* linop, int a, int m) { return int(linop->Grids(a, m).size()); }
+void amrex_b200_linop_level_boxes (const MLLinOp* linop, int a, int m, int* boxes6, int* pmap, int* domain6) { level_out(linop->hierarchy(), a, m, boxes6, pmap, domain6); }
+
+// --------------------------------------------------------------------------------------------- MLMG
+void amrex_fi_new_multigrid (MLMG** mlmg, MLLinOp* lp) { FI_VOID( *mlmg = new MLMG(*lp); (*mlmg)->setThrowException(true); ) }
+void amrex_fi_delete_multigrid (MLMG* mlmg) { FI_VOID( delete mlmg; ) }
+Real amrex_fi_multigrid_solve (MLMG* mlmg, MultiFab* a_sol[], MultiFab* a_rhs[], Real a_tol_rel, Real a_tol_abs)
+{
+    FI_TRY
+        const int n = mlmg->numAMRLevels();
+        return mlmg->solve(Vector<MultiFab*>(a_sol, a_sol + n), Vector<const MultiFab*>(a_rhs, a_rhs + n), a_tol_rel, a_tol_abs);
+    FI_CATCH(return kNaN)
+}
+void amrex_fi_multigrid_comp_residual (MLMG* mlmg, MultiFab* a_res[], MultiFab* a_sol[], MultiFab* a_rhs[])
+{
+    FI_VOID( const int n = mlmg->numAMRLevels();
+             mlmg->compResidual(Vector<MultiFab*>(a_res, a_res + n), Vector<MultiFab*>(a_sol, a_sol + n), Vector<const MultiFab*>(a_rhs, a_rhs + n)); )
+}
+void amrex_fi_multigrid_set_verbose (MLMG* mlmg, int v) { mlmg->setVerbose(v); }
+void amrex_fi_multigrid_set_max_iter (MLMG* mlmg, int n) { mlmg->setMaxIter(n); }
+void amrex_fi_multigrid_set_max_fmg_iter (MLMG* mlmg, int n) { mlmg->setMaxFmgIter(n); }
+void amrex_fi_multigrid_set_fixed_iter (MLMG* mlmg, int n) { mlmg->setFixedIter(n); }
+void amrex_fi_multigrid_set_bottom_solver (MLMG* mlmg, int s)
+{
+    FI_VOID(
+        if (s == 0) { mlmg->setBottomSolver(BottomSolver::smoother); }
+        else if (s == 1) { mlmg->setBottomSolver(BottomSolver::bicgstab); }
+        else if (s == 2) { mlmg->setBottomSolver(BottomSolver::cg); }
+        else { Abort("amrex_fi_multigrid_set_bottom_solver: unknown or unavailable bottom solver"); } )
+}
+void amrex_fi_multigrid_set_bottom_verbose (MLMG* mlmg, int n) { mlmg->setBottomVerbose(n); }
+void amrex_fi_multigrid_set_always_use_bnorm (MLMG* mlmg, int f) { mlmg->setAlwaysUseBNorm(f); }
+void amrex_fi_multigrid_set_final_fill_bc (MLMG* mlmg, int f) { mlmg->setFinalFillBC(f); }
+int amrex_b200_multigrid_num_iters (const MLMG* mlmg) { return mlmg->getNumIters(); }
+int amrex_b200_multigrid_residual_history (const MLMG* mlmg, Real* hist, int capacity)
+{
+    auto const& h = mlmg->getResidualHistory();
+    for (int i = 0; i < capacity && i < int(h.size()); ++i) { hist[i] = h[i]; }
+    return int(h.size());
+}
+Real amrex_b200_multigrid_init_rhs (const MLMG* mlmg) { return mlmg->getInitRHS(); }
+Real amrex_b200_multigrid_init_residual (const MLMG* mlmg) { return mlmg->getInitResidual(); }
+int amrex_b200_multigrid_cg_iters (const MLMG* mlmg, int* iters, int capacity)
+{
+    auto const& h = mlmg->getNumCGIters();
+    for (int i = 0; i < capacity && i < int(h.size()); ++i) { iters[i] = h[i]; }
+    return int(h.size());
+}
+void amrex_b200_multigrid_timers (const MLMG* mlmg, double t[3]) { auto a = mlmg->getTimers(); t[0] = a[0]; t[1] = a[1]; t[2] = a[2]; }
+
+// ------------------------------------------------------------------------------- host-only metadata
+void* amrex_b200_hierarchy_new (int nlevels, const Geometry* geom[], const BoxArray* ba[], const DistributionMapping* dm[],
+                                int agglomeration, int consolidation, int max_coarsening_level, int agg_grid_size, int con_grid_size, int nprocs)
+{
+    FI_TRY
+        Vector<Geometry> g; Vector<BoxArray> b; Vector<DistributionMapping> d;
+        for (int i = 0; i < nlevels; ++i) { g.push_back(*geom[i]); b.push_back(*ba[i]); d.push_back(*dm[i]); }
+        LPInfo info = make_info(agglomeration, consolidation, max_coarsening_level);
+        info.setAgglomerationGridSize(agg_grid_size); info.setConsolidationGridSize(con_grid_size);
+        auto* H = new MGHierarchy;
+        H->define(g, b, d, info, nprocs);
+        return H;
+    FI_CATCH(return nullptr)
+}
+void amrex_b200_hierarchy_delete (void* h) { delete static_cast<MGHierarchy*>(h); }
+int amrex_b200_hierarchy_num_mg_levels (const void* h, int amrlev) { return static_cast<const MGHierarchy*>(h)->num_mg_levels[amrlev]; }
+int amrex_b200_hierarchy_nboxes (const void* h, int a, int m) { return int(static_cast<const MGHierarchy*>(h)->grids[a][m].size()); }
+void amrex_b200_hierarchy_level (const void* h, int a, int m, int* boxes6, int* pmap, int* domain6) { level_out(*static_cast<const MGHierarchy*>(h), a, m, boxes6, pmap, domain6); }
+
+namespace {
+int write_tags (CommMetaData const& cmd, int kind, int* out, int capacity)
+{
+    int n = 0;
+    auto put = [&] (CopyComTag const& t, int peer) {
+        if (out && n < capacity) {
+            int* p = out + 15 * n;
+            for (int d = 0; d < 3; ++d) { p[d] = t.dbox.smallEnd(d); p[3 + d] = t.dbox.bigEnd(d); p[6 + d] = t.sbox.smallEnd(d); p[9 + d] = t.sbox.bigEnd(d); }
+            p[12] = t.dstIndex; p[13] = t.srcIndex; p[14] = peer;
+        }
+        ++n;
+    };
+    if (kind == 0) { for (auto const& t : cmd.LocTags) { put(t, -1); } }
+    else { for (auto const& kv : (kind == 1 ? cmd.SndTags : cmd.RcvTags)) { for (auto const& t : kv.second) { put(t, kv.first); } } }
+    return n;
+}
+}
+int amrex_b200_fb_tags (const BoxArray* ba, const DistributionMapping* dm, int ng, int cross, const int period[3], int myproc, int kind, int* out, int capacity)
+{
+    FI_TRY
+        CommMetaData cmd;
+        define_fb_metadata(cmd, *ba, *dm, IntVect(ng), cross != 0, Periodicity(IntVect(period[0], period[1], period[2])), myproc);
+        return write_tags(cmd, kind, out, capacity);
+    FI_CATCH(return -1)
+}
+int amrex_b200_cpc_tags (const BoxArray* ba_dst, const DistributionMapping* dm_dst, int ng_dst, const BoxArray* ba_src, const DistributionMapping* dm_src,
+                         int ng_src, const int period[3], int myproc, int kind, int* out, int capacity)
+{
+    FI_TRY
+        CommMetaData cmd;
+        define_cpc_metadata(cmd, *ba_dst, *dm_dst, IntVect(ng_dst), *ba_src, *dm_src, IntVect(ng_src),
+                            Periodicity(IntVect(period[0], period[1], period[2])), false, myproc);
+        return write_tags(cmd, kind, out, capacity);
+    FI_CATCH(return -1)
+}
+
+} // extern "C"

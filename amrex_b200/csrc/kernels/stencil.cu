@@ -1,0 +1,390 @@
+// Colour-sweep smoother, operator apply / residual, normalisation and boundary-condition kernels.
+// Reference rows: K1/K2 (GSRB), K4/K5 (adotx), K9 (apply_bc), K11 (comp_interp_coef0), K13 (normalize).
+#include "common.cuh"
+#include "stencil_math.cuh"
+
+using namespace b200mg;
+
+namespace {
+
+struct FaceCoefs { double c[6]; };
+
+// cf0..cf5 of the reference GSRB kernels: slab value f at the cell if the cell lies on that face of its
+// box AND the ghost cell beyond the face is an uncovered (mask>0) boundary cell.
+__device__ __forceinline__ FaceCoefs
+face_coefs (int i, int j, int k, const b200mg_box& vb, const b200mg_fab* f6, const b200mg_ifab* m6)
+{
+    FaceCoefs r;
+#pragma unroll
+    for (int n = 0; n < 6; ++n) { r.c[n] = 0.0; }
+    if (i == vb.lo[0]) { if (view(m6[0])(i - 1, j, k) > 0) { r.c[0] = view(f6[0])(i, j, k); } }
+    if (j == vb.lo[1]) { if (view(m6[1])(i, j - 1, k) > 0) { r.c[1] = view(f6[1])(i, j, k); } }
+    if (k == vb.lo[2]) { if (view(m6[2])(i, j, k - 1) > 0) { r.c[2] = view(f6[2])(i, j, k); } }
+    if (i == vb.hi[0]) { if (view(m6[3])(i + 1, j, k) > 0) { r.c[3] = view(f6[3])(i, j, k); } }
+    if (j == vb.hi[1]) { if (view(m6[4])(i, j + 1, k) > 0) { r.c[4] = view(f6[4])(i, j, k); } }
+    if (k == vb.hi[2]) { if (view(m6[5])(i, j, k + 1) > 0) { r.c[5] = view(f6[5])(i, j, k); } }
+    return r;
+}
+
+__device__ __forceinline__ bool on_surface (int i, int j, int k, const b200mg_box& vb)
+{
+    return i == vb.lo[0] || i == vb.hi[0] || j == vb.lo[1] || j == vb.hi[1] || k == vb.lo[2] || k == vb.hi[2];
+}
+
+struct AbecArgs {
+    const b200mg_fab *phi, *rhs, *a, *bx, *by, *bz, *f;
+    const b200mg_ifab* m;
+    double alpha, dhx, dhy, dhz;
+};
+struct PoisArgs {
+    const b200mg_fab *phi, *rhs, *f;
+    const b200mg_ifab* m;
+    double dhx, dhy, dhz;
+};
+
+__device__ __forceinline__ void
+gsrb_abec_at (int i, int j, int k, int box, const b200mg_box& vb, const AbecArgs& A)
+{
+    const auto phi = view(A.phi[box]); const auto rhs = view(A.rhs[box]); const auto a = view(A.a[box]);
+    const auto bx = view(A.bx[box]); const auto by = view(A.by[box]); const auto bz = view(A.bz[box]);
+    double* pc = phi.ptr(i, j, k);
+    const double p = *pc;
+    double r;
+    if (on_surface(i, j, k, vb)) {
+        const FaceCoefs cf = face_coefs(i, j, k, vb, A.f + 6 * box, A.m + 6 * box);
+        r = gsrb_abec_cell(p, pc[-1], pc[1], pc[-phi.js], pc[phi.js], pc[-phi.ks], pc[phi.ks],
+                           rhs(i, j, k), a(i, j, k), bx(i, j, k), bx(i + 1, j, k), by(i, j, k), by(i, j + 1, k),
+                           bz(i, j, k), bz(i, j, k + 1), cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5],
+                           A.alpha, A.dhx, A.dhy, A.dhz);
+    } else {
+        r = gsrb_abec_cell_interior(p, pc[-1], pc[1], pc[-phi.js], pc[phi.js], pc[-phi.ks], pc[phi.ks],
+                                    rhs(i, j, k), a(i, j, k), bx(i, j, k), bx(i + 1, j, k), by(i, j, k), by(i, j + 1, k),
+                                    bz(i, j, k), bz(i, j, k + 1), A.alpha, A.dhx, A.dhy, A.dhz);
+    }
+    *pc = r;
+}
+
+__device__ __forceinline__ void
+gsrb_poisson_at (int i, int j, int k, int box, const b200mg_box& vb, const PoisArgs& A)
+{
+    const auto phi = view(A.phi[box]); const auto rhs = view(A.rhs[box]);
+    double* pc = phi.ptr(i, j, k);
+    FaceCoefs cf;
+    if (on_surface(i, j, k, vb)) { cf = face_coefs(i, j, k, vb, A.f + 6 * box, A.m + 6 * box); }
+    else {
+#pragma unroll
+        for (int n = 0; n < 6; ++n) { cf.c[n] = 0.0; }
+    }
+    *pc = gsrb_poisson_cell(*pc, pc[-1], pc[1], pc[-phi.js], pc[phi.js], pc[-phi.ks], pc[phi.ks], rhs(i, j, k),
+                            cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], A.dhx, A.dhy, A.dhz);
+}
+
+// one colour; each thread owns the cell pair (i0,i0+1) and updates the one with the right parity
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_gsrb_abec (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, AbecArgs A, int redblack)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const int j = t.j0 + int(threadIdx.y);
+    if (j > vb.hi[1]) { return; }
+    const int khi = min(t.k0 + B200MG_TILE_Z - 1, vb.hi[2]);
+    for (int k = t.k0; k <= khi; ++k) {
+        const int off = (vb.lo[0] + j + k + redblack) & 1;
+        for (int i = vb.lo[0] + off + 2 * int(threadIdx.x); i <= vb.hi[0]; i += 2 * int(blockDim.x)) {
+            gsrb_abec_at(i, j, k, t.box, vb, A);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_gsrb_poisson (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, PoisArgs A, int redblack)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const int j = t.j0 + int(threadIdx.y);
+    if (j > vb.hi[1]) { return; }
+    const int khi = min(t.k0 + B200MG_TILE_Z - 1, vb.hi[2]);
+    for (int k = t.k0; k <= khi; ++k) {
+        const int off = (vb.lo[0] + j + k + redblack) & 1;
+        for (int i = vb.lo[0] + off + 2 * int(threadIdx.x); i <= vb.hi[0]; i += 2 * int(blockDim.x)) {
+            gsrb_poisson_at(i, j, k, t.box, vb, A);
+        }
+    }
+}
+
+// Surface shell sweep: blockIdx.x = box*6 + face; every shell cell belongs to exactly one face
+// (x faces own their edges/corners, y faces exclude the x extremes, z faces exclude x and y extremes).
+template <class ARGS, class F>
+__device__ __forceinline__ void shell_loop (const b200mg_box& vb, int face, int redblack, F&& f)
+{
+    const int d = face % 3;
+    const int fix = (face < 3) ? vb.lo[d] : vb.hi[d];
+    if (face >= 3 && vb.lo[d] == vb.hi[d]) { return; }   // one-cell-thick box: low face owns it
+    int lo[3] = {vb.lo[0], vb.lo[1], vb.lo[2]}, hi[3] = {vb.hi[0], vb.hi[1], vb.hi[2]};
+    if (d >= 1) { lo[0] += 1; hi[0] -= 1; }
+    if (d == 2) { lo[1] += 1; hi[1] -= 1; }
+    lo[d] = hi[d] = fix;
+    const int n0 = hi[0] - lo[0] + 1, n1 = hi[1] - lo[1] + 1, n2 = hi[2] - lo[2] + 1;
+    if (n0 <= 0 || n1 <= 0 || n2 <= 0) { return; }
+    const int n = n0 * n1 * n2;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int i = lo[0] + t % n0, j = lo[1] + (t / n0) % n1, k = lo[2] + t / (n0 * n1);
+        if (((i + j + k + redblack) & 1) == 0) { f(i, j, k); }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_gsrb_shell_abec (const b200mg_box* __restrict__ vbox, AbecArgs A, int redblack)
+{
+    const int box = blockIdx.x / 6, face = blockIdx.x % 6;
+    const b200mg_box vb = vbox[box];
+    shell_loop<AbecArgs>(vb, face, redblack, [&] (int i, int j, int k) { gsrb_abec_at(i, j, k, box, vb, A); });
+}
+
+__global__ void __launch_bounds__(256)
+k_gsrb_shell_poisson (const b200mg_box* __restrict__ vbox, PoisArgs A, int redblack)
+{
+    const int box = blockIdx.x / 6, face = blockIdx.x % 6;
+    const b200mg_box vb = vbox[box];
+    shell_loop<PoisArgs>(vb, face, redblack, [&] (int i, int j, int k) { gsrb_poisson_at(i, j, k, box, vb, A); });
+}
+
+// ---------------------------------------------------------------------------------------- adotx
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_adotx_abec (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox,
+              const b200mg_fab* yf, const b200mg_fab* xf, const b200mg_fab* rf, const b200mg_fab* af,
+              const b200mg_fab* bxf, const b200mg_fab* byf, const b200mg_fab* bzf,
+              double alpha, double dhx, double dhy, double dhz)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto y = view(yf[t.box]); const auto x = view(xf[t.box]); const auto a = view(af[t.box]);
+    const auto bx = view(bxf[t.box]); const auto by = view(byf[t.box]); const auto bz = view(bzf[t.box]);
+    const bool has_r = (rf != nullptr);
+    View<double> r = has_r ? view(rf[t.box]) : y;
+    tile_for(t, vb, 0, [&] (int i, int j, int k) {
+        const double* xc = x.ptr(i, j, k);
+        const double v = adotx_abec_cell(*xc, xc[-1], xc[1], xc[-x.js], xc[x.js], xc[-x.ks], xc[x.ks],
+                                         a(i, j, k), bx(i, j, k), bx(i + 1, j, k), by(i, j, k), by(i, j + 1, k),
+                                         bz(i, j, k), bz(i, j, k + 1), alpha, dhx, dhy, dhz);
+        y(i, j, k) = has_r ? (r(i, j, k) + (-1.0) * v) : v;   // Xpay(y,-1,b): y = b + (-1)*y
+    });
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_adotx_poisson (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox,
+                 const b200mg_fab* yf, const b200mg_fab* xf, const b200mg_fab* rf,
+                 double dhx, double dhy, double dhz)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto y = view(yf[t.box]); const auto x = view(xf[t.box]);
+    const bool has_r = (rf != nullptr);
+    View<double> r = has_r ? view(rf[t.box]) : y;
+    tile_for(t, vb, 0, [&] (int i, int j, int k) {
+        const double* xc = x.ptr(i, j, k);
+        const double v = adotx_poisson_cell(*xc, xc[-1], xc[1], xc[-x.js], xc[x.js], xc[-x.ks], xc[x.ks], dhx, dhy, dhz);
+        y(i, j, k) = has_r ? (r(i, j, k) + (-1.0) * v) : v;
+    });
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_normalize_abec (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox,
+                  const b200mg_fab* xf, const b200mg_fab* af,
+                  const b200mg_fab* bxf, const b200mg_fab* byf, const b200mg_fab* bzf,
+                  double alpha, double dhx, double dhy, double dhz)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto x = view(xf[t.box]); const auto a = view(af[t.box]);
+    const auto bx = view(bxf[t.box]); const auto by = view(byf[t.box]); const auto bz = view(bzf[t.box]);
+    tile_for(t, vb, 0, [&] (int i, int j, int k) {   // AMReX_MLABecLap_3D_K.H:71-74
+        x(i, j, k) /= alpha * a(i, j, k) + dhx * (bx(i, j, k) + bx(i + 1, j, k))
+            + dhy * (by(i, j, k) + by(i, j + 1, k)) + dhz * (bz(i, j, k) + bz(i, j, k + 1));
+    });
+}
+
+// --------------------------------------------------------------------------------- boundary conditions
+constexpr int kBcDirichlet = 101, kBcNeumann = 102, kBcReflectOdd = 103;
+
+// one block per (box, face) item; threads sweep the face's ghost cells (tangential extent = valid box)
+template <class F>
+__device__ __forceinline__ void face_loop (const b200mg_box& vb, int face, F&& f)
+{
+    const int d = face % 3;
+    const int g = (face < 3) ? vb.lo[d] - 1 : vb.hi[d] + 1;   // ghost index in the normal direction
+    const int d1 = (d == 0) ? 1 : 0, d2 = (d == 2) ? 1 : 2;    // tangential dirs, d1 fastest
+    const int n1 = vb.hi[d1] - vb.lo[d1] + 1, n2 = vb.hi[d2] - vb.lo[d2] + 1;
+    for (int t = threadIdx.x + blockIdx.y * blockDim.x; t < n1 * n2; t += blockDim.x * gridDim.y) {
+        int idx[3];
+        idx[d] = g; idx[d1] = vb.lo[d1] + t % n1; idx[d2] = vb.lo[d2] + t / n1;
+        f(idx[0], idx[1], idx[2]);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_apply_bc (const b200mg_bcface* __restrict__ faces, const b200mg_box* __restrict__ vbox,
+            const b200mg_fab* phif, const b200mg_ifab* mf, const b200mg_fab* bvf,
+            int maxorder, double dxi0, double dxi1, double dxi2, int inhomog)
+{
+    const b200mg_bcface fc = faces[blockIdx.x];
+    const b200mg_box vb = vbox[fc.box];
+    const auto phi = view(phif[fc.box]);
+    const auto mask = view(mf[fc.box * 6 + fc.face]);
+    const int d = fc.face % 3;
+    const int s = (fc.face < 3) ? 1 : -1;                 // towards the interior
+    const long long st = (d == 0) ? 1 : ((d == 1) ? phi.js : phi.ks);
+    const double dxinv = (d == 0) ? dxi0 : ((d == 1) ? dxi1 : dxi2);
+    if (fc.bctype == kBcNeumann) {
+        face_loop(vb, fc.face, [&] (int i, int j, int k) {
+            if (mask(i, j, k) > 0) { double* p = phi.ptr(i, j, k); *p = p[s * st]; } });
+    } else if (fc.bctype == kBcReflectOdd) {
+        face_loop(vb, fc.face, [&] (int i, int j, int k) {
+            if (mask(i, j, k) > 0) { double* p = phi.ptr(i, j, k); *p = -p[s * st]; } });
+    } else if (fc.bctype == kBcDirichlet) {
+        const int NX = min(fc.blen + 1, maxorder);
+        double x[4] = {-fc.bcloc * dxinv, 0.5, 1.5, 2.5};
+        double coef[4] = {0., 0., 0., 0.};
+        poly_interp_coeff(-0.5, x, NX, coef);
+        const bool inh = inhomog && (bvf != nullptr);
+        face_loop(vb, fc.face, [&] (int i, int j, int k) {
+            if (mask(i, j, k) > 0) {
+                double* p = phi.ptr(i, j, k);
+                double tmp = 0.0;
+                for (int m = 1; m < NX; ++m) { tmp += p[m * s * st] * coef[m]; }
+                if (inh) { tmp += view(bvf[fc.box * 6 + fc.face])(i, j, k) * coef[0]; }
+                *p = tmp;
+            } });
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_comp_interp_coef0 (const b200mg_bcface* __restrict__ faces, const b200mg_box* __restrict__ vbox,
+                     const b200mg_fab* ff, const b200mg_ifab* mf,
+                     int maxorder, double dxi0, double dxi1, double dxi2)
+{
+    const b200mg_bcface fc = faces[blockIdx.x];
+    const b200mg_box vb = vbox[fc.box];
+    const auto f = view(ff[fc.box * 6 + fc.face]);
+    const auto mask = view(mf[fc.box * 6 + fc.face]);
+    const int d = fc.face % 3;
+    const int s = (fc.face < 3) ? 1 : -1;
+    const double dxinv = (d == 0) ? dxi0 : ((d == 1) ? dxi1 : dxi2);
+    double c1 = 0.0;
+    if (fc.bctype == kBcDirichlet) {
+        const int NX = min(fc.blen + 1, maxorder);
+        double x[4] = {-fc.bcloc * dxinv, 0.5, 1.5, 2.5};
+        double coef[4] = {0., 0., 0., 0.};
+        poly_interp_coeff(-0.5, x, NX, coef);
+        c1 = coef[1];
+    }
+    const int bct = fc.bctype;
+    face_loop(vb, fc.face, [&] (int i, int j, int k) {
+        int ii = i, jj = j, kk = k;
+        if (d == 0) { ii += s; } else if (d == 1) { jj += s; } else { kk += s; }
+        if (bct == kBcNeumann) { f(ii, jj, kk) = 1.0; }
+        else if (bct == kBcReflectOdd) { f(ii, jj, kk) = (mask(i, j, k) > 0) ? 1.0 : 0.0; }
+        else if (bct == kBcDirichlet) { f(ii, jj, kk) = (mask(i, j, k) > 0) ? c1 : 0.0; }
+    });
+}
+
+} // namespace
+
+extern "C" {
+
+int b200mg_gsrb_abec (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                      const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,
+                      const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                      const b200mg_fab* f, const b200mg_ifab* m,
+                      double alpha, double dhx, double dhy, double dhz, int redblack, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    AbecArgs A{phi, rhs, a, bx, by, bz, f, m, alpha, dhx, dhy, dhz};
+    k_gsrb_abec<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, A, redblack);
+    return last_error();
+}
+
+int b200mg_gsrb_poisson (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                         const b200mg_fab* phi, const b200mg_fab* rhs,
+                         const b200mg_fab* f, const b200mg_ifab* m,
+                         double dhx, double dhy, double dhz, int redblack, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    PoisArgs A{phi, rhs, f, m, dhx, dhy, dhz};
+    k_gsrb_poisson<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, A, redblack);
+    return last_error();
+}
+
+int b200mg_gsrb_shell_abec (int nboxes, const b200mg_box* vbox,
+                            const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,
+                            const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                            const b200mg_fab* f, const b200mg_ifab* m,
+                            double alpha, double dhx, double dhy, double dhz, int redblack, cudaStream_t s)
+{
+    if (nboxes <= 0) { return 0; }
+    AbecArgs A{phi, rhs, a, bx, by, bz, f, m, alpha, dhx, dhy, dhz};
+    k_gsrb_shell_abec<<<nboxes * 6, 256, 0, s>>>(vbox, A, redblack);
+    return last_error();
+}
+
+int b200mg_gsrb_shell_poisson (int nboxes, const b200mg_box* vbox,
+                               const b200mg_fab* phi, const b200mg_fab* rhs,
+                               const b200mg_fab* f, const b200mg_ifab* m,
+                               double dhx, double dhy, double dhz, int redblack, cudaStream_t s)
+{
+    if (nboxes <= 0) { return 0; }
+    PoisArgs A{phi, rhs, f, m, dhx, dhy, dhz};
+    k_gsrb_shell_poisson<<<nboxes * 6, 256, 0, s>>>(vbox, A, redblack);
+    return last_error();
+}
+
+int b200mg_adotx_abec (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                       const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs, const b200mg_fab* a,
+                       const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                       double alpha, double dhx, double dhy, double dhz, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_adotx_abec<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, a, bx, by, bz, alpha, dhx, dhy, dhz);
+    return last_error();
+}
+
+int b200mg_adotx_poisson (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                          const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs,
+                          double dhx, double dhy, double dhz, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_adotx_poisson<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, dhx, dhy, dhz);
+    return last_error();
+}
+
+int b200mg_normalize_abec (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                           const b200mg_fab* x, const b200mg_fab* a,
+                           const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                           double alpha, double dhx, double dhy, double dhz, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_normalize_abec<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, x, a, bx, by, bz, alpha, dhx, dhy, dhz);
+    return last_error();
+}
+
+int b200mg_apply_bc (int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
+                     const b200mg_fab* phi, const b200mg_ifab* m, const b200mg_fab* bcval,
+                     int maxorder, double dxinv0, double dxinv1, double dxinv2, int inhomog, cudaStream_t s)
+{
+    if (nfaces <= 0) { return 0; }
+    k_apply_bc<<<dim3(nfaces, 8), 128, 0, s>>>(faces, vbox, phi, m, bcval, maxorder, dxinv0, dxinv1, dxinv2, inhomog);
+    return last_error();
+}
+
+int b200mg_comp_interp_coef0 (int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
+                              const b200mg_fab* f, const b200mg_ifab* m,
+                              int maxorder, double dxinv0, double dxinv1, double dxinv2, cudaStream_t s)
+{
+    if (nfaces <= 0) { return 0; }
+    k_comp_interp_coef0<<<dim3(nfaces, 8), 128, 0, s>>>(faces, vbox, f, m, maxorder, dxinv0, dxinv1, dxinv2);
+    return last_error();
+}
+
+const char* b200mg_version (void) { return "amrex_b200 0.1 (sm_100a)"; }
+
+} // extern "C"

@@ -1,0 +1,226 @@
+// Vector operations, reductions and halo copy kernels.  Reference rows K6, K10, K12.
+#include "common.cuh"
+
+using namespace b200mg;
+
+namespace {
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_setval (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* yf, double v, int ng)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto y = view(yf[t.box]);
+    tile_for(t, vb, ng, [&] (int i, int j, int k) { y(i, j, k) = v; });
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_setbndry (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* yf, double v, int ng)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto y = view(yf[t.box]);
+    tile_for(t, vb, ng, [&] (int i, int j, int k) {
+        const bool inside = i >= vb.lo[0] && i <= vb.hi[0] && j >= vb.lo[1] && j <= vb.hi[1] && k >= vb.lo[2] && k <= vb.hi[2];
+        if (!inside) { y(i, j, k) = v; }
+    });
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_copy (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* yf, const b200mg_fab* xf, int ng)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto y = view(yf[t.box]); const auto x = view(xf[t.box]);
+    tile_for(t, vb, ng, [&] (int i, int j, int k) { y(i, j, k) = x(i, j, k); });
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_lincomb (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* yf,
+           double a, const b200mg_fab* xf, double b, int ng)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto y = view(yf[t.box]); const auto x = view(xf[t.box]);
+    tile_for(t, vb, ng, [&] (int i, int j, int k) { y(i, j, k) = a * x(i, j, k) + b * y(i, j, k); });
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_plus (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* yf, double v, int ng)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto y = view(yf[t.box]);
+    tile_for(t, vb, ng, [&] (int i, int j, int k) { y(i, j, k) += v; });
+}
+
+// Two-stage deterministic reduction: per-block partials in scratch[0..n), the last block to finish
+// (ticket in scratch[n]) folds them in index order and resets the ticket.
+template <class Op, class F>
+__device__ __forceinline__ void reduce_tiles (const b200mg_tile t, const b200mg_box& vb, double* result, double* scratch, F&& f)
+{
+    double acc = Op::id();
+    tile_for(t, vb, 0, [&] (int i, int j, int k) { acc = Op::ap(acc, f(i, j, k)); });
+    acc = block_reduce<Op>(acc);
+    __shared__ bool is_last;
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int n = gridDim.x;
+    if (tid == 0) {
+        scratch[blockIdx.x] = acc;
+        __threadfence();
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + n);
+        const unsigned int prev = atomicAdd(ticket, 1u);
+        is_last = (prev == unsigned(n - 1));
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double v = Op::id();
+        const int nt = blockDim.x * blockDim.y;
+        // fixed partition: thread t folds partials t, t+nt, ... in order; then a block tree
+        for (int b = tid; b < n; b += nt) { v = Op::ap(v, reinterpret_cast<volatile double*>(scratch)[b]); }
+        __syncthreads();
+        v = block_reduce<Op>(v);
+        if (tid == 0) {
+            result[0] = v;
+            *reinterpret_cast<unsigned int*>(scratch + n) = 0u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_norminf (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* xf,
+           const b200mg_ifab* mf, double* result, double* scratch)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto x = view(xf[t.box]);
+    if (mf) {
+        const auto m = view(mf[t.box]);
+        reduce_tiles<OpMax>(t, vb, result, scratch, [&] (int i, int j, int k) { return m(i, j, k) ? fabs(x(i, j, k)) : 0.0; });
+    } else {
+        reduce_tiles<OpMax>(t, vb, result, scratch, [&] (int i, int j, int k) { return fabs(x(i, j, k)); });
+    }
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_dot (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* xf,
+       const b200mg_fab* yf, double* result, double* scratch)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto x = view(xf[t.box]); const auto y = view(yf[t.box]);
+    reduce_tiles<OpSum>(t, vb, result, scratch, [&] (int i, int j, int k) { return x(i, j, k) * y(i, j, k); });
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_sum (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* xf,
+       double* result, double* scratch)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto x = view(xf[t.box]);
+    reduce_tiles<OpSum>(t, vb, result, scratch, [&] (int i, int j, int k) { return x(i, j, k); });
+}
+
+// fab_to_fab / pack / unpack (AMReX_FBI.H:53-70, 729-893).  blockIdx.x = tag; threads sweep the tag box,
+// x fastest, then y, z, component -- the order that also defines the linear buffer layout (AMReX_FBI.H:765-771).
+__global__ void __launch_bounds__(256)
+k_copy_tags (const b200mg_copytag* __restrict__ tags, const b200mg_fab* dstf, const b200mg_fab* srcf,
+             double* __restrict__ buf, int ncomp, int scomp, int dcomp, int op)
+{
+    const b200mg_copytag t = tags[blockIdx.x];
+    const int n0 = t.hi[0] - t.lo[0] + 1, n1 = t.hi[1] - t.lo[1] + 1, n2 = t.hi[2] - t.lo[2] + 1;
+    const long long npts = (long long)n0 * n1 * n2;
+    const long long ntot = npts * ncomp;
+    for (long long idx = threadIdx.x + (long long)blockIdx.y * blockDim.x; idx < ntot; idx += (long long)blockDim.x * gridDim.y) {
+        const int n = int(idx / npts);
+        const long long r = idx - n * npts;
+        const int i = t.lo[0] + int(r % n0), j = t.lo[1] + int((r / n0) % n1), k = t.lo[2] + int(r / ((long long)n0 * n1));
+        double v;
+        if (t.src_fab >= 0) { v = view(srcf[t.src_fab])(i + t.shift[0], j + t.shift[1], k + t.shift[2], n + scomp); }
+        else { v = buf[t.buf_offset + idx]; }
+        if (t.dst_fab >= 0) {
+            double& d = view(dstf[t.dst_fab])(i, j, k, n + dcomp);
+            if (op == 0) { d = v; } else { d += v; }
+        } else {
+            buf[t.buf_offset + idx] = v;
+        }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int b200mg_setval (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y, double v, int ng, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_setval<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, v, ng);
+    return last_error();
+}
+
+int b200mg_setbndry (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y, double v, int ng, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_setbndry<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, v, ng);
+    return last_error();
+}
+
+int b200mg_copy (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y, const b200mg_fab* x, int ng, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_copy<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, ng);
+    return last_error();
+}
+
+int b200mg_lincomb (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y,
+                    double a, const b200mg_fab* x, double b, int ng, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_lincomb<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, a, x, b, ng);
+    return last_error();
+}
+
+int b200mg_plus (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y, double v, int ng, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_plus<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, v, ng);
+    return last_error();
+}
+
+long long b200mg_reduce_scratch_doubles (int ntiles) { return (long long)ntiles + 2; }
+
+int b200mg_norminf (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x,
+                    const b200mg_ifab* mask, double* result, double* scratch, cudaStream_t s)
+{
+    if (ntiles <= 0) { return int(cudaMemsetAsync(result, 0, sizeof(double), s)); }
+    k_norminf<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, x, mask, result, scratch);
+    return last_error();
+}
+
+int b200mg_dot (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x,
+                const b200mg_fab* y, double* result, double* scratch, cudaStream_t s)
+{
+    if (ntiles <= 0) { return int(cudaMemsetAsync(result, 0, sizeof(double), s)); }
+    k_dot<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, x, y, result, scratch);
+    return last_error();
+}
+
+int b200mg_sum (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x,
+                double* result, double* scratch, cudaStream_t s)
+{
+    if (ntiles <= 0) { return int(cudaMemsetAsync(result, 0, sizeof(double), s)); }
+    k_sum<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, x, result, scratch);
+    return last_error();
+}
+
+int b200mg_copy_tags (int ntags, const b200mg_copytag* tags, const b200mg_fab* dst, const b200mg_fab* src,
+                      double* buf, int ncomp, int scomp, int dcomp, int op, cudaStream_t s)
+{
+    if (ntags <= 0) { return 0; }
+    k_copy_tags<<<dim3(ntags, 4), 256, 0, s>>>(tags, dst, src, buf, ncomp, scomp, dcomp, op);
+    return last_error();
+}
+
+} // extern "C"

@@ -1,0 +1,795 @@
+// MG hierarchy, boundary bookkeeping and level operations of the cell-centred operators.
+#include "AMReX_MLMG.H"
+
+#include <cuda_runtime.h>
+
+namespace amrex {
+
+#define B200_KCALL(call) do { int e__ = (call); amrex::Gpu::countLaunch(); if (e__ != 0) amrex::Gpu::check(e__, #call, __FILE__, __LINE__); } while (0)
+
+// ================================================================================ MGHierarchy::define
+// Restates MLLinOpT::defineGrids (AMReX_MLLinOp.H:795-1165) without semicoarsening / hidden dimensions / EB.
+void MGHierarchy::define (Vector<Geometry> const& a_geom, Vector<BoxArray> const& a_grids,
+                          Vector<DistributionMapping> const& a_dmap, LPInfo info, int nprocs)
+{
+    if (info.agg_grid_size <= 0) { info.agg_grid_size = LPInfo::getDefaultAgglomerationGridSize(); }
+    if (info.con_grid_size <= 0) { info.con_grid_size = LPInfo::getDefaultConsolidationGridSize(); }
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(!info.do_semicoarsening && info.hidden_direction < 0,
+                                     "semicoarsening / hidden dimension are outside this library's scope");
+    constexpr int mg_coarsen_ratio = 2, mg_box_min_width = 2, mg_domain_min_width = 2;
+
+    num_amr_levels = 0;
+    for (std::size_t a = 0; a < a_geom.size(); ++a) { if (!a_grids[a].empty()) { ++num_amr_levels; } }
+    amr_ref_ratio.assign(num_amr_levels, 0);   // entry amrlev: ratio between amrlev and amrlev+1
+    num_mg_levels.assign(num_amr_levels, 0);
+    geom.assign(num_amr_levels, {}); grids.assign(num_amr_levels, {}); dmap.assign(num_amr_levels, {});
+    mg_coarsen_ratio_vec.clear();
+
+    const RealBox rb = a_geom[0].ProbDomain();
+    const int coord = a_geom[0].Coord();
+    const Array<int, 3> is_per = a_geom[0].isPeriodic();
+    const IntVect rr2(mg_coarsen_ratio);
+
+    for (int amrlev = num_amr_levels - 1; amrlev > 0; --amrlev) {
+        num_mg_levels[amrlev] = 1;
+        geom[amrlev].push_back(a_geom[amrlev]);
+        grids[amrlev].push_back(a_grids[amrlev]);
+        dmap[amrlev].push_back(a_dmap[amrlev]);
+        IntVect rr = rr2;
+        const Box dom = a_geom[amrlev].Domain();
+        for (int i = 0; i < 2; ++i) {
+            if (!dom.coarsenable(rr)) { Abort("MLLinOp: Uncoarsenable domain"); }
+            const Box cdom = amrex::coarsen(dom, rr);
+            if (cdom == a_geom[amrlev - 1].Domain()) { break; }
+            ++num_mg_levels[amrlev];
+            geom[amrlev].emplace_back(cdom, rb, coord, is_per);
+            grids[amrlev].push_back(amrex::coarsen(a_grids[amrlev], rr));
+            dmap[amrlev].push_back(a_dmap[amrlev]);
+            rr *= rr2;
+        }
+        amr_ref_ratio[amrlev - 1] = rr[0];
+    }
+
+    num_mg_levels[0] = 1;
+    geom[0].push_back(a_geom[0]);
+    grids[0].push_back(a_grids[0]);
+    dmap[0].push_back(a_dmap[0]);
+
+    domain_covered.assign(num_amr_levels, 0);
+    const Long npts0 = grids[0][0].numPts();
+    domain_covered[0] = (npts0 == geom[0][0].Domain().numPts());
+    for (int amrlev = 1; amrlev < num_amr_levels; ++amrlev) {
+        if (!domain_covered[amrlev - 1]) { break; }
+        domain_covered[amrlev] = (grids[amrlev][0].numPts() == geom[amrlev][0].Domain().numPts());
+    }
+
+    Box aggbox;
+    bool aggable = false;
+    if (grids[0][0].size() > 1 && info.do_agglomeration) {
+        if (domain_covered[0]) { aggbox = geom[0][0].Domain(); aggable = true; }
+        else { aggbox = grids[0][0].minimalBox(); aggable = (aggbox.numPts() == npts0); }
+    }
+
+    agged = false; coned = false; agg_lev = 0; con_lev = 0;
+
+    if (info.do_agglomeration && aggable) {
+        Box dbx = geom[0][0].Domain();
+        Box bbx = aggbox;
+        const Real nbxs = Real(grids[0][0].size());
+        const Real threshold_npts = Real(info.agg_grid_size) * Real(info.agg_grid_size) * Real(info.agg_grid_size);
+        Vector<Box> domainboxes{dbx}, boundboxes{bbx};
+        Vector<int> agg_flag{0};
+        Vector<IntVect> accum{IntVect(1)};
+        for (int lev = 0; lev < info.max_coarsening_level; ++lev) {
+            bool ok = true;
+            for (int d = 0; d < 3; ++d) {
+                IntVect rr_dir(1); rr_dir[d] = mg_coarsen_ratio;
+                ok = ok && dbx.coarsenable(rr_dir, IntVect(mg_domain_min_width)) && bbx.coarsenable(rr_dir, IntVect(mg_box_min_width));
+            }
+            if (!ok) { break; }
+            accum.push_back(accum.back() * rr2);
+            domainboxes.push_back(dbx.coarsen(rr2));
+            boundboxes.push_back(bbx.coarsen(rr2));
+            const bool to_agg = (bbx.d_numPts() / nbxs) < 0.999 * threshold_npts;
+            agg_flag.push_back(to_agg);
+        }
+        for (int lev = 1, nlevs = int(domainboxes.size()); lev < nlevs; ++lev) {
+            if (!agged && !agg_flag[lev] && a_grids[0].coarsenable(accum[lev], IntVect(mg_box_min_width))) {
+                grids[0].push_back(amrex::coarsen(a_grids[0], accum[lev]));
+                dmap[0].push_back(a_dmap[0]);
+            } else {
+                IntVect cr = domainboxes[lev - 1].length() / domainboxes[lev].length();
+                if (!grids[0].back().coarsenable(cr)) { break; }
+                BoxArray nba(boundboxes[lev]);
+                nba.maxSize(IntVect(info.agg_grid_size));
+                grids[0].push_back(nba);
+                dmap[0].push_back(DistributionMapping());
+                if (!agged) { agged = true; agg_lev = lev; }
+            }
+            geom[0].emplace_back(domainboxes[lev], rb, coord, is_per);
+        }
+    } else {
+        Long consolidation_threshold = 0;
+        Real avg_npts = 0.0;
+        if (info.do_consolidation) {
+            avg_npts = Real(a_grids[0].d_numPts()) / Real(nprocs);
+            consolidation_threshold = Long(info.con_grid_size) * info.con_grid_size * info.con_grid_size;
+        }
+        const Box dom0 = a_geom[0].Domain();
+        IntVect rr_vec(1);
+        for (int lev = 0; lev < info.max_coarsening_level; ++lev) {
+            bool ok = true;
+            for (int d = 0; d < 3; ++d) {
+                IntVect rr_dir(1); rr_dir[d] = rr_vec[d] * mg_coarsen_ratio;
+                ok = ok && dom0.coarsenable(rr_dir, IntVect(mg_domain_min_width)) && a_grids[0].coarsenable(rr_dir, IntVect(mg_box_min_width));
+            }
+            if (!ok) { break; }
+            rr_vec *= rr2;
+            geom[0].emplace_back(amrex::coarsen(dom0, rr_vec), rb, coord, is_per);
+            grids[0].push_back(amrex::coarsen(a_grids[0], rr_vec));
+            if (info.do_consolidation) {
+                if (avg_npts / Real(Long(rr_vec[0]) * rr_vec[1] * rr_vec[2]) < Real(0.999) * Real(consolidation_threshold)) {
+                    coned = true; con_lev = int(dmap[0].size());
+                    dmap[0].push_back(DistributionMapping());
+                } else {
+                    dmap[0].push_back(dmap[0].back());
+                }
+            } else {
+                dmap[0].push_back(a_dmap[0]);
+            }
+        }
+    }
+
+    num_mg_levels[0] = int(grids[0].size());
+    for (int mglev = 0; mglev < num_mg_levels[0] - 1; ++mglev) {
+        mg_coarsen_ratio_vec.push_back(geom[0][mglev].Domain().length() / geom[0][mglev + 1].Domain().length());
+    }
+    for (int amrlev = 0; amrlev + 1 < num_amr_levels; ++amrlev) {
+        if (amr_ref_ratio[amrlev] == 4 && mg_coarsen_ratio_vec.empty()) { mg_coarsen_ratio_vec.push_back(IntVect(2)); }
+    }
+
+    if (agged) {   // makeAgglomeratedDMap, AMReX_MLLinOp.H:1294-1319
+        for (std::size_t i = 1; i < grids[0].size(); ++i) {
+            if (dmap[0][i].empty()) {
+                auto sfc = DistributionMapping::makeSFC(grids[0][i], true, nprocs);
+                Vector<int> pmap(grids[0][i].size());
+                for (int ip = 0; ip < nprocs; ++ip) { for (int ib : sfc[ip]) { pmap[ib] = ip; } }
+                dmap[0][i].define(std::move(pmap));
+            }
+        }
+    } else if (coned) {   // makeConsolidatedDMap, AMReX_MLLinOp.H:1323-1375
+        int factor = 1;
+        const int ratio = info.con_ratio, strategy = info.con_strategy;
+        for (std::size_t i = 1; i < grids[0].size(); ++i) {
+            if (!dmap[0][i].empty()) { continue; }
+            factor *= ratio;
+            Vector<int> pmap = dmap[0][i - 1].ProcessorMap();
+            if (strategy == 1) { for (auto& x : pmap) { x /= ratio; } }
+            else if (strategy == 2) {
+                const int nprocs_con = int(std::ceil(Real(nprocs) / Real(factor)));
+                for (auto& x : pmap) { x = x % nprocs_con; }
+            } else if (strategy == 3) {
+                if (factor == ratio) {
+                    auto sfc = DistributionMapping::makeSFC(grids[0][i], true, nprocs);
+                    for (int ip = 0; ip < nprocs; ++ip) { for (int ib : sfc[ip]) { pmap[ib] = ip; } }
+                }
+                for (auto& x : pmap) { x /= ratio; }
+            }
+            dmap[0][i].define(std::move(pmap));
+        }
+    }
+
+    for (int amrlev = 1; amrlev < num_amr_levels; ++amrlev) {
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(grids[amrlev][0].coarsenable(amr_ref_ratio[amrlev - 1]),
+                                         "MLLinOp: grids not coarsenable between AMR levels");
+    }
+}
+
+// ========================================================================================= BndrySlabs
+template <class T>
+void BndrySlabs<T>::define (LevelLayout const& L, bool inside)
+{
+    clear();
+    const int nl = L.numLocal();
+    m_boxes.resize(nl * 6); m_offs.resize(nl * 6); m_hdesc.resize(nl * 6);
+    std::size_t total = 0;
+    for (int li = 0; li < nl; ++li) {
+        for (int f = 0; f < 6; ++f) {
+            const Orientation face(f);
+            const Box b = inside ? insideCell(L.box(li), face, 1) : adjCell(L.box(li), face, 1);
+            m_boxes[li * 6 + f] = b;
+            m_offs[li * 6 + f] = total;
+            total += std::size_t(b.numPts());
+            total = (total + 1) / 2 * 2;
+        }
+    }
+    m_nelem = total; m_defined = true;
+    if (total) {
+        m_data = static_cast<T*>(The_Arena()->alloc(total * sizeof(T)));
+        Gpu::memset_async(m_data, 0, total * sizeof(T));
+    }
+    for (int n = 0; n < nl * 6; ++n) {
+        Desc& d = m_hdesc[n]; Box const& b = m_boxes[n];
+        d.p = m_data + m_offs[n];
+        for (int a = 0; a < 3; ++a) { d.lo[a] = b.smallEnd(a); d.hi[a] = b.bigEnd(a); }
+        d.jstride = b.length(0); d.kstride = Long(b.length(0)) * b.length(1); d.nstride = d.kstride * b.length(2);
+    }
+    m_ddesc.assign(m_hdesc);
+}
+
+template <class T>
+void BndrySlabs<T>::clear ()
+{
+    if (m_data) { The_Arena()->free(m_data); m_data = nullptr; }
+    m_boxes.clear(); m_offs.clear(); m_hdesc.clear(); m_ddesc.clear(); m_nelem = 0; m_defined = false;
+}
+
+template <class T>
+void BndrySlabs<T>::upload (std::vector<T> const& h)
+{
+    AMREX_ALWAYS_ASSERT(h.size() == m_nelem);
+    if (m_nelem) { Gpu::htod_memcpy_async(m_data, h.data(), m_nelem * sizeof(T)); Gpu::streamSynchronize(); }
+}
+
+template <class T>
+void BndrySlabs<T>::setVal (T v)
+{
+    std::vector<T> h(m_nelem, v); upload(h);
+}
+
+template class BndrySlabs<double>;
+template class BndrySlabs<int>;
+
+// ============================================================================================= MLLinOp
+void MLLinOp::define (Vector<Geometry> const& a_geom, Vector<BoxArray> const& a_grids,
+                      Vector<DistributionMapping> const& a_dmap, LPInfo const& a_info)
+{
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(Gpu::Initialized(), "amrex::Initialize (GPU) must be called before defining a linear operator");
+    info = a_info;
+    H.define(a_geom, a_grids, a_dmap, a_info, ParallelDescriptor::NProcs());
+    m_needs_coarse_data_for_bc = !H.domain_covered[0];
+    defineAuxData();
+}
+
+void MLLinOp::defineAuxData ()
+{
+    m_lev.resize(H.num_amr_levels);
+    for (int a = 0; a < H.num_amr_levels; ++a) {
+        m_lev[a].resize(H.num_mg_levels[a]);
+        for (int m = 0; m < H.num_mg_levels[a]; ++m) {
+            m_lev[a][m] = std::make_unique<LevelData>();
+            LevelData& L = *m_lev[a][m];
+            L.layout = LevelLayout::get(H.grids[a][m], H.dmap[a][m]);
+            L.undrrelxr.define(*L.layout, true);
+            buildMasks(a, m);
+        }
+    }
+    m_bndry_sol.resize(H.num_amr_levels);
+    m_bndry_cor.resize(H.num_amr_levels);
+    for (int a = 0; a < H.num_amr_levels; ++a) {
+        m_bndry_sol[a] = std::make_unique<BndrySlabs<double>>();
+        m_bndry_sol[a]->define(*lev(a, 0).layout, false);
+        if (a > 0) {
+            m_bndry_cor[a] = std::make_unique<BndrySlabs<double>>();
+            m_bndry_cor[a]->define(*lev(a, 0).layout, false);
+        }
+    }
+    m_norm_fine_mask.resize(std::max(0, H.num_amr_levels - 1));
+    for (int a = 0; a + 1 < H.num_amr_levels; ++a) {
+        m_norm_fine_mask[a] = std::make_unique<iMultiFab>(
+            makeFineMask(H.grids[a][0], H.dmap[a][0], H.grids[a + 1][0], H.amr_ref_ratio[a], 1, 0));
+    }
+}
+
+// MultiMask::define with in_rad=0, out_rad=1, extent_rad=0 (AMReX_MultiMask.cpp:24-70)
+void MLLinOp::buildMasks (int a, int m)
+{
+    LevelData& L = lev(a, m);
+    L.mask.define(*L.layout, false);
+    Geometry const& geom = H.geom[a][m];
+    BoxArray const& ba = H.grids[a][m];
+    Box domain = geom.Domain();
+    for (int d = 0; d < 3; ++d) { if (geom.isPeriodic(d)) { domain.grow(d, 1); } }
+    const auto pshifts = geom.periodicity().shiftIntVect();
+    std::vector<int> h(L.mask.numElements(), 0);
+    std::vector<std::pair<int, Box>> isects;
+    for (int li = 0; li < L.layout->numLocal(); ++li) {
+        for (int f = 0; f < 6; ++f) {
+            Box const& sb = L.mask.box(li, f);
+            int* p = h.data() + L.mask.offset(li, f);
+            const Long nx = sb.length(0), ny = sb.length(1);
+            auto at = [&] (int i, int j, int k) -> int& {
+                return p[(i - sb.smallEnd(0)) + nx * ((j - sb.smallEnd(1)) + ny * (k - sb.smallEnd(2)))];
+            };
+            for (int k = sb.smallEnd(2); k <= sb.bigEnd(2); ++k) for (int j = sb.smallEnd(1); j <= sb.bigEnd(1); ++j)
+                for (int i = sb.smallEnd(0); i <= sb.bigEnd(0); ++i) { at(i, j, k) = domain.contains(i, j, k) ? 1 : 2; }
+            for (auto const& pit : pshifts) {
+                ba.intersections(sb + pit, isects);
+                for (auto const& is : isects) {
+                    const Box b = is.second - pit;
+                    for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k) for (int j = b.smallEnd(1); j <= b.bigEnd(1); ++j)
+                        for (int i = b.smallEnd(0); i <= b.bigEnd(0); ++i) { at(i, j, k) = 0; }
+                }
+            }
+        }
+    }
+    L.mask.upload(h);
+    // which faces have any uncovered ghost cell (only those need boundary-condition work)
+    L.bcfaces_h.clear();
+    for (int li = 0; li < L.layout->numLocal(); ++li) {
+        for (int f = 0; f < 6; ++f) {
+            Box const& sb = L.mask.box(li, f);
+            const int* p = h.data() + L.mask.offset(li, f);
+            bool any = false;
+            for (Long n = 0, N = sb.numPts(); n < N && !any; ++n) { any = p[n] > 0; }
+            if (any) {
+                b200mg_bcface fc; fc.box = li; fc.face = f; fc.bctype = 0; fc.blen = L.layout->box(li).length(f % 3); fc.bcloc = 0.0;
+                L.bcfaces_h.push_back(fc);
+            }
+        }
+    }
+}
+
+void MLLinOp::setDomainBC (Array<BCType, 3> const& a_lobc, Array<BCType, 3> const& a_hibc)
+{
+    m_lobc = a_lobc; m_hibc = a_hibc; m_lobc_orig = m_lobc; m_hibc_orig = m_hibc;
+    for (int d = 0; d < 3; ++d) {
+        if (H.geom[0][0].isPeriodic(d)) {
+            AMREX_ALWAYS_ASSERT(m_lobc[d] == BCType::Periodic && m_hibc[d] == BCType::Periodic);
+        } else {
+            AMREX_ALWAYS_ASSERT(m_lobc[d] != BCType::Periodic && m_hibc[d] != BCType::Periodic);
+        }
+        if (m_lobc[d] == BCType::inhomogNeumann || m_lobc[d] == BCType::Robin) { Abort("inhomogeneous Neumann / Robin BC not supported yet"); }
+        if (m_hibc[d] == BCType::inhomogNeumann || m_hibc[d] == BCType::Robin) { Abort("inhomogeneous Neumann / Robin BC not supported yet"); }
+    }
+}
+
+void MLLinOp::setCoarseFineBC (const MultiFab* crse, int crse_ratio, LinOpBCType bc_type)
+{
+    m_coarse_data_for_bc = crse; m_coarse_data_crse_ratio = crse_ratio; m_coarse_fine_bc_type = bc_type;
+}
+
+// MLMGBndry::setBoxBC (AMReX_MLMGBndry.H:113-161) for every local box of the level
+void MLLinOp::buildBCFaces (int a, int m)
+{
+    LevelData& L = lev(a, m);
+    Geometry const& geom = H.geom[a][m];
+    const Box domain = geom.Domain();
+    const Real* dx0 = H.geom[a][0].CellSize();
+    const int ratio = (a == 0) ? (m_needs_coarse_data_for_bc ? m_coarse_data_crse_ratio : 1) : H.amr_ref_ratio[a - 1];
+    const int cf_type = (a == 0) ? int(m_coarse_fine_bc_type) : int(LinOpBCType::Dirichlet);
+    const int nl = L.layout->numLocal();
+    L.bcond.resize(nl); L.bcloc.resize(nl);
+    for (int li = 0; li < nl; ++li) {
+        Box const& bx = L.layout->box(li);
+        for (int f = 0; f < 6; ++f) {
+            const int d = f % 3; const bool low = f < 3;
+            const int dface = low ? domain.smallEnd(d) : domain.bigEnd(d);
+            const int bface = low ? bx.smallEnd(d) : bx.bigEnd(d);
+            if (dface == bface && !geom.isPeriodic(d)) {
+                L.bcloc[li][f] = low ? m_domain_bloc_lo[d] : m_domain_bloc_hi[d];
+                const BCType t = low ? m_lobc[d] : m_hibc[d];
+                if (t == BCType::Dirichlet) { L.bcond[li][f] = 101; }
+                else if (t == BCType::Neumann) { L.bcond[li][f] = 102; }
+                else if (t == BCType::reflect_odd) { L.bcond[li][f] = 103; }
+                else { Abort("MLMGBndry::setBoxBC: Unknown LinOpBCType"); }
+            } else {
+                L.bcond[li][f] = cf_type;
+                L.bcloc[li][f] = (ratio > 0) ? Real(0.5) * Real(ratio) * dx0[d] : 0.0;
+            }
+        }
+    }
+    for (auto& fc : L.bcfaces_h) { fc.bctype = L.bcond[fc.box][fc.face]; fc.bcloc = L.bcloc[fc.box][fc.face]; }
+    L.bcfaces.assign(L.bcfaces_h);
+}
+
+// MLCellLinOpT::setLevelBC (AMReX_MLCellLinOp.H:513-642): physical-boundary ghost values of levelbcdata are copied
+// into the level's boundary slabs (InterpBndryData::setPhysBndryValues, AMReX_InterpBndryData.H:128-156).
+void MLLinOp::setLevelBC (int amrlev, const MultiFab* levelbcdata)
+{
+    AMREX_ALWAYS_ASSERT(amrlev >= 0 && amrlev < H.num_amr_levels);
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_lobc[0] != BCType::bogus, "setDomainBC must be called before setLevelBC");
+    if (levelbcdata) { AMREX_ALWAYS_ASSERT(levelbcdata->nGrow() >= 1); }
+    LevelData& L = lev(amrlev, 0);
+    BndrySlabs<double>& B = *m_bndry_sol[amrlev];
+    B.setVal(0.0);
+    if (amrlev == 0 && m_needs_coarse_data_for_bc) {
+        Abort("level solve with coarse/fine boundary data (setCoarseFineBC) is not implemented yet");
+    }
+    if (levelbcdata) {
+        Geometry const& geom = H.geom[amrlev][0];
+        const Box domain = geom.Domain();
+        std::vector<b200mg_copytag> tags;
+        for (int li = 0; li < L.layout->numLocal(); ++li) {
+            Box const& bx = L.layout->box(li);
+            for (int f = 0; f < 6; ++f) {
+                const int d = f % 3; const bool low = f < 3;
+                const int dface = low ? domain.smallEnd(d) : domain.bigEnd(d);
+                const int bface = low ? bx.smallEnd(d) : bx.bigEnd(d);
+                if (dface == bface && !geom.isPeriodic(d)) {
+                    Box const& sb = B.box(li, f);
+                    b200mg_copytag t;
+                    for (int x = 0; x < 3; ++x) { t.lo[x] = sb.smallEnd(x); t.hi[x] = sb.bigEnd(x); t.shift[x] = 0; }
+                    t.dst_fab = li * 6 + f; t.src_fab = li; t.pad = 0; t.buf_offset = 0;
+                    tags.push_back(t);
+                }
+            }
+        }
+        if (!tags.empty()) {
+            DeviceTable<b200mg_copytag> dt(tags);
+            B200_KCALL(b200mg_copy_tags(int(tags.size()), dt.data(), B.d_table(), levelbcdata->d_fabs(), nullptr, 1, 0, 0, 0, Gpu::gpuStream()));
+            Gpu::streamSynchronize();
+        }
+    }
+    for (int m = 0; m < H.num_mg_levels[amrlev]; ++m) { buildBCFaces(amrlev, m); }
+}
+
+bool MLLinOp::isMFIterSafe (int amrlev, int mglev1, int mglev2) const
+{
+    if (!(H.dmap[amrlev][mglev1] == H.dmap[amrlev][mglev2])) { return false; }
+    BoxArray const& f = H.grids[amrlev][mglev1];
+    BoxArray const& c = H.grids[amrlev][mglev2];
+    if (f.size() != c.size()) { return false; }
+    const IntVect r = (amrlev > 0) ? IntVect(2) : H.mg_coarsen_ratio_vec[mglev1];
+    for (int i = 0, N = int(f.size()); i < N; ++i) { if (amrex::coarsen(f[i], r) != c[i]) { return false; } }
+    return true;
+}
+
+// MLCellLinOpT::prepareForSolve (AMReX_MLCellLinOp.H:1617-1926): fill the relaxation-coefficient slabs
+void MLLinOp::prepareForSolve ()
+{
+    for (int a = 0; a < H.num_amr_levels; ++a) {
+        for (int m = 0; m < H.num_mg_levels[a]; ++m) {
+            LevelData& L = lev(a, m);
+            AMREX_ALWAYS_ASSERT_WITH_MESSAGE(L.bcond.size() == std::size_t(L.layout->numLocal()), "setLevelBC must be called on every AMR level before solve");
+            // every face (not only uncovered ones): Neumann faces get 1 regardless of the mask
+            std::vector<b200mg_bcface> all;
+            for (int li = 0; li < L.layout->numLocal(); ++li) for (int f = 0; f < 6; ++f) {
+                b200mg_bcface fc; fc.box = li; fc.face = f; fc.bctype = L.bcond[li][f]; fc.blen = L.layout->box(li).length(f % 3); fc.bcloc = L.bcloc[li][f];
+                all.push_back(fc);
+            }
+            if (all.empty()) { continue; }
+            DeviceTable<b200mg_bcface> dall(all);
+            const Real* dxi = H.geom[a][m].InvCellSize();
+            B200_KCALL(b200mg_comp_interp_coef0(int(all.size()), dall.data(), L.layout->d_vbox(), L.undrrelxr.d_table(), L.mask.d_table(),
+                                                maxorder, dxi[0], dxi[1], dxi[2], Gpu::gpuStream()));
+            Gpu::streamSynchronize();
+        }
+    }
+}
+
+// MLCellLinOpT::applyBC (AMReX_MLCellLinOp.H:684-893), cross stencil
+void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, StateMode, const BndrySlabs<double>* bndry,
+                       bool skip_fillboundary) const
+{
+    AMREX_ALWAYS_ASSERT(mglev == 0 || bc_mode == BCMode::Homogeneous);
+    AMREX_ALWAYS_ASSERT(bndry != nullptr || bc_mode == BCMode::Homogeneous);
+    if (!skip_fillboundary) { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
+    LevelData const& L = lev(amrlev, mglev);
+    const int nf = int(L.bcfaces_h.size());
+    if (nf == 0) { return; }
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    const int flagbc = (bc_mode == BCMode::Inhomogeneous);
+    B200_KCALL(b200mg_apply_bc(nf, L.bcfaces.data(), L.layout->d_vbox(), in.d_fabs(), L.mask.d_table(),
+                               bndry ? bndry->d_table() : nullptr, maxorder, dxi[0], dxi[1], dxi[2], flagbc, Gpu::gpuStream()));
+}
+
+void MLLinOp::apply (int amrlev, int mglev, MultiFab& out, MultiFab& in, BCMode bc_mode, StateMode s_mode, const BndrySlabs<double>* bndry) const
+{
+    applyBC(amrlev, mglev, in, bc_mode, s_mode, bndry);
+    Fapply(amrlev, mglev, out, in);
+}
+
+// MLCellLinOpT::smooth (AMReX_MLCellLinOp.H:1206-1217): for each colour, refresh halos + BCs, then sweep.
+// Fused schedule (default): identical arithmetic and identical update order, but the red sweep and the part of the
+// black sweep that cannot depend on other boxes' red values run in ONE pass over memory (out of place); the black
+// sweep on the 1-cell surface shell runs after the second halo refresh.
+void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, bool skip_fillboundary) const
+{
+    LevelData const& L = lev(amrlev, mglev);
+    const bool fuse = m_fuse_colors && m_use_gauss_seidel && L.layout->localCells() >= 4096 * Long(std::max(1, L.layout->numLocal()));
+    if (!fuse) {
+        for (int redblack = 0; redblack < 2; ++redblack) {
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary);
+            Fsmooth(amrlev, mglev, sol, rhs, redblack);
+            skip_fillboundary = false;
+        }
+        return;
+    }
+    if (!L.scratch) { L.scratch = std::make_unique<MultiFab>(sol.boxArray(), sol.DistributionMap(), 1, sol.nGrow()); }
+    applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary);
+    Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs);
+    sol.swap(*L.scratch);
+    applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false);
+    FsmoothShell(amrlev, mglev, sol, rhs, 1);
+}
+
+void MLLinOp::solutionResidual (int amrlev, MultiFab& resid, MultiFab& x, MultiFab const& b, const MultiFab* crse_bcdata)
+{
+    if (crse_bcdata != nullptr) { Abort("solutionResidual with coarse BC data: AMR composite path not implemented yet"); }
+    applyBC(amrlev, 0, x, BCMode::Inhomogeneous, StateMode::Solution, m_bndry_sol[amrlev].get());
+    Fapply(amrlev, 0, resid, x, &b);    // resid = b - L(x), fused (== Fapply + Xpay(resid,-1,b))
+}
+
+void MLLinOp::correctionResidual (int amrlev, int mglev, MultiFab& resid, MultiFab& x, MultiFab const& b, BCMode bc_mode, const MultiFab* crse_bcdata)
+{
+    if (bc_mode == BCMode::Inhomogeneous) {
+        if (crse_bcdata) { Abort("correctionResidual with coarse BC data: AMR composite path not implemented yet"); }
+        applyBC(amrlev, mglev, x, BCMode::Inhomogeneous, StateMode::Correction, m_bndry_cor[amrlev].get());
+    } else {
+        applyBC(amrlev, mglev, x, BCMode::Homogeneous, StateMode::Correction, nullptr);
+    }
+    Fapply(amrlev, mglev, resid, x, &b);
+}
+
+void MLLinOp::restriction (int amrlev, int cmglev, MultiFab& crse, MultiFab& fine) const
+{
+    const int ratio = (amrlev > 0) ? 2 : H.mg_coarsen_ratio_vec[cmglev - 1][0];
+    if (isMFIterSafe(amrlev, cmglev - 1, cmglev)) {
+        auto const& T = crse.layout().tiles(0);
+        B200_KCALL(b200mg_restrict_cc(T.n, T.d.data(), crse.layout().d_vbox(), crse.d_fabs(), fine.d_fabs(), ratio, Gpu::gpuStream()));
+    } else {   // average_down through a coarsened-fine temporary + ParallelCopy (AMReX_MultiFabUtil.H:582-650)
+        LevelData const& L = lev(amrlev, cmglev - 1);
+        if (!L.restrict_tmp) { L.restrict_tmp = std::make_unique<MultiFab>(amrex::coarsen(fine.boxArray(), ratio), fine.DistributionMap(), 1, 0); }
+        MultiFab& tmp = *L.restrict_tmp;
+        auto const& T = tmp.layout().tiles(0);
+        B200_KCALL(b200mg_restrict_cc(T.n, T.d.data(), tmp.layout().d_vbox(), tmp.d_fabs(), fine.d_fabs(), ratio, Gpu::gpuStream()));
+        crse.ParallelCopy(tmp, 0, 0, 1);
+    }
+}
+
+void MLLinOp::avgDownResMG (int clev, MultiFab& cres, MultiFab const& fres) const
+{
+    restriction(0, clev, cres, const_cast<MultiFab&>(fres));
+}
+
+// piecewise-constant V-cycle prolongation (AMReX_MLCellLinOp.H:956-999); crse must be on fine's coarsened layout
+void MLLinOp::interpolation (int amrlev, int fmglev, MultiFab& fine, MultiFab const& crse) const
+{
+    const int ratio = (amrlev > 0) ? 2 : H.mg_coarsen_ratio_vec[fmglev][0];
+    AMREX_ALWAYS_ASSERT(ratio == 2);
+    auto const& T = fine.layout().tiles(0);
+    B200_KCALL(b200mg_prolong_add(T.n, T.d.data(), fine.layout().d_vbox(), fine.d_fabs(), crse.d_fabs(), Gpu::gpuStream()));
+}
+
+// trilinear interpolation used by the F-cycle (AMReX_MLCellLinOp.H:1003-1092)
+void MLLinOp::interpAssign (int amrlev, int fmglev, MultiFab& fine, MultiFab& crse) const
+{
+    Geometry const& cgeom = H.geom[amrlev][fmglev + 1];
+    const MultiFab* cmf = &crse;
+    if (isMFIterSafe(amrlev, fmglev, fmglev + 1)) {
+        crse.FillBoundary(0, 1, IntVect(crse.nGrow()), cgeom.periodicity(), false);
+    } else {
+        LevelData const& L = lev(amrlev, fmglev);
+        if (!L.interp_tmp) { L.interp_tmp = std::make_unique<MultiFab>(amrex::coarsen(fine.boxArray(), 2), fine.DistributionMap(), 1, crse.nGrow()); }
+        L.interp_tmp->setVal(0.0);
+        L.interp_tmp->ParallelCopy(crse, 0, 0, 1, 0, crse.nGrow(), cgeom.periodicity());
+        cmf = L.interp_tmp.get();
+    }
+    auto const& T = fine.layout().tiles(0);
+    B200_KCALL(b200mg_interp_cc_r2(T.n, T.d.data(), fine.layout().d_vbox(), fine.d_fabs(), cmf->d_fabs(), 0, Gpu::gpuStream()));
+}
+
+Real MLLinOp::xdoty (int, int, MultiFab const& x, MultiFab const& y, bool local) const { return MultiFab::Dot(x, y, local); }
+
+Real MLLinOp::normInf (int amrlev, MultiFab const& mf, bool local) const
+{
+    const int finest = H.num_amr_levels - 1;
+    return (amrlev == finest) ? mf.norminf(local) : mf.norminf(*m_norm_fine_mask[amrlev], local);
+}
+
+Vector<Real> MLLinOp::getSolvabilityOffset (int amrlev, int mglev, MultiFab const& rhs) const
+{
+    if (m_volinv.empty()) {   // computeVolInv, AMReX_MLCellLinOp.H:1944-2004
+        m_volinv.resize(H.num_amr_levels);
+        for (int a = 0; a < H.num_amr_levels; ++a) { m_volinv[a].assign(H.num_mg_levels[a], 0.0); }
+        auto f = [&] (int a, int m) {
+            if (m_coarse_fine_bc_type == LinOpBCType::Dirichlet) { m_volinv[a][m] = Real(1.0 / H.geom[a][m].Domain().d_numPts()); }
+            else { m_volinv[a][m] = Real(1.0 / H.grids[a][m].d_numPts()); }
+        };
+        f(0, 0); f(0, H.num_mg_levels[0] - 1);
+    }
+    Vector<Real> offset(1);
+    offset[0] = rhs.sum(true) * m_volinv[amrlev][mglev];
+    ParallelDescriptor::ReduceRealSum(offset.data(), 1);
+    return offset;
+}
+
+void MLLinOp::fixSolvabilityByOffset (int, int, MultiFab& rhs, Vector<Real> const& offset) const { rhs.plus(-offset[0], 0); }
+
+void MLLinOp::averageDownAndSync (Vector<MultiFab>& sol) const
+{
+    for (int falev = H.num_amr_levels - 1; falev > 0; --falev) { average_down(sol[falev], sol[falev - 1], 0, 1, H.amr_ref_ratio[falev - 1]); }
+}
+
+// ====================================================================================== MLABecLaplacian
+void MLABecLaplacian::define (Vector<Geometry> const& a_geom, Vector<BoxArray> const& a_grids,
+                              Vector<DistributionMapping> const& a_dmap, LPInfo const& a_info)
+{
+    MLLinOp::define(a_geom, a_grids, a_dmap, a_info);
+    m_a_coeffs.resize(H.num_amr_levels); m_b_coeffs.resize(H.num_amr_levels);
+    for (int a = 0; a < H.num_amr_levels; ++a) {
+        m_a_coeffs[a].resize(H.num_mg_levels[a]); m_b_coeffs[a].resize(H.num_mg_levels[a]);
+        for (int m = 0; m < H.num_mg_levels[a]; ++m) {
+            m_a_coeffs[a][m].define(H.grids[a][m], H.dmap[a][m], 1, 0);
+            for (int d = 0; d < 3; ++d) {
+                m_b_coeffs[a][m][d].define(amrex::convert(H.grids[a][m], IntVect::TheDimensionVector(d)), H.dmap[a][m], 1, 0);
+            }
+        }
+    }
+}
+
+void MLABecLaplacian::setScalars (Real a, Real b) noexcept
+{
+    m_a_scalar = a; m_b_scalar = b;
+    if (a == 0.0) { for (int l = 0; l < H.num_amr_levels; ++l) { m_a_coeffs[l][0].setVal(0.0); } }
+}
+
+void MLABecLaplacian::setACoeffs (int amrlev, MultiFab const& alpha)
+{
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(alpha.nComp() == 1, "MLABecLaplacian::setACoeffs: alpha is supposed to be single component.");
+    m_a_coeffs[amrlev][0].ParallelCopy(alpha, 0, 0, 1);   // LocalCopy when layouts agree
+    m_needs_update = true;
+}
+
+void MLABecLaplacian::setACoeffs (int amrlev, Real alpha) { m_a_coeffs[amrlev][0].setVal(alpha); m_needs_update = true; }
+
+void MLABecLaplacian::setBCoeffs (int amrlev, Array<MultiFab const*, 3> const& beta)
+{
+    for (int d = 0; d < 3; ++d) { m_b_coeffs[amrlev][0][d].ParallelCopy(*beta[d], 0, 0, 1); }
+    m_needs_update = true;
+}
+
+void MLABecLaplacian::setBCoeffs (int amrlev, Real beta)
+{
+    for (int d = 0; d < 3; ++d) { m_b_coeffs[amrlev][0][d].setVal(beta); }
+    m_needs_update = true;
+}
+
+void MLABecLaplacian::averageDownCoeffs ()
+{
+    for (int amrlev = H.num_amr_levels - 1; amrlev >= 0; --amrlev) {
+        auto& a = m_a_coeffs[amrlev]; auto& b = m_b_coeffs[amrlev];
+        for (int mglev = 1; mglev < int(a.size()); ++mglev) {   // averageDownCoeffsSameAmrLevel, AMReX_MLABecLaplacian.H:631-655
+            const int ratio = (amrlev > 0) ? 2 : H.mg_coarsen_ratio_vec[mglev - 1][0];
+            if (m_a_scalar == 0.0) { a[mglev].setVal(0.0); }
+            else { average_down(a[mglev - 1], a[mglev], 0, 1, ratio); }
+            for (int d = 0; d < 3; ++d) { average_down_faces(b[mglev - 1][d], b[mglev][d], d, ratio); }
+        }
+        if (amrlev > 0) {   // averageDownCoeffsToCoarseAmrLevel, :693-712
+            if (m_a_scalar != 0.0) { average_down(m_a_coeffs[amrlev].back(), m_a_coeffs[amrlev - 1].front(), 0, 1, 2); }
+            for (int d = 0; d < 3; ++d) { average_down_faces(m_b_coeffs[amrlev].back()[d], m_b_coeffs[amrlev - 1].front()[d], d, 2); }
+        }
+    }
+}
+
+void MLABecLaplacian::update_singular_flags ()
+{
+    m_is_singular.assign(H.num_amr_levels, 0);
+    bool no_dirichlet = true;
+    for (int d = 0; d < 3; ++d) { if (m_lobc[d] == BCType::Dirichlet || m_hibc[d] == BCType::Dirichlet) { no_dirichlet = false; } }
+    if (no_dirichlet) {
+        for (int alev = 0; alev < H.num_amr_levels; ++alev) {
+            if (H.domain_covered[alev]) {
+                if (m_a_scalar == 0.0) { m_is_singular[alev] = 1; }
+                else {
+                    const Real asum = m_a_coeffs[alev].back().sum();
+                    const Real amax = m_a_coeffs[alev].back().norminf();
+                    m_is_singular[alev] = (std::abs(asum) <= amax * Real(1.e-12));
+                }
+            }
+        }
+    }
+}
+
+void MLABecLaplacian::prepareForSolve ()
+{
+    MLLinOp::prepareForSolve();
+    averageDownCoeffs();
+    update_singular_flags();
+    m_needs_update = false;
+}
+
+void MLABecLaplacian::update ()
+{
+    averageDownCoeffs();
+    update_singular_flags();
+    m_needs_update = false;
+}
+
+void MLABecLaplacian::normalize (int amrlev, int mglev, MultiFab& mf) const
+{
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    auto const& T = mf.layout().tiles(0);
+    B200_KCALL(b200mg_normalize_abec(T.n, T.d.data(), mf.layout().d_vbox(), mf.d_fabs(), m_a_coeffs[amrlev][mglev].d_fabs(),
+                                     m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(), m_b_coeffs[amrlev][mglev][2].d_fabs(),
+                                     m_a_scalar, m_b_scalar * dxi[0] * dxi[0], m_b_scalar * dxi[1] * dxi[1], m_b_scalar * dxi[2] * dxi[2], Gpu::gpuStream()));
+}
+
+void MLABecLaplacian::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab const& in, const MultiFab* rhs) const
+{
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();   // dh = beta*dxinv^2 (AMReX_MLABecLap_3D_K.H:18-20)
+    auto const& T = out.layout().tiles(0);
+    B200_KCALL(b200mg_adotx_abec(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
+                                 m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(),
+                                 m_b_coeffs[amrlev][mglev][2].d_fabs(), m_a_scalar, m_b_scalar * dxi[0] * dxi[0], m_b_scalar * dxi[1] * dxi[1],
+                                 m_b_scalar * dxi[2] * dxi[2], Gpu::gpuStream()));
+}
+
+namespace { inline void gsrb_dh (Geometry const& g, Real b, Real dh[3]) { const Real* h = g.CellSize(); for (int d = 0; d < 3; ++d) { dh[d] = b / (h[d] * h[d]); } } }
+
+void MLABecLaplacian::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
+{
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_use_gauss_seidel, "Jacobi smoothing is not implemented (setGaussSeidel(false))");
+    LevelData const& L = lev(amrlev, mglev);
+    Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);   // dh = beta/h^2 (AMReX_MLABecLaplacian.H:907-909)
+    auto const& T = sol.layout().tiles(0);
+    B200_KCALL(b200mg_gsrb_abec(T.n, T.d.data(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), m_a_coeffs[amrlev][mglev].d_fabs(),
+                                m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(), m_b_coeffs[amrlev][mglev][2].d_fabs(),
+                                L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, Gpu::gpuStream()));
+}
+
+void MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab const& sol_in, MultiFab const& rhs) const
+{
+    LevelData const& L = lev(amrlev, mglev);
+    Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
+    B200_KCALL(b200mg_gsrb2_abec(L.layout->numLocal(), nullptr, L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
+                                 m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(),
+                                 m_b_coeffs[amrlev][mglev][2].d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
+                                 m_a_scalar, dh[0], dh[1], dh[2], 0, 0, Gpu::gpuStream()));
+}
+
+void MLABecLaplacian::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
+{
+    LevelData const& L = lev(amrlev, mglev);
+    Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
+    B200_KCALL(b200mg_gsrb_shell_abec(L.layout->numLocal(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), m_a_coeffs[amrlev][mglev].d_fabs(),
+                                      m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(), m_b_coeffs[amrlev][mglev][2].d_fabs(),
+                                      L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, Gpu::gpuStream()));
+}
+
+// ============================================================================================ MLPoisson
+void MLPoisson::prepareForSolve ()
+{
+    MLLinOp::prepareForSolve();
+    m_is_singular.assign(H.num_amr_levels, 0);
+    bool no_dirichlet = true;
+    for (int d = 0; d < 3; ++d) { if (m_lobc[d] == BCType::Dirichlet || m_hibc[d] == BCType::Dirichlet) { no_dirichlet = false; } }
+    if (no_dirichlet) { for (int alev = 0; alev < H.num_amr_levels; ++alev) { if (H.domain_covered[alev]) { m_is_singular[alev] = 1; } } }
+}
+
+void MLPoisson::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab const& in, const MultiFab* rhs) const
+{
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    auto const& T = out.layout().tiles(0);
+    B200_KCALL(b200mg_adotx_poisson(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
+                                    dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream()));
+}
+
+void MLPoisson::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
+{
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_use_gauss_seidel, "Jacobi smoothing is not implemented (setGaussSeidel(false))");
+    LevelData const& L = lev(amrlev, mglev);
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    auto const& T = sol.layout().tiles(0);
+    B200_KCALL(b200mg_gsrb_poisson(T.n, T.d.data(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
+                                   dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, Gpu::gpuStream()));
+}
+
+void MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab const& sol_in, MultiFab const& rhs) const
+{
+    LevelData const& L = lev(amrlev, mglev);
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    B200_KCALL(b200mg_gsrb2_poisson(L.layout->numLocal(), nullptr, L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
+                                    L.undrrelxr.d_table(), L.mask.d_table(), dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], 0, 0, Gpu::gpuStream()));
+}
+
+void MLPoisson::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
+{
+    LevelData const& L = lev(amrlev, mglev);
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    B200_KCALL(b200mg_gsrb_shell_poisson(L.layout->numLocal(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
+                                         dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, Gpu::gpuStream()));
+}
+
+} // namespace amrex

@@ -1,0 +1,462 @@
+// MLMG cycle driver and Krylov bottom solver (host control flow; all arithmetic is in device kernels).
+// Follows the algorithm of MLMGT (AMReX_MLMG.H:356-541, 937-1116, 1228-1629, 1634-1873) and
+// MLCGSolverT (AMReX_MLCGSolver.H:98-410).
+#include "AMReX_MLMG.H"
+
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+namespace amrex {
+
+namespace {
+void Print0 (std::string const& s) { if (ParallelDescriptor::IOProcessor()) { std::cout << s << std::flush; } }
+template <class... A> std::string cat (A const&... a) { std::ostringstream o; o << std::setprecision(10); (o << ... << a); return o.str(); }
+}
+
+// ========================================================================================== MLCGSolver
+void MLCGSolver::ensure_temps (MultiFab const& sol)
+{
+    if (p.empty() || !(p.boxArray() == sol.boxArray()) || !(p.DistributionMap() == sol.DistributionMap())) {
+        const int ng = sol.nGrow();
+        p = Lp.make(amrlev, mglev, ng); r = Lp.make(amrlev, mglev, ng);
+        rh = Lp.make(amrlev, mglev, 0); v = Lp.make(amrlev, mglev, 0); t = Lp.make(amrlev, mglev, 0);
+        q = Lp.make(amrlev, mglev, 0); sorig = Lp.make(amrlev, mglev, 0);
+    }
+}
+
+int MLCGSolver::solve (MultiFab& sol, MultiFab const& rhs, Real eps_rel, Real eps_abs)
+{
+    return (solver_type == Type::BiCGStab) ? solve_bicgstab(sol, rhs, eps_rel, eps_abs) : solve_cg(sol, rhs, eps_rel, eps_abs);
+}
+
+int MLCGSolver::solve_bicgstab (MultiFab& sol, MultiFab const& rhs, Real eps_rel, Real eps_abs)
+{
+    using BCMode = MLLinOp::BCMode; using StateMode = MLLinOp::StateMode;
+    ensure_temps(sol);
+    p.setVal(0.0); r.setVal(0.0);
+    if (initial_vec_zeroed) { MultiFab::Copy(r, rhs, 0, 0, 1, 0); }
+    else {
+        Lp.correctionResidual(amrlev, mglev, r, sol, rhs, BCMode::Homogeneous);
+        MultiFab::Copy(sorig, sol, 0, 0, 1, 0);
+        sol.setVal(0.0);
+    }
+    Lp.normalize(amrlev, mglev, r);
+    MultiFab::Copy(rh, r, 0, 0, 1, 0);
+
+    Real rnorm = norm_inf(r);
+    const Real rnorm0 = rnorm;
+    if (verbose > 0) { Print0(cat("MLCGSolver_BiCGStab: Initial error (error0) =        ", rnorm0, "\n")); }
+    int ret = 0;
+    iter = 1;
+    Real rho_1 = 0, alpha = 0, omega = 0;
+    if (rnorm0 == 0 || rnorm0 < eps_abs) { return ret; }
+
+    for (; iter <= maxiter; ++iter) {
+        const Real rho = dotxy(rh, r);
+        if (rho == 0) { ret = 1; break; }
+        if (iter == 1) { MultiFab::Copy(p, r, 0, 0, 1, 0); }
+        else {
+            const Real beta = (rho / rho_1) * (alpha / omega);
+            MultiFab::Saxpy(p, -omega, v, 0, 0, 1, 0);
+            MultiFab::Xpay(p, beta, r, 0, 0, 1, 0);
+        }
+        Lp.apply(amrlev, mglev, v, p, BCMode::Homogeneous, StateMode::Correction);
+        Lp.normalize(amrlev, mglev, v);
+        const Real rhTv = dotxy(rh, v);
+        if (rhTv != Real(0.0)) { alpha = rho / rhTv; } else { ret = 2; break; }
+        MultiFab::Saxpy(sol, alpha, p, 0, 0, 1, 0);
+        MultiFab::Saxpy(r, -alpha, v, 0, 0, 1, 0);
+        rnorm = norm_inf(r);
+        if (verbose > 2) { Print0(cat("MLCGSolver_BiCGStab: Half Iter ", std::setw(11), iter, " rel. err. ", rnorm / rnorm0, "\n")); }
+        if (rnorm < eps_rel * rnorm0 || rnorm < eps_abs) { break; }
+        Lp.apply(amrlev, mglev, t, r, BCMode::Homogeneous, StateMode::Correction);
+        Lp.normalize(amrlev, mglev, t);
+        Real tvals[2] = {dotxy(t, t, true), dotxy(t, r, true)};
+        ParallelDescriptor::ReduceRealSum(tvals, 2);
+        if (tvals[0] != Real(0.0)) { omega = tvals[1] / tvals[0]; } else { ret = 3; break; }
+        MultiFab::Saxpy(sol, omega, r, 0, 0, 1, 0);
+        MultiFab::Saxpy(r, -omega, t, 0, 0, 1, 0);
+        rnorm = norm_inf(r);
+        if (verbose > 2) { Print0(cat("MLCGSolver_BiCGStab: Iteration ", std::setw(11), iter, " rel. err. ", rnorm / rnorm0, "\n")); }
+        if (rnorm < eps_rel * rnorm0 || rnorm < eps_abs) { break; }
+        if (omega == 0) { ret = 4; break; }
+        rho_1 = rho;
+    }
+    if (verbose > 0) { Print0(cat("MLCGSolver_BiCGStab: Final: Iteration ", std::setw(4), iter, " rel. err. ", rnorm / rnorm0, "\n")); }
+    if (ret == 0 && rnorm > eps_rel * rnorm0 && rnorm > eps_abs) { ret = 8; }
+    if ((ret == 0 || ret == 8) && (rnorm < rnorm0)) {
+        if (!initial_vec_zeroed) { MultiFab::Add(sol, sorig, 0, 0, 1, 0); }
+        if (ret == 8) { ret = 9; }
+    } else {
+        sol.setVal(0.0);
+        if (!initial_vec_zeroed) { MultiFab::Add(sol, sorig, 0, 0, 1, 0); }
+    }
+    return ret;
+}
+
+int MLCGSolver::solve_cg (MultiFab& sol, MultiFab const& rhs, Real eps_rel, Real eps_abs)
+{
+    using BCMode = MLLinOp::BCMode; using StateMode = MLLinOp::StateMode;
+    ensure_temps(sol);
+    p.setVal(0.0);
+    MultiFab& rr = rh;   // ng = 0 residual
+    if (initial_vec_zeroed) { MultiFab::Copy(rr, rhs, 0, 0, 1, 0); }
+    else {
+        Lp.correctionResidual(amrlev, mglev, rr, sol, rhs, BCMode::Homogeneous);
+        MultiFab::Copy(sorig, sol, 0, 0, 1, 0);
+        sol.setVal(0.0);
+    }
+    Real rnorm = norm_inf(rr);
+    const Real rnorm0 = rnorm;
+    if (verbose > 0) { Print0(cat("MLCGSolver_CG: Initial error (error0) :        ", rnorm0, "\n")); }
+    Real rho_1 = 0; int ret = 0; iter = 1;
+    if (rnorm0 == 0 || rnorm0 < eps_abs) { return ret; }
+    for (; iter <= maxiter; ++iter) {
+        const Real rho = dotxy(rr, rr);
+        if (rho == 0) { ret = 1; break; }
+        if (iter == 1) { MultiFab::Copy(p, rr, 0, 0, 1, 0); }
+        else { const Real beta = rho / rho_1; MultiFab::Xpay(p, beta, rr, 0, 0, 1, 0); }
+        Lp.apply(amrlev, mglev, q, p, BCMode::Homogeneous, StateMode::Correction);
+        Real alpha;
+        const Real pw = dotxy(p, q);
+        if (pw != Real(0.0)) { alpha = rho / pw; } else { ret = 1; break; }
+        MultiFab::Saxpy(sol, alpha, p, 0, 0, 1, 0);
+        MultiFab::Saxpy(rr, -alpha, q, 0, 0, 1, 0);
+        rnorm = norm_inf(rr);
+        if (verbose > 2) { Print0(cat("MLCGSolver_cg:       Iteration", std::setw(4), iter, " rel. err. ", rnorm / rnorm0, "\n")); }
+        if (rnorm < eps_rel * rnorm0 || rnorm < eps_abs) { break; }
+        rho_1 = rho;
+    }
+    if (verbose > 0) { Print0(cat("MLCGSolver_cg: Final Iteration", std::setw(4), iter, " rel. err. ", rnorm / rnorm0, "\n")); }
+    if (ret == 0 && rnorm > eps_rel * rnorm0 && rnorm > eps_abs) { ret = 8; }
+    if ((ret == 0 || ret == 8) && (rnorm < rnorm0)) {
+        if (!initial_vec_zeroed) { MultiFab::Add(sol, sorig, 0, 0, 1, 0); }
+        if (ret == 8) { ret = 9; }
+    } else {
+        sol.setVal(0.0);
+        if (!initial_vec_zeroed) { MultiFab::Add(sol, sorig, 0, 0, 1, 0); }
+    }
+    return ret;
+}
+
+// ================================================================================================ MLMG
+MLMG::MLMG (MLLinOp& a_lp) : linop(a_lp), namrlevs(a_lp.NAMRLevels()), finest_amr_lev(a_lp.NAMRLevels() - 1) {}
+
+Real MLMG::solve (Vector<MultiFab*> const& a_sol, Vector<MultiFab const*> const& a_rhs, Real a_tol_rel, Real a_tol_abs)
+{
+    if (bottom_solver == BottomSolver::Default) { bottom_solver = linop.getDefaultBottomSolver(); }
+    if (bottom_solver == BottomSolver::hypre || bottom_solver == BottomSolver::petsc) { Abort("hypre/petsc bottom solvers are not available"); }
+
+    const double solve_start_time = ParallelDescriptor::second();
+    Real& composite_norminf = m_final_resnorm0;
+    m_niters_cg.clear();
+    m_iter_fine_resnorm0.clear();
+
+    prepareForSolve(a_sol, a_rhs);
+    computeMLResidual(finest_amr_lev);
+
+    Real norms[2] = {MLResNormInf(finest_amr_lev, true), MLRhsNormInf(true)};
+    ParallelDescriptor::ReduceRealMax(norms, 2);
+    const Real resnorm0 = norms[0], rhsnorm0 = norms[1];
+    if (verbose >= 1) { Print0(cat("MLMG: Initial rhs               = ", rhsnorm0, "\n", "MLMG: Initial residual (resid0) = ", resnorm0, "\n")); }
+    m_init_resnorm0 = resnorm0; m_rhsnorm0 = rhsnorm0;
+
+    Real max_norm; std::string norm_name;
+    if (always_use_bnorm || rhsnorm0 >= resnorm0) { norm_name = "bnorm"; max_norm = rhsnorm0; }
+    else { norm_name = "resid0"; max_norm = resnorm0; }
+    const Real res_target = std::max(a_tol_abs, std::max(a_tol_rel, Real(1.e-16)) * max_norm);
+
+    timer[1] = 0.0;
+    if (resnorm0 <= res_target) {
+        composite_norminf = resnorm0;
+        if (verbose >= 1) { Print0("MLMG: No iterations needed\n"); }
+    } else {
+        const double iter_start_time = ParallelDescriptor::second();
+        bool converged = false;
+        const int niters = do_fixed_number_of_iters ? do_fixed_number_of_iters : max_iters;
+        for (int iter = 0; iter < niters; ++iter) {
+            oneIter(iter);
+            converged = false;
+            computeResidual(finest_amr_lev);
+            const Real fine_norminf = ResNormInf(finest_amr_lev);
+            m_iter_fine_resnorm0.push_back(fine_norminf);
+            composite_norminf = fine_norminf;
+            if (verbose >= 2) { Print0(cat("MLMG: Iteration ", std::setw(3), iter + 1, " Fine resid/", norm_name, " = ", fine_norminf / max_norm, "\n")); }
+            const bool fine_converged = (fine_norminf <= res_target);
+            if (namrlevs == 1 && fine_converged) { converged = true; }
+            else if (fine_converged) {
+                computeMLResidual(finest_amr_lev - 1);
+                const Real crse_norminf = MLResNormInf(finest_amr_lev - 1);
+                if (verbose >= 2) { Print0(cat("MLMG: Iteration ", std::setw(3), iter + 1, " Crse resid/", norm_name, " = ", crse_norminf / max_norm, "\n")); }
+                converged = (crse_norminf <= res_target);
+                composite_norminf = std::max(fine_norminf, crse_norminf);
+            }
+            if (converged) {
+                if (verbose >= 1) { Print0(cat("MLMG: Final Iter. ", iter + 1, " resid, resid/", norm_name, " = ", composite_norminf, ", ", composite_norminf / max_norm, "\n")); }
+                break;
+            } else if (composite_norminf > Real(1.e20) * max_norm) {
+                if (verbose > 0) { Print0(cat("MLMG: Failing to converge after ", iter + 1, " iterations. resid, resid/", norm_name, " = ", composite_norminf, ", ", composite_norminf / max_norm, "\n")); }
+                if (throw_exception) { throw error("MLMG blew up."); } else { Abort("MLMG failing so lets stop here"); }
+            }
+        }
+        if (!converged && do_fixed_number_of_iters == 0) {
+            if (verbose > 0) { Print0(cat("MLMG: Failed to converge after ", max_iters, " iterations. resid, resid/", norm_name, " = ", composite_norminf, ", ", composite_norminf / max_norm, "\n")); }
+            if (throw_exception) { throw error("MLMG failed to converge."); } else { Abort("MLMG failed."); }
+        }
+        timer[1] = ParallelDescriptor::second() - iter_start_time;
+    }
+
+    const int ng_back = final_fill_bc ? 1 : 0;
+    for (int alev = 0; alev < namrlevs; ++alev) {
+        MultiFab::Copy(*a_sol[alev], sol[alev], 0, 0, 1, std::min(ng_back, a_sol[alev]->nGrow()));
+    }
+    Gpu::streamSynchronize();
+    timer[0] = ParallelDescriptor::second() - solve_start_time;
+    if (verbose >= 1) { Print0(cat("MLMG: Timers: Solve = ", timer[0], " Iter = ", timer[1], " Bottom = ", timer[2], "\n")); }
+    ++solve_called;
+    return composite_norminf;
+}
+
+// The reference aliases the user's sol when it has exactly one ghost cell (AMReX_MLMG.H:983-987).  Here the solver
+// always works on its own (aligned, ping-pong capable) copy and copies the result back: two extra passes per solve.
+void MLMG::prepareForSolve (Vector<MultiFab*> const& a_sol, Vector<MultiFab const*> const& a_rhs)
+{
+    AMREX_ALWAYS_ASSERT(namrlevs <= int(a_sol.size()) && namrlevs <= int(a_rhs.size()));
+    timer[0] = timer[1] = timer[2] = 0.0;
+    if (!linop_prepared) { linop.prepareForSolve(); linop_prepared = true; }
+    else if (linop.needsUpdate()) { linop.update(); }
+
+    if (!solve_called) {
+        sol.resize(namrlevs); rhs.resize(namrlevs);
+        res.resize(namrlevs); rescor.resize(namrlevs); cor.resize(namrlevs); cor_hold.resize(std::max(namrlevs - 1, 1));
+        for (int alev = 0; alev < namrlevs; ++alev) {
+            sol[alev] = linop.make(alev, 0, 1);
+            rhs[alev] = linop.make(alev, 0, 0);
+            const int nmg = linop.NMGLevels(alev);
+            res[alev].resize(nmg); rescor[alev].resize(nmg); cor[alev].resize(nmg);
+            for (int m = 0; m < nmg; ++m) {
+                res[alev][m] = linop.make(alev, m, 0); rescor[alev][m] = linop.make(alev, m, 0); cor[alev][m] = linop.make(alev, m, 1);
+            }
+        }
+        const int nmg0 = linop.NMGLevels(0);
+        cor_hold[0].resize(nmg0);
+        for (int m = 0; m < nmg0 - 1; ++m) { cor_hold[0][m] = linop.make(0, m, 1); }
+        for (int alev = 1; alev < finest_amr_lev; ++alev) { cor_hold[alev].resize(1); cor_hold[alev][0] = linop.make(alev, 0, 1); }
+        cfine_mg.resize(nmg0);
+    }
+    for (int alev = 0; alev < namrlevs; ++alev) {
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(a_sol[alev]->boxArray() == linop.Grids(alev) && a_sol[alev]->DistributionMap() == linop.DMap(alev),
+                                         "MLMG::solve: sol must live on the operator's grids");
+        MultiFab::Copy(sol[alev], *a_sol[alev], 0, 0, 1, 0);
+        sol[alev].setBndry(0.0);
+        MultiFab::Copy(rhs[alev], *a_rhs[alev], 0, 0, 1, 0);
+    }
+    for (int falev = finest_amr_lev; falev > 0; --falev) {
+        average_down(sol[falev], sol[falev - 1], 0, 1, linop.AMRRefRatio(falev - 1));
+        average_down(rhs[falev], rhs[falev - 1], 0, 1, linop.AMRRefRatio(falev - 1));
+    }
+    if (linop.isSingular(0) && linop.getEnforceSingularSolvable()) { makeSolvable(); }
+    for (int alev = 0; alev <= finest_amr_lev; ++alev) {
+        for (int m = 0; m < linop.NMGLevels(alev); ++m) {
+            res[alev][m].setVal(0.0); rescor[alev][m].setVal(0.0); cor[alev][m].setVal(0.0);
+            if (alev == 0 && m < linop.NMGLevels(0) - 1) { cor_hold[0][m].setVal(0.0); }
+        }
+    }
+    for (int alev = 1; alev < finest_amr_lev; ++alev) { cor_hold[alev][0].setVal(0.0); }
+    if (verbose >= 2) {
+        Print0(cat("MLMG: # of AMR levels: ", namrlevs, "\n", "      # of MG levels on the coarsest AMR level: ", linop.NMGLevels(0), "\n"));
+    }
+}
+
+void MLMG::oneIter (int iter)
+{
+    if (finest_amr_lev > 0) { Abort("multi-level composite solve is not implemented yet"); }
+    if (linop.isSingular(0) && linop.getEnforceSingularSolvable()) { makeSolvable(0, 0, res[0][0]); }
+    if (iter < max_fmg_iters) { mgFcycle(); } else { mgVcycle(0, 0); }
+    MultiFab::Add(sol[0], cor[0][0], 0, 0, 1, 0);
+    linop.averageDownAndSync(sol);
+}
+
+void MLMG::mgVcycle (int amrlev, int mglev_top)
+{
+    const int mglev_bottom = linop.NMGLevels(amrlev) - 1;
+    for (int mglev = mglev_top; mglev < mglev_bottom; ++mglev) {
+        cor[amrlev][mglev].setVal(0.0);
+        bool skip_fillboundary = true;
+        for (int i = 0; i < nu1; ++i) {
+            linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev], skip_fillboundary);
+            skip_fillboundary = false;
+        }
+        computeResOfCorrection(amrlev, mglev);
+        linop.restriction(amrlev, mglev + 1, res[amrlev][mglev + 1], rescor[amrlev][mglev]);
+    }
+    if (amrlev == 0) { bottomSolve(); }
+    else {
+        cor[amrlev][mglev_bottom].setVal(0.0);
+        bool skip_fillboundary = true;
+        for (int i = 0; i < nu1; ++i) {
+            linop.smooth(amrlev, mglev_bottom, cor[amrlev][mglev_bottom], res[amrlev][mglev_bottom], skip_fillboundary);
+            skip_fillboundary = false;
+        }
+    }
+    for (int mglev = mglev_bottom - 1; mglev >= mglev_top; --mglev) {
+        addInterpCorrection(amrlev, mglev);
+        for (int i = 0; i < nu2; ++i) { linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev]); }
+    }
+}
+
+void MLMG::mgFcycle ()
+{
+    const int amrlev = 0;
+    const int mg_bottom_lev = linop.NMGLevels(amrlev) - 1;
+    for (int mglev = 1; mglev <= mg_bottom_lev; ++mglev) { linop.avgDownResMG(mglev, res[amrlev][mglev], res[amrlev][mglev - 1]); }
+    bottomSolve();
+    for (int mglev = mg_bottom_lev - 1; mglev >= 0; --mglev) {
+        interpCorrection(amrlev, mglev);
+        computeResOfCorrection(amrlev, mglev);
+        MultiFab::Copy(res[amrlev][mglev], rescor[amrlev][mglev], 0, 0, 1, 0);
+        std::swap(cor[amrlev][mglev], cor_hold[amrlev][mglev]);
+        mgVcycle(amrlev, mglev);
+        MultiFab::Add(cor[amrlev][mglev], cor_hold[amrlev][mglev], 0, 0, 1, 0);
+    }
+}
+
+void MLMG::bottomSolve ()
+{
+    const double t0 = ParallelDescriptor::second();
+    const int amrlev = 0;
+    const int mglev = linop.NMGLevels(amrlev) - 1;
+    MultiFab& x = cor[amrlev][mglev];
+    MultiFab& b = res[amrlev][mglev];
+    x.setVal(0.0);
+    if (bottom_solver == BottomSolver::smoother) {
+        bool skip_fillboundary = true;
+        for (int i = 0; i < nuf; ++i) { linop.smooth(amrlev, mglev, x, b, skip_fillboundary); skip_fillboundary = false; }
+    } else {
+        MultiFab* pb = &b;
+        if (linop.isBottomSingular() && linop.getEnforceSingularSolvable()) {
+            if (!bottom_b) { bottom_b = std::make_unique<MultiFab>(linop.make(amrlev, mglev, 0)); }
+            MultiFab::Copy(*bottom_b, b, 0, 0, 1, 0);
+            pb = bottom_b.get();
+            makeSolvable(amrlev, mglev, *pb);
+        }
+        MLCGSolver::Type cg_type = (bottom_solver == BottomSolver::cg || bottom_solver == BottomSolver::cgbicg)
+            ? MLCGSolver::Type::CG : MLCGSolver::Type::BiCGStab;
+        int ret = bottomSolveWithCG(x, *pb, cg_type);
+        if (ret != 0 && (bottom_solver == BottomSolver::cgbicg || bottom_solver == BottomSolver::bicgcg)) {
+            cg_type = (bottom_solver == BottomSolver::cgbicg) ? MLCGSolver::Type::BiCGStab : MLCGSolver::Type::CG;
+            cor[amrlev][mglev].setVal(0.0);
+            ret = bottomSolveWithCG(x, *pb, cg_type);
+            if (ret == 0) { bottom_solver = (cg_type == MLCGSolver::Type::CG) ? BottomSolver::cg : BottomSolver::bicgstab; }
+        }
+        if (ret != 0 && ret != 9) { cor[amrlev][mglev].setVal(0.0); }
+        const int n = (ret == 0) ? nub : nuf;
+        for (int i = 0; i < n; ++i) { linop.smooth(amrlev, mglev, x, b); }
+    }
+    timer[2] += ParallelDescriptor::second() - t0;
+}
+
+int MLMG::bottomSolveWithCG (MultiFab& x, MultiFab const& b, MLCGSolver::Type type)
+{
+    if (!cg_solver) { cg_solver = std::make_unique<MLCGSolver>(linop); }
+    cg_solver->setSolver(type);
+    cg_solver->setVerbose(bottom_verbose);
+    cg_solver->setMaxIter(bottom_maxiter);
+    cg_solver->setInitSolnZeroed(true);
+    const int ret = cg_solver->solve(x, b, bottom_reltol, bottom_abstol);
+    if (ret != 0 && verbose > 1) { Print0("MLMG: Bottom solve failed.\n"); }
+    m_niters_cg.push_back(cg_solver->getNumIters());
+    return ret;
+}
+
+void MLMG::computeMLResidual (int amrlevmax)
+{
+    for (int alev = amrlevmax; alev >= 0; --alev) {
+        const MultiFab* crse_bcdata = (alev > 0) ? &sol[alev - 1] : nullptr;
+        linop.solutionResidual(alev, res[alev][0], sol[alev], rhs[alev], crse_bcdata);
+        if (alev < finest_amr_lev) { Abort("reflux: multi-level composite solve is not implemented yet"); }
+    }
+}
+
+void MLMG::computeResidual (int alev)
+{
+    const MultiFab* crse_bcdata = (alev > 0) ? &sol[alev - 1] : nullptr;
+    linop.solutionResidual(alev, res[alev][0], sol[alev], rhs[alev], crse_bcdata);
+}
+
+void MLMG::computeResOfCorrection (int amrlev, int mglev)
+{
+    linop.correctionResidual(amrlev, mglev, rescor[amrlev][mglev], cor[amrlev][mglev], res[amrlev][mglev], MLLinOp::BCMode::Homogeneous);
+}
+
+void MLMG::interpCorrection (int alev, int mglev)
+{
+    linop.interpAssign(alev, mglev, cor[alev][mglev], cor[alev][mglev + 1]);
+}
+
+void MLMG::addInterpCorrection (int alev, int mglev)
+{
+    MultiFab const& crse_cor = cor[alev][mglev + 1];
+    MultiFab& fine_cor = cor[alev][mglev];
+    const MultiFab* cmf = &crse_cor;
+    if (!linop.isMFIterSafe(alev, mglev, mglev + 1)) {
+        AMREX_ALWAYS_ASSERT(alev == 0);
+        if (!cfine_mg[mglev]) {
+            cfine_mg[mglev] = std::make_unique<MultiFab>(amrex::coarsen(linop.Grids(alev, mglev), 2), linop.DMap(alev, mglev), 1, 0);
+        }
+        cfine_mg[mglev]->ParallelCopy(crse_cor, 0, 0, 1);
+        cmf = cfine_mg[mglev].get();
+    }
+    linop.interpolation(alev, mglev, fine_cor, *cmf);
+}
+
+Real MLMG::ResNormInf (int alev, bool local) { return linop.normInf(alev, res[alev][0], local); }
+
+Real MLMG::MLResNormInf (int alevmax, bool local)
+{
+    Real r = 0.0;
+    for (int alev = 0; alev <= alevmax; ++alev) { r = std::max(r, ResNormInf(alev, true)); }
+    if (!local) { ParallelDescriptor::ReduceRealMax(&r, 1); }
+    return r;
+}
+
+Real MLMG::MLRhsNormInf (bool local)
+{
+    Real r = 0.0;
+    for (int alev = 0; alev <= finest_amr_lev; ++alev) { r = std::max(r, linop.normInf(alev, rhs[alev], true)); }
+    if (!local) { ParallelDescriptor::ReduceRealMax(&r, 1); }
+    return r;
+}
+
+void MLMG::makeSolvable ()
+{
+    auto const offset = linop.getSolvabilityOffset(0, 0, rhs[0]);
+    for (int alev = 0; alev < namrlevs; ++alev) { linop.fixSolvabilityByOffset(alev, 0, rhs[alev], offset); }
+}
+
+void MLMG::makeSolvable (int amrlev, int mglev, MultiFab& mf)
+{
+    auto const offset = linop.getSolvabilityOffset(amrlev, mglev, mf);
+    linop.fixSolvabilityByOffset(amrlev, mglev, mf, offset);
+}
+
+void MLMG::compResidual (Vector<MultiFab*> const& a_res, Vector<MultiFab*> const& a_sol, Vector<MultiFab const*> const& a_rhs)
+{
+    if (!linop_prepared) { linop.prepareForSolve(); linop_prepared = true; }
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(namrlevs == 1, "compResidual: single level only for now");
+    MultiFab s = linop.make(0, 0, 1);
+    MultiFab::Copy(s, *a_sol[0], 0, 0, 1, 0);
+    linop.solutionResidual(0, *a_res[0], s, *a_rhs[0], nullptr);
+}
+
+void MLMG::apply (Vector<MultiFab*> const& out, Vector<MultiFab*> const& in)
+{
+    if (!linop_prepared) { linop.prepareForSolve(); linop_prepared = true; }
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(namrlevs == 1, "apply: single level only for now");
+    MultiFab s = linop.make(0, 0, 1);
+    MultiFab::Copy(s, *in[0], 0, 0, 1, 0);
+    linop.apply(0, 0, *out[0], s, MLLinOp::BCMode::Inhomogeneous, MLLinOp::StateMode::Solution, linop.m_bndry_sol[0].get());
+}
+
+} // namespace amrex

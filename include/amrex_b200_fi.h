@@ -1,0 +1,187 @@
+/* amrex_b200_fi.h -- object-level C ABI of libamrex_b200.so: the drop-in boundary of the MLMG path.
+ *
+ * The amrex_fi_* entries have the names, argument order and meaning of the reference's own C ABI
+ * (Src/F_Interfaces, the layer its Fortran module binds): each declaration cites the reference definition it
+ * replaces.  `T**` here is ABI-identical to the reference's `T*&`.  Objects are opaque heap pointers created
+ * and destroyed by new_/delete_ pairs; ownership rules are the reference's (MLMG keeps a
+ * reference to the linop; the linop copies coefficients and BC values).
+ *
+ * The amrex_b200_* entries are what a process-per-GPU launcher needs and the reference gets from MPI / the
+ * host: runtime init, NCCL bootstrap, host<->device field transfer, results of the last solve, and the
+ * host-only metadata queries used for bit-exact parity checks.
+ *
+ * Error convention: the reference aborts the process (amrex::Abort).  Here every failure (assertion, CUDA
+ * error, non-convergence) is caught at this boundary: the call returns, amrex_b200_last_error() returns a
+ * non-NULL message until amrex_b200_clear_error(), and value-returning calls return NaN / -1 / NULL.
+ * There is no CPU fallback: any call that needs the device fails with such an error when no GPU is present.
+ */
+#ifndef AMREX_B200_FI_H_
+#define AMREX_B200_FI_H_
+
+#ifdef __cplusplus
+extern "C" {
+#define B200_OPAQUE(T) namespace amrex { class T; } typedef amrex::T T
+B200_OPAQUE(BoxArray); B200_OPAQUE(DistributionMapping); B200_OPAQUE(Geometry); B200_OPAQUE(MultiFab);
+B200_OPAQUE(MLLinOp); B200_OPAQUE(MLMG);
+#undef B200_OPAQUE
+#else
+typedef struct BoxArray BoxArray; typedef struct DistributionMapping DistributionMapping;
+typedef struct Geometry Geometry; typedef struct MultiFab MultiFab;
+typedef struct MLLinOp MLLinOp; typedef struct MLMG MLMG;
+#endif
+typedef double Real;
+
+/* ---- runtime (reference: amrex::Initialize/Finalize Src/Base/AMReX.cpp:332,725; ParallelDescriptor) ---- */
+int  amrex_b200_init(int device_id);                 /* select GPU, create streams; 0 on success */
+void amrex_b200_finalize(void);
+int  amrex_b200_initialized(void);
+int  amrex_b200_nccl_unique_id_bytes(void);
+int  amrex_b200_nccl_get_unique_id(void* out);       /* rank 0 */
+int  amrex_b200_comm_init(int rank, int nranks, const void* unique_id);   /* all ranks; nranks==1: no NCCL */
+void amrex_b200_comm_finalize(void);
+int  amrex_b200_myproc(void);
+int  amrex_b200_nprocs(void);
+const char* amrex_b200_last_error(void);
+void amrex_b200_clear_error(void);
+void amrex_b200_synchronize(void);
+long long amrex_b200_launch_count(void);             /* kernels launched by this library since the last reset */
+void amrex_b200_reset_launch_count(void);
+void* amrex_b200_stream(void);                       /* the cudaStream_t every kernel is launched on */
+
+/* ---- Geometry (Src/F_Interfaces/Base/AMReX_geometry_fi.cpp:7-40) ---- */
+void amrex_b200_geometry_setup(const Real problo[3], const Real probhi[3], const int is_periodic[3]); /* Geometry::Setup */
+void amrex_fi_new_geometry(Geometry** geom, int lo[3], int hi[3]);
+void amrex_fi_delete_geometry(Geometry* geom);
+void amrex_fi_geometry_get_intdomain(const Geometry* geom, int lo[3], int hi[3]);
+
+/* ---- BoxArray (AMReX_boxarray_fi.cpp:10-93) ---- */
+void amrex_fi_new_boxarray(BoxArray** ba, int lo[3], int hi[3]);
+void amrex_fi_new_boxarray_from_bxfarr(BoxArray** ba, const int* bxs, const int nsides, const int ndims, const int nbxs);
+void amrex_fi_delete_boxarray(BoxArray* ba);
+void amrex_fi_clone_boxarray(BoxArray** bao, const BoxArray* bai);
+void amrex_fi_boxarray_maxsize(BoxArray* ba, int sz[]);
+long long amrex_fi_boxarray_nboxes(const BoxArray* ba);
+void amrex_fi_boxarray_get_box(const BoxArray* ba, int i, int lo[3], int hi[3]);
+void amrex_fi_boxarray_nodal_type(const BoxArray* ba, int inodal[3]);
+long long amrex_fi_boxarray_numpts(const BoxArray* ba);
+int  amrex_fi_boxarray_issame(const BoxArray* baa, const BoxArray* bab);
+void amrex_b200_boxarray_coarsen(BoxArray* ba, int ratio);   /* BoxArray::coarsen */
+void amrex_b200_boxarray_refine(BoxArray* ba, int ratio);
+
+/* ---- DistributionMapping (AMReX_distromap_fi.cpp:9-50) ---- */
+void amrex_fi_new_distromap(DistributionMapping** dm, const BoxArray* ba);
+void amrex_fi_new_distromap_from_pmap(DistributionMapping** dm, const int* pmap, const int plen);
+void amrex_fi_delete_distromap(DistributionMapping* dm);
+void amrex_fi_distromap_get_pmap(const DistributionMapping* dm, int* pmap, const int plen);
+/* SFC map for an explicit rank count, no device needed (DistributionMapping::makeSFC, AMReX_DistributionMapping.cpp:1891) */
+void amrex_b200_new_distromap_sfc(DistributionMapping** dm, const BoxArray* ba, int nprocs);
+
+/* ---- MultiFab (AMReX_multifab_fi.cpp:10-216) ---- */
+void amrex_fi_new_multifab(MultiFab** mf, const BoxArray** ba, const DistributionMapping** dm, int nc, const int* ng, const int* nodal);
+void amrex_fi_delete_multifab(MultiFab* mf);
+int  amrex_fi_multifab_ncomp(const MultiFab* mf);
+void amrex_fi_multifab_ngrow(const MultiFab* mf, int* ngv);
+const BoxArray* amrex_fi_multifab_boxarray(const MultiFab* mf);
+const DistributionMapping* amrex_fi_multifab_distromap(const MultiFab* mf);
+/* device pointer and GROWN bounds of local grid igrd; rows are padded: use amrex_b200_multifab_strides */
+void amrex_fi_multifab_dataptr_int(MultiFab* mf, int igrd, Real** dp, int lo[3], int hi[3]);
+void amrex_b200_multifab_strides(const MultiFab* mf, int igrd, long long strides[3]);
+Real amrex_fi_multifab_sum(const MultiFab* mf, int comp);
+Real amrex_fi_multifab_norm0(const MultiFab* mf, int comp);
+void amrex_fi_multifab_setval(MultiFab* mf, Real val, int ic, int nc, const int* ng);
+void amrex_fi_multifab_plus(MultiFab* mf, Real val, int ic, int nc, int ng);
+void amrex_fi_multifab_mult(MultiFab* mf, Real val, int ic, int nc, int ng);
+void amrex_fi_multifab_add(MultiFab* dstmf, const MultiFab* srcmf, int srccomp, int dstcomp, int nc, const int* ng);
+void amrex_fi_multifab_subtract(MultiFab* dstmf, const MultiFab* srcmf, int srccomp, int dstcomp, int nc, const int* ng);
+void amrex_fi_multifab_saxpy(MultiFab* dstmf, Real a, const MultiFab* srcmf, int srccomp, int dstcomp, int nc, const int* ng);
+void amrex_fi_multifab_copy(MultiFab* dstmf, const MultiFab* srcmf, int srccomp, int dstcomp, int nc, const int* ng);
+void amrex_fi_multifab_parallelcopy(MultiFab* dstmf, const MultiFab* srcmf, int srccomp, int dstcomp, int nc, int srcng, int dstng, const Geometry* geom);
+void amrex_fi_multifab_fill_boundary(MultiFab* mf, const Geometry* geom, int c, int nc, int cross);
+Real amrex_b200_multifab_dot(const MultiFab* x, const MultiFab* y);   /* amrex::Dot, AMReX_FabArrayUtility.H:1554 */
+/* host <-> device: `h` is a Fortran-order array covering exactly the index box [lo,hi] (of the MultiFab's index
+ * type); cells of every local fab inside grow(validbox,ng) are transferred.  Host memory may be pinned. */
+void amrex_b200_multifab_upload(MultiFab* mf, const Real* h, const int lo[3], const int hi[3], int comp, int ng);
+void amrex_b200_multifab_download(const MultiFab* mf, Real* h, const int lo[3], const int hi[3], int comp, int ng);
+/* cell centres -> faces (amrex::average_cellcenter_to_face, Src/Base/AMReX_MultiFabUtil.cpp:226) */
+void amrex_b200_average_cellcenter_to_face(MultiFab* fx, MultiFab* fy, MultiFab* fz, const MultiFab* cc, const Geometry* geom);
+
+/* ---- linear operators (Src/F_Interfaces/LinearSolvers/AMReX_abeclaplacian_fi.cpp:8-48, AMReX_poisson_fi.cpp:8,
+ *      AMReX_linop_fi.cpp:8-40) ---- */
+void amrex_fi_new_abeclaplacian(MLLinOp** linop, int nlevels, const Geometry* geom[], const BoxArray* ba[],
+                                const DistributionMapping* dm[], int metric_term, int agglomeration,
+                                int consolidation, int max_coarsening_level);
+void amrex_fi_new_poisson(MLLinOp** linop, int nlevels, const Geometry* geom[], const BoxArray* ba[],
+                          const DistributionMapping* dm[], int metric_term, int agglomeration,
+                          int consolidation, int max_coarsening_level);
+void amrex_fi_delete_linop(MLLinOp* linop);
+void amrex_fi_linop_set_maxorder(MLLinOp* linop, int ord);
+void amrex_fi_linop_set_domain_bc(MLLinOp* linop, const int* ilobc, const int* ihibc);   /* LinOpBCType values */
+void amrex_fi_linop_set_coarse_fine_bc(MLLinOp* linop, const MultiFab* crse, int crse_ratio);
+void amrex_fi_linop_set_level_bc(MLLinOp* linop, int amrlev, const MultiFab* levelbcdata);
+void amrex_fi_abeclap_set_scalars(MLLinOp* linop, Real a, Real b);
+void amrex_fi_abeclap_set_acoeffs(MLLinOp* linop, int amrlev, const MultiFab* alpha);
+void amrex_fi_abeclap_set_bcoeffs(MLLinOp* linop, int amrlev, const MultiFab* beta[]);
+/* LPInfo::setAgglomerationGridSize / setConsolidationGridSize variant of the constructors (grid size <= 0: default 32) */
+void amrex_b200_new_linop(MLLinOp** linop, int kind /*0 abeclap, 1 poisson*/, int nlevels, const Geometry* geom[],
+                          const BoxArray* ba[], const DistributionMapping* dm[], int agglomeration, int consolidation,
+                          int max_coarsening_level, int agg_grid_size, int con_grid_size);
+void amrex_b200_linop_set_smoother_fusion(MLLinOp* linop, int fuse);   /* 0: reference schedule, 1: fused colours */
+/* primitives of the operator on (amrlev 0, mglev), exposed for parity tests (MLCellLinOp::smooth/apply/...) */
+int  amrex_b200_linop_num_mg_levels(const MLLinOp* linop, int amrlev);
+void amrex_b200_linop_prepare(MLLinOp* linop);
+void amrex_b200_linop_make(MLLinOp* linop, MultiFab** mf, int amrlev, int mglev, int ng);
+void amrex_b200_linop_smooth(MLLinOp* linop, int amrlev, int mglev, MultiFab* sol, const MultiFab* rhs, int skip_fillboundary);
+void amrex_b200_linop_apply(MLLinOp* linop, int amrlev, int mglev, MultiFab* out, MultiFab* in, int inhomog);
+void amrex_b200_linop_residual(MLLinOp* linop, int amrlev, int mglev, MultiFab* resid, MultiFab* x, const MultiFab* b, int inhomog);
+void amrex_b200_linop_restriction(MLLinOp* linop, int amrlev, int cmglev, MultiFab* crse, MultiFab* fine);
+void amrex_b200_linop_interp_add(MLLinOp* linop, int amrlev, int fmglev, MultiFab* fine, const MultiFab* crse);
+void amrex_b200_linop_get_coeff(MLLinOp* linop, int amrlev, int mglev, int which /*0 a, 1..3 b*/, const MultiFab** mf);
+/* MG hierarchy of the operator: boxes (6 ints each) and owner ranks of (amrlev, mglev) */
+int  amrex_b200_linop_level_nboxes(const MLLinOp* linop, int amrlev, int mglev);
+void amrex_b200_linop_level_boxes(const MLLinOp* linop, int amrlev, int mglev, int* boxes6, int* pmap, int* domain6);
+
+/* ---- MLMG (AMReX_multigrid_fi.cpp:8-113) ---- */
+void amrex_fi_new_multigrid(MLMG** mlmg, MLLinOp* lp);
+void amrex_fi_delete_multigrid(MLMG* mlmg);
+Real amrex_fi_multigrid_solve(MLMG* mlmg, MultiFab* a_sol[], MultiFab* a_rhs[], Real a_tol_rel, Real a_tol_abs);
+void amrex_fi_multigrid_comp_residual(MLMG* mlmg, MultiFab* a_res[], MultiFab* a_sol[], MultiFab* a_rhs[]);
+void amrex_fi_multigrid_set_verbose(MLMG* mlmg, int v);
+void amrex_fi_multigrid_set_max_iter(MLMG* mlmg, int n);
+void amrex_fi_multigrid_set_max_fmg_iter(MLMG* mlmg, int n);
+void amrex_fi_multigrid_set_fixed_iter(MLMG* mlmg, int n);
+void amrex_fi_multigrid_set_bottom_solver(MLMG* mlmg, int s);   /* 0 smoother, 1 bicgstab, 2 cg */
+void amrex_fi_multigrid_set_bottom_verbose(MLMG* mlmg, int n);
+void amrex_fi_multigrid_set_always_use_bnorm(MLMG* mlmg, int f);
+void amrex_fi_multigrid_set_final_fill_bc(MLMG* mlmg, int f);
+/* results of the last solve (MLMG::getNumIters/getResidualHistory/getInitRHS/getInitResidual/getNumCGIters) */
+int  amrex_b200_multigrid_num_iters(const MLMG* mlmg);
+int  amrex_b200_multigrid_residual_history(const MLMG* mlmg, Real* hist, int capacity);
+Real amrex_b200_multigrid_init_rhs(const MLMG* mlmg);
+Real amrex_b200_multigrid_init_residual(const MLMG* mlmg);
+int  amrex_b200_multigrid_cg_iters(const MLMG* mlmg, int* iters, int capacity);
+void amrex_b200_multigrid_timers(const MLMG* mlmg, double t[3]);   /* solve, iter, bottom wall seconds */
+
+/* ---- host-only metadata (no device): bit-exact parity targets ---- */
+/* MG hierarchy as MLLinOpT::defineGrids would build it for `nprocs` ranks (AMReX_MLLinOp.H:795-1165).
+ * Returns a handle; query with the functions below; free with amrex_b200_hierarchy_delete. */
+void* amrex_b200_hierarchy_new(int nlevels, const Geometry* geom[], const BoxArray* ba[], const DistributionMapping* dm[],
+                               int agglomeration, int consolidation, int max_coarsening_level,
+                               int agg_grid_size, int con_grid_size, int nprocs);
+void amrex_b200_hierarchy_delete(void* h);
+int  amrex_b200_hierarchy_num_mg_levels(const void* h, int amrlev);
+int  amrex_b200_hierarchy_nboxes(const void* h, int amrlev, int mglev);
+void amrex_b200_hierarchy_level(const void* h, int amrlev, int mglev, int* boxes6, int* pmap, int* domain6);
+/* FillBoundary / ParallelCopy tag lists as rank `myproc` sees them (AMReX_FabArrayBase.cpp:658-877, 324-467).
+ * kind: 0 LocTags, 1 SndTags, 2 RcvTags.  Each tag is written as 15 ints:
+ * dbox lo[3] hi[3], sbox lo[3] hi[3], dstIndex, srcIndex, peer rank (-1 for local).  Returns the tag count
+ * (call with out == NULL to size the buffer). */
+int  amrex_b200_fb_tags(const BoxArray* ba, const DistributionMapping* dm, int ng, int cross, const int period[3],
+                        int myproc, int kind, int* out, int capacity);
+int  amrex_b200_cpc_tags(const BoxArray* ba_dst, const DistributionMapping* dm_dst, int ng_dst,
+                         const BoxArray* ba_src, const DistributionMapping* dm_src, int ng_src,
+                         const int period[3], int myproc, int kind, int* out, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

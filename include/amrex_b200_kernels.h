@@ -1,0 +1,180 @@
+/* amrex_b200_kernels.h -- kernel-level C ABI of the B200 MLMG path (libamrex_b200.so).
+ *
+ * One entry per device lambda of the reference's cell-centred MLMG path.
+ * Every entry takes plain device pointers / POD descriptor tables and a cudaStream_t, launches hand-written
+ * sm_100a kernels asynchronously on that stream and returns 0 or a cudaError_t value.  Nothing here
+ * allocates, synchronises or falls back to the CPU.
+ *
+ * Descriptor tables (b200mg_fab etc.) live in DEVICE memory, one element per local box of a level, all
+ * tables of one call indexed by the same local box number.  Layout of a fab: Fortran order,
+ * element (i,j,k,n) at p[(i-lo[0]) + (j-lo[1])*jstride + (k-lo[2])*kstride + n*nstride], where lo/hi bound
+ * the GROWN (valid + ghost) box -- the contract of Array4 (reference Src/Base/AMReX_Array4.H:85-137), except
+ * that jstride may exceed the grown x-extent (rows are padded so that the first VALID cell of every row is
+ * 128-byte aligned).
+ */
+#ifndef AMREX_B200_KERNELS_H_
+#define AMREX_B200_KERNELS_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+struct CUstream_st;
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+typedef struct b200mg_fab {
+    double* p;                 /* address of element (lo[0],lo[1],lo[2],0) */
+    int lo[3], hi[3];          /* grown box, inclusive */
+    long long jstride, kstride, nstride;   /* in elements */
+} b200mg_fab;
+
+typedef struct b200mg_ifab {
+    int* p;
+    int lo[3], hi[3];
+    long long jstride, kstride, nstride;
+} b200mg_ifab;
+
+typedef struct b200mg_box { int lo[3], hi[3]; } b200mg_box;
+
+/* A unit of work of a cell kernel: rows [j0, j0+B200MG_TILE_Y) x planes [k0, k0+B200MG_TILE_Z) x all i of
+ * local box `box` (clipped to the box).  Tables of tiles are built once per level (amrex::LevelLayout). */
+typedef struct b200mg_tile { int box, j0, k0, pad; } b200mg_tile;
+#define B200MG_TILE_Y 4
+#define B200MG_TILE_Z 4
+
+/* boundary-condition work item: one face of one box (reference MLMGABCTag, AMReX_MLCellLinOp.H:724-760) */
+typedef struct b200mg_bcface {
+    int box;          /* local box number */
+    int face;         /* Orientation value: dir + 3*side */
+    int bctype;       /* 101 Dirichlet, 102 Neumann, 103 reflect-odd (AMReX_LO_BCTYPES.H:5-15) */
+    int blen;         /* valid-box length in the face-normal direction */
+    double bcloc;     /* distance of the BC point from the face */
+} b200mg_bcface;
+
+/* copy work item of FillBoundary / ParallelCopy (reference CopyComTag + Array4CopyTag, AMReX_FBI.H:53-70).
+ * Copies the box [lo,hi] of the DESTINATION index space; source index = destination index + shift.
+ * dst_fab / src_fab are local box numbers into the fab tables, or -1 when that side is the linear buffer,
+ * in which case buf_offset is the element offset of this item's first value (x fastest, then y, z, comp). */
+typedef struct b200mg_copytag {
+    int lo[3], hi[3];
+    int shift[3];
+    int dst_fab, src_fab;
+    int pad;
+    long long buf_offset;
+} b200mg_copytag;
+
+/* ---- smoother: one red or black sweep (K1 abec_gsrb AMReX_MLABecLap_3D_K.H:210-264,
+ *      K2 mlpoisson_gsrb AMReX_MLPoisson_3D_K.H:155-196).  f / m: tables of 6*nboxes slabs, [box*6+face]. */
+int b200mg_gsrb_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                     const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,
+                     const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                     const b200mg_fab* f, const b200mg_ifab* m,
+                     double alpha, double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+int b200mg_gsrb_poisson(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                        const b200mg_fab* phi, const b200mg_fab* rhs,
+                        const b200mg_fab* f, const b200mg_ifab* m,
+                        double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+/* Fused red+black pass: red sweep on every valid cell and black sweep on the cells that do not touch the
+ * box surface, out of place (phi_in -> phi_out).  The black surface shell is finished by b200mg_gsrb_*
+ * restricted to shell tiles after the halo refresh.  Same arithmetic and update order as two sweeps. */
+int b200mg_gsrb2_abec(int nblocks, const b200mg_tile* tiles, const b200mg_box* vbox,
+                      const b200mg_fab* phi_in, const b200mg_fab* phi_out, const b200mg_fab* rhs, const b200mg_fab* a,
+                      const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                      const b200mg_fab* f, const b200mg_ifab* m,
+                      double alpha, double dhx, double dhy, double dhz, int tile_y, int chunk_z, cudaStream_t s);
+int b200mg_gsrb2_poisson(int nblocks, const b200mg_tile* tiles, const b200mg_box* vbox,
+                         const b200mg_fab* phi_in, const b200mg_fab* phi_out, const b200mg_fab* rhs,
+                         const b200mg_fab* f, const b200mg_ifab* m,
+                         double dhx, double dhy, double dhz, int tile_y, int chunk_z, cudaStream_t s);
+/* black (redblack=1) or red sweep restricted to the 1-cell surface shell of every box */
+int b200mg_gsrb_shell_abec(int nboxes, const b200mg_box* vbox,
+                           const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,
+                           const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                           const b200mg_fab* f, const b200mg_ifab* m,
+                           double alpha, double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+int b200mg_gsrb_shell_poisson(int nboxes, const b200mg_box* vbox,
+                              const b200mg_fab* phi, const b200mg_fab* rhs,
+                              const b200mg_fab* f, const b200mg_ifab* m,
+                              double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+
+/* ---- operator apply / residual (K4 mlabeclap_adotx AMReX_MLABecLap_3D_K.H:9-28, K5 mlpoisson_adotx
+ *      AMReX_MLPoisson_3D_K.H:9-16).  If rhs != NULL writes y = rhs - L(x)  (== Xpay(y,-1,rhs),
+ *      AMReX_MLCellLinOp.H:1234), else y = L(x).  dx*: beta*dxinv^2 (abec) or dxinv^2 (poisson). */
+int b200mg_adotx_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                      const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs, const b200mg_fab* a,
+                      const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                      double alpha, double dhx, double dhy, double dhz, cudaStream_t s);
+int b200mg_adotx_poisson(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                         const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs,
+                         double dhx, double dhy, double dhz, cudaStream_t s);
+/* K13 mlabeclap_normalize AMReX_MLABecLap_3D_K.H:60-75 */
+int b200mg_normalize_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                          const b200mg_fab* x, const b200mg_fab* a,
+                          const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                          double alpha, double dhx, double dhy, double dhz, cudaStream_t s);
+
+/* ---- boundary conditions (K9 mllinop_apply_bc_* AMReX_MLLinOp_K.H:14-327; K11 comp_interp_coef0 :329-571).
+ *      m, f, bcval: [box*6+face] tables.  bcval may be NULL (homogeneous). */
+int b200mg_apply_bc(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
+                    const b200mg_fab* phi, const b200mg_ifab* m, const b200mg_fab* bcval,
+                    int maxorder, double dxinv0, double dxinv1, double dxinv2, int inhomog, cudaStream_t s);
+int b200mg_comp_interp_coef0(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
+                             const b200mg_fab* f, const b200mg_ifab* m,
+                             int maxorder, double dxinv0, double dxinv1, double dxinv2, cudaStream_t s);
+
+/* ---- grid transfer (K7 amrex_avgdown AMReX_MultiFabUtil_3D_C.H:377-395, amrex_avgdown_faces :173-217;
+ *      K8 prolongation AMReX_MLCellLinOp.H:970-977; K8b mlmg_lin_cc_interp_r2 AMReX_MLMG_3D_K.H:9-39).
+ *      tiles/vbox describe the COARSE boxes for restriction and the FINE boxes for prolongation. */
+int b200mg_restrict_cc(int ntiles, const b200mg_tile* tiles, const b200mg_box* cbox,
+                       const b200mg_fab* crse, const b200mg_fab* fine, int ratio, cudaStream_t s);
+int b200mg_restrict_faces(int ntiles, const b200mg_tile* tiles, const b200mg_box* cbox,
+                          const b200mg_fab* crse, const b200mg_fab* fine, int dir, int ratio, cudaStream_t s);
+int b200mg_prolong_add(int ntiles, const b200mg_tile* tiles, const b200mg_box* fbox,
+                       const b200mg_fab* fine, const b200mg_fab* crse, cudaStream_t s);
+int b200mg_interp_cc_r2(int ntiles, const b200mg_tile* tiles, const b200mg_box* fbox,
+                        const b200mg_fab* fine, const b200mg_fab* crse, int add, cudaStream_t s);
+
+/* arithmetic cell-centre -> face average (amrex::average_cellcenter_to_face, AMReX_MultiFabUtil_3D_C.H:81-89) */
+int b200mg_cc_to_face(int ntiles, const b200mg_tile* tiles, const b200mg_box* fbox,
+                      const b200mg_fab* face, const b200mg_fab* cc, int dir, cudaStream_t s);
+
+/* ---- vector operations on the valid box grown by ng (K6; AMReX_FabArray.H:179-260,2918-3006) */
+int b200mg_setval(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y,
+                  double v, int ng, cudaStream_t s);
+int b200mg_copy(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y,
+                const b200mg_fab* x, int ng, cudaStream_t s);
+/* y = a*x + b*y   (a=1,b=1: LocalAdd; b=1: Saxpy; a=1: Xpay; a=0: scale) */
+int b200mg_lincomb(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y,
+                   double a, const b200mg_fab* x, double b, int ng, cudaStream_t s);
+int b200mg_plus(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y,
+                double v, int ng, cudaStream_t s);
+/* ghost cells only (setBndry) */
+int b200mg_setbndry(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y,
+                    double v, int ng, cudaStream_t s);
+
+/* ---- reductions over valid cells (K12).  result: DEVICE double[ntiles>0 ? 1 : 1]; the kernel leaves the
+ *      final value in result[0] (two-stage: warp shuffles + last-block finish), no host sync.
+ *      mask (may be NULL): only cells with mask != 0 count (AMReX_FabArray.H:3577-3625). */
+int b200mg_norminf(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x,
+                   const b200mg_ifab* mask, double* result, double* scratch, cudaStream_t s);
+int b200mg_dot(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x,
+               const b200mg_fab* y, double* result, double* scratch, cudaStream_t s);
+int b200mg_sum(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x,
+               double* result, double* scratch, cudaStream_t s);
+/* scratch must hold b200mg_reduce_scratch_doubles(ntiles) doubles */
+long long b200mg_reduce_scratch_doubles(int ntiles);
+
+/* ---- halo / redistribution copies (K10 fab_to_fab, pack, unpack; AMReX_FBI.H:53-70,272-328,729-893).
+ *      op: 0 = copy, 1 = add.  buf: linear staging buffer (may be NULL when no tag uses it). */
+int b200mg_copy_tags(int ntags, const b200mg_copytag* tags, const b200mg_fab* dst, const b200mg_fab* src,
+                     double* buf, int ncomp, int scomp, int dcomp, int op, cudaStream_t s);
+
+/* library identification */
+const char* b200mg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,109 @@
+"""Shared helpers for the parity tests.
+
+`run_ref` executes oracle/_ref/ref_driver -- the UNMODIFIED reference (AMReX 24.10, CPU/OpenMP) built by oracle/Makefile,
+which travels to the GPU box as a prebuilt binary.  Nothing here reads /root/reference.
+"""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DRIVER = os.path.join(REPO, "oracle", "_ref", "ref_driver")
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+
+def have_ref():
+    return os.path.exists(REF_DRIVER) and os.access(REF_DRIVER, os.X_OK)
+
+
+def run_ref(dump=False, threads=None, **kw):
+    """Run the reference driver; returns (result dict, dump dict name->(lo, ndarray[F])) ."""
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(threads or os.cpu_count() or 1)
+    args = [REF_DRIVER] + [f"{k}={v}" for k, v in kw.items()]
+    tmp = None
+    if dump:
+        tmp = tempfile.mkdtemp(prefix="refdump_")
+        args.append(f"dump_dir={tmp}")
+    out = subprocess.run(args, capture_output=True, text=True, env=env, cwd=tempfile.gettempdir(), timeout=1800)
+    if out.returncode != 0:
+        raise RuntimeError(f"ref_driver failed: {out.stdout[-2000:]}\n{out.stderr[-2000:]}")
+    res = None
+    for line in out.stdout.splitlines():
+        if line.startswith("RESULT "):
+            res = json.loads(line[7:])
+    if kw.get("mode") == "meta":
+        s = out.stdout
+        res = json.loads(s[s.index("META") + 5:])
+    d = load_dump(tmp) if dump else None
+    if tmp:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    return res, d
+
+
+def load_dump(path):
+    man = json.load(open(os.path.join(path, "manifest.json")))
+    out = {}
+    for name, info in man.items():
+        if name.startswith("_"):
+            continue
+        a = np.fromfile(os.path.join(path, name + ".bin"), dtype=np.float64).reshape(info["shape"], order="F")
+        out[name] = (tuple(info["lo"]), a)
+    return out
+
+
+def build_problem(ab, prob_type, n_cell, max_grid_size, dump, maxorder=2, agg_grid_size=-1, nprocs=None, fusion=None,
+                  max_coarsening_level=30):
+    """Create geometry / grids / operator for one AMR level from a reference dump (bit-identical inputs)."""
+    per = 1 if prob_type == 5 else 0
+    ab.Geometry.setup((0., 0., 0.), (1., 1., 1.), (per, per, per))
+    geom = ab.Geometry((0, 0, 0), (n_cell - 1,) * 3)
+    ba = ab.BoxArray((0, 0, 0), (n_cell - 1,) * 3).maxSize(max_grid_size)
+    dm = ab.DistributionMapping(ba) if nprocs is None else ab.DistributionMapping(ba, nprocs=nprocs)
+    sol = ab.MultiFab(ba, dm, 1, 1)
+    rhs = ab.MultiFab(ba, dm, 1, 0)
+    lo, a = dump["sol0_lev0"]
+    sol.upload(a, lo, ng=1)
+    lo, a = dump["rhs_lev0"]
+    rhs.upload(a, lo)
+    D, N, P = ab.LinOpBCType.Dirichlet, ab.LinOpBCType.Neumann, ab.LinOpBCType.Periodic
+    keep = []
+    if prob_type == 2:
+        op = ab.MLABecLaplacian([geom], [ba], [dm], agg_grid_size=agg_grid_size, con_grid_size=agg_grid_size,
+                                max_coarsening_level=max_coarsening_level)
+        op.setMaxOrder(maxorder)
+        op.setDomainBC((D, N, N), (N, D, N))
+        op.setLevelBC(0, sol)
+        op.setScalars(1.e-3, 1.0)
+        acoef = ab.MultiFab(ba, dm, 1, 0)
+        lo, a = dump["acoef_lev0"]
+        acoef.upload(a, lo)
+        op.setACoeffs(0, acoef)
+        faces = []
+        for d, nm in enumerate(("bx", "by", "bz")):
+            nodal = [0, 0, 0]
+            nodal[d] = 1
+            f = ab.MultiFab(ba, dm, 1, 0, nodal=nodal)
+            lo, a = dump[nm + "_lev0"]
+            f.upload(a, lo)
+            faces.append(f)
+        op.setBCoeffs(0, faces)
+        keep += [acoef] + faces
+    else:
+        op = ab.MLPoisson([geom], [ba], [dm], agg_grid_size=agg_grid_size, con_grid_size=agg_grid_size,
+                          max_coarsening_level=max_coarsening_level)
+        op.setMaxOrder(maxorder)
+        t = P if prob_type == 5 else D
+        op.setDomainBC((t, t, t), (t, t, t))
+        op.setLevelBC(0, sol)
+    if fusion is not None:
+        op.setSmootherFusion(fusion)
+    return dict(geom=geom, ba=ba, dm=dm, sol=sol, rhs=rhs, op=op, keep=keep, n=n_cell)
+
+
+def rel_maxdiff(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))

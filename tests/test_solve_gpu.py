@@ -1,0 +1,79 @@
+"""Parity of the full MLMG solve (through the amrex_fi_* C ABI) against the reference run on identical inputs.
+
+Bar (BASELINE.json north_star): same V-cycle count (+-1), solution max-norm difference <= 1e-10 relative (fp64)."""
+import numpy as np
+import pytest
+
+from common import build_problem, have_ref, rel_maxdiff, run_ref
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_ref(), reason="oracle/_ref/ref_driver not built")]
+
+SOL_TOL = 1e-10
+
+
+def solve_case(ab, prob_type, n_cell, mgs, maxorder=2, fusion=None, bottom=None, **refkw):
+    ref, dump = run_ref(dump=True, mode="solve", prob_type=prob_type, n_cell=n_cell, max_grid_size=mgs,
+                        linop_maxorder=maxorder, agg_grid_size=32, **refkw)
+    P = build_problem(ab, prob_type, n_cell, mgs, dump, maxorder=maxorder, fusion=fusion)
+    mlmg = ab.MLMG(P["op"])
+    mlmg.setVerbose(0)
+    mlmg.setMaxIter(100)
+    if bottom:
+        mlmg.setBottomSolver(bottom)
+    mlmg.solve([P["sol"]], [P["rhs"]], 1e-10, 0.0)
+    lo, refsol = dump["sol_lev0"]
+    n = n_cell
+    mine = P["sol"].download((0, 0, 0), (n, n, n))
+    refv = refsol[1:-1, 1:-1, 1:-1]
+    if prob_type == 5:   # singular: defined up to a constant
+        mine = mine - mine.mean()
+        refv = refv - refv.mean()
+    return ref, mlmg, rel_maxdiff(mine, refv)
+
+
+@pytest.mark.parametrize("fusion", [0, 1])
+def test_poisson_128_config1(ab, fusion):
+    ref, mlmg, diff = solve_case(ab, 1, 128, 64, fusion=fusion)
+    assert ref["iters"] == 10
+    assert abs(mlmg.numIters() - ref["iters"]) <= 1
+    assert mlmg.initRHS() == pytest.approx(ref["rhsnorm0"], rel=1e-13)
+    h, rh = mlmg.residualHistory(), ref["history"]
+    for a, b in zip(h, rh):
+        assert a == pytest.approx(b, rel=1e-6)
+    assert diff <= SOL_TOL
+
+
+@pytest.mark.parametrize("n,mgs,fusion", [(64, 32, 0), (64, 32, 1), (128, 64, 1)])
+def test_abeclap(ab, n, mgs, fusion):
+    ref, mlmg, diff = solve_case(ab, 2, n, mgs, fusion=fusion)
+    assert abs(mlmg.numIters() - ref["iters"]) <= 1
+    assert mlmg.initResidual() == pytest.approx(ref["resnorm0"], rel=1e-12)
+    for a, b in zip(mlmg.residualHistory(), ref["history"]):
+        assert a == pytest.approx(b, rel=1e-5)
+    assert diff <= SOL_TOL
+
+
+def test_abeclap_256_config2(ab):
+    ref, mlmg, diff = solve_case(ab, 2, 256, 128)
+    assert ref["iters"] == 9
+    assert abs(mlmg.numIters() - ref["iters"]) <= 1
+    assert diff <= SOL_TOL
+
+
+def test_abeclap_maxorder3(ab):
+    ref, mlmg, diff = solve_case(ab, 2, 64, 32, maxorder=3)
+    assert abs(mlmg.numIters() - ref["iters"]) <= 1
+    assert diff <= SOL_TOL
+
+
+def test_periodic_poisson(ab):
+    ref, mlmg, diff = solve_case(ab, 5, 64, 32)
+    assert abs(mlmg.numIters() - ref["iters"]) <= 1
+    assert diff <= 1e-9
+
+
+@pytest.mark.parametrize("bottom", ["smoother", "cg"])
+def test_bottom_solvers(ab, bottom):
+    ref, mlmg, diff = solve_case(ab, 1, 64, 32, bottom=bottom, **{"bottom": bottom})
+    assert abs(mlmg.numIters() - ref["iters"]) <= 1
+    assert diff <= SOL_TOL
