@@ -44,7 +44,7 @@ _SIGS = {
     "amrex_b200_boxarray_coarsen": (None, [_P, _I]), "amrex_b200_boxarray_refine": (None, [_P, _I]),
     "amrex_fi_new_distromap": (None, [_PP, _P]), "amrex_fi_new_distromap_from_pmap": (None, [_PP, _IP, _I]),
     "amrex_fi_delete_distromap": (None, [_P]), "amrex_fi_distromap_get_pmap": (None, [_P, _IP, _I]),
-    "amrex_b200_new_distromap_sfc": (None, [_PP, _P, _I]),
+    "amrex_b200_new_distromap_sfc": (None, [_PP, _P, _I]), "amrex_b200_make_sfc": (None, [_P, _I, _IP]),
     "amrex_fi_new_multifab": (None, [_PP, _PP, _PP, _I, _IP, _IP]), "amrex_fi_delete_multifab": (None, [_P]),
     "amrex_fi_multifab_sum": (_D, [_P, _I]), "amrex_fi_multifab_norm0": (_D, [_P, _I]),
     "amrex_fi_multifab_setval": (None, [_P, _D, _I, _I, _IP]),
@@ -507,6 +507,15 @@ def hierarchy(geom, ba, dm, nprocs, agglomeration=1, consolidation=1, max_coarse
         out.append(levs)
     lib.amrex_b200_hierarchy_delete(h)
     return out
+
+
+def make_sfc(ba, nprocs):
+    """Bucket (rank before the weight sort) of every box, DistributionMapping::makeSFC. No GPU needed."""
+    n = ba.size()
+    a = (C.c_int * n)()
+    lib.amrex_b200_make_sfc(ba.ptr, nprocs, a)
+    check()
+    return list(a)
 
 
 def _tags(n, buf):

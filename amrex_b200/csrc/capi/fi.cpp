@@ -104,6 +104,13 @@ void amrex_fi_distromap_get_pmap (const DistributionMapping* dm, int* pmap, cons
 }
 void amrex_b200_new_distromap_sfc (DistributionMapping** dm, const BoxArray* ba, int nprocs) { FI_VOID( *dm = new DistributionMapping(*ba, nprocs); ) }
 
+void amrex_b200_make_sfc (const BoxArray* ba, int nprocs, int* bucket_of_box)
+{
+    FI_VOID(
+        auto buckets = DistributionMapping::makeSFC(*ba, true, nprocs);
+        for (int r = 0; r < nprocs; ++r) { for (int b : buckets[r]) { bucket_of_box[b] = r; } } )
+}
+
 // ----------------------------------------------------------------------------------------- MultiFab
 void amrex_fi_new_multifab (MultiFab** mf, const BoxArray** ba, const DistributionMapping** dm, int nc, const int* ng, const int* nodal)
 {

@@ -5,7 +5,33 @@
 #ifndef AMREX_B200_STENCIL_MATH_CUH_
 #define AMREX_B200_STENCIL_MATH_CUH_
 
+#include "common.cuh"
+
 namespace b200mg {
+
+struct FaceCoefs { double c[6]; };
+
+// cf0..cf5 of the reference GSRB kernels: slab value f at the cell if the cell lies on that face of its
+// box AND the ghost cell beyond the face is an uncovered (mask>0) boundary cell.
+__device__ __forceinline__ FaceCoefs
+face_coefs (int i, int j, int k, const b200mg_box& vb, const b200mg_fab* f6, const b200mg_ifab* m6)
+{
+    FaceCoefs r;
+#pragma unroll
+    for (int n = 0; n < 6; ++n) { r.c[n] = 0.0; }
+    if (i == vb.lo[0]) { if (view(m6[0])(i - 1, j, k) > 0) { r.c[0] = view(f6[0])(i, j, k); } }
+    if (j == vb.lo[1]) { if (view(m6[1])(i, j - 1, k) > 0) { r.c[1] = view(f6[1])(i, j, k); } }
+    if (k == vb.lo[2]) { if (view(m6[2])(i, j, k - 1) > 0) { r.c[2] = view(f6[2])(i, j, k); } }
+    if (i == vb.hi[0]) { if (view(m6[3])(i + 1, j, k) > 0) { r.c[3] = view(f6[3])(i, j, k); } }
+    if (j == vb.hi[1]) { if (view(m6[4])(i, j + 1, k) > 0) { r.c[4] = view(f6[4])(i, j, k); } }
+    if (k == vb.hi[2]) { if (view(m6[5])(i, j, k + 1) > 0) { r.c[5] = view(f6[5])(i, j, k); } }
+    return r;
+}
+
+__device__ __forceinline__ bool on_surface (int i, int j, int k, const b200mg_box& vb)
+{
+    return i == vb.lo[0] || i == vb.hi[0] || j == vb.lo[1] || j == vb.hi[1] || k == vb.lo[2] || k == vb.hi[2];
+}
 
 constexpr double kOmega = 1.15;   // over-relaxation factor of both GSRB kernels
 

@@ -484,10 +484,47 @@ void MLLinOp::apply (int amrlev, int mglev, MultiFab& out, MultiFab& in, BCMode 
 // Fused schedule (default): identical arithmetic and identical update order, but the red sweep and the part of the
 // black sweep that cannot depend on other boxes' red values run in ONE pass over memory (out of place); the black
 // sweep on the 1-cell surface shell runs after the second halo refresh.
+// Tile table of the fused smoother for one level.  Eligible: every local box has an even x extent <= 256 and the level
+// is big enough for the tiling to pay (small levels are launch-latency bound either way).
+bool MLLinOp::planFused (LevelData const& L) const
+{
+    if (L.fused_state >= 0) { return L.fused_state == 1; }
+    L.fused_state = 0;
+    const int nl = L.layout->numLocal();
+    if (nl == 0 || L.layout->localCells() < 32768 * Long(nl)) { return false; }
+    int nxmax = 0, nymax = 0, nzmax = 0;
+    for (int li = 0; li < nl; ++li) {
+        Box const& b = L.layout->box(li);
+        if (b.length(0) % 2 != 0 || b.length(0) > 256 || b.length(0) < 16) { return false; }
+        nxmax = std::max(nxmax, b.length(0)); nymax = std::max(nymax, b.length(1)); nzmax = std::max(nzmax, b.length(2));
+    }
+    static const int env_ty = std::getenv("B200MG_FUSED_TILE_Y") ? std::atoi(std::getenv("B200MG_FUSED_TILE_Y")) : 0;
+    static const int env_cz = std::getenv("B200MG_FUSED_CHUNK_Z") ? std::atoi(std::getenv("B200MG_FUSED_CHUNK_Z")) : 0;
+    const int tx = ((nxmax / 2 + 31) / 32) * 32;
+    int tile_y = std::min(1024 / tx - 4, 12);
+    if (env_ty > 0) { tile_y = std::min(env_ty, 1024 / tx - 4); }
+    tile_y = std::max(1, std::min(tile_y, nymax));
+    // enough CTAs for >= 4 waves over the 148 SMs when the level allows it
+    const Long ytiles = Long(nl) * ((nymax + tile_y - 1) / tile_y);
+    int chunk_z = nzmax;
+    while (chunk_z > 16 && ytiles * ((nzmax + chunk_z - 1) / chunk_z) < 4 * 148) { chunk_z /= 2; }
+    if (env_cz > 0) { chunk_z = env_cz; }
+    std::vector<b200mg_tile> ht;
+    for (int li = 0; li < nl; ++li) {
+        Box const& b = L.layout->box(li);
+        for (int k = b.smallEnd(2); k <= b.bigEnd(2); k += chunk_z)
+            for (int j = b.smallEnd(1); j <= b.bigEnd(1); j += tile_y) { ht.push_back(b200mg_tile{li, j, k, 0}); }
+    }
+    L.fused_tx = tx; L.fused_tile_y = tile_y; L.fused_chunk_z = chunk_z; L.fused_nblocks = int(ht.size());
+    L.fused_tiles.assign(ht);
+    L.fused_state = 1;
+    return true;
+}
+
 void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, bool skip_fillboundary) const
 {
     LevelData const& L = lev(amrlev, mglev);
-    const bool fuse = m_fuse_colors && m_use_gauss_seidel && L.layout->localCells() >= 4096 * Long(std::max(1, L.layout->numLocal()));
+    const bool fuse = m_fuse_colors && m_use_gauss_seidel && planFused(L);
     if (!fuse) {
         for (int redblack = 0; redblack < 2; ++redblack) {
             applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary);
@@ -733,10 +770,10 @@ void MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiF
 {
     LevelData const& L = lev(amrlev, mglev);
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
-    B200_KCALL(b200mg_gsrb2_abec(L.layout->numLocal(), nullptr, L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
+    B200_KCALL(b200mg_gsrb2_abec(L.fused_nblocks, L.fused_tiles.data(), L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
                                  m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(),
                                  m_b_coeffs[amrlev][mglev][2].d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
-                                 m_a_scalar, dh[0], dh[1], dh[2], 0, 0, Gpu::gpuStream()));
+                                 m_a_scalar, dh[0], dh[1], dh[2], L.fused_tx, L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));
 }
 
 void MLABecLaplacian::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
@@ -780,8 +817,9 @@ void MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab con
 {
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
-    B200_KCALL(b200mg_gsrb2_poisson(L.layout->numLocal(), nullptr, L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
-                                    L.undrrelxr.d_table(), L.mask.d_table(), dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], 0, 0, Gpu::gpuStream()));
+    B200_KCALL(b200mg_gsrb2_poisson(L.fused_nblocks, L.fused_tiles.data(), L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
+                                    L.undrrelxr.d_table(), L.mask.d_table(), dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2],
+                                    L.fused_tx, L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));
 }
 
 void MLPoisson::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const

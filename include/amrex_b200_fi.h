@@ -75,6 +75,8 @@ void amrex_fi_delete_distromap(DistributionMapping* dm);
 void amrex_fi_distromap_get_pmap(const DistributionMapping* dm, int* pmap, const int plen);
 /* SFC map for an explicit rank count, no device needed (DistributionMapping::makeSFC, AMReX_DistributionMapping.cpp:1891) */
 void amrex_b200_new_distromap_sfc(DistributionMapping** dm, const BoxArray* ba, int nprocs);
+/* raw bucket number of every box from DistributionMapping::makeSFC(ba, true, nprocs) (same file :1891-1921); host only */
+void amrex_b200_make_sfc(const BoxArray* ba, int nprocs, int* bucket_of_box);
 
 /* ---- MultiFab (AMReX_multifab_fi.cpp:10-216) ---- */
 void amrex_fi_new_multifab(MultiFab** mf, const BoxArray** ba, const DistributionMapping** dm, int nc, const int* ng, const int* nodal);

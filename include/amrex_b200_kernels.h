@@ -76,18 +76,20 @@ int b200mg_gsrb_poisson(int ntiles, const b200mg_tile* tiles, const b200mg_box* 
                         const b200mg_fab* phi, const b200mg_fab* rhs,
                         const b200mg_fab* f, const b200mg_ifab* m,
                         double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
-/* Fused red+black pass: red sweep on every valid cell and black sweep on the cells that do not touch the
- * box surface, out of place (phi_in -> phi_out).  The black surface shell is finished by b200mg_gsrb_*
- * restricted to shell tiles after the halo refresh.  Same arithmetic and update order as two sweeps. */
+/* Fused red+black pass (one sweep over memory per smooth): red update of every valid cell and black update of the
+ * cells that do not touch the box surface, out of place (phi_in -> phi_out).  The black surface shell is finished by
+ * b200mg_gsrb_shell_* after the halo refresh.  Same arithmetic and update order as two colour sweeps.
+ * tiles: one entry per CTA = rows [j0, j0+tile_y) x planes [k0, k0+chunk_z) x all x of a box (clipped to the box).
+ * Requirements: every box has an even x extent <= 4*tx; tx in {32,64,96,128}; tx*(tile_y+4) <= 1024. */
 int b200mg_gsrb2_abec(int nblocks, const b200mg_tile* tiles, const b200mg_box* vbox,
                       const b200mg_fab* phi_in, const b200mg_fab* phi_out, const b200mg_fab* rhs, const b200mg_fab* a,
                       const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
                       const b200mg_fab* f, const b200mg_ifab* m,
-                      double alpha, double dhx, double dhy, double dhz, int tile_y, int chunk_z, cudaStream_t s);
+                      double alpha, double dhx, double dhy, double dhz, int tx, int tile_y, int chunk_z, cudaStream_t s);
 int b200mg_gsrb2_poisson(int nblocks, const b200mg_tile* tiles, const b200mg_box* vbox,
                          const b200mg_fab* phi_in, const b200mg_fab* phi_out, const b200mg_fab* rhs,
                          const b200mg_fab* f, const b200mg_ifab* m,
-                         double dhx, double dhy, double dhz, int tile_y, int chunk_z, cudaStream_t s);
+                         double dhx, double dhy, double dhz, int tx, int tile_y, int chunk_z, cudaStream_t s);
 /* black (redblack=1) or red sweep restricted to the 1-cell surface shell of every box */
 int b200mg_gsrb_shell_abec(int nboxes, const b200mg_box* vbox,
                            const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,

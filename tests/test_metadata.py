@@ -1,0 +1,114 @@
+"""Bit-exact parity of the host-side integer metadata with the reference (a9, a26, a30).
+
+Targets come from tests/golden/meta_*.json (written by tests/golden/make_golden.py from the UNMODIFIED reference) and,
+when oracle/_ref/ref_driver is present, from a live run of it.  No GPU is needed: these entry points are pure host code.
+"""
+import glob
+import json
+import os
+
+import pytest
+
+import amrex_b200 as ab
+from common import GOLDEN, have_ref, run_ref
+
+
+def _box6(b):
+    return tuple(b[:6])
+
+
+def _setup(args):
+    per = 1 if args["prob_type"] == 5 else 0
+    ab.Geometry.setup((0., 0., 0.), (1., 1., 1.), (per, per, per))
+    n, mgs = args["n_cell"], args["max_grid_size"]
+    nlev = args.get("max_level", 0) + 1
+    geoms, bas = [], []
+    lo, hi = [0, 0, 0], [n - 1] * 3
+    glo, ghi = list(lo), list(hi)
+    for l in range(nlev):
+        geoms.append(ab.Geometry(glo, ghi))
+        bas.append(ab.BoxArray(lo, hi).maxSize(mgs))
+        # next level: central half of this level, refined by 2 (Tests/LinearSolvers/ABecLaplacian_C/MyTest.cpp:612-619)
+        g = n // 4
+        lo = [2 * (x + g) for x in lo]
+        hi = [2 * (x - g + 1) - 1 for x in hi]
+        glo = [2 * x for x in glo]
+        ghi = [2 * (x + 1) - 1 for x in ghi]
+    return geoms, bas, per
+
+
+def check_meta(meta):
+    args = meta["_args"]
+    geoms, bas, per = _setup(args)
+    nlev = len(bas)
+    dms = [ab.DistributionMapping(ba, nprocs=1) for ba in bas]
+    # --- MG hierarchy (MLLinOpT::defineGrids)
+    H = ab.hierarchy(geoms, bas, dms, nprocs=1, agg_grid_size=args["agg_grid_size"], con_grid_size=args["agg_grid_size"])
+    ref = meta["hierarchy"]
+    assert len(H) == len(ref)
+    for a in range(nlev):
+        assert len(H[a]) == len(ref[a]), f"amr level {a}: {len(H[a])} MG levels, reference {len(ref[a])}"
+        for m, (mine, r) in enumerate(zip(H[a], ref[a])):
+            assert mine["domain"] == _box6(r["domain"]), (a, m)
+            assert mine["boxes"] == [_box6(b) for b in r["boxes"]], (a, m)
+            assert mine["dmap"] == r["dmap"], (a, m)
+    # --- FillBoundary local tags, cross and full stencil, in the reference's order
+    for l in range(nlev):
+        dom = meta["hierarchy"][l][0]["domain"]
+        period = [(dom[3 + d] - dom[d] + 1) * per for d in range(3)]
+        for key, cross in ((f"fb_cross_ng1_lev{l}", True), (f"fb_full_ng1_lev{l}", False)):
+            mine = ab.fb_tags(bas[l], dms[l], 1, cross, period, 0, 0)
+            r = meta[key]
+            assert len(mine) == len(r), key
+            for t, u in zip(mine, r):
+                assert t["dbox"] == _box6(u["dbox"]) and t["sbox"] == _box6(u["sbox"]), key
+                assert t["dst"] == u["dst"] and t["src"] == u["src"], key
+    # --- SFC processor maps
+    for key, pm in meta["sfc"].items():
+        np_, lev = int(key.split("_")[0][2:]), int(key.split("lev")[1])
+        assert ab.make_sfc(bas[lev], np_) == pm, key
+
+
+GOLDEN_META = sorted(glob.glob(os.path.join(GOLDEN, "meta_*.json")))
+
+
+@pytest.mark.parametrize("path", GOLDEN_META, ids=[os.path.basename(p)[5:-5] for p in GOLDEN_META])
+def test_metadata_vs_golden(path):
+    check_meta(json.load(open(path)))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/ref_driver not built")
+@pytest.mark.parametrize("kw", [dict(prob_type=1, n_cell=48, max_grid_size=16), dict(prob_type=2, n_cell=160, max_grid_size=32),
+                                dict(prob_type=5, n_cell=96, max_grid_size=24), dict(prob_type=1, n_cell=64, max_grid_size=16, max_level=1)],
+                         ids=["p1_48_16", "p2_160_32", "p5_96_24", "p1_64_16_lev1"])
+def test_metadata_vs_live_reference(kw):
+    meta, _ = run_ref(mode="meta", agg_grid_size=32, **kw)
+    meta["_args"] = dict(kw, agg_grid_size=32)
+    check_meta(meta)
+
+
+def test_multirank_tags_are_symmetric():
+    """For nprocs > 1 the reference cannot run here (no MPI); the pinned property is the one its own debug build checks
+    (CheckRcvStats, AMReX_FabArrayCommI.H:195-200): rank r's send list to q equals rank q's receive list from r."""
+    ab.Geometry.setup((0., 0., 0.), (1., 1., 1.), (1, 1, 0))
+    ba = ab.BoxArray((0, 0, 0), (63, 63, 63)).maxSize(16)
+    for nprocs in (2, 3, 8):
+        dm = ab.DistributionMapping(ba, nprocs=nprocs)
+        for cross in (True, False):
+            snd = {r: ab.fb_tags(ba, dm, 1, cross, (64, 64, 0), r, 1) for r in range(nprocs)}
+            rcv = {r: ab.fb_tags(ba, dm, 1, cross, (64, 64, 0), r, 2) for r in range(nprocs)}
+            for r in range(nprocs):
+                for q in range(nprocs):
+                    s = [(t["dbox"], t["sbox"], t["dst"], t["src"]) for t in snd[r] if t["peer"] == q]
+                    v = [(t["dbox"], t["sbox"], t["dst"], t["src"]) for t in rcv[q] if t["peer"] == r]
+                    assert s == v, (nprocs, cross, r, q)
+            # full stencil: every ghost cell the serial pattern fills is filled by local + received tags (the cross
+            # stencil trims only the remote tags to faces, AMReX_FabArrayBase.cpp:835-854, so volumes differ there)
+            if cross:
+                continue
+            serial = ab.fb_tags(ba, ab.DistributionMapping(ba, nprocs=1), 1, cross, (64, 64, 0), 0, 0)
+            vol = lambda b: (b[3] - b[0] + 1) * (b[4] - b[1] + 1) * (b[5] - b[2] + 1)
+            tot_serial = sum(vol(t["dbox"]) for t in serial)
+            tot = sum(vol(t["dbox"]) for r in range(nprocs) for t in ab.fb_tags(ba, dm, 1, cross, (64, 64, 0), r, 0)) \
+                + sum(vol(t["dbox"]) for r in range(nprocs) for t in rcv[r])
+            assert tot == tot_serial, (nprocs, cross)

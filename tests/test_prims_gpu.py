@@ -1,0 +1,103 @@
+"""Kernel-level parity (through the C ABI) of the operator primitives with the reference: apply (FillBoundary + BC +
+stencil), red-black smooth, correction / solution residual, restriction, prolongation-add, coefficient average-down.
+
+Targets: committed golden dumps of the reference at 16^3 (tests/golden/prim_*.npz) and live runs of oracle/_ref/ref_driver
+at larger sizes.  fp64 tolerance 1e-13 relative to the field's max norm (the kernels keep the reference's association
+order, so most outputs are bit-identical)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from common import GOLDEN, build_problem, have_ref, rel_maxdiff, run_ref
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-13
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, f"prim_{name}.npz"))
+    args = json.loads(bytes(z["_args"]).decode())
+    dump = {k: (tuple(int(v) for v in z[k + "__lo"]), z[k]) for k in z.files if not k.endswith("__lo") and k != "_args"}
+    return args, dump
+
+
+def run_prims(ab, args, dump, fusion):
+    n, mgs, m = args["n_cell"], args["max_grid_size"], args["prim_mglev"]
+    P = build_problem(ab, args["prob_type"], n, mgs, dump, maxorder=args["linop_maxorder"],
+                      agg_grid_size=args.get("agg_grid_size", -1), fusion=fusion)
+    op = P["op"]
+    op.prepareForSolve()
+    nm = n >> m
+    up = lambda mf, key, ng: mf.upload(dump[key][1], dump[key][0], ng=ng)
+    val = lambda mf, nn=nm: mf.download((0, 0, 0), (nn, nn, nn))
+    ref = lambda key: dump[key][1]
+    out = {}
+    if args["prob_type"] == 2:   # averaged-down coefficients of the level
+        a = op.coeff(0, m, 0)
+        out["acoef"] = rel_maxdiff(val(a), ref("prim_acoef_mg"))
+        for d, k in enumerate(("prim_bx_mg", "prim_by_mg", "prim_bz_mg")):
+            shp = [nm, nm, nm]
+            shp[d] += 1
+            out[k] = rel_maxdiff(op.coeff(0, m, 1 + d).download((0, 0, 0), tuple(shp)), ref(k))
+    x = op.make(0, m, 1)
+    b = op.make(0, m, 0)
+    y = op.make(0, m, 0)
+    up(x, "prim_x", 1)
+    up(b, "prim_b", 0)
+    op.apply(0, m, y, x)
+    out["apply"] = rel_maxdiff(val(y), ref("prim_apply_homog"))
+    xg = x.download((-1, -1, -1), (nm + 2,) * 3, ng=1)
+    rg = ref("prim_x_after_bc_homog")
+    # faces only: edge/corner ghosts are not part of the cross stencil
+    for d in range(3):
+        sl = [slice(1, -1)] * 3
+        for s in (0, -1):
+            sl[d] = s
+            out[f"bc_homog_{d}{s}"] = rel_maxdiff(xg[tuple(sl)], rg[tuple(sl)])
+    up(x, "prim_x", 1)
+    op.smooth(0, m, x, b)
+    out["smooth1"] = rel_maxdiff(val(x), ref("prim_smooth1"))
+    op.smooth(0, m, x, b)
+    out["smooth2"] = rel_maxdiff(val(x), ref("prim_smooth2"))
+    op.residual(0, m, y, x, b)
+    out["corres"] = rel_maxdiff(val(y), ref("prim_corres"))
+    if "prim_restrict" in dump:
+        c = op.make(0, m + 1, 0)
+        op.restriction(0, m + 1, c, y)
+        out["restrict"] = rel_maxdiff(val(c, nm // 2), ref("prim_restrict"))
+        f = op.make(0, m, 0)
+        f.copy_from(x)
+        op.interp_add(0, m, f, c)
+        out["interp_add"] = rel_maxdiff(val(f), ref("prim_interp_add"))
+    if m == 0:
+        up(x, "prim_x", 1)
+        op.residual(0, 0, y, x, b, inhomog=True)
+        out["solres"] = rel_maxdiff(val(y), ref("prim_solres"))
+    return out
+
+
+@pytest.mark.parametrize("fusion", [0, 1])
+@pytest.mark.parametrize("name", ["p2_n16_g8_m0", "p1_n16_g8_m0", "p2_n16_g8_m1"])
+def test_prims_vs_golden(ab, name, fusion):
+    args, dump = load_golden(name)
+    out = run_prims(ab, args, dump, fusion)
+    bad = {k: v for k, v in out.items() if not v <= TOL}
+    assert not bad, bad
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/ref_driver not built")
+@pytest.mark.parametrize("fusion", [0, 1])
+@pytest.mark.parametrize("kw", [
+    dict(prob_type=2, n_cell=128, max_grid_size=64, linop_maxorder=2, prim_mglev=0, agg_grid_size=32),
+    dict(prob_type=2, n_cell=128, max_grid_size=32, linop_maxorder=3, prim_mglev=1, agg_grid_size=32),
+    dict(prob_type=1, n_cell=96, max_grid_size=32, linop_maxorder=3, prim_mglev=0, agg_grid_size=32),
+    dict(prob_type=5, n_cell=64, max_grid_size=32, linop_maxorder=2, prim_mglev=0, agg_grid_size=32),
+    dict(prob_type=2, n_cell=64, max_grid_size=32, linop_maxorder=2, prim_mglev=1, agg_grid_size=32),   # re-gridded coarse level
+], ids=["abec128", "abec128_m1_mo3", "pois96_mo3", "periodic64", "abec64_m1_agg"])
+def test_prims_vs_live_reference(ab, kw, fusion):
+    _, dump = run_ref(dump=True, mode="prim", **kw)
+    out = run_prims(ab, kw, dump, fusion)
+    bad = {k: v for k, v in out.items() if not v <= TOL}
+    assert not bad, bad
