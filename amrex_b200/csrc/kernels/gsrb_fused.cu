@@ -159,6 +159,10 @@ int launch (int nblocks, const b200mg_tile* tiles, const b200mg_box* vbox, const
         auto kern = k_gsrb2<ABEC, 512>;
         if (smem > 48 * 1024) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); }
         kern<<<nblocks, block, smem, s>>>(tiles, vbox, A);
+    } else if (nthreads <= 768) {
+        auto kern = k_gsrb2<ABEC, 768>;
+        if (smem > 48 * 1024) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); }
+        kern<<<nblocks, block, smem, s>>>(tiles, vbox, A);
     } else {
         auto kern = k_gsrb2<ABEC, 1024>;
         if (smem > 48 * 1024) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); }
