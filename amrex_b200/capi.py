@@ -35,6 +35,7 @@ _SIGS = {
     "amrex_b200_last_error": (C.c_char_p, []), "amrex_b200_clear_error": (None, []),
     "amrex_b200_synchronize": (None, []), "amrex_b200_launch_count": (_LL, []), "amrex_b200_reset_launch_count": (None, []),
     "amrex_b200_stream": (_P, []),
+    "amrex_b200_profile_enable": (None, [_I]), "amrex_b200_profile_report": (_I, [C.c_char_p, _I]),
     "amrex_b200_geometry_setup": (None, [_DP, _DP, _IP]),
     "amrex_fi_new_geometry": (None, [_PP, _IP, _IP]), "amrex_fi_delete_geometry": (None, [_P]),
     "amrex_fi_new_boxarray": (None, [_PP, _IP, _IP]), "amrex_fi_new_boxarray_from_bxfarr": (None, [_PP, _IP, _I, _I, _I]),
@@ -141,6 +142,23 @@ def init(device_id=None):
     if lib.amrex_b200_init(device_id) != 0:
         check()
         raise AmrexError("amrex_b200_init failed")
+
+
+def profile_enable(on=True):
+    lib.amrex_b200_profile_enable(int(on))
+
+
+def profile_report():
+    """[(kernel, scope, launches, total_ms, min_ms, max_ms)] of the launches since profiling was enabled / last report."""
+    n = lib.amrex_b200_profile_report(None, 0)
+    check()
+    buf = C.create_string_buffer(n + 1)
+    lib.amrex_b200_profile_report(buf, n + 1)
+    out = []
+    for line in buf.value.decode().splitlines():
+        f = line.split()
+        out.append((f[0], int(f[1]), int(f[2]), float(f[3]), float(f[4]), float(f[5])))
+    return out
 
 
 def finalize():

@@ -8,7 +8,6 @@
 
 namespace amrex {
 
-#define B200_KCALL(call) do { int e__ = (call); amrex::Gpu::countLaunch(); if (e__ != 0) amrex::Gpu::check(e__, #call, __FILE__, __LINE__); } while (0)
 
 // =============================================================================== communication metadata
 void define_fb_metadata (CommMetaData& cmd, BoxArray const& ba, DistributionMapping const& dm, IntVect const& nghost,

@@ -9,6 +9,9 @@
 #include <map>
 #include <mutex>
 #include <unordered_map>
+#include <string>
+#include <vector>
+#include <algorithm>
 
 namespace amrex {
 
@@ -80,6 +83,54 @@ void memset_async (void* d, int v, std::size_t n) { AMREX_CUDA_SAFE_CALL(cudaMem
 long long launchCount () noexcept { return g_launches; }
 void resetLaunchCount () noexcept { g_launches = 0; }
 void countLaunch (int n) noexcept { g_launches += n; }
+
+namespace {
+    struct ProfRec { std::string name; int scope; cudaEvent_t e0, e1; };
+    bool g_prof_on = false;
+    int g_prof_scope = -1;
+    std::vector<ProfRec> g_prof;
+    std::vector<cudaEvent_t> g_prof_pool;
+    cudaEvent_t prof_event ()
+    {
+        if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+        cudaEvent_t e; AMREX_CUDA_SAFE_CALL(cudaEventCreate(&e)); return e;
+    }
+}
+void profileEnable (bool on) { g_prof_on = on; }
+bool profiling () noexcept { return g_prof_on; }
+void profileScope (int s) noexcept { g_prof_scope = s; }
+int profileScope () noexcept { return g_prof_scope; }
+void profileBegin (const char* call_text)
+{
+    const char* p = std::strchr(call_text, '(');
+    ProfRec r{p ? std::string(call_text, p - call_text) : std::string(call_text), g_prof_scope, prof_event(), prof_event()};
+    while (!r.name.empty() && r.name.back() == ' ') { r.name.pop_back(); }
+    AMREX_CUDA_SAFE_CALL(cudaEventRecord(r.e0, gpuStream()));
+    g_prof.push_back(std::move(r));
+}
+void profileEnd () { AMREX_CUDA_SAFE_CALL(cudaEventRecord(g_prof.back().e1, gpuStream())); }
+std::string profileReport ()
+{
+    AMREX_CUDA_SAFE_CALL(cudaStreamSynchronize(gpuStream()));
+    struct Acc { long long n = 0; double tot = 0, mn = 1e30, mx = 0; };
+    std::map<std::pair<std::string, int>, Acc> acc;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        AMREX_CUDA_SAFE_CALL(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        Acc& a = acc[{r.name, r.scope}];
+        a.n++; a.tot += ms; a.mn = std::min(a.mn, double(ms)); a.mx = std::max(a.mx, double(ms));
+        g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
+    }
+    g_prof.clear();
+    std::string out;
+    char line[256];
+    for (auto const& kv : acc) {
+        std::snprintf(line, sizeof(line), "%s %d %lld %.6f %.6f %.6f\n", kv.first.first.c_str(), kv.first.second, kv.second.n,
+                      kv.second.tot, kv.second.mn, kv.second.mx);
+        out += line;
+    }
+    return out;
+}
 
 } // namespace Gpu
 

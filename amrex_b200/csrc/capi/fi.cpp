@@ -42,6 +42,20 @@ void amrex_b200_synchronize (void) { FI_VOID( Gpu::streamSynchronize(); ) }
 long long amrex_b200_launch_count (void) { return Gpu::launchCount(); }
 void amrex_b200_reset_launch_count (void) { Gpu::resetLaunchCount(); }
 void* amrex_b200_stream (void) { return Gpu::gpuStream(); }
+void amrex_b200_profile_enable (int on) { Gpu::profileEnable(on != 0); }
+int amrex_b200_profile_report (char* buf, int capacity)
+{
+    static std::string pending;
+    FI_TRY
+        if (pending.empty()) { pending = Gpu::profileReport(); }
+        const int n = int(pending.size());
+        if (buf == nullptr) { return n; }
+        const int m = std::min(n, capacity - 1);
+        std::memcpy(buf, pending.data(), m); buf[m] = 0;
+        pending.clear();
+        return n;
+    FI_CATCH(return -1)
+}
 
 // ----------------------------------------------------------------------------------------- Geometry
 void amrex_b200_geometry_setup (const Real problo[3], const Real probhi[3], const int is_periodic[3])

@@ -5,7 +5,6 @@
 
 namespace amrex {
 
-#define B200_KCALL(call) do { int e__ = (call); amrex::Gpu::countLaunch(); if (e__ != 0) amrex::Gpu::check(e__, #call, __FILE__, __LINE__); } while (0)
 
 // ================================================================================ MGHierarchy::define
 // Restates MLLinOpT::defineGrids (AMReX_MLLinOp.H:795-1165) without semicoarsening / hidden dimensions / EB.
@@ -462,6 +461,7 @@ void MLLinOp::prepareForSolve ()
 void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, StateMode, const BndrySlabs<double>* bndry,
                        bool skip_fillboundary) const
 {
+    Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     AMREX_ALWAYS_ASSERT(mglev == 0 || bc_mode == BCMode::Homogeneous);
     AMREX_ALWAYS_ASSERT(bndry != nullptr || bc_mode == BCMode::Homogeneous);
     if (!skip_fillboundary) { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
@@ -476,6 +476,7 @@ void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, Stat
 
 void MLLinOp::apply (int amrlev, int mglev, MultiFab& out, MultiFab& in, BCMode bc_mode, StateMode s_mode, const BndrySlabs<double>* bndry) const
 {
+    Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     applyBC(amrlev, mglev, in, bc_mode, s_mode, bndry);
     Fapply(amrlev, mglev, out, in);
 }
@@ -523,6 +524,7 @@ bool MLLinOp::planFused (LevelData const& L) const
 
 void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, bool skip_fillboundary) const
 {
+    Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     LevelData const& L = lev(amrlev, mglev);
     const bool fuse = m_fuse_colors && m_use_gauss_seidel && planFused(L);
     if (!fuse) {
@@ -543,6 +545,7 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
 
 void MLLinOp::solutionResidual (int amrlev, MultiFab& resid, MultiFab& x, MultiFab const& b, const MultiFab* crse_bcdata)
 {
+    Gpu::ProfScope prof_scope__(amrlev * 100 + 0);
     if (crse_bcdata != nullptr) { Abort("solutionResidual with coarse BC data: AMR composite path not implemented yet"); }
     applyBC(amrlev, 0, x, BCMode::Inhomogeneous, StateMode::Solution, m_bndry_sol[amrlev].get());
     Fapply(amrlev, 0, resid, x, &b);    // resid = b - L(x), fused (== Fapply + Xpay(resid,-1,b))
@@ -550,6 +553,7 @@ void MLLinOp::solutionResidual (int amrlev, MultiFab& resid, MultiFab& x, MultiF
 
 void MLLinOp::correctionResidual (int amrlev, int mglev, MultiFab& resid, MultiFab& x, MultiFab const& b, BCMode bc_mode, const MultiFab* crse_bcdata)
 {
+    Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     if (bc_mode == BCMode::Inhomogeneous) {
         if (crse_bcdata) { Abort("correctionResidual with coarse BC data: AMR composite path not implemented yet"); }
         applyBC(amrlev, mglev, x, BCMode::Inhomogeneous, StateMode::Correction, m_bndry_cor[amrlev].get());
@@ -561,6 +565,7 @@ void MLLinOp::correctionResidual (int amrlev, int mglev, MultiFab& resid, MultiF
 
 void MLLinOp::restriction (int amrlev, int cmglev, MultiFab& crse, MultiFab& fine) const
 {
+    Gpu::ProfScope prof_scope__(amrlev * 100 + (cmglev - 1));
     const int ratio = (amrlev > 0) ? 2 : H.mg_coarsen_ratio_vec[cmglev - 1][0];
     if (isMFIterSafe(amrlev, cmglev - 1, cmglev)) {
         auto const& T = crse.layout().tiles(0);
@@ -583,6 +588,7 @@ void MLLinOp::avgDownResMG (int clev, MultiFab& cres, MultiFab const& fres) cons
 // piecewise-constant V-cycle prolongation (AMReX_MLCellLinOp.H:956-999); crse must be on fine's coarsened layout
 void MLLinOp::interpolation (int amrlev, int fmglev, MultiFab& fine, MultiFab const& crse) const
 {
+    Gpu::ProfScope prof_scope__(amrlev * 100 + fmglev);
     const int ratio = (amrlev > 0) ? 2 : H.mg_coarsen_ratio_vec[fmglev][0];
     AMREX_ALWAYS_ASSERT(ratio == 2);
     auto const& T = fine.layout().tiles(0);
@@ -592,6 +598,7 @@ void MLLinOp::interpolation (int amrlev, int fmglev, MultiFab& fine, MultiFab co
 // trilinear interpolation used by the F-cycle (AMReX_MLCellLinOp.H:1003-1092)
 void MLLinOp::interpAssign (int amrlev, int fmglev, MultiFab& fine, MultiFab& crse) const
 {
+    Gpu::ProfScope prof_scope__(amrlev * 100 + fmglev);
     Geometry const& cgeom = H.geom[amrlev][fmglev + 1];
     const MultiFab* cmf = &crse;
     if (isMFIterSafe(amrlev, fmglev, fmglev + 1)) {

@@ -272,6 +272,7 @@ void MLMG::prepareForSolve (Vector<MultiFab*> const& a_sol, Vector<MultiFab cons
 void MLMG::oneIter (int iter)
 {
     if (finest_amr_lev > 0) { Abort("multi-level composite solve is not implemented yet"); }
+    Gpu::ProfScope prof_scope__(0);
     if (linop.isSingular(0) && linop.getEnforceSingularSolvable()) { makeSolvable(0, 0, res[0][0]); }
     if (iter < max_fmg_iters) { mgFcycle(); } else { mgVcycle(0, 0); }
     MultiFab::Add(sol[0], cor[0][0], 0, 0, 1, 0);
@@ -282,6 +283,7 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
 {
     const int mglev_bottom = linop.NMGLevels(amrlev) - 1;
     for (int mglev = mglev_top; mglev < mglev_bottom; ++mglev) {
+        Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
         cor[amrlev][mglev].setVal(0.0);
         bool skip_fillboundary = true;
         for (int i = 0; i < nu1; ++i) {
@@ -301,6 +303,7 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
         }
     }
     for (int mglev = mglev_bottom - 1; mglev >= mglev_top; --mglev) {
+        Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
         addInterpCorrection(amrlev, mglev);
         for (int i = 0; i < nu2; ++i) { linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev]); }
     }
@@ -327,6 +330,7 @@ void MLMG::bottomSolve ()
     const double t0 = ParallelDescriptor::second();
     const int amrlev = 0;
     const int mglev = linop.NMGLevels(amrlev) - 1;
+    Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     MultiFab& x = cor[amrlev][mglev];
     MultiFab& b = res[amrlev][mglev];
     x.setVal(0.0);

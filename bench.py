@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 MLMG path on BASELINE.json's metric: MLMG solve time & DOF/s of the 512^3 variable-coefficient
+MLABecLaplacian solve (max_grid_size 128, 64 boxes, tol_rel 1e-10), strong-scaled over 1/2/4/8 GPUs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n-cell 512]          (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...       times the UNMODIFIED reference (oracle/_ref/ref_driver, CPU OpenMP) instead
+
+A step = one complete MLMG::solve (reset of the initial guess included).  `value` = cells / (device time per step), inputs
+resident in HBM; `e2e` = the same through the C ABI with HOST buffers: per step the rhs and initial guess are copied from
+pinned host memory, solved, and the solution is copied back, all inside the timed region.  After the timed region one
+extra solve runs with per-kernel CUDA events to get the finest-level smoother's duration for the roofline figure, and
+(rank 0, N=1) the reference is timed on the host cores on a bounded sample as `cpu_baseline`.
+Nothing here reads /root/reference; oracle/_ref/ref_driver is the prebuilt checker / CPU baseline only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "mlmg_solve_dof_per_s"
+UNIT = "DOF/s"
+TOL_REL = 1e-10
+GSRB_BYTES_PER_CELL = 56.0     # fused red+black ABecLap smooth: phi 8 + rhs 8 + a 8 + b 24 + phi_out 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-cell", type=int, default=512)
+    ap.add_argument("--max-grid-size", type=int, default=128)
+    ap.add_argument("--fusion", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(n, mgs):
+    return f"single-level {n}^3 variable-coefficient MLABecLaplacian (prob_type 2), max_grid_size={mgs}, tol_rel=1e-10, V-cycles"
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def run_reference_solve(n, mgs, nsolve, threads):
+    from common import REF_DRIVER, have_ref, run_ref
+    if not have_ref():
+        raise RuntimeError(f"{REF_DRIVER} missing (built by __graft_entry__.build() where /root/reference is mounted)")
+    res, _ = run_ref(threads=threads, mode="solve", prob_type=2, n_cell=n, max_grid_size=mgs, linop_maxorder=2,
+                     agg_grid_size=32, nsolve=nsolve)
+    return res
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    # bounded sample: the full 512^3 solve costs ~35 s on 8 cores; fall back to the 256^3 instance of the same problem
+    # (1/8 of the cells, same operator, same tolerance) when the requested steps would not finish within a few minutes
+    n = args.n_cell
+    per_solve_est = 36.0 * (n / 512.0) ** 3 * 8.0 / cores + 8.0 * (n / 512.0) ** 3
+    if total * per_solve_est > 240.0 and n > 256:
+        n = 256
+    res = run_reference_solve(n, min(args.max_grid_size, n), total, cores)
+    times = res["solve_times"][args.warmup:]
+    t = sum(times) / len(times)
+    value = res["ncells"] / t
+    sample = (f"{n}^3 instance of the workload, {len(times)} full solves to 1e-10 ({res['iters']} V-cycles) after {args.warmup} warm-up, "
+              f"reference AMReX 24.10 CPU OpenMP build (oracle/_ref/ref_driver), {res['omp_threads']} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.n_cell, args.max_grid_size), "timed_instance_n_cell": n, "iters": res["iters"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["omp_threads"], "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_copy_gbs", "hbm_gb_s"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------- B200 arm
+def b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import amrex_b200 as ab
+    from common import synth_abeclap
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device - the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    ab.init(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ab.comm_init_from_torch()
+    n, mgs = args.n_cell, args.max_grid_size
+    P = synth_abeclap(ab, n, mgs, fusion=args.fusion, keep_host=True)
+    mlmg = ab.MLMG(P["op"])
+    mlmg.setVerbose(0)
+    stream = torch.cuda.ExternalStream(ab.lib.amrex_b200_stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        ab.lib.amrex_b200_synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        P["sol"].copy_from(P["sol0"], ng=1)
+        mlmg.solve([P["sol"]], [P["rhs"]], TOL_REL, 0.0)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ab.lib.amrex_b200_reset_launch_count()
+    ms = timed(step, args.steps)
+    launches = int(ab.lib.amrex_b200_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    iters = mlmg.numIters()
+    hist = mlmg.residualHistory()
+    ms_per_step = ms / args.steps
+    cells = n ** 3
+    value = cells / (ms_per_step * 1e-3)
+
+    # correctness of what was timed: error against the analytic solution (reference prints the same norm)
+    err = 0.0
+    for g, h in P["host"].items():
+        b = h["box"]
+        mine = P["sol"].download(b[:3], tuple(b[3 + d] - b[d] + 1 for d in range(3)))
+        err = max(err, float(np.max(np.abs(mine - h["exact"]))))
+    errt = torch.tensor([err], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(errt, op=dist.ReduceOp.MAX)
+    err = float(errt.item())
+
+    # ---- e2e: host buffers in, host buffer out, through the C ABI
+    e2e = None
+    if not args.no_e2e:
+        pin = {}
+        for g, h in P["host"].items():
+            r = torch.empty(h["rhs"].shape[::-1], dtype=torch.float64).pin_memory()      # Fortran order == reversed C shape
+            r.copy_(torch.from_numpy(np.ascontiguousarray(h["rhs"].transpose(2, 1, 0))))
+            s = torch.zeros_like(r).pin_memory()
+            o = torch.empty_like(r).pin_memory()
+            pin[g] = (r, s, o)
+        nbytes = sum(t[0].numel() * 8 for t in pin.values())
+
+        def e2e_step():
+            for g, (r, s, o) in pin.items():
+                b = P["host"][g]["box"]
+                P["rhs"].upload_ptr(r.data_ptr(), b[:3], b[3:])
+                P["sol"].upload_ptr(s.data_ptr(), b[:3], b[3:])
+            mlmg.solve([P["sol"]], [P["rhs"]], TOL_REL, 0.0)
+            for g, (r, s, o) in pin.items():
+                b = P["host"][g]["box"]
+                P["sol"].download_ptr(o.data_ptr(), b[:3], b[3:])
+
+        e2e_step()
+        k = max(1, min(args.steps, 3))
+        ems = timed(e2e_step, k) / k
+        h2d = torch.tensor([2.0 * nbytes, 1.0 * nbytes], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(h2d)
+        e2e = {"value": cells / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems, "h2d_bytes_per_step": int(h2d[0].item()),
+               "d2h_bytes_per_step": int(h2d[1].item()), "steps": k,
+               "what": "pinned host rhs + initial guess -> device, MLMG solve, solution -> pinned host; operator (coefficients, BCs) resident"}
+
+    # ---- roofline of the dominant kernel (finest-level fused smoother), one extra solve with per-kernel CUDA events
+    ab.profile_enable(True)
+    step()
+    rep = ab.profile_report()
+    ab.profile_enable(False)
+    tot_ms = sum(r[3] for r in rep)
+    kern = "b200mg_gsrb2_abec" if args.fusion else "b200mg_gsrb_abec"
+    top = [r for r in rep if r[0] == kern and r[1] == 0]
+    peak, peak_src = measured_peak_gbs()
+    roofline = None
+    if top:
+        _, _, cnt, tms, mn, mx = top[0]
+        local_cells = sum(int(np.prod(h["rhs"].shape)) for h in P["host"].values())
+        bpc = GSRB_BYTES_PER_CELL if args.fusion else 44.0
+        avg_s = tms / cnt * 1e-3
+        achieved = bpc * local_cells / avg_s / 1e9
+        roofline = {"bound": "hbm", "kernel": kern + " (finest MG level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_cell": bpc,
+                    "cells_per_launch": local_cells, "launches": cnt, "avg_launch_ms": tms / cnt,
+                    "share_of_solve_kernel_time": tms / tot_ms if tot_ms > 0 else None}
+    by_kernel = {}
+    for r in rep:
+        by_kernel[r[0]] = by_kernel.get(r[0], 0.0) + r[3]
+    top5 = sorted(by_kernel.items(), key=lambda kv: -kv[1])[:8]
+
+    # ---- CPU baseline (rank 0, N = 1): the reference itself on the host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cores = os.cpu_count() or 1
+            nb = min(n, 256)
+            res = run_reference_solve(nb, min(mgs, nb), 1, cores)
+            cpu = {"value": res["ncells"] / res["solve_times"][0], "unit": UNIT, "cores": res["omp_threads"], "kind": "reference",
+                   "sample": f"one full solve of the {nb}^3 instance of the workload ({res['iters']} V-cycles, {res['solve_times'][0]:.2f} s), "
+                             f"reference AMReX 24.10 CPU OpenMP build (oracle/_ref/ref_driver)"}
+        except Exception as e:  # the GPU number stands on its own
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(n, mgs), "n_cell": n, "max_grid_size": mgs, "boxes": P["ba"].size(),
+                       "l2": "inputs_exceed_l2 (every finest-level field is >= 1 GiB at 512^3)", "smoother_fusion": args.fusion,
+                       "iters": iters, "final_resid_over_norm": hist[-1] / max(mlmg.initRHS(), mlmg.initResidual()) if hist else None,
+                       "max_err_vs_analytic": err, "solve_time_s": ms_per_step * 1e-3},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "kernel_time_top": [[k, round(v, 3)] for k, v in top5], "kernel_time_total_ms": round(tot_ms, 3),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        ab.lib.amrex_b200_comm_finalize()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,7 +46,12 @@ void amrex_b200_clear_error(void);
 void amrex_b200_synchronize(void);
 long long amrex_b200_launch_count(void);             /* kernels launched by this library since the last reset */
 void amrex_b200_reset_launch_count(void);
-void* amrex_b200_stream(void);                       /* the cudaStream_t every kernel is launched on */
+void* amrex_b200_stream(void);
+/* per-kernel device timing (CUDA events around every launch); report: lines "kernel scope launches total_ms min_ms max_ms",
+ * scope = amrlev*100 + mglev of the level the launch worked on (-1: none).  Returns the report length; call with
+ * buf == NULL to size the buffer (the report is then kept until read). */
+void amrex_b200_profile_enable(int on);
+int  amrex_b200_profile_report(char* buf, int capacity);                       /* the cudaStream_t every kernel is launched on */
 
 /* ---- Geometry (Src/F_Interfaces/Base/AMReX_geometry_fi.cpp:7-40) ---- */
 void amrex_b200_geometry_setup(const Real problo[3], const Real probhi[3], const int is_periodic[3]); /* Geometry::Setup */

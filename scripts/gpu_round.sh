@@ -1,0 +1,34 @@
+#!/bin/bash
+# One GPU-box session: parity tests, benchmark, ncu launch list and a full capture of the dominant kernel.
+# Usage (from the repo root, under gpurun):  bash scripts/gpu_round.sh [tag] [what...]   what: tests bench ncu_list ncu_full
+TAG=${1:-r01}; shift
+WHAT=${@:-tests bench ncu_list ncu_full}
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $OUT/gpu.txt 2>&1
+nproc > $OUT/nproc.txt
+for w in $WHAT; do
+case $w in
+tests)
+  timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log ;;
+smoke)
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke exit $?" >> $OUT/smoke.log ;;
+bench)
+  timeout 1200 python bench.py --steps 5 --warmup 3 > $OUT/bench.log 2> $OUT/bench.err; echo "bench exit $?" >> $OUT/bench.err ;;
+bench256)
+  timeout 600 python bench.py --steps 5 --warmup 3 --n-cell 256 --no-cpu-baseline > $OUT/bench256.log 2> $OUT/bench256.err ;;
+bench_ref)
+  timeout 1200 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.log 2> $OUT/bench_ref.err ;;
+ncu_list)
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches.csv \
+     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_list.log 2>&1 ;;
+ncu_full)
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_gsrb2 -s 8 -c 2 -f -o $OUT/prof_gsrb2 \
+     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_full.log 2>&1 ;;
+tune)
+  for ty in 4 8 12; do for cz in 16 32 64 128; do
+    echo "== tile_y=$ty chunk_z=$cz" >> $OUT/tune.log
+    B200MG_FUSED_TILE_Y=$ty B200MG_FUSED_CHUNK_Z=$cz timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e >> $OUT/tune.log 2>&1
+  done; done ;;
+esac
+done
+ls -la $OUT
