@@ -174,6 +174,7 @@ std::shared_ptr<LevelLayout> LevelLayout::get (BoxArray const& ba, DistributionM
         L->m_index.push_back(i);
         L->m_boxes.push_back(ba[i]);
         L->m_cells += ba[i].numPts();
+        if (ba[i].length(0) % 2 != 0 || ba[i].length(0) > 128 || !ba[i].cellCentered()) { L->m_pairable = false; }
         b200mg_box b; for (int d = 0; d < 3; ++d) { b.lo[d] = ba[i].smallEnd(d); b.hi[d] = ba[i].bigEnd(d); }
         hb.push_back(b);
     }
@@ -188,11 +189,15 @@ LevelLayout::Tiles const& LevelLayout::tiles (int ng)
 {
     auto it = m_tiles.find(ng);
     if (it != m_tiles.end()) { return it->second; }
+    // tile depth: deep tiles on big levels (fewer, longer-running CTAs that stream along z), 4 planes on small ones
+    // so that coarse levels still spread over the SMs
+    int tz = B200MG_TILE_Z;
+    while (tz < 16 && m_cells / (Long(64) * B200MG_TILE_Y * 2 * tz) >= 8 * 148) { tz *= 2; }
     std::vector<b200mg_tile> ht;
     for (int li = 0; li < numLocal(); ++li) {
         const Box g = amrex::grow(m_boxes[li], ng);
-        for (int k = g.smallEnd(2); k <= g.bigEnd(2); k += B200MG_TILE_Z)
-            for (int j = g.smallEnd(1); j <= g.bigEnd(1); j += B200MG_TILE_Y) { ht.push_back(b200mg_tile{li, j, k, 0}); }
+        for (int k = g.smallEnd(2); k <= g.bigEnd(2); k += tz)
+            for (int j = g.smallEnd(1); j <= g.bigEnd(1); j += B200MG_TILE_Y) { ht.push_back(b200mg_tile{li, j, k, tz}); }
     }
     Tiles& T = m_tiles[ng];
     T.n = int(ht.size());

@@ -34,13 +34,15 @@ __device__ __forceinline__ View<int> view (const b200mg_ifab& f) noexcept {
 // Tile loop: blockDim = (TX, B200MG_TILE_Y); thread row j = j0 + threadIdx.y, planes k0..k0+TILE_Z-1,
 // i strides by blockDim.x starting at the (grown) lower x bound -> consecutive lanes touch consecutive
 // doubles of one row (coalesced 256 B per warp-load).
+__device__ __forceinline__ int tile_nk (const b200mg_tile& t) noexcept { return t.nk > 0 ? t.nk : B200MG_TILE_Z; }
+
 template <class F>
 __device__ __forceinline__ void tile_for (const b200mg_tile t, const b200mg_box& b, int ng, F&& f)
 {
     const int j = t.j0 + int(threadIdx.y);
     const int jhi = b.hi[1] + ng;
     if (j > jhi) { return; }
-    const int khi = min(t.k0 + B200MG_TILE_Z - 1, b.hi[2] + ng);
+    const int khi = min(t.k0 + tile_nk(t) - 1, b.hi[2] + ng);
     const int ilo = b.lo[0] - ng, ihi = b.hi[0] + ng;
     for (int k = t.k0; k <= khi; ++k) {
         for (int i = ilo + int(threadIdx.x); i <= ihi; i += int(blockDim.x)) { f(i, j, k); }

@@ -31,19 +31,48 @@ struct FusedArgs {
 __device__ __forceinline__ double sel (const double2& v, int c) { return c ? v.y : v.x; }
 __device__ __forceinline__ void put (double2& v, int c, double x) { if (c) { v.y = x; } else { v.x = x; } }
 
+// Per-thread cursors into the coefficient arrays: 32-bit element offsets of (i0, j, red plane) from each fab's base,
+// advanced by one plane per step; bases and strides are CTA-uniform.  Loaded ONCE from the descriptor tables (no
+// per-access descriptor traffic or 64-bit index arithmetic in the loop).  The black plane is one plane stride behind.
+template <bool ABEC>
+struct Cursors {
+    const double *rhs, *a, *bx, *by, *bz;            // fab bases (uniform)
+    int rhs_ks, a_ks, bx_ks, by_ks, bz_ks, by_js;    // strides (uniform)
+    int o_rhs, o_a, o_bx, o_by, o_bz;                // per-thread offsets at the red plane
+    __device__ __forceinline__ void init (const FusedArgs& A, int box, int i0, int j, int k)
+    {
+        const auto r = view(A.rhs[box]);
+        rhs = r.p; rhs_ks = int(r.ks); o_rhs = int(r.ptr(i0, j, k) - r.p);
+        if constexpr (ABEC) {
+            const auto va = view(A.a[box]); const auto vx = view(A.bx[box]); const auto vy = view(A.by[box]); const auto vz = view(A.bz[box]);
+            a = va.p; bx = vx.p; by = vy.p; bz = vz.p;
+            a_ks = int(va.ks); bx_ks = int(vx.ks); by_ks = int(vy.ks); bz_ks = int(vz.ks); by_js = int(vy.js);
+            o_a = int(va.ptr(i0, j, k) - va.p); o_bx = int(vx.ptr(i0, j, k) - vx.p);
+            o_by = int(vy.ptr(i0, j, k) - vy.p); o_bz = int(vz.ptr(i0, j, k) - vz.p);
+        }
+    }
+    __device__ __forceinline__ void advance ()
+    {
+        o_rhs += rhs_ks;
+        if constexpr (ABEC) { o_a += a_ks; o_bx += bx_ks; o_by += by_ks; o_bz += bz_ks; }
+    }
+};
+
+// update of cell c of the pair at the cursors' current plane
 template <bool ABEC>
 __device__ __forceinline__ double
-update_cell (int i, int j, int k, int box, const b200mg_box& vb, const FusedArgs& A, bool surface,
+update_cell (const Cursors<ABEC>& C, int back, int c, int i, int j, int k, int box, const b200mg_box& vb, const FusedArgs& A, bool surface,
              double p, double xm, double xp, double ym, double yp, double zm, double zp)
 {
-    const double rhs = __ldg(view(A.rhs[box]).ptr(i, j, k));
+    const double rhs = __ldg(C.rhs + (C.o_rhs - back * C.rhs_ks + c));
     if constexpr (ABEC) {
-        const auto bx = view(A.bx[box]); const auto by = view(A.by[box]); const auto bz = view(A.bz[box]);
-        const double a = __ldg(view(A.a[box]).ptr(i, j, k));
-        const double* pbx = bx.ptr(i, j, k); const double* pby = by.ptr(i, j, k); const double* pbz = bz.ptr(i, j, k);
+        const double a = __ldg(C.a + (C.o_a - back * C.a_ks + c));
+        const double* pbx = C.bx + (C.o_bx - back * C.bx_ks + c);
+        const double* pby = C.by + (C.o_by - back * C.by_ks + c);
+        const double* pbz = C.bz + (C.o_bz - back * C.bz_ks + c);
         const double bxm = __ldg(pbx), bxp = __ldg(pbx + 1);
-        const double bym = __ldg(pby), byp = __ldg(pby + by.js);
-        const double bzm = __ldg(pbz), bzp = __ldg(pbz + bz.ks);
+        const double bym = __ldg(pby), byp = __ldg(pby + C.by_js);
+        const double bzm = __ldg(pbz), bzp = __ldg(pbz + C.bz_ks);
         if (surface) {
             const FaceCoefs cf = face_coefs(i, j, k, vb, A.f + 6 * box, A.m + 6 * box);
             return gsrb_abec_cell(p, xm, xp, ym, yp, zm, zp, rhs, a, bxm, bxp, bym, byp, bzm, bzp,
@@ -83,15 +112,23 @@ k_gsrb2 (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ v
     const bool row_black = xact && (j >= t.j0) && (j <= j1);
     const bool gl = row_load && (tx == 0), gr = row_load && (i0 + 1 == vb.hi[0]);   // who carries the x ghost cells
     const bool jsurf = (j == vb.lo[1]) || (j == vb.hi[1]);
+    const bool isurf0 = (i0 == vb.lo[0]), isurf1 = (i0 + 1 == vb.hi[0]);
+    const int par0 = (i0 + j) & 1;
 
     const auto pin = view(A.pin[t.box]);
     const auto pout = view(A.pout[t.box]);
+    const int pin_ks = int(pin.ks), pout_ks = int(pout.ks);
+    const double* qin = pin.ptr(i0, j, k0 + 1);          // plane kk+3 of loop step kk (k0+1 at the first step)
+    double* qout = pout.ptr(i0, j, k0);
     const int srow = ty * SX + 2 * tx + 2;
 
-    auto load_plane = [&] (int k, double2& v, double& vl, double& vr) {
+    // cursor at the red plane (kk+1); the black plane (kk) is one stride behind; the loop starts at kk = k0-2
+    Cursors<ABEC> cr;
+    cr.init(A, t.box, i0, j, k0 - 1);
+
+    auto load_at = [&] (const double* p, int k, double2& v, double& vl, double& vr) {
         v = make_double2(0.0, 0.0); vl = 0.0; vr = 0.0;
         if (row_load && k >= vb.lo[2] - 1 && k <= vb.hi[2] + 1) {
-            const double* p = pin.ptr(i0, j, k);
             v = *reinterpret_cast<const double2*>(p);
             if (gl) { vl = p[-1]; }
             if (gr) { vr = p[2]; }
@@ -105,21 +142,21 @@ k_gsrb2 (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ v
 
     double2 pm1 = make_double2(0.0, 0.0), pk, pp1, pp2;
     double gl0, gr0, gl1, gr1;
-    load_plane(k0 - 2, pk, gl0, gr0);
-    load_plane(k0 - 1, pp1, gl0, gr0);
+    load_at(qin - 3 * pin_ks, k0 - 2, pk, gl0, gr0);
+    load_at(qin - 2 * pin_ks, k0 - 1, pp1, gl0, gr0);
     store_plane(sB, pp1, gl0, gr0);
-    load_plane(k0, pp2, gl1, gr1);          // ghost x values of the plane that sits in registers (pp2) travel with it
+    load_at(qin - pin_ks, k0, pp2, gl1, gr1);            // ghost x values of the plane that sits in registers travel with it
     __syncthreads();
 
+    const int kr_lo = max(k0 - 1, vb.lo[2]), kr_hi = min(k1 + 1, vb.hi[2]);
     for (int kk = k0 - 2; kk <= k1; ++kk) {
         // ---- phase 1: red update of plane kk+1, in place in sB and pp1
         const int kr = kk + 1;
-        if (row_red && kr >= max(k0 - 1, vb.lo[2]) && kr <= min(k1 + 1, vb.hi[2])) {
-            const int c = (i0 + j + kr) & 1;            // which cell of the pair is red
-            const int i = i0 + c;
+        if (row_red && kr >= kr_lo && kr <= kr_hi) {
+            const int c = (par0 + kr) & 1;              // which cell of the pair is red
             const double* s = sB + srow + c;
-            const bool surf = jsurf || (i == vb.lo[0]) || (i == vb.hi[0]) || (kr == vb.lo[2]) || (kr == vb.hi[2]);
-            const double v = update_cell<ABEC>(i, j, kr, t.box, vb, A, surf, sel(pp1, c), s[-1], s[1], s[-SX], s[SX],
+            const bool surf = jsurf || (c ? isurf1 : isurf0) || (kr == vb.lo[2]) || (kr == vb.hi[2]);
+            const double v = update_cell<ABEC>(cr, 0, c, i0 + c, j, kr, t.box, vb, A, surf, sel(pp1, c), s[-1], s[1], s[-SX], s[SX],
                                                sel(pk, c), sel(pp2, c));
             put(pp1, c, v);
             sB[srow + c] = v;
@@ -127,20 +164,22 @@ k_gsrb2 (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ v
         __syncthreads();
         // ---- phase 2: black update of plane kk (reads sA: new red neighbours), write the finished plane
         if (row_black && kk >= k0) {
-            const int c = 1 - ((i0 + j + kk) & 1);      // which cell of the pair is black
-            const int i = i0 + c;
-            const bool surf = jsurf || (i == vb.lo[0]) || (i == vb.hi[0]) || (kk == vb.lo[2]) || (kk == vb.hi[2]);
+            const int c = 1 - ((par0 + kk) & 1);        // which cell of the pair is black
+            const bool surf = jsurf || (c ? isurf1 : isurf0) || (kk == vb.lo[2]) || (kk == vb.hi[2]);
             double2 o = pk;
             if (!surf) {
                 const double* s = sA + srow + c;
-                put(o, c, update_cell<ABEC>(i, j, kk, t.box, vb, A, false, sel(pk, c), s[-1], s[1], s[-SX], s[SX],
+                put(o, c, update_cell<ABEC>(cr, 1, c, i0 + c, j, kk, t.box, vb, A, false, sel(pk, c), s[-1], s[1], s[-SX], s[SX],
                                             sel(pm1, c), sel(pp1, c)));
             }
-            *reinterpret_cast<double2*>(pout.ptr(i0, j, kk)) = o;
+            *reinterpret_cast<double2*>(qout) = o;
+            qout += pout_ks;
         }
         store_plane(sC, pp2, gl1, gr1);                 // old plane kk+2 for the next step's red phase
         pm1 = pk; pk = pp1; pp1 = pp2;
-        load_plane(kk + 3, pp2, gl1, gr1);
+        load_at(qin, kk + 3, pp2, gl1, gr1);
+        qin += pin_ks;
+        cr.advance();
         __syncthreads();
         double* tmp = sA; sA = sB; sB = sC; sC = tmp;
     }

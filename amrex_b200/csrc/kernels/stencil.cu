@@ -18,41 +18,57 @@ struct PoisArgs {
     double dhx, dhy, dhz;
 };
 
+// descriptors of one box, loaded once per kernel (not per cell)
+struct AbecViews {
+    View<double> phi, rhs, a, bx, by, bz;
+    const b200mg_fab* f6; const b200mg_ifab* m6;
+    double alpha, dhx, dhy, dhz;
+    __device__ __forceinline__ AbecViews (const AbecArgs& A, int box)
+        : phi(view(A.phi[box])), rhs(view(A.rhs[box])), a(view(A.a[box])), bx(view(A.bx[box])), by(view(A.by[box])), bz(view(A.bz[box])),
+          f6(A.f + 6 * box), m6(A.m + 6 * box), alpha(A.alpha), dhx(A.dhx), dhy(A.dhy), dhz(A.dhz) {}
+};
+struct PoisViews {
+    View<double> phi, rhs;
+    const b200mg_fab* f6; const b200mg_ifab* m6;
+    double dhx, dhy, dhz;
+    __device__ __forceinline__ PoisViews (const PoisArgs& A, int box)
+        : phi(view(A.phi[box])), rhs(view(A.rhs[box])), f6(A.f + 6 * box), m6(A.m + 6 * box), dhx(A.dhx), dhy(A.dhy), dhz(A.dhz) {}
+};
+
 __device__ __forceinline__ void
-gsrb_abec_at (int i, int j, int k, int box, const b200mg_box& vb, const AbecArgs& A)
+gsrb_at (int i, int j, int k, const b200mg_box& vb, const AbecViews& V)
 {
-    const auto phi = view(A.phi[box]); const auto rhs = view(A.rhs[box]); const auto a = view(A.a[box]);
-    const auto bx = view(A.bx[box]); const auto by = view(A.by[box]); const auto bz = view(A.bz[box]);
-    double* pc = phi.ptr(i, j, k);
+    double* pc = V.phi.ptr(i, j, k);
     const double p = *pc;
+    const int js = int(V.phi.js), ks = int(V.phi.ks);
+    const double* pbx = V.bx.ptr(i, j, k); const double* pby = V.by.ptr(i, j, k); const double* pbz = V.bz.ptr(i, j, k);
     double r;
     if (on_surface(i, j, k, vb)) {
-        const FaceCoefs cf = face_coefs(i, j, k, vb, A.f + 6 * box, A.m + 6 * box);
-        r = gsrb_abec_cell(p, pc[-1], pc[1], pc[-phi.js], pc[phi.js], pc[-phi.ks], pc[phi.ks],
-                           rhs(i, j, k), a(i, j, k), bx(i, j, k), bx(i + 1, j, k), by(i, j, k), by(i, j + 1, k),
-                           bz(i, j, k), bz(i, j, k + 1), cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5],
-                           A.alpha, A.dhx, A.dhy, A.dhz);
+        const FaceCoefs cf = face_coefs(i, j, k, vb, V.f6, V.m6);
+        r = gsrb_abec_cell(p, pc[-1], pc[1], pc[-js], pc[js], pc[-ks], pc[ks],
+                           V.rhs(i, j, k), V.a(i, j, k), pbx[0], pbx[1], pby[0], pby[V.by.js], pbz[0], pbz[V.bz.ks],
+                           cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], V.alpha, V.dhx, V.dhy, V.dhz);
     } else {
-        r = gsrb_abec_cell_interior(p, pc[-1], pc[1], pc[-phi.js], pc[phi.js], pc[-phi.ks], pc[phi.ks],
-                                    rhs(i, j, k), a(i, j, k), bx(i, j, k), bx(i + 1, j, k), by(i, j, k), by(i, j + 1, k),
-                                    bz(i, j, k), bz(i, j, k + 1), A.alpha, A.dhx, A.dhy, A.dhz);
+        r = gsrb_abec_cell_interior(p, pc[-1], pc[1], pc[-js], pc[js], pc[-ks], pc[ks],
+                                    V.rhs(i, j, k), V.a(i, j, k), pbx[0], pbx[1], pby[0], pby[V.by.js], pbz[0], pbz[V.bz.ks],
+                                    V.alpha, V.dhx, V.dhy, V.dhz);
     }
     *pc = r;
 }
 
 __device__ __forceinline__ void
-gsrb_poisson_at (int i, int j, int k, int box, const b200mg_box& vb, const PoisArgs& A)
+gsrb_at (int i, int j, int k, const b200mg_box& vb, const PoisViews& V)
 {
-    const auto phi = view(A.phi[box]); const auto rhs = view(A.rhs[box]);
-    double* pc = phi.ptr(i, j, k);
+    double* pc = V.phi.ptr(i, j, k);
+    const int js = int(V.phi.js), ks = int(V.phi.ks);
     FaceCoefs cf;
-    if (on_surface(i, j, k, vb)) { cf = face_coefs(i, j, k, vb, A.f + 6 * box, A.m + 6 * box); }
+    if (on_surface(i, j, k, vb)) { cf = face_coefs(i, j, k, vb, V.f6, V.m6); }
     else {
 #pragma unroll
         for (int n = 0; n < 6; ++n) { cf.c[n] = 0.0; }
     }
-    *pc = gsrb_poisson_cell(*pc, pc[-1], pc[1], pc[-phi.js], pc[phi.js], pc[-phi.ks], pc[phi.ks], rhs(i, j, k),
-                            cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], A.dhx, A.dhy, A.dhz);
+    *pc = gsrb_poisson_cell(*pc, pc[-1], pc[1], pc[-js], pc[js], pc[-ks], pc[ks], V.rhs(i, j, k),
+                            cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], V.dhx, V.dhy, V.dhz);
 }
 
 // one colour; each thread owns the cell pair (i0,i0+1) and updates the one with the right parity
@@ -63,11 +79,12 @@ k_gsrb_abec (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict
     const b200mg_box vb = vbox[t.box];
     const int j = t.j0 + int(threadIdx.y);
     if (j > vb.hi[1]) { return; }
-    const int khi = min(t.k0 + B200MG_TILE_Z - 1, vb.hi[2]);
+    const int khi = min(t.k0 + tile_nk(t) - 1, vb.hi[2]);
+    const AbecViews V(A, t.box);
     for (int k = t.k0; k <= khi; ++k) {
         const int off = (vb.lo[0] + j + k + redblack) & 1;
         for (int i = vb.lo[0] + off + 2 * int(threadIdx.x); i <= vb.hi[0]; i += 2 * int(blockDim.x)) {
-            gsrb_abec_at(i, j, k, t.box, vb, A);
+            gsrb_at(i, j, k, vb, V);
         }
     }
 }
@@ -79,18 +96,22 @@ k_gsrb_poisson (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restr
     const b200mg_box vb = vbox[t.box];
     const int j = t.j0 + int(threadIdx.y);
     if (j > vb.hi[1]) { return; }
-    const int khi = min(t.k0 + B200MG_TILE_Z - 1, vb.hi[2]);
+    const int khi = min(t.k0 + tile_nk(t) - 1, vb.hi[2]);
+    const PoisViews V(A, t.box);
     for (int k = t.k0; k <= khi; ++k) {
         const int off = (vb.lo[0] + j + k + redblack) & 1;
         for (int i = vb.lo[0] + off + 2 * int(threadIdx.x); i <= vb.hi[0]; i += 2 * int(blockDim.x)) {
-            gsrb_poisson_at(i, j, k, t.box, vb, A);
+            gsrb_at(i, j, k, vb, V);
         }
     }
 }
 
-// Surface shell sweep: blockIdx.x = box*6 + face; every shell cell belongs to exactly one face
-// (x faces own their edges/corners, y faces exclude the x extremes, z faces exclude x and y extremes).
-template <class ARGS, class F>
+// Surface shell sweep: blockIdx.x = box*6 + face, blockIdx.y = chunk of the face; every shell cell belongs to exactly one
+// face (x faces own their edges/corners, y faces exclude the x extremes, z faces exclude x and y extremes).  Threads run
+// along the face's fastest-varying tangential direction (x for y/z faces: coalesced).
+constexpr int kShellChunks = 8;
+
+template <class F>
 __device__ __forceinline__ void shell_loop (const b200mg_box& vb, int face, int redblack, F&& f)
 {
     const int d = face % 3;
@@ -100,12 +121,15 @@ __device__ __forceinline__ void shell_loop (const b200mg_box& vb, int face, int 
     if (d >= 1) { lo[0] += 1; hi[0] -= 1; }
     if (d == 2) { lo[1] += 1; hi[1] -= 1; }
     lo[d] = hi[d] = fix;
-    const int n0 = hi[0] - lo[0] + 1, n1 = hi[1] - lo[1] + 1, n2 = hi[2] - lo[2] + 1;
-    if (n0 <= 0 || n1 <= 0 || n2 <= 0) { return; }
-    const int n = n0 * n1 * n2;
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        const int i = lo[0] + t % n0, j = lo[1] + (t / n0) % n1, k = lo[2] + t / (n0 * n1);
-        if (((i + j + k + redblack) & 1) == 0) { f(i, j, k); }
+    const int du = (d == 0) ? 1 : 0, dv = (d == 2) ? 1 : 2;     // tangential directions, u fastest in memory
+    const int nu = hi[du] - lo[du] + 1, nv = hi[dv] - lo[dv] + 1;
+    if (nu <= 0 || nv <= 0) { return; }
+    const unsigned n = unsigned(nu) * unsigned(nv);
+    for (unsigned t = threadIdx.x + blockIdx.y * blockDim.x; t < n; t += blockDim.x * gridDim.y) {
+        const unsigned v = t / unsigned(nu), u = t - v * unsigned(nu);
+        int idx[3];
+        idx[d] = fix; idx[du] = lo[du] + int(u); idx[dv] = lo[dv] + int(v);
+        if (((idx[0] + idx[1] + idx[2] + redblack) & 1) == 0) { f(idx[0], idx[1], idx[2]); }
     }
 }
 
@@ -114,7 +138,8 @@ k_gsrb_shell_abec (const b200mg_box* __restrict__ vbox, AbecArgs A, int redblack
 {
     const int box = blockIdx.x / 6, face = blockIdx.x % 6;
     const b200mg_box vb = vbox[box];
-    shell_loop<AbecArgs>(vb, face, redblack, [&] (int i, int j, int k) { gsrb_abec_at(i, j, k, box, vb, A); });
+    const AbecViews V(A, box);
+    shell_loop(vb, face, redblack, [&] (int i, int j, int k) { gsrb_at(i, j, k, vb, V); });
 }
 
 __global__ void __launch_bounds__(256)
@@ -122,7 +147,8 @@ k_gsrb_shell_poisson (const b200mg_box* __restrict__ vbox, PoisArgs A, int redbl
 {
     const int box = blockIdx.x / 6, face = blockIdx.x % 6;
     const b200mg_box vb = vbox[box];
-    shell_loop<PoisArgs>(vb, face, redblack, [&] (int i, int j, int k) { gsrb_poisson_at(i, j, k, box, vb, A); });
+    const PoisViews V(A, box);
+    shell_loop(vb, face, redblack, [&] (int i, int j, int k) { gsrb_at(i, j, k, vb, V); });
 }
 
 // ---------------------------------------------------------------------------------------- adotx
@@ -162,6 +188,72 @@ k_adotx_poisson (const b200mg_tile* __restrict__ tiles, const b200mg_box* __rest
         const double v = adotx_poisson_cell(*xc, xc[-1], xc[1], xc[-x.js], xc[x.js], xc[-x.ks], xc[x.ks], dhx, dhy, dhz);
         y(i, j, k) = has_r ? (r(i, j, k) + (-1.0) * v) : v;
     });
+}
+
+// z-marching operator apply / residual: each thread owns the cell pair (i0, i0+1) of one row and streams through the
+// planes of its tile; the x pair of planes k-1, k, k+1 and the z-face coefficient stay in registers, everything is read with
+// 16-byte loads (x/y neighbour loads hit L1).  Requires even x extents (16-byte aligned pairs); nx <= 2 * blockDim.x.
+template <bool ABEC>
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y, 4)
+k_adotx_pair (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox,
+              const b200mg_fab* yf, const b200mg_fab* xf, const b200mg_fab* rf, const b200mg_fab* af,
+              const b200mg_fab* bxf, const b200mg_fab* byf, const b200mg_fab* bzf,
+              double alpha, double dhx, double dhy, double dhz)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const int i0 = vb.lo[0] + 2 * int(threadIdx.x);
+    const int j = t.j0 + int(threadIdx.y);
+    if (i0 >= vb.hi[0] || j > vb.hi[1]) { return; }
+    const int k0 = t.k0, k1 = min(t.k0 + tile_nk(t) - 1, vb.hi[2]);
+    const auto x = view(xf[t.box]); const auto y = view(yf[t.box]);
+    const int x_js = int(x.js), x_ks = int(x.ks), y_ks = int(y.ks);
+    const double* px = x.ptr(i0, j, k0);
+    double* py = y.ptr(i0, j, k0);
+    const bool has_r = (rf != nullptr);
+    const double* pr = nullptr; int r_ks = 0;
+    if (has_r) { const auto r = view(rf[t.box]); pr = r.ptr(i0, j, k0); r_ks = int(r.ks); }
+    const double *pa = nullptr, *pbx = nullptr, *pby = nullptr, *pbz = nullptr;
+    int a_ks = 0, bx_ks = 0, by_ks = 0, by_js = 0, bz_ks = 0;
+    double2 bzlo = make_double2(0.0, 0.0);
+    if constexpr (ABEC) {
+        const auto a = view(af[t.box]); const auto bx = view(bxf[t.box]); const auto by = view(byf[t.box]); const auto bz = view(bzf[t.box]);
+        pa = a.ptr(i0, j, k0); pbx = bx.ptr(i0, j, k0); pby = by.ptr(i0, j, k0); pbz = bz.ptr(i0, j, k0);
+        a_ks = int(a.ks); bx_ks = int(bx.ks); by_ks = int(by.ks); by_js = int(by.js); bz_ks = int(bz.ks);
+        bzlo = __ldg(reinterpret_cast<const double2*>(pbz));
+    }
+    double2 xm = *reinterpret_cast<const double2*>(px - x_ks);
+    double2 xc = *reinterpret_cast<const double2*>(px);
+    for (int k = k0; k <= k1; ++k) {
+        const double2 xp = *reinterpret_cast<const double2*>(px + x_ks);
+        const double xl = px[-1], xr = px[2];
+        const double2 ylo = *reinterpret_cast<const double2*>(px - x_js);
+        const double2 yhi = *reinterpret_cast<const double2*>(px + x_js);
+        double2 v;
+        if constexpr (ABEC) {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(pa));
+            const double2 bx = __ldg(reinterpret_cast<const double2*>(pbx));
+            const double bx2 = __ldg(pbx + 2);
+            const double2 bylo = __ldg(reinterpret_cast<const double2*>(pby));
+            const double2 byhi = __ldg(reinterpret_cast<const double2*>(pby + by_js));
+            const double2 bzhi = __ldg(reinterpret_cast<const double2*>(pbz + bz_ks));
+            v.x = adotx_abec_cell(xc.x, xl, xc.y, ylo.x, yhi.x, xm.x, xp.x, a.x, bx.x, bx.y, bylo.x, byhi.x, bzlo.x, bzhi.x, alpha, dhx, dhy, dhz);
+            v.y = adotx_abec_cell(xc.y, xc.x, xr, ylo.y, yhi.y, xm.y, xp.y, a.y, bx.y, bx2, bylo.y, byhi.y, bzlo.y, bzhi.y, alpha, dhx, dhy, dhz);
+            bzlo = bzhi;
+            pa += a_ks; pbx += bx_ks; pby += by_ks; pbz += bz_ks;
+        } else {
+            v.x = adotx_poisson_cell(xc.x, xl, xc.y, ylo.x, yhi.x, xm.x, xp.x, dhx, dhy, dhz);
+            v.y = adotx_poisson_cell(xc.y, xc.x, xr, ylo.y, yhi.y, xm.y, xp.y, dhx, dhy, dhz);
+        }
+        if (has_r) {   // Xpay(y,-1,b): y = b + (-1)*y
+            const double2 r = __ldg(reinterpret_cast<const double2*>(pr));
+            v.x = r.x + (-1.0) * v.x; v.y = r.y + (-1.0) * v.y;
+            pr += r_ks;
+        }
+        *reinterpret_cast<double2*>(py) = v;
+        xm = xc; xc = xp;
+        px += x_ks; py += y_ks;
+    }
 }
 
 __global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
@@ -299,7 +391,7 @@ int b200mg_gsrb_shell_abec (int nboxes, const b200mg_box* vbox,
 {
     if (nboxes <= 0) { return 0; }
     AbecArgs A{phi, rhs, a, bx, by, bz, f, m, alpha, dhx, dhy, dhz};
-    k_gsrb_shell_abec<<<nboxes * 6, 256, 0, s>>>(vbox, A, redblack);
+    k_gsrb_shell_abec<<<dim3(nboxes * 6, kShellChunks), 256, 0, s>>>(vbox, A, redblack);
     return last_error();
 }
 
@@ -310,7 +402,7 @@ int b200mg_gsrb_shell_poisson (int nboxes, const b200mg_box* vbox,
 {
     if (nboxes <= 0) { return 0; }
     PoisArgs A{phi, rhs, f, m, dhx, dhy, dhz};
-    k_gsrb_shell_poisson<<<nboxes * 6, 256, 0, s>>>(vbox, A, redblack);
+    k_gsrb_shell_poisson<<<dim3(nboxes * 6, kShellChunks), 256, 0, s>>>(vbox, A, redblack);
     return last_error();
 }
 
@@ -358,6 +450,25 @@ int b200mg_comp_interp_coef0 (int nfaces, const b200mg_bcface* faces, const b200
 {
     if (nfaces <= 0) { return 0; }
     k_comp_interp_coef0<<<dim3(nfaces, 8), 128, 0, s>>>(faces, vbox, f, m, maxorder, dxinv0, dxinv1, dxinv2);
+    return last_error();
+}
+
+int b200mg_adotx_abec_pairs (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                             const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs, const b200mg_fab* a,
+                             const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                             double alpha, double dhx, double dhy, double dhz, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_adotx_pair<true><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, a, bx, by, bz, alpha, dhx, dhy, dhz);
+    return last_error();
+}
+
+int b200mg_adotx_poisson_pairs (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                                const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs,
+                                double dhx, double dhy, double dhz, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_adotx_pair<false><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, nullptr, nullptr, nullptr, nullptr, 0.0, dhx, dhy, dhz);
     return last_error();
 }
 

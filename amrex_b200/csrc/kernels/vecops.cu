@@ -130,21 +130,26 @@ k_copy_tags (const b200mg_copytag* __restrict__ tags, const b200mg_fab* dstf, co
              double* __restrict__ buf, int ncomp, int scomp, int dcomp, int op)
 {
     const b200mg_copytag t = tags[blockIdx.x];
-    const int n0 = t.hi[0] - t.lo[0] + 1, n1 = t.hi[1] - t.lo[1] + 1, n2 = t.hi[2] - t.lo[2] + 1;
-    const long long npts = (long long)n0 * n1 * n2;
-    const long long ntot = npts * ncomp;
-    for (long long idx = threadIdx.x + (long long)blockIdx.y * blockDim.x; idx < ntot; idx += (long long)blockDim.x * gridDim.y) {
-        const int n = int(idx / npts);
-        const long long r = idx - n * npts;
-        const int i = t.lo[0] + int(r % n0), j = t.lo[1] + int((r / n0) % n1), k = t.lo[2] + int(r / ((long long)n0 * n1));
-        double v;
-        if (t.src_fab >= 0) { v = view(srcf[t.src_fab])(i + t.shift[0], j + t.shift[1], k + t.shift[2], n + scomp); }
-        else { v = buf[t.buf_offset + idx]; }
-        if (t.dst_fab >= 0) {
-            double& d = view(dstf[t.dst_fab])(i, j, k, n + dcomp);
-            if (op == 0) { d = v; } else { d += v; }
-        } else {
-            buf[t.buf_offset + idx] = v;
+    const unsigned n0 = unsigned(t.hi[0] - t.lo[0] + 1), n1 = unsigned(t.hi[1] - t.lo[1] + 1), n2 = unsigned(t.hi[2] - t.lo[2] + 1);
+    const unsigned n01 = n0 * n1;
+    const unsigned npts = n01 * n2;                      // a tag never exceeds one fab (< 2^31 points)
+    View<double> src, dst;
+    if (t.src_fab >= 0) { src = view(srcf[t.src_fab]); }
+    if (t.dst_fab >= 0) { dst = view(dstf[t.dst_fab]); }
+    for (int n = 0; n < ncomp; ++n) {
+        double* b = buf ? buf + t.buf_offset + (long long)n * npts : nullptr;
+        for (unsigned r = threadIdx.x + blockIdx.y * blockDim.x; r < npts; r += blockDim.x * gridDim.y) {
+            const unsigned k = r / n01, r2 = r - k * n01, j = r2 / n0, i = r2 - j * n0;
+            const int ii = t.lo[0] + int(i), jj = t.lo[1] + int(j), kk = t.lo[2] + int(k);
+            double v;
+            if (t.src_fab >= 0) { v = src(ii + t.shift[0], jj + t.shift[1], kk + t.shift[2], n + scomp); }
+            else { v = b[r]; }
+            if (t.dst_fab >= 0) {
+                double& d = dst(ii, jj, kk, n + dcomp);
+                if (op == 0) { d = v; } else { d += v; }
+            } else {
+                b[r] = v;
+            }
         }
     }
 }

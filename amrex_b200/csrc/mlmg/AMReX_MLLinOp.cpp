@@ -514,7 +514,7 @@ bool MLLinOp::planFused (LevelData const& L) const
     for (int li = 0; li < nl; ++li) {
         Box const& b = L.layout->box(li);
         for (int k = b.smallEnd(2); k <= b.bigEnd(2); k += chunk_z)
-            for (int j = b.smallEnd(1); j <= b.bigEnd(1); j += tile_y) { ht.push_back(b200mg_tile{li, j, k, 0}); }
+            for (int j = b.smallEnd(1); j <= b.bigEnd(1); j += tile_y) { ht.push_back(b200mg_tile{li, j, k, chunk_z}); }
     }
     L.fused_tx = tx; L.fused_tile_y = tile_y; L.fused_chunk_z = chunk_z; L.fused_nblocks = int(ht.size());
     L.fused_tiles.assign(ht);
@@ -754,6 +754,13 @@ void MLABecLaplacian::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab con
 {
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();   // dh = beta*dxinv^2 (AMReX_MLABecLap_3D_K.H:18-20)
     auto const& T = out.layout().tiles(0);
+    if (out.layout().pairable()) {
+        B200_KCALL(b200mg_adotx_abec_pairs(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
+                                           m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(),
+                                           m_b_coeffs[amrlev][mglev][2].d_fabs(), m_a_scalar, m_b_scalar * dxi[0] * dxi[0], m_b_scalar * dxi[1] * dxi[1],
+                                           m_b_scalar * dxi[2] * dxi[2], Gpu::gpuStream()));
+        return;
+    }
     B200_KCALL(b200mg_adotx_abec(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
                                  m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(),
                                  m_b_coeffs[amrlev][mglev][2].d_fabs(), m_a_scalar, m_b_scalar * dxi[0] * dxi[0], m_b_scalar * dxi[1] * dxi[1],
@@ -806,6 +813,11 @@ void MLPoisson::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab const& in
 {
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
     auto const& T = out.layout().tiles(0);
+    if (out.layout().pairable()) {
+        B200_KCALL(b200mg_adotx_poisson_pairs(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
+                                              dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream()));
+        return;
+    }
     B200_KCALL(b200mg_adotx_poisson(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
                                     dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream()));
 }

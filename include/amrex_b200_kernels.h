@@ -38,9 +38,9 @@ typedef struct b200mg_ifab {
 
 typedef struct b200mg_box { int lo[3], hi[3]; } b200mg_box;
 
-/* A unit of work of a cell kernel: rows [j0, j0+B200MG_TILE_Y) x planes [k0, k0+B200MG_TILE_Z) x all i of
- * local box `box` (clipped to the box).  Tables of tiles are built once per level (amrex::LevelLayout). */
-typedef struct b200mg_tile { int box, j0, k0, pad; } b200mg_tile;
+/* A unit of work of a cell kernel: rows [j0, j0+B200MG_TILE_Y) x planes [k0, k0+nk) x all i of local box `box`
+ * (clipped to the box); nk == 0 means B200MG_TILE_Z.  Tables of tiles are built once per level (amrex::LevelLayout). */
+typedef struct b200mg_tile { int box, j0, k0, nk; } b200mg_tile;
 #define B200MG_TILE_Y 4
 #define B200MG_TILE_Z 4
 
@@ -111,6 +111,15 @@ int b200mg_adotx_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box* vb
 int b200mg_adotx_poisson(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
                          const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs,
                          double dhx, double dhy, double dhz, cudaStream_t s);
+/* Same operators for levels whose boxes all have an even x extent <= 128: one thread per cell PAIR, streaming along z with
+ * 16-byte loads (the fast path; results are bit-identical to the entries above). */
+int b200mg_adotx_abec_pairs(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                            const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs, const b200mg_fab* a,
+                            const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                            double alpha, double dhx, double dhy, double dhz, cudaStream_t s);
+int b200mg_adotx_poisson_pairs(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                               const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs,
+                               double dhx, double dhy, double dhz, cudaStream_t s);
 /* K13 mlabeclap_normalize AMReX_MLABecLap_3D_K.H:60-75 */
 int b200mg_normalize_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
                           const b200mg_fab* x, const b200mg_fab* a,

@@ -24,8 +24,13 @@ ncu_list)
 ncu_full)
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_gsrb2 -s 8 -c 2 -f -o $OUT/prof_gsrb2 \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_full.log 2>&1 ;;
+ncu_k)
+  # full capture of the finest-level launches of every hot kernel of the path
+  timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"${KREGEX:-k_gsrb2|k_adotx|k_gsrb_shell|k_copy_tags|k_apply_bc}" -c ${KCOUNT:-9} \
+     -f -o $OUT/prof_kernels python scripts/prof_kernels.py ${NCELL:-512} smooth residual > $OUT/ncu_k.log 2>&1
+  ls -la $OUT/prof_kernels.ncu-rep ;;
 tune)
-  for ty in 4 8 12; do for cz in 16 32 64 128; do
+  for ty in ${TUNE_TY:-4 8 12}; do for cz in ${TUNE_CZ:-32 128}; do
     echo "== tile_y=$ty chunk_z=$cz" >> $OUT/tune.log
     B200MG_FUSED_TILE_Y=$ty B200MG_FUSED_CHUNK_Z=$cz timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e >> $OUT/tune.log 2>&1
   done; done ;;

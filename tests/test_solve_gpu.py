@@ -12,6 +12,8 @@ SOL_TOL = 1e-10
 
 
 def solve_case(ab, prob_type, n_cell, mgs, maxorder=2, fusion=None, bottom=None, **refkw):
+    if bottom:
+        refkw["bottom"] = bottom
     ref, dump = run_ref(dump=True, mode="solve", prob_type=prob_type, n_cell=n_cell, max_grid_size=mgs,
                         linop_maxorder=maxorder, agg_grid_size=32, **refkw)
     P = build_problem(ab, prob_type, n_cell, mgs, dump, maxorder=maxorder, fusion=fusion)
@@ -74,6 +76,6 @@ def test_periodic_poisson(ab):
 
 @pytest.mark.parametrize("bottom", ["smoother", "cg"])
 def test_bottom_solvers(ab, bottom):
-    ref, mlmg, diff = solve_case(ab, 1, 64, 32, bottom=bottom, **{"bottom": bottom})
+    ref, mlmg, diff = solve_case(ab, 1, 64, 32, bottom=bottom)
     assert abs(mlmg.numIters() - ref["iters"]) <= 1
     assert diff <= SOL_TOL
