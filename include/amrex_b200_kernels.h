@@ -76,6 +76,17 @@ int b200mg_gsrb_poisson(int ntiles, const b200mg_tile* tiles, const b200mg_box* 
                         const b200mg_fab* phi, const b200mg_fab* rhs,
                         const b200mg_fab* f, const b200mg_ifab* m,
                         double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+/* Same colour sweeps for levels whose boxes all have an even x extent <= 128: one thread per cell PAIR streaming along z
+ * (the fast path; results are bit-identical to the entries above). */
+int b200mg_gsrb_abec_pairs(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                           const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,
+                           const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                           const b200mg_fab* f, const b200mg_ifab* m,
+                           double alpha, double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+int b200mg_gsrb_poisson_pairs(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                              const b200mg_fab* phi, const b200mg_fab* rhs,
+                              const b200mg_fab* f, const b200mg_ifab* m,
+                              double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
 /* Fused red+black pass (one sweep over memory per smooth): red update of every valid cell and black update of the
  * cells that do not touch the box surface, out of place (phi_in -> phi_out).  The black surface shell is finished by
  * b200mg_gsrb_shell_* after the halo refresh.  Same arithmetic and update order as two colour sweeps.
