@@ -26,7 +26,18 @@ struct FusedArgs {
     const b200mg_ifab* m;
     double alpha, dhx, dhy, dhz;
     int tile_y, chunk_z;
+    int pf;              // L2 prefetch distance in planes (0: off)
 };
+
+int g_prefetch_planes = 3;
+
+// One instruction pulls `bytes` (multiple of 16, 16-byte aligned address) of global memory into L2 without occupying a
+// register or a shared-memory slot: the DRAM latency of the plane that is D steps ahead is paid here, the real loads
+// later only see L2 latency.
+__device__ __forceinline__ void l2_prefetch (const void* p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
 
 __device__ __forceinline__ double sel (const double2& v, int c) { return c ? v.y : v.x; }
 __device__ __forceinline__ void put (double2& v, int c, double x) { if (c) { v.y = x; } else { v.x = x; } }
@@ -149,7 +160,24 @@ k_gsrb2 (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ v
     __syncthreads();
 
     const int kr_lo = max(k0 - 1, vb.lo[2]), kr_hi = min(k1 + 1, vb.hi[2]);
+    // L2 prefetch: lanes 0..5 of every row pull that row of one array each, A.pf planes ahead of the loads below
+    const unsigned pf_bytes = unsigned(vb.hi[0] - vb.lo[0] + 1) * 8u;
+    const bool pf_phi = (A.pf > 0) && (tx == 0) && (j >= vb.lo[1] - 1) && (j <= min(j1 + 2, vb.hi[1] + 1));
+    const bool pf_coef = (A.pf > 0) && ((j >= max(t.j0 - 1, vb.lo[1])) && (j <= min(j1 + 1, vb.hi[1]))) && (tx >= 1) && (tx <= (ABEC ? 5 : 1));
+    const double* pf_ptr = nullptr; int pf_ks = 0;
+    if (pf_phi) { pf_ptr = pin.ptr(vb.lo[0], j, k0 + 1 + A.pf); pf_ks = pin_ks; }
+    if (pf_coef) {
+        const b200mg_fab* fab = (tx == 1) ? A.rhs : (tx == 2) ? A.a : (tx == 3) ? A.bx : (tx == 4) ? A.by : A.bz;
+        const auto v = view(fab[t.box]);
+        pf_ptr = v.ptr(vb.lo[0], j, k0 - 1 + A.pf); pf_ks = int(v.ks);
+    }
+    const int pf_klast = min(k1 + 1, vb.hi[2]);
     for (int kk = k0 - 2; kk <= k1; ++kk) {
+        if (pf_phi || pf_coef) {
+            const int kp = (pf_phi ? kk + 3 : kk + 1) + A.pf;      // plane the pointer addresses at this step
+            if (kp <= pf_klast) { l2_prefetch(pf_ptr, pf_bytes); }
+            pf_ptr += pf_ks;
+        }
         // ---- phase 1: red update of plane kk+1, in place in sB and pp1
         const int kr = kk + 1;
         if (row_red && kr >= kr_lo && kr <= kr_hi) {
@@ -161,7 +189,7 @@ k_gsrb2 (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ v
             put(pp1, c, v);
             sB[srow + c] = v;
         }
-        __syncthreads();
+        // (no barrier here: phase 1 touches sB only -- red cells written, black cells read -- and phase 2 reads sA only)
         // ---- phase 2: black update of plane kk (reads sA: new red neighbours), write the finished plane
         if (row_black && kk >= k0) {
             const int c = 1 - ((par0 + kk) & 1);        // which cell of the pair is black
@@ -220,7 +248,7 @@ int b200mg_gsrb2_abec (int nblocks, const b200mg_tile* tiles, const b200mg_box* 
                        const b200mg_fab* f, const b200mg_ifab* m,
                        double alpha, double dhx, double dhy, double dhz, int tx, int tile_y, int chunk_z, cudaStream_t s)
 {
-    FusedArgs A{phi_in, phi_out, rhs, a, bx, by, bz, f, m, alpha, dhx, dhy, dhz, tile_y, chunk_z};
+    FusedArgs A{phi_in, phi_out, rhs, a, bx, by, bz, f, m, alpha, dhx, dhy, dhz, tile_y, chunk_z, g_prefetch_planes};
     return launch<true>(nblocks, tiles, vbox, A, tx, s);
 }
 
@@ -229,8 +257,10 @@ int b200mg_gsrb2_poisson (int nblocks, const b200mg_tile* tiles, const b200mg_bo
                           const b200mg_fab* f, const b200mg_ifab* m,
                           double dhx, double dhy, double dhz, int tx, int tile_y, int chunk_z, cudaStream_t s)
 {
-    FusedArgs A{phi_in, phi_out, rhs, nullptr, nullptr, nullptr, nullptr, f, m, 0.0, dhx, dhy, dhz, tile_y, chunk_z};
+    FusedArgs A{phi_in, phi_out, rhs, nullptr, nullptr, nullptr, nullptr, f, m, 0.0, dhx, dhy, dhz, tile_y, chunk_z, g_prefetch_planes};
     return launch<false>(nblocks, tiles, vbox, A, tx, s);
 }
+
+void b200mg_set_gsrb2_prefetch (int planes) { g_prefetch_planes = planes < 0 ? 0 : planes; }
 
 } // extern "C"

@@ -499,8 +499,7 @@ bool MLLinOp::planFused (LevelData const& L) const
         if (b.length(0) % 2 != 0 || b.length(0) > 256 || b.length(0) < 16) { return false; }
         nxmax = std::max(nxmax, b.length(0)); nymax = std::max(nymax, b.length(1)); nzmax = std::max(nzmax, b.length(2));
     }
-    static const int env_ty = std::getenv("B200MG_FUSED_TILE_Y") ? std::atoi(std::getenv("B200MG_FUSED_TILE_Y")) : 0;
-    static const int env_cz = std::getenv("B200MG_FUSED_CHUNK_Z") ? std::atoi(std::getenv("B200MG_FUSED_CHUNK_Z")) : 0;
+    const int env_ty = m_fused_tile_y, env_cz = m_fused_chunk_z;
     const int tx = ((nxmax / 2 + 31) / 32) * 32;
     int tile_y = std::min(1024 / tx - 4, 12);
     if (env_ty > 0) { tile_y = std::min(env_ty, 1024 / tx - 4); }
@@ -520,6 +519,14 @@ bool MLLinOp::planFused (LevelData const& L) const
     L.fused_tiles.assign(ht);
     L.fused_state = 1;
     return true;
+}
+
+
+void MLLinOp::setFusedPlan (int tile_y, int chunk_z, int prefetch_planes)
+{
+    m_fused_tile_y = tile_y; m_fused_chunk_z = chunk_z;
+    if (prefetch_planes >= 0) { b200mg_set_gsrb2_prefetch(prefetch_planes); }
+    for (auto& av : m_lev) { for (auto& L : av) { L->fused_state = -1; } }
 }
 
 void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, bool skip_fillboundary) const

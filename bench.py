@@ -253,7 +253,7 @@ def b200_arm(args):
     rep = ab.profile_report()
     ab.profile_enable(False)
     tot_ms = sum(r[3] for r in rep)
-    kern = "b200mg_gsrb2_abec" if args.fusion else "b200mg_gsrb_abec"
+    kern = "b200mg_gsrb2_abec" if args.fusion else "b200mg_gsrb_abec_pairs"
     top = [r for r in rep if r[0] == kern and r[1] == 0]
     peak, peak_src = measured_peak_gbs()
     roofline = None

@@ -101,6 +101,8 @@ int b200mg_gsrb2_poisson(int nblocks, const b200mg_tile* tiles, const b200mg_box
                          const b200mg_fab* phi_in, const b200mg_fab* phi_out, const b200mg_fab* rhs,
                          const b200mg_fab* f, const b200mg_ifab* m,
                          double dhx, double dhy, double dhz, int tx, int tile_y, int chunk_z, cudaStream_t s);
+/* L2 prefetch distance (planes ahead of the loads) of the fused pass; 0 switches the prefetch off */
+void b200mg_set_gsrb2_prefetch(int planes);
 /* black (redblack=1) or red sweep restricted to the 1-cell surface shell of every box */
 int b200mg_gsrb_shell_abec(int nboxes, const b200mg_box* vbox,
                            const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,

@@ -30,10 +30,11 @@ ncu_k)
      -f -o $OUT/prof_kernels python scripts/prof_kernels.py ${NCELL:-512} smooth residual > $OUT/ncu_k.log 2>&1
   ls -la $OUT/prof_kernels.ncu-rep ;;
 tune)
-  for ty in ${TUNE_TY:-4 8 12}; do for cz in ${TUNE_CZ:-32 128}; do
-    echo "== tile_y=$ty chunk_z=$cz" >> $OUT/tune.log
-    B200MG_FUSED_TILE_Y=$ty B200MG_FUSED_CHUNK_Z=$cz timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e >> $OUT/tune.log 2>&1
-  done; done ;;
+  timeout 900 python scripts/tune_smoother.py ${NCELL:-512} 10 > $OUT/tune.log 2>&1; echo "tune exit $?" >> $OUT/tune.log ;;
+bench_f0)
+  timeout 900 python bench.py --steps 5 --warmup 3 --fusion 0 --no-cpu-baseline > $OUT/bench_f0.log 2> $OUT/bench_f0.err; echo "exit $?" >> $OUT/bench_f0.err ;;
+bench_f1)
+  timeout 900 python bench.py --steps 5 --warmup 3 --fusion 1 --no-cpu-baseline > $OUT/bench_f1.log 2> $OUT/bench_f1.err; echo "exit $?" >> $OUT/bench_f1.err ;;
 esac
 done
 ls -la $OUT

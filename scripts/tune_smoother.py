@@ -1,0 +1,77 @@
+"""Times one finest-level smooth (red+black, incl. halo refresh and BCs) of the benchmark workload under every smoother
+variant in ONE process: the reference schedule with the pair colour kernel, and the fused pass for a grid of
+(tile_y, chunk_z, L2-prefetch distance).  Prints one line per variant: ms per smooth and the bandwidth figures.
+
+  python scripts/tune_smoother.py [n_cell] [reps]
+"""
+import itertools
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+import amrex_b200 as ab  # noqa: E402
+from common import synth_abeclap  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+ab.init(0)
+P = synth_abeclap(ab, n, 128 if n >= 128 else n, fusion=0)
+op = P["op"]
+op.prepareForSolve()
+x = op.make(0, 0, 1)
+b = op.make(0, 0, 0)
+b.copy_from(P["rhs"])
+stream = torch.cuda.ExternalStream(ab.lib.amrex_b200_stream(), device=torch.device("cuda", 0))
+cells = n ** 3
+
+
+def time_smooth():
+    x.setVal(0.0, ng=1)
+    for _ in range(3):
+        op.smooth(0, 0, x, b)
+    ab.lib.amrex_b200_synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        op.smooth(0, 0, x, b)
+    e1.record(stream)
+    ab.lib.amrex_b200_synchronize()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def kernel_ms(name):
+    """average duration of kernel `name` on the finest level from the per-launch CUDA events of the launch layer"""
+    ab.profile_enable(True)
+    for _ in range(reps):
+        op.smooth(0, 0, x, b)
+    rep = ab.profile_report()
+    ab.profile_enable(False)
+    r = [q for q in rep if q[0] == name]
+    return (sum(q[3] for q in r) / sum(q[2] for q in r)) if r else None
+
+
+out = []
+op.setSmootherFusion(0)
+ms = time_smooth()
+k = kernel_ms("b200mg_gsrb_abec_pairs")
+out.append(dict(variant="pair colour sweeps", ms_per_smooth=ms, kernel_ms=k, kernel_gbs_44=44.0 * cells / (k * 1e-3) / 1e9 if k else None))
+print(json.dumps(out[-1]), flush=True)
+ref = x.norm0()
+
+op.setSmootherFusion(1)
+grid = list(itertools.product([4, 8, 12], [32, 128], [0, 2, 4]))
+if os.environ.get("TUNE_GRID"):
+    grid = [tuple(int(v) for v in g.split(",")) for g in os.environ["TUNE_GRID"].split(";")]
+for ty, cz, pf in grid:
+    op.setFusedPlan(ty, cz, pf)
+    ms = time_smooth()
+    k = kernel_ms("b200mg_gsrb2_abec")
+    same = (x.norm0() == ref)
+    out.append(dict(variant=f"fused ty={ty} cz={cz} pf={pf}", ms_per_smooth=ms, kernel_ms=k,
+                    kernel_gbs_56=56.0 * cells / (k * 1e-3) / 1e9 if k else None, same_norm_as_pair=bool(same)))
+    print(json.dumps(out[-1]), flush=True)

@@ -40,7 +40,8 @@ def test_reference_reproduces_golden(name):
     assert res["iters"] == g["iters"]
     assert res["cg_iters"] == g["cg_iters"]
     for a, b in zip(res["history"], g["history"]):
-        assert a == pytest.approx(b, rel=1e-6)   # OpenMP reduction order may differ between hosts
+        # OpenMP reduction order differs between hosts/runs: rounding noise of order eps*|rhs| sits under every residual
+        assert a == pytest.approx(b, rel=1e-6, abs=1e-13 * g["rhsnorm0"])
     assert res["err_inf"] == pytest.approx(g["err_inf"], rel=1e-9)
 
 
