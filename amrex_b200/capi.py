@@ -489,6 +489,10 @@ class MLMG(_Obj):
         check()
         return r
 
+    def compResidual(self, res, sol, rhs):
+        lib.amrex_fi_multigrid_comp_residual(self.ptr, _ptr_array(res), _ptr_array(sol), _ptr_array(rhs))
+        check()
+
     def numIters(self):
         return lib.amrex_b200_multigrid_num_iters(self.ptr)
 

@@ -29,7 +29,7 @@ struct FusedArgs {
     int pf;              // L2 prefetch distance in planes (0: off)
 };
 
-int g_prefetch_planes = 3;
+int g_prefetch_planes = 0;     // measured on B200 (profiles/r01_s8_tune_smoother.txt): the fused pass is not DRAM-latency bound, prefetch costs 3-4 %
 
 // One instruction pulls `bytes` (multiple of 16, 16-byte aligned address) of global memory into L2 without occupying a
 // register or a shared-memory slot: the DRAM latency of the plane that is D steps ahead is paid here, the real loads

@@ -146,7 +146,8 @@ k_copy_tags (const b200mg_copytag* __restrict__ tags, const b200mg_fab* dstf, co
             else { v = b[r]; }
             if (t.dst_fab >= 0) {
                 double& d = dst(ii, jj, kk, n + dcomp);
-                if (op == 0) { d = v; } else { d += v; }
+                // ADD: destination boxes of different tags may overlap (flux-register patches): no lost updates
+                if (op == 0) { d = v; } else if (v != 0.0) { atomicAdd(&d, v); }
             } else {
                 b[r] = v;
             }

@@ -186,7 +186,7 @@ void MGHierarchy::define (Vector<Geometry> const& a_geom, Vector<BoxArray> const
 
 // ========================================================================================= BndrySlabs
 template <class T>
-void BndrySlabs<T>::define (LevelLayout const& L, bool inside)
+void BndrySlabs<T>::define (LevelLayout const& L, bool inside, int rad, int extent)
 {
     clear();
     const int nl = L.numLocal();
@@ -195,7 +195,8 @@ void BndrySlabs<T>::define (LevelLayout const& L, bool inside)
     for (int li = 0; li < nl; ++li) {
         for (int f = 0; f < 6; ++f) {
             const Orientation face(f);
-            const Box b = inside ? insideCell(L.box(li), face, 1) : adjCell(L.box(li), face, 1);
+            Box b = inside ? insideCell(L.box(li), face, rad) : adjCell(L.box(li), face, rad);
+            for (int d = 0; d < 3; ++d) { if (d != face.coordDir()) { b.grow(d, extent); } }
             m_boxes[li * 6 + f] = b;
             m_offs[li * 6 + f] = total;
             total += std::size_t(b.numPts());
@@ -278,24 +279,23 @@ void MLLinOp::defineAuxData ()
         m_norm_fine_mask[a] = std::make_unique<iMultiFab>(
             makeFineMask(H.grids[a][0], H.dmap[a][0], H.grids[a + 1][0], H.amr_ref_ratio[a], 1, 0));
     }
+    defineAmrData();
 }
 
-// MultiMask::define with in_rad=0, out_rad=1, extent_rad=0 (AMReX_MultiMask.cpp:24-70)
-void MLLinOp::buildMasks (int a, int m)
+// MultiMask::define (AMReX_MultiMask.cpp:24-70) on the slabs of M: 2 outside the (periodically grown) domain, 1 inside and
+// not covered by the level's grids, 0 covered.  ngrow = max(out_rad, extent_rad) of the slabs.
+namespace {
+void fill_masks (BndrySlabs<int> const& M, LevelLayout const& layout, Geometry const& geom, BoxArray const& ba, int ngrow, std::vector<int>& h)
 {
-    LevelData& L = lev(a, m);
-    L.mask.define(*L.layout, false);
-    Geometry const& geom = H.geom[a][m];
-    BoxArray const& ba = H.grids[a][m];
     Box domain = geom.Domain();
-    for (int d = 0; d < 3; ++d) { if (geom.isPeriodic(d)) { domain.grow(d, 1); } }
+    for (int d = 0; d < 3; ++d) { if (geom.isPeriodic(d)) { domain.grow(d, ngrow); } }
     const auto pshifts = geom.periodicity().shiftIntVect();
-    std::vector<int> h(L.mask.numElements(), 0);
+    h.assign(M.numElements(), 0);
     std::vector<std::pair<int, Box>> isects;
-    for (int li = 0; li < L.layout->numLocal(); ++li) {
+    for (int li = 0; li < layout.numLocal(); ++li) {
         for (int f = 0; f < 6; ++f) {
-            Box const& sb = L.mask.box(li, f);
-            int* p = h.data() + L.mask.offset(li, f);
+            Box const& sb = M.box(li, f);
+            int* p = h.data() + M.offset(li, f);
             const Long nx = sb.length(0), ny = sb.length(1);
             auto at = [&] (int i, int j, int k) -> int& {
                 return p[(i - sb.smallEnd(0)) + nx * ((j - sb.smallEnd(1)) + ny * (k - sb.smallEnd(2)))];
@@ -312,6 +312,16 @@ void MLLinOp::buildMasks (int a, int m)
             }
         }
     }
+}
+}
+
+// m_maskvals: MultiMask with in_rad=0, out_rad=1, extent_rad=0 (cross stencil, AMReX_MLCellLinOp.H:393-408)
+void MLLinOp::buildMasks (int a, int m)
+{
+    LevelData& L = lev(a, m);
+    L.mask.define(*L.layout, false);
+    std::vector<int> h;
+    fill_masks(L.mask, *L.layout, H.geom[a][m], H.grids[a][m], 1, h);
     L.mask.upload(h);
     // which faces have any uncovered ghost cell (only those need boundary-condition work)
     L.bcfaces_h.clear();
@@ -501,7 +511,7 @@ bool MLLinOp::planFused (LevelData const& L) const
     }
     const int env_ty = m_fused_tile_y, env_cz = m_fused_chunk_z;
     const int tx = ((nxmax / 2 + 31) / 32) * 32;
-    int tile_y = std::min(1024 / tx - 4, 12);
+    int tile_y = std::min(1024 / tx - 4, 8);    // 768-thread CTAs: best of the measured grid (profiles/r01_s8_tune_smoother.txt)
     if (env_ty > 0) { tile_y = std::min(env_ty, 1024 / tx - 4); }
     tile_y = std::max(1, std::min(tile_y, nymax));
     // enough CTAs for >= 4 waves over the 148 SMs when the level allows it
@@ -553,7 +563,7 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
 void MLLinOp::solutionResidual (int amrlev, MultiFab& resid, MultiFab& x, MultiFab const& b, const MultiFab* crse_bcdata)
 {
     Gpu::ProfScope prof_scope__(amrlev * 100 + 0);
-    if (crse_bcdata != nullptr) { Abort("solutionResidual with coarse BC data: AMR composite path not implemented yet"); }
+    if (crse_bcdata != nullptr) { updateSolBC(amrlev, *crse_bcdata); }
     applyBC(amrlev, 0, x, BCMode::Inhomogeneous, StateMode::Solution, m_bndry_sol[amrlev].get());
     Fapply(amrlev, 0, resid, x, &b);    // resid = b - L(x), fused (== Fapply + Xpay(resid,-1,b))
 }
@@ -562,7 +572,7 @@ void MLLinOp::correctionResidual (int amrlev, int mglev, MultiFab& resid, MultiF
 {
     Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     if (bc_mode == BCMode::Inhomogeneous) {
-        if (crse_bcdata) { Abort("correctionResidual with coarse BC data: AMR composite path not implemented yet"); }
+        if (crse_bcdata) { AMREX_ALWAYS_ASSERT(mglev == 0 && amrlev > 0); updateCorBC(amrlev, *crse_bcdata); }
         applyBC(amrlev, mglev, x, BCMode::Inhomogeneous, StateMode::Correction, m_bndry_cor[amrlev].get());
     } else {
         applyBC(amrlev, mglev, x, BCMode::Homogeneous, StateMode::Correction, nullptr);
@@ -619,6 +629,237 @@ void MLLinOp::interpAssign (int amrlev, int fmglev, MultiFab& fine, MultiFab& cr
     }
     auto const& T = fine.layout().tiles(0);
     B200_KCALL(b200mg_interp_cc_r2(T.n, T.d.data(), fine.layout().d_vbox(), fine.d_fabs(), cmf->d_fabs(), 0, Gpu::gpuStream()));
+}
+
+
+// =========================================================================== multi-level (AMR) coupling
+void MLLinOp::CrseBndryReg::define (BoxArray const& cba, DistributionMapping const& dm)
+{
+    for (int f = 0; f < 6; ++f) {
+        const Orientation face(f);
+        std::vector<Box> bl;
+        bl.reserve(cba.size());
+        for (int i = 0, N = int(cba.size()); i < N; ++i) {
+            Box b = adjCell(cba[i], face, 1);
+            for (int d = 0; d < 3; ++d) { if (d != face.coordDir()) { b.grow(d, 2); } }
+            bl.push_back(b);
+        }
+        mf[f].define(BoxArray(std::move(bl)), dm, 1, 0);
+        mf[f].setVal(0.0);
+    }
+    const int nl = mf[0].local_size();
+    std::vector<b200mg_fab> h(std::size_t(nl) * 6);
+    for (int li = 0; li < nl; ++li) { for (int f = 0; f < 6; ++f) { h[li * 6 + f] = mf[f].desc(li); } }
+    table.assign(h);
+}
+
+// BndryRegisterT::copyFrom (AMReX_BndryRegister.H:266-275): one ParallelCopy per face
+void MLLinOp::CrseBndryReg::copyFrom (MultiFab const& crse, Periodicity const& period)
+{
+    for (int f = 0; f < 6; ++f) { mf[f].ParallelCopy(crse, 0, 0, 1, 0, 0, period); }
+}
+
+void MLLinOp::defineAmrData ()
+{
+    const int nlev = H.num_amr_levels;
+    m_amr_bndry.resize(nlev);
+    m_fluxreg.resize(std::max(0, nlev - 1));
+    for (int a = 1; a < nlev; ++a) {
+        m_amr_bndry[a] = std::make_unique<AmrBndry>();
+        AmrBndry& A = *m_amr_bndry[a];
+        LevelLayout const& layout = *lev(a, 0).layout;
+        Geometry const& geom = H.geom[a][0];
+        // BndryData masks: in_rad 0, out_rad 2, extent NTangHalfWidth = 5 (AMReX_BndryData.H:156,265)
+        A.bmask.define(layout, false, 2, 5);
+        std::vector<int> h;
+        fill_masks(A.bmask, layout, geom, H.grids[a][0], 5, h);
+        A.bmask.upload(h);
+        const BoxArray cba = amrex::coarsen(H.grids[a][0], H.amr_ref_ratio[a - 1]);
+        A.crse_sol_br.define(cba, H.dmap[a][0]);
+        A.crse_cor_br.define(cba, H.dmap[a][0]);
+        // faces that get interpolated coarse data: everything but non-periodic physical boundaries
+        // (InterpBndryDataT::setBndryValues, AMReX_InterpBndryData.H:177-181)
+        const Box domain = geom.Domain();
+        for (int li = 0; li < layout.numLocal(); ++li) {
+            Box const& bx = layout.box(li);
+            for (int f = 0; f < 6; ++f) {
+                const int d = f % 3; const bool low = f < 3;
+                const int dface = low ? domain.smallEnd(d) : domain.bigEnd(d);
+                const int bface = low ? bx.smallEnd(d) : bx.bigEnd(d);
+                if (bface != dface || geom.isPeriodic(d)) {
+                    b200mg_bcface fc; fc.box = li; fc.face = f; fc.bctype = 0; fc.blen = bx.length(d); fc.bcloc = 0.0;
+                    A.cf_faces_h.push_back(fc);
+                }
+            }
+        }
+        A.cf_faces.assign(A.cf_faces_h);
+    }
+
+    for (int a = 0; a + 1 < nlev; ++a) {   // YAFluxRegisterT::define
+        m_fluxreg[a] = std::make_unique<FluxReg>();
+        FluxReg& R = *m_fluxreg[a];
+        BoxArray const& cba = H.grids[a][0];
+        DistributionMapping const& cdm = H.dmap[a][0];
+        DistributionMapping const& fdm = H.dmap[a + 1][0];
+        Geometry const& cgeom = H.geom[a][0];
+        const int ratio = H.amr_ref_ratio[a];
+        R.crse_data.define(cba, cdm, 1, 0);
+        R.crse_flag.define(cba, cdm, 1, 1);
+        const auto pshifts = cgeom.periodicity().shiftIntVect();
+        const BoxArray cfba = amrex::coarsen(H.grids[a + 1][0], ratio);
+        Box cdomain = cgeom.Domain();
+        for (int d = 0; d < 3; ++d) { if (cgeom.isPeriodic(d)) { cdomain.grow(d, 1); } }
+        std::vector<std::pair<int, Box>> isects;
+        // flags: 0 coarse cell, 1 coarse cell next to the fine level, 2 covered by the fine level
+        for (int li = 0; li < R.crse_flag.local_size(); ++li) {
+            const Box gbx = R.crse_flag.fabbox(li);
+            std::vector<int> h(gbx.numPts(), 0);
+            auto fill = [&] (Box const& b, int v) {
+                for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k) for (int j = b.smallEnd(1); j <= b.bigEnd(1); ++j)
+                    for (int i = b.smallEnd(0); i <= b.bigEnd(0); ++i) {
+                        h[(i - gbx.smallEnd(0)) + Long(gbx.length(0)) * ((j - gbx.smallEnd(1)) + Long(gbx.length(1)) * (k - gbx.smallEnd(2)))] = v;
+                    }
+            };
+            for (int pass = 0; pass < 2; ++pass) {
+                for (auto const& iv : pshifts) {
+                    cfba.intersections(gbx + iv, isects, false, IntVect(pass == 0 ? 1 : 0));
+                    for (auto const& is : isects) { fill(is.second - iv, pass == 0 ? 1 : 2); }
+                }
+            }
+            R.crse_flag.copyFromHost(h.data(), gbx, 0, 1);
+        }
+        // coarse/fine patches: the one-cell shell around every coarsened fine box that no fine box covers
+        std::vector<Box> cfp_boxes; Vector<int> cfp_pmap;
+        std::vector<b200mg_box> cfbox_h; std::vector<int> findex_h;
+        const int myproc = ParallelDescriptor::MyProc();
+        int nlocal_fine = 0;
+        for (int i = 0, N = int(cfba.size()); i < N; ++i) {
+            Box bx = amrex::grow(cfba[i], 1);
+            bx &= cdomain;
+            const BoxList bl = cfba.complementIn(bx);
+            const int proc = fdm[i];
+            for (auto const& b : bl) {
+                cfp_boxes.push_back(b); cfp_pmap.push_back(proc);
+                if (proc == myproc) {
+                    b200mg_box cb;
+                    for (int d = 0; d < 3; ++d) { cb.lo[d] = cfba[i].smallEnd(d); cb.hi[d] = cfba[i].bigEnd(d); }
+                    cfbox_h.push_back(cb); findex_h.push_back(nlocal_fine);
+                }
+            }
+            if (proc == myproc) { ++nlocal_fine; }
+        }
+        if (!cfp_boxes.empty()) {
+            const BoxArray cfp_ba{std::vector<Box>(cfp_boxes)};
+            const DistributionMapping cfp_dm{Vector<int>(cfp_pmap)};
+            R.cfpatch.define(cfp_ba, cfp_dm, 1, 0);
+            AMREX_ALWAYS_ASSERT(R.cfpatch.local_size() == int(cfbox_h.size()));
+            R.cfbox.assign(cfbox_h); R.fine_index.assign(findex_h);
+            if (cgeom.isAnyPeriodic()) {   // patch cells beyond a periodic boundary that a fine box covers do not count
+                R.cfp_mask = std::make_unique<MultiFab>(cfp_ba, cfp_dm, 1, 0);
+                const Box domainbox = cgeom.Domain();
+                for (int li = 0; li < R.cfp_mask->local_size(); ++li) {
+                    const Box bx = R.cfp_mask->validbox(li);
+                    std::vector<double> h(bx.numPts(), 1.0);
+                    if (!domainbox.contains(bx)) {
+                        for (auto const& iv : pshifts) {
+                            if (iv == IntVect(0)) { continue; }
+                            cfba.intersections(bx + iv, isects);
+                            for (auto const& is : isects) {
+                                const Box b = is.second - iv;
+                                for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k) for (int j = b.smallEnd(1); j <= b.bigEnd(1); ++j)
+                                    for (int i = b.smallEnd(0); i <= b.bigEnd(0); ++i) {
+                                        h[(i - bx.smallEnd(0)) + Long(bx.length(0)) * ((j - bx.smallEnd(1)) + Long(bx.length(1)) * (k - bx.smallEnd(2)))] = 0.0;
+                                    }
+                            }
+                        }
+                    }
+                    R.cfp_mask->copyFromHost(h.data(), bx, 0, 0);
+                }
+            }
+        }
+    }
+}
+
+// InterpBndryDataT::updateBndryValues (AMReX_InterpBndryData.H:161-268), max_order 3
+void MLLinOp::interpBndry (int amrlev, BndrySlabs<double>& bndry, CrseBndryReg const& br) const
+{
+    AmrBndry const& A = *m_amr_bndry[amrlev];
+    const int nf = int(A.cf_faces_h.size());
+    if (nf == 0) { return; }
+    B200_KCALL(b200mg_interp_bndry_o3(nf, A.cf_faces.data(), lev(amrlev, 0).layout->d_vbox(), bndry.d_table(), br.table.data(),
+                                      A.bmask.d_table(), H.amr_ref_ratio[amrlev - 1], Gpu::gpuStream()));
+}
+
+void MLLinOp::updateSolBC (int amrlev, MultiFab const& crse_bcdata) const
+{
+    AMREX_ALWAYS_ASSERT(amrlev > 0);
+    Gpu::ProfScope prof_scope__(amrlev * 100);
+    AmrBndry& A = *m_amr_bndry[amrlev];
+    A.crse_sol_br.copyFrom(crse_bcdata, H.geom[amrlev - 1][0].periodicity());
+    interpBndry(amrlev, *m_bndry_sol[amrlev], A.crse_sol_br);
+}
+
+void MLLinOp::updateCorBC (int amrlev, MultiFab const& crse_bcdata) const
+{
+    AMREX_ALWAYS_ASSERT(amrlev > 0);
+    Gpu::ProfScope prof_scope__(amrlev * 100);
+    AmrBndry& A = *m_amr_bndry[amrlev];
+    A.crse_cor_br.copyFrom(crse_bcdata, H.geom[amrlev - 1][0].periodicity());
+    interpBndry(amrlev, *m_bndry_cor[amrlev], A.crse_cor_br);
+}
+
+// MLCellLinOpT::reflux (AMReX_MLCellLinOp.H:1274-1344): res(crse) += [coarse flux - average of fine fluxes] / dx on the
+// coarse cells that touch the fine level from outside.
+void MLLinOp::reflux (int crse_amrlev, MultiFab& res, MultiFab const& crse_sol, MultiFab& fine_sol) const
+{
+    Gpu::ProfScope prof_scope__(crse_amrlev * 100);
+    FluxReg& R = *m_fluxreg[crse_amrlev];
+    const int fine_amrlev = crse_amrlev + 1;
+    const int ratio = H.amr_ref_ratio[crse_amrlev];
+    applyBC(fine_amrlev, 0, fine_sol, BCMode::Inhomogeneous, StateMode::Solution, m_bndry_sol[fine_amrlev].get());
+    const Real* cdx = H.geom[crse_amrlev][0].CellSize();
+    const Real* fdx = H.geom[fine_amrlev][0].CellSize();
+    const Real* cdxi = H.geom[crse_amrlev][0].InvCellSize();
+    const Real* fdxi = H.geom[fine_amrlev][0].InvCellSize();
+    const Real dt = 1.0;
+    Array<MultiFab const*, 3> cb, fb; Real bscalar = 0.0;
+    getFluxCoeffs(crse_amrlev, cb, bscalar);
+    getFluxCoeffs(fine_amrlev, fb, bscalar);
+    {
+        auto const& T = R.crse_data.layout().tiles(0);
+        B200_KCALL(b200mg_reflux_crse(T.n, T.d.data(), R.crse_data.layout().d_vbox(), R.crse_data.d_fabs(), R.crse_flag.d_fabs(), crse_sol.d_fabs(),
+                                      cb[0] ? cb[0]->d_fabs() : nullptr, cb[1] ? cb[1]->d_fabs() : nullptr, cb[2] ? cb[2]->d_fabs() : nullptr,
+                                      bscalar * cdxi[0], bscalar * cdxi[1], bscalar * cdxi[2], dt / cdx[0], dt / cdx[1], dt / cdx[2], Gpu::gpuStream()));
+    }
+    if (!R.cfpatch.empty()) {
+        const Real r3 = Real(ratio) * ratio * ratio;
+        B200_KCALL(b200mg_reflux_fine(R.cfpatch.local_size(), R.cfpatch.d_fabs(), R.cfbox.data(), R.fine_index.data(),
+                                      R.cfp_mask ? R.cfp_mask->d_fabs() : nullptr, fine_sol.d_fabs(),
+                                      fb[0] ? fb[0]->d_fabs() : nullptr, fb[1] ? fb[1]->d_fabs() : nullptr, fb[2] ? fb[2]->d_fabs() : nullptr,
+                                      bscalar * fdxi[0], bscalar * fdxi[1], bscalar * fdxi[2],
+                                      dt / (fdx[0] * r3), dt / (fdx[1] * r3), dt / (fdx[2] * r3), ratio, Gpu::gpuStream()));
+        R.crse_data.ParallelCopy(R.cfpatch, 0, 0, 1, 0, 0, H.geom[crse_amrlev][0].periodicity(), CpOp::ADD);
+    }
+    MultiFab::Add(res, R.crse_data, 0, 0, 1, 0);
+}
+
+MultiFab MLLinOp::makeCoarseAmr (int famrlev, int ng) const
+{
+    return MultiFab(amrex::coarsen(H.grids[famrlev][0], H.amr_ref_ratio[famrlev - 1]), H.dmap[famrlev][0], 1, ng);
+}
+
+// trilinear cell-centred interpolation between AMR levels (AMReX_MLCellLinOp.H:1096-1181, mlmg_lin_cc_interp_r2)
+void MLLinOp::interpolationAmr (int famrlev, MultiFab& fine, MultiFab const& crse) const
+{
+    Gpu::ProfScope prof_scope__(famrlev * 100);
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(H.amr_ref_ratio[famrlev - 1] == 2, "interpolationAmr: only refinement ratio 2 is implemented");
+    auto const& T = fine.layout().tiles(0);
+    B200_KCALL(b200mg_interp_cc_r2(T.n, T.d.data(), fine.layout().d_vbox(), fine.d_fabs(), crse.d_fabs(), 0, Gpu::gpuStream()));
+}
+
+void MLLinOp::avgDownResAmr (int clev, MultiFab& cres, MultiFab const& fres) const
+{
+    average_down(fres, cres, 0, 1, H.amr_ref_ratio[clev]);
 }
 
 Real MLLinOp::xdoty (int, int, MultiFab const& x, MultiFab const& y, bool local) const { return MultiFab::Dot(x, y, local); }

@@ -269,13 +269,31 @@ void MLMG::prepareForSolve (Vector<MultiFab*> const& a_sol, Vector<MultiFab cons
     }
 }
 
+// MLMGT::oneIter (AMReX_MLMG.H:1228-1293): down the AMR hierarchy (fine smooth, coarse composite residual), MG cycle on
+// level 0, then back up (interpolate the coarse correction, fine residual with coarse BC, fine smooth).
 void MLMG::oneIter (int iter)
 {
-    if (finest_amr_lev > 0) { Abort("multi-level composite solve is not implemented yet"); }
-    Gpu::ProfScope prof_scope__(0);
-    if (linop.isSingular(0) && linop.getEnforceSingularSolvable()) { makeSolvable(0, 0, res[0][0]); }
-    if (iter < max_fmg_iters) { mgFcycle(); } else { mgVcycle(0, 0); }
-    MultiFab::Add(sol[0], cor[0][0], 0, 0, 1, 0);
+    for (int alev = finest_amr_lev; alev > 0; --alev) {
+        miniCycle(alev);
+        MultiFab::Add(sol[alev], cor[alev][0], 0, 0, 1, 0);
+        computeResWithCrseSolFineCor(alev - 1, alev);
+        if (alev != finest_amr_lev) { std::swap(cor_hold[alev][0], cor[alev][0]); }   // saved for the up cycle
+    }
+    {
+        Gpu::ProfScope prof_scope__(0);
+        if (linop.isSingular(0) && linop.getEnforceSingularSolvable()) { makeSolvable(0, 0, res[0][0]); }
+        if (iter < max_fmg_iters) { mgFcycle(); } else { mgVcycle(0, 0); }
+        MultiFab::Add(sol[0], cor[0][0], 0, 0, 1, 0);
+    }
+    for (int alev = 1; alev <= finest_amr_lev; ++alev) {
+        interpCorrection(alev);                                   // (fine AMR correction) = I(coarse AMR correction)
+        MultiFab::Add(sol[alev], cor[alev][0], 0, 0, 1, 0);
+        if (alev != finest_amr_lev) { MultiFab::Add(cor_hold[alev][0], cor[alev][0], 0, 0, 1, 0); }
+        computeResWithCrseCorFineCor(alev);
+        miniCycle(alev);
+        MultiFab::Add(sol[alev], cor[alev][0], 0, 0, 1, 0);
+        if (alev != finest_amr_lev) { MultiFab::Add(cor[alev][0], cor_hold[alev][0], 0, 0, 1, 0); }
+    }
     linop.averageDownAndSync(sol);
 }
 
@@ -379,7 +397,7 @@ void MLMG::computeMLResidual (int amrlevmax)
     for (int alev = amrlevmax; alev >= 0; --alev) {
         const MultiFab* crse_bcdata = (alev > 0) ? &sol[alev - 1] : nullptr;
         linop.solutionResidual(alev, res[alev][0], sol[alev], rhs[alev], crse_bcdata);
-        if (alev < finest_amr_lev) { Abort("reflux: multi-level composite solve is not implemented yet"); }
+        if (alev < finest_amr_lev) { linop.reflux(alev, res[alev][0], sol[alev], sol[alev + 1]); }
     }
 }
 
@@ -392,6 +410,35 @@ void MLMG::computeResidual (int alev)
 void MLMG::computeResOfCorrection (int amrlev, int mglev)
 {
     linop.correctionResidual(amrlev, mglev, rescor[amrlev][mglev], cor[amrlev][mglev], res[amrlev][mglev], MLLinOp::BCMode::Homogeneous);
+}
+
+// AMReX_MLMG.H:1662-1690: coarse composite residual from the coarse solution and the fine correction
+void MLMG::computeResWithCrseSolFineCor (int calev, int falev)
+{
+    const MultiFab* crse_bcdata = (calev > 0) ? &sol[calev - 1] : nullptr;
+    linop.solutionResidual(calev, res[calev][0], sol[calev], rhs[calev], crse_bcdata);
+    linop.correctionResidual(falev, 0, rescor[falev][0], cor[falev][0], res[falev][0], MLLinOp::BCMode::Homogeneous);
+    MultiFab::Copy(res[falev][0], rescor[falev][0], 0, 0, 1, 0);
+    linop.reflux(calev, res[calev][0], sol[calev], sol[falev]);
+    linop.avgDownResAmr(calev, res[calev][0], res[falev][0]);
+}
+
+// AMReX_MLMG.H:1695-1714: fine_res -= L(fine_cor) with the coarse correction as boundary data
+void MLMG::computeResWithCrseCorFineCor (int falev)
+{
+    linop.correctionResidual(falev, 0, rescor[falev][0], cor[falev][0], res[falev][0], MLLinOp::BCMode::Inhomogeneous, &cor[falev - 1][0]);
+    MultiFab::Copy(res[falev][0], rescor[falev][0], 0, 0, 1, 0);
+}
+
+// AMReX_MLMG.H:1719-1747: trilinear interpolation of the coarse AMR correction through a ghosted coarsened-fine temporary
+void MLMG::interpCorrection (int alev)
+{
+    if (int(cfine_amr.size()) <= alev) { cfine_amr.resize(alev + 1); }
+    if (!cfine_amr[alev]) { cfine_amr[alev] = std::make_unique<MultiFab>(linop.makeCoarseAmr(alev, 1)); }
+    MultiFab& cfine = *cfine_amr[alev];
+    cfine.setVal(0.0);
+    cfine.ParallelCopy(cor[alev - 1][0], 0, 0, 1, 0, 1, linop.Geom(alev - 1, 0).periodicity());
+    linop.interpolationAmr(alev, cor[alev][0], cfine);
 }
 
 void MLMG::interpCorrection (int alev, int mglev)
@@ -445,13 +492,25 @@ void MLMG::makeSolvable (int amrlev, int mglev, MultiFab& mf)
     linop.fixSolvabilityByOffset(amrlev, mglev, mf, offset);
 }
 
+// MLMGT::compResidual (AMReX_MLMG.H:792-856): composite residual b - L(sol) on every AMR level
 void MLMG::compResidual (Vector<MultiFab*> const& a_res, Vector<MultiFab*> const& a_sol, Vector<MultiFab const*> const& a_rhs)
 {
     if (!linop_prepared) { linop.prepareForSolve(); linop_prepared = true; }
-    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(namrlevs == 1, "compResidual: single level only for now");
-    MultiFab s = linop.make(0, 0, 1);
-    MultiFab::Copy(s, *a_sol[0], 0, 0, 1, 0);
-    linop.solutionResidual(0, *a_res[0], s, *a_rhs[0], nullptr);
+    else if (linop.needsUpdate()) { linop.update(); }
+    Vector<MultiFab> s(namrlevs);
+    for (int alev = 0; alev < namrlevs; ++alev) {
+        s[alev] = linop.make(alev, 0, 1);
+        MultiFab::Copy(s[alev], *a_sol[alev], 0, 0, 1, 0);
+    }
+    for (int alev = finest_amr_lev; alev >= 0; --alev) {
+        const MultiFab* crse_bcdata = (alev > 0) ? &s[alev - 1] : nullptr;
+        linop.solutionResidual(alev, *a_res[alev], s[alev], *a_rhs[alev], crse_bcdata);
+        if (alev < finest_amr_lev) {
+            linop.reflux(alev, *a_res[alev], s[alev], s[alev + 1]);
+            average_down(*a_res[alev + 1], *a_res[alev], 0, 1, linop.AMRRefRatio(alev));
+        }
+    }
+    Gpu::streamSynchronize();
 }
 
 void MLMG::apply (Vector<MultiFab*> const& out, Vector<MultiFab*> const& in)

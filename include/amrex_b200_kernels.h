@@ -160,6 +160,26 @@ int b200mg_prolong_add(int ntiles, const b200mg_tile* tiles, const b200mg_box* f
 int b200mg_interp_cc_r2(int ntiles, const b200mg_tile* tiles, const b200mg_box* fbox,
                         const b200mg_fab* fine, const b200mg_fab* crse, int add, cudaStream_t s);
 
+/* ---- coarse/fine coupling of the multi-level solve.
+ *      interp_bndry_o3: interpbndrydata_{x,y,z}_o3 (Src/Boundary/AMReX_InterpBndryData_3D_K.H:22-119) for every listed
+ *      (box, face): bdry / crse / mask are [box*6+face] tables (bdry: 1-cell slab outside the fine face; crse: boundary
+ *      register of the coarsened box, tangential extent 2; mask: 2 cells outside, tangential extent 5, 1 = not covered).
+ *      reflux_crse / reflux_fine: YAFluxRegister CrseAdd / FineAdd (Src/Boundary/AMReX_YAFluxRegister_3D_K.H:11-199)
+ *      with the operator's face fluxes -fac*b*(sol(i)-sol(i-1)) (AMReX_MLABecLap_3D_K.H:79-95; b tables NULL: b = 1)
+ *      evaluated in place.  fac* = b_scalar*dxinv; crse: dtd* = dt/dx_crse; fine: dtd* = dt/(dx_fine*ratio^3).
+ *      reflux_fine: one entry per coarse/fine patch fab: cfbox = coarsened fine box it surrounds, fine_index = local
+ *      index of that fine box; mask (may be NULL) multiplies the result (periodic self-overlap). */
+int b200mg_interp_bndry_o3(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
+                           const b200mg_fab* bdry, const b200mg_fab* crse, const b200mg_ifab* mask, int ratio, cudaStream_t s);
+int b200mg_reflux_crse(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                       const b200mg_fab* crse_data, const b200mg_ifab* flag, const b200mg_fab* sol,
+                       const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                       double facx, double facy, double facz, double dtdx, double dtdy, double dtdz, cudaStream_t s);
+int b200mg_reflux_fine(int npatches, const b200mg_fab* cfpatch, const b200mg_box* cfbox, const int* fine_index,
+                       const b200mg_fab* mask, const b200mg_fab* fine_sol,
+                       const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                       double facx, double facy, double facz, double dtdx, double dtdy, double dtdz, int ratio, cudaStream_t s);
+
 /* arithmetic cell-centre -> face average (amrex::average_cellcenter_to_face, AMReX_MultiFabUtil_3D_C.H:81-89) */
 int b200mg_cc_to_face(int ntiles, const b200mg_tile* tiles, const b200mg_box* fbox,
                       const b200mg_fab* face, const b200mg_fab* cc, int dir, cudaStream_t s);

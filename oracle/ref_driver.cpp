@@ -386,6 +386,47 @@ int run_meta (Params const& p)
     return 0;
 }
 
+// ---- mode=amr -----------------------------------------------------------------------------------------------
+// Stages of the multi-level composite solve through the reference's public API: composite residual of the initial
+// guess (coarse/fine boundary interpolation + reflux), and the solution after 1 and 2 fixed MLMG iterations.
+int run_amr (Params const& p)
+{
+    Problem P; build_problem(p, P);
+    std::ofstream man(p.dump_dir+"/manifest.json"); man << "{\n";
+    dump_inputs(p, P, man);
+    std::unique_ptr<MLLinOp> op;
+    LPInfo info = make_info(p);
+    if (p.prob_type == 2) {
+        auto o = std::make_unique<MLABecLaplacian>(P.geom, P.grids, P.dmap, info); setup_abec(p, P, *o); op = std::move(o);
+    } else {
+        auto o = std::make_unique<MLPoisson>(P.geom, P.grids, P.dmap, info); setup_poisson(p, P, *o); op = std::move(o);
+    }
+    const int nlev = p.max_level+1;
+    Vector<MultiFab> sol0(nlev), res(nlev);
+    for (int l = 0; l < nlev; ++l) {
+        sol0[l].define(P.grids[l], P.dmap[l], 1, 1); MultiFab::Copy(sol0[l], P.sol[l], 0, 0, 1, 1);
+        res[l].define(P.grids[l], P.dmap[l], 1, 0);
+    }
+    {
+        MLMG mlmg(*op);
+        mlmg.setVerbose(0);
+        mlmg.compResidual(GetVecOfPtrs(res), GetVecOfPtrs(P.sol), GetVecOfConstPtrs(P.rhs));
+        for (int l = 0; l < nlev; ++l) { dump_mf(p.dump_dir, "amr_res_lev"+std::to_string(l), res[l], 0, man); }
+    }
+    std::vector<double> h1;
+    for (int nit = 1; nit <= 2; ++nit) {
+        for (int l = 0; l < nlev; ++l) { MultiFab::Copy(P.sol[l], sol0[l], 0, 0, 1, 1); }
+        MLMG mlmg(*op);
+        mlmg.setVerbose(0); mlmg.setFixedIter(nit); set_bottom(p, mlmg);
+        mlmg.solve(GetVecOfPtrs(P.sol), GetVecOfConstPtrs(P.rhs), p.tol_rel, p.tol_abs);
+        for (int l = 0; l < nlev; ++l) { dump_mf(p.dump_dir, "amr_sol"+std::to_string(nit)+"_lev"+std::to_string(l), P.sol[l], 0, man); }
+        h1.push_back(mlmg.getResidualHistory().back());
+    }
+    man << "\"_end\": 0\n}\n";
+    std::printf("RESULT {\"mode\":\"amr\",\"resid_after_iter\":[%.17g,%.17g]}\n", h1[0], h1[1]);
+    return 0;
+}
+
 // ---- mode=prim ----------------------------------------------------------------------------------------------
 // Runs single primitives of the linop on deterministic pseudo-random data and dumps in/outputs.
 void fill_pseudo (MultiFab& mf, int ng, unsigned seed)
@@ -482,6 +523,7 @@ int main (int argc, char* argv[])
         if (p.mode == "solve") rc = run_solve(p);
         else if (p.mode == "meta") rc = run_meta(p);
         else if (p.mode == "prim") rc = run_prim(p);
+        else if (p.mode == "amr") rc = run_amr(p);
         else { std::fprintf(stderr, "unknown mode\n"); rc = 2; }
     }
     amrex::Finalize();

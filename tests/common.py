@@ -105,6 +105,64 @@ def build_problem(ab, prob_type, n_cell, max_grid_size, dump, maxorder=2, agg_gr
     return dict(geom=geom, ba=ba, dm=dm, sol=sol, rhs=rhs, op=op, keep=keep, n=n_cell)
 
 
+def build_problem_amr(ab, prob_type, n_cell, max_grid_size, dump, max_level=1, maxorder=3, agg_grid_size=-1, fusion=None):
+    """Multi-level version of build_problem: level l has the domain refined by 2^l, grids = the central half of the
+    coarser level's grids refined by 2 and chopped at max_grid_size (as oracle/ref_driver.cpp build_problem)."""
+    assert prob_type in (1, 2)
+    ab.Geometry.setup((0., 0., 0.), (1., 1., 1.), (0, 0, 0))
+    geoms, bas, dms, sols, rhss, keep = [], [], [], [], [], []
+    dlo, dhi = [0, 0, 0], [n_cell - 1] * 3      # domain of the level
+    glo, ghi = [0, 0, 0], [n_cell - 1] * 3      # region covered by the level's grids
+    for l in range(max_level + 1):
+        geoms.append(ab.Geometry(tuple(dlo), tuple(dhi)))
+        bas.append(ab.BoxArray(tuple(glo), tuple(ghi)).maxSize(max_grid_size))
+        dms.append(ab.DistributionMapping(bas[-1]))
+        sol = ab.MultiFab(bas[-1], dms[-1], 1, 1)
+        rhs = ab.MultiFab(bas[-1], dms[-1], 1, 0)
+        lo, a = dump[f"sol0_lev{l}"]
+        sol.upload(a, lo, ng=1)
+        lo, a = dump[f"rhs_lev{l}"]
+        rhs.upload(a, lo)
+        sols.append(sol)
+        rhss.append(rhs)
+        glo = [2 * (v + n_cell // 4) for v in glo]
+        ghi = [2 * (v - n_cell // 4) + 1 for v in ghi]
+        dlo = [2 * v for v in dlo]
+        dhi = [2 * v + 1 for v in dhi]
+    D, N = ab.LinOpBCType.Dirichlet, ab.LinOpBCType.Neumann
+    if prob_type == 2:
+        op = ab.MLABecLaplacian(geoms, bas, dms, agg_grid_size=agg_grid_size, con_grid_size=agg_grid_size)
+        op.setMaxOrder(maxorder)
+        op.setDomainBC((D, N, N), (N, D, N))
+        for l in range(max_level + 1):
+            op.setLevelBC(l, sols[l])
+        op.setScalars(1.e-3, 1.0)
+        for l in range(max_level + 1):
+            acoef = ab.MultiFab(bas[l], dms[l], 1, 0)
+            lo, a = dump[f"acoef_lev{l}"]
+            acoef.upload(a, lo)
+            op.setACoeffs(l, acoef)
+            faces = []
+            for d, nm in enumerate(("bx", "by", "bz")):
+                nodal = [0, 0, 0]
+                nodal[d] = 1
+                f = ab.MultiFab(bas[l], dms[l], 1, 0, nodal=nodal)
+                lo, a = dump[f"{nm}_lev{l}"]
+                f.upload(a, lo)
+                faces.append(f)
+            op.setBCoeffs(l, faces)
+            keep += [acoef] + faces
+    else:
+        op = ab.MLPoisson(geoms, bas, dms, agg_grid_size=agg_grid_size, con_grid_size=agg_grid_size)
+        op.setMaxOrder(maxorder)
+        op.setDomainBC((D, D, D), (D, D, D))
+        for l in range(max_level + 1):
+            op.setLevelBC(l, sols[l])
+    if fusion is not None:
+        op.setSmootherFusion(fusion)
+    return dict(geom=geoms, ba=bas, dm=dms, sol=sols, rhs=rhss, op=op, keep=keep, n=n_cell)
+
+
 def rel_maxdiff(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 

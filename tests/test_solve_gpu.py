@@ -4,7 +4,7 @@ Bar (BASELINE.json north_star): same V-cycle count (+-1), solution max-norm diff
 import numpy as np
 import pytest
 
-from common import build_problem, have_ref, rel_maxdiff, run_ref
+from common import build_problem, build_problem_amr, have_ref, rel_maxdiff, run_ref
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_ref(), reason="oracle/_ref/ref_driver not built")]
 
@@ -79,3 +79,25 @@ def test_bottom_solvers(ab, bottom):
     ref, mlmg, diff = solve_case(ab, 1, 64, 32, bottom=bottom)
     assert abs(mlmg.numIters() - ref["iters"]) <= 1
     assert diff <= SOL_TOL
+
+
+# ---- 2-level AMR composite solves (BASELINE config #4 at reduced size): coarse/fine interpolation, reflux
+@pytest.mark.parametrize("prob_type,n,mgs,maxorder", [(1, 64, 32, 3), (2, 64, 32, 3), (2, 64, 32, 2), (2, 128, 64, 3)])
+def test_two_level_composite(ab, prob_type, n, mgs, maxorder):
+    ref, dump = run_ref(dump=True, mode="solve", prob_type=prob_type, n_cell=n, max_grid_size=mgs, linop_maxorder=maxorder,
+                        agg_grid_size=32, max_level=1)
+    P = build_problem_amr(ab, prob_type, n, mgs, dump, max_level=1, maxorder=maxorder)
+    mlmg = ab.MLMG(P["op"])
+    mlmg.setVerbose(0)
+    mlmg.setMaxIter(100)
+    mlmg.solve(P["sol"], P["rhs"], 1e-10, 0.0)
+    assert abs(mlmg.numIters() - ref["iters"]) <= 1
+    assert mlmg.initRHS() == pytest.approx(ref["rhsnorm0"], rel=1e-13)
+    assert mlmg.initResidual() == pytest.approx(ref["resnorm0"], rel=1e-10)
+    for a, b in zip(mlmg.residualHistory(), ref["history"]):
+        assert a == pytest.approx(b, rel=1e-5)
+    for lev in range(2):
+        lo, refsol = dump[f"sol_lev{lev}"]
+        refv = refsol[1:-1, 1:-1, 1:-1]
+        mine = P["sol"][lev].download(tuple(v + 1 for v in lo), refv.shape)
+        assert rel_maxdiff(mine, refv) <= SOL_TOL
