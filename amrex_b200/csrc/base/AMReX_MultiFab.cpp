@@ -175,6 +175,7 @@ std::shared_ptr<LevelLayout> LevelLayout::get (BoxArray const& ba, DistributionM
         L->m_boxes.push_back(ba[i]);
         L->m_cells += ba[i].numPts();
         if (ba[i].length(0) % 2 != 0 || ba[i].length(0) > 128 || !ba[i].cellCentered()) { L->m_pairable = false; }
+        if (ba[i].length(0) < 4 || ba[i].length(1) < 2) { L->m_lean = false; }
         b200mg_box b; for (int d = 0; d < 3; ++d) { b.lo[d] = ba[i].smallEnd(d); b.hi[d] = ba[i].bigEnd(d); }
         hb.push_back(b);
     }

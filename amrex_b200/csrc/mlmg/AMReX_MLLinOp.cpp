@@ -1023,6 +1023,12 @@ void MLABecLaplacian::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab co
     LevelData const& L = lev(amrlev, mglev);
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);   // dh = beta/h^2 (AMReX_MLABecLaplacian.H:907-909)
     auto const& T = sol.layout().tiles(0);
+    if (sol.layout().leanable()) {
+        B200_KCALL(b200mg_gsrb_abec_pairs_lean(T.n, T.d.data(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), m_a_coeffs[amrlev][mglev].d_fabs(),
+                                               m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(), m_b_coeffs[amrlev][mglev][2].d_fabs(),
+                                               L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, Gpu::gpuStream()));
+        return;
+    }
     if (sol.layout().pairable()) {
         B200_KCALL(b200mg_gsrb_abec_pairs(T.n, T.d.data(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), m_a_coeffs[amrlev][mglev].d_fabs(),
                                           m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(), m_b_coeffs[amrlev][mglev][2].d_fabs(),
@@ -1082,6 +1088,11 @@ void MLPoisson::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& r
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
     auto const& T = sol.layout().tiles(0);
+    if (sol.layout().leanable()) {
+        B200_KCALL(b200mg_gsrb_poisson_pairs_lean(T.n, T.d.data(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
+                                                  dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, Gpu::gpuStream()));
+        return;
+    }
     if (sol.layout().pairable()) {
         B200_KCALL(b200mg_gsrb_poisson_pairs(T.n, T.d.data(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
                                              dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, Gpu::gpuStream()));

@@ -87,6 +87,18 @@ int b200mg_gsrb_poisson_pairs(int ntiles, const b200mg_tile* tiles, const b200mg
                               const b200mg_fab* phi, const b200mg_fab* rhs,
                               const b200mg_fab* f, const b200mg_ifab* m,
                               double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+/* Lean variants of the pair sweeps: additionally require nx >= 4 and ny >= 2 for every box (identical results). */
+int b200mg_gsrb_abec_pairs_lean(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                                const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,
+                                const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                                const b200mg_fab* f, const b200mg_ifab* m,
+                                double alpha, double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+int b200mg_gsrb_poisson_pairs_lean(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                                   const b200mg_fab* phi, const b200mg_fab* rhs,
+                                   const b200mg_fab* f, const b200mg_ifab* m,
+                                   double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+/* resident CTAs per SM the lean sweeps are compiled for: 4 (64 registers, default) or 3 (80 registers); <= 0 selects the generic pair sweep */
+void b200mg_set_gsrb_lean_occupancy(int min_blocks);
 /* Fused red+black pass (one sweep over memory per smooth): red update of every valid cell and black update of the
  * cells that do not touch the box surface, out of place (phi_in -> phi_out).  The black surface shell is finished by
  * b200mg_gsrb_shell_* after the halo refresh.  Same arithmetic and update order as two colour sweeps.

@@ -57,11 +57,18 @@ def kernel_ms(name):
 
 out = []
 op.setSmootherFusion(0)
-ms = time_smooth()
-k = kernel_ms("b200mg_gsrb_abec_pairs")
-out.append(dict(variant="pair colour sweeps", ms_per_smooth=ms, kernel_ms=k, kernel_gbs_44=44.0 * cells / (k * 1e-3) / 1e9 if k else None))
-print(json.dumps(out[-1]), flush=True)
-ref = x.norm0()
+ref = None
+for minb, label in ((0, "generic pair colour sweeps"), (4, "lean pair sweeps, 4 CTAs/SM (64 regs)"), (3, "lean pair sweeps, 3 CTAs/SM (80 regs)")):
+    ab.lib.b200mg_set_gsrb_lean_occupancy(minb)
+    ms = time_smooth()
+    k = kernel_ms("b200mg_gsrb_abec_pairs_lean")
+    nrm = x.norm0()
+    ref = nrm if ref is None else ref
+    out.append(dict(variant=label, ms_per_smooth=ms, kernel_ms=k, kernel_gbs_44=44.0 * cells / (k * 1e-3) / 1e9 if k else None,
+                    same_norm=bool(nrm == ref)))
+    print(json.dumps(out[-1]), flush=True)
+if os.environ.get("TUNE_SKIP_FUSED"):
+    sys.exit(0)
 
 op.setSmootherFusion(1)
 grid = list(itertools.product([4, 8, 12], [32, 128], [0, 2, 4]))
