@@ -43,6 +43,7 @@ _SIGS = {
     "amrex_fi_boxarray_maxsize": (None, [_P, _IP]), "amrex_fi_boxarray_nboxes": (_LL, [_P]),
     "amrex_fi_boxarray_get_box": (None, [_P, _I, _IP, _IP]), "amrex_fi_boxarray_numpts": (_LL, [_P]),
     "amrex_b200_boxarray_coarsen": (None, [_P, _I]), "amrex_b200_boxarray_refine": (None, [_P, _I]),
+    "amrex_b200_boxarray_convert": (None, [_P, C.POINTER(C.c_int)]),
     "amrex_fi_new_distromap": (None, [_PP, _P]), "amrex_fi_new_distromap_from_pmap": (None, [_PP, _IP, _I]),
     "amrex_fi_delete_distromap": (None, [_P]), "amrex_fi_distromap_get_pmap": (None, [_P, _IP, _I]),
     "amrex_b200_new_distromap_sfc": (None, [_PP, _P, _I]), "amrex_b200_make_sfc": (None, [_P, _I, _IP]),
@@ -241,6 +242,11 @@ class BoxArray(_Obj):
     def maxSize(self, n):
         sz = (n, n, n) if np.isscalar(n) else n
         lib.amrex_fi_boxarray_maxsize(self.ptr, _i3(sz))
+        check()
+        return self
+
+    def convert(self, nodal):
+        lib.amrex_b200_boxarray_convert(self.ptr, _i3(nodal))
         check()
         return self
 

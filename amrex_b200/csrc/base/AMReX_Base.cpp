@@ -240,7 +240,8 @@ void BoxArray::intersections (Box const& bx, std::vector<std::pair<int, Box>>& i
     Box gbx = amrex::grow(bx, ng);
     // a nodal query box can touch a cell-keyed bin one further out (role of doiHi, AMReX_BoxArray.H:163)
     gbx.setSmall(gbx.smallEnd() - R.ixtype.ixType());
-    gbx = amrex::enclosedCells(gbx);
+    // coarsened as a box of the array's own index type (AMReX_BoxArray.cpp:1240): a nodal upper bound that sits exactly on a
+    // bin boundary must reach the bin above -- a one-node-thick face plane shared by two boxes is found from both sides
     gbx.coarsen(R.crsn);
     IntVect sm = amrex::max(gbx.smallEnd() - 1, R.bbox.smallEnd());
     IntVect bg = amrex::min(gbx.bigEnd(), R.bbox.bigEnd());

@@ -1,4 +1,5 @@
 #include "AMReX_MultiFab.H"
+#include <cstdio>
 
 #include <cuda_runtime.h>
 #include <nccl.h>
@@ -498,10 +499,21 @@ void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, i
         B200_KCALL(b200mg_copy_tags(P.nsnd, P.d_snd.data(), nullptr, src.d_fabs(), P.sndbuf, ncomp, scomp, dcomp, 0, s));
         ncclComm_t comm = static_cast<ncclComm_t>(ParallelDescriptor::Comm());
         AMREX_ALWAYS_ASSERT_WITH_MESSAGE(comm != nullptr, "multi-rank exchange without an NCCL communicator");
+        if (Gpu::debugSync()) {
+            static long long opno = 0;
+            std::fprintf(stderr, "[comm %lld] rank %d ncomp %d op %d dst ba %llu (%ld boxes, ng %d, type %d%d%d) src ba %llu (%ld boxes): snd_total %lld rcv_total %lld sndbuf %p rcvbuf %p",
+                         opno++, ParallelDescriptor::MyProc(), ncomp, int(op), (unsigned long long)dst.boxArray().id(), long(dst.boxArray().size()), dst.nGrow(),
+                         int(dst.ixType().test(0)), int(dst.ixType().test(1)), int(dst.ixType().test(2)),
+                         (unsigned long long)src.boxArray().id(), long(src.boxArray().size()), P.snd_total, P.rcv_total, (void*)P.sndbuf, (void*)P.rcvbuf);
+            for (auto const& p : P.rcv_peers) { std::fprintf(stderr, " | recv from %d off %lld n %lld", p.rank, p.offset, p.count); }
+            for (auto const& p : P.snd_peers) { std::fprintf(stderr, " | send to %d off %lld n %lld", p.rank, p.offset, p.count); }
+            std::fprintf(stderr, "\n");
+        }
         ncclGroupStart();
         for (auto const& p : P.rcv_peers) { ncclRecv(P.rcvbuf + p.offset * ncomp, p.count * ncomp, ncclDouble, p.rank, comm, s); }
         for (auto const& p : P.snd_peers) { ncclSend(P.sndbuf + p.offset * ncomp, p.count * ncomp, ncclDouble, p.rank, comm, s); }
         ncclGroupEnd();
+        if (Gpu::debugSync()) { Gpu::check(Gpu::debugSyncNow(), "[B200MG_DEBUG_SYNC] ncclSend/ncclRecv group", __FILE__, __LINE__); }
     }
     B200_KCALL(b200mg_copy_tags(P.nloc, P.d_loc.data(), dst.d_fabs(), src.d_fabs(), nullptr, ncomp, scomp, dcomp, int(op), s));
     if (remote) {

@@ -5,6 +5,7 @@
 #include <nccl.h>
 
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -70,6 +71,8 @@ void Finalize ()
 }
 
 bool Initialized () noexcept { return g_gpu_init; }
+bool debugSync () noexcept { static const bool on = std::getenv("B200MG_DEBUG_SYNC") != nullptr; return on; }
+int debugSyncNow () noexcept { return int(cudaDeviceSynchronize()); }
 int deviceId () noexcept { return g_device; }
 cudaStream_t gpuStream () noexcept { return g_override ? g_override : g_stream; }
 cudaStream_t commStream () noexcept { return g_comm_stream; }

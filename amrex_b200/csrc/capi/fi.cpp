@@ -103,6 +103,7 @@ long long amrex_fi_boxarray_numpts (const BoxArray* ba) { return ba->numPts(); }
 int amrex_fi_boxarray_issame (const BoxArray* a, const BoxArray* b) { return *a == *b; }
 void amrex_b200_boxarray_coarsen (BoxArray* ba, int ratio) { FI_VOID( ba->coarsen(ratio); ) }
 void amrex_b200_boxarray_refine (BoxArray* ba, int ratio) { FI_VOID( ba->refine(ratio); ) }
+void amrex_b200_boxarray_convert (BoxArray* ba, const int nodal[3]) { FI_VOID( ba->convert(IntVect(nodal[0], nodal[1], nodal[2])); ) }
 
 // ------------------------------------------------------------------------------ DistributionMapping
 void amrex_fi_new_distromap (DistributionMapping** dm, const BoxArray* ba) { FI_VOID( *dm = new DistributionMapping(*ba); ) }

@@ -72,6 +72,7 @@ long long amrex_fi_boxarray_numpts(const BoxArray* ba);
 int  amrex_fi_boxarray_issame(const BoxArray* baa, const BoxArray* bab);
 void amrex_b200_boxarray_coarsen(BoxArray* ba, int ratio);   /* BoxArray::coarsen */
 void amrex_b200_boxarray_refine(BoxArray* ba, int ratio);
+void amrex_b200_boxarray_convert(BoxArray* ba, const int nodal[3]);   /* BoxArray::convert(IndexType) */
 
 /* ---- DistributionMapping (AMReX_distromap_fi.cpp:9-50) ---- */
 void amrex_fi_new_distromap(DistributionMapping** dm, const BoxArray* ba);

@@ -112,3 +112,37 @@ def test_multirank_tags_are_symmetric():
             tot = sum(vol(t["dbox"]) for r in range(nprocs) for t in ab.fb_tags(ba, dm, 1, cross, (64, 64, 0), r, 0)) \
                 + sum(vol(t["dbox"]) for r in range(nprocs) for t in rcv[r])
             assert tot == tot_serial, (nprocs, cross)
+
+
+# ---- send/recv symmetry of ParallelCopy tags for FACE-centred arrays across an MG agglomeration transition: the
+# one-node-thick face plane on the rank boundary is owned by boxes of both ranks (regression: 2-GPU 512^3 run)
+@pytest.mark.parametrize("nprocs", [2, 4, 8])
+@pytest.mark.parametrize("d", [0, 1, 2])
+def test_cpc_face_symmetry_across_agglomeration(d, nprocs):
+    import amrex_b200 as ab
+    from amrex_b200 import capi
+    ab.Geometry.setup((0., 0., 0.), (1., 1., 1.), (0, 0, 0))
+    nodal = [0, 0, 0]
+    nodal[d] = 1
+    src = ab.BoxArray((0, 0, 0), (127, 127, 127)).maxSize(32)
+    dms = ab.DistributionMapping(src, nprocs=nprocs)
+    src.convert(nodal)
+    src.coarsen(2)
+    dst = ab.BoxArray((0, 0, 0), (63, 63, 63)).maxSize(32)
+    dmd = ab.DistributionMapping(dst, nprocs=nprocs)
+    dst.convert(nodal)
+
+    def vol(b):
+        return (b[3] - b[0] + 1) * (b[4] - b[1] + 1) * (b[5] - b[2] + 1)
+
+    snd = {}
+    rcv = {}
+    covered = 0
+    for me in range(nprocs):
+        for t in capi.cpc_tags(dst, dmd, 0, src, dms, 0, (0, 0, 0), me, 1):
+            snd[(me, t["peer"])] = snd.get((me, t["peer"]), 0) + vol(t["dbox"])
+        for t in capi.cpc_tags(dst, dmd, 0, src, dms, 0, (0, 0, 0), me, 2):
+            rcv[(t["peer"], me)] = rcv.get((t["peer"], me), 0) + vol(t["dbox"])
+        covered += sum(vol(t["dbox"]) for t in capi.cpc_tags(dst, dmd, 0, src, dms, 0, (0, 0, 0), me, 0))
+    assert snd == rcv          # what rank a packs for rank b is exactly what b expects from a
+    assert any(v > 0 for v in snd.values()) or nprocs == 1
