@@ -145,4 +145,5 @@ def test_cpc_face_symmetry_across_agglomeration(d, nprocs):
             rcv[(t["peer"], me)] = rcv.get((t["peer"], me), 0) + vol(t["dbox"])
         covered += sum(vol(t["dbox"]) for t in capi.cpc_tags(dst, dmd, 0, src, dms, 0, (0, 0, 0), me, 0))
     assert snd == rcv          # what rank a packs for rank b is exactly what b expects from a
-    assert any(v > 0 for v in snd.values()) or nprocs == 1
+    if d == 2:   # the SFC split of 2/4/8 ranks always cuts across z: the shared face plane must be exchanged
+        assert any(v > 0 for v in snd.values())
