@@ -68,6 +68,7 @@ _SIGS = {
     "amrex_fi_abeclap_set_bcoeffs": (None, [_P, _I, _PP]),
     "amrex_b200_linop_set_smoother_fusion": (None, [_P, _I]),
     "amrex_b200_linop_set_fused_plan": (None, [_P, _I, _I, _I]),
+    "amrex_b200_linop_set_fused_version": (None, [_P, _I]),
     "amrex_b200_linop_num_mg_levels": (_I, [_P, _I]), "amrex_b200_linop_prepare": (None, [_P]),
     "amrex_b200_linop_make": (None, [_P, _PP, _I, _I, _I]),
     "amrex_b200_linop_smooth": (None, [_P, _I, _I, _P, _P, _I]),
@@ -400,6 +401,9 @@ class MLLinOp(_Obj):
 
     def setSmootherFusion(self, f):
         lib.amrex_b200_linop_set_smoother_fusion(self.ptr, int(f))
+
+    def setFusedVersion(self, v):
+        lib.amrex_b200_linop_set_fused_version(self.ptr, int(v))
 
     def setFusedPlan(self, tile_y=0, chunk_z=0, prefetch=-1):
         lib.amrex_b200_linop_set_fused_plan(self.ptr, int(tile_y), int(chunk_z), int(prefetch))

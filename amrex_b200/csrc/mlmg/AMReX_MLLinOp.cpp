@@ -506,7 +506,7 @@ bool MLLinOp::planFused (LevelData const& L) const
     int nxmax = 0, nymax = 0, nzmax = 0;
     for (int li = 0; li < nl; ++li) {
         Box const& b = L.layout->box(li);
-        if (b.length(0) % 2 != 0 || b.length(0) > 256 || b.length(0) < 16) { return false; }
+        if (b.length(0) % 2 != 0 || b.length(0) > 256 || b.length(0) < 16 || b.length(1) < 2) { return false; }
         nxmax = std::max(nxmax, b.length(0)); nymax = std::max(nymax, b.length(1)); nzmax = std::max(nzmax, b.length(2));
     }
     const int env_ty = m_fused_tile_y, env_cz = m_fused_chunk_z;
@@ -524,6 +524,11 @@ bool MLLinOp::planFused (LevelData const& L) const
         Box const& b = L.layout->box(li);
         for (int k = b.smallEnd(2); k <= b.bigEnd(2); k += chunk_z)
             for (int j = b.smallEnd(1); j <= b.bigEnd(1); j += tile_y) { ht.push_back(b200mg_tile{li, j, k, chunk_z}); }
+    }
+    L.h_vbox.resize(nl);
+    for (int li = 0; li < nl; ++li) {
+        Box const& b = L.layout->box(li);
+        for (int d = 0; d < 3; ++d) { L.h_vbox[li].lo[d] = b.smallEnd(d); L.h_vbox[li].hi[d] = b.bigEnd(d); }
     }
     L.fused_tx = tx; L.fused_tile_y = tile_y; L.fused_chunk_z = chunk_z; L.fused_nblocks = int(ht.size());
     L.fused_tiles.assign(ht);
@@ -1044,6 +1049,13 @@ void MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiF
 {
     LevelData const& L = lev(amrlev, mglev);
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
+    if (m_fused_version >= 3) {
+        auto const& ac = m_a_coeffs[amrlev][mglev]; auto const& bc = m_b_coeffs[amrlev][mglev];
+        B200_KCALL(b200mg_gsrb3(1, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), &ac.desc(0),
+                                &bc[0].desc(0), &bc[1].desc(0), &bc[2].desc(0), L.undrrelxr.h_table(), L.mask.h_table(),
+                                m_a_scalar, dh[0], dh[1], dh[2], L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));
+        return;
+    }
     B200_KCALL(b200mg_gsrb2_abec(L.fused_nblocks, L.fused_tiles.data(), L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
                                  m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(),
                                  m_b_coeffs[amrlev][mglev][2].d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
@@ -1106,6 +1118,12 @@ void MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab con
 {
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    if (m_fused_version >= 3) {
+        B200_KCALL(b200mg_gsrb3(0, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), nullptr,
+                                nullptr, nullptr, nullptr, L.undrrelxr.h_table(), L.mask.h_table(),
+                                0.0, dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));
+        return;
+    }
     B200_KCALL(b200mg_gsrb2_poisson(L.fused_nblocks, L.fused_tiles.data(), L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
                                     L.undrrelxr.d_table(), L.mask.d_table(), dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2],
                                     L.fused_tx, L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));

@@ -269,8 +269,15 @@ def b200_arm(args):
         bpc = GSRB_BYTES_PER_CELL if args.fusion else 44.0
         avg_s = tms / cnt * 1e-3
         achieved = bpc * local_cells / avg_s / 1e9
+        traffic, traffic_src = None, None
+        try:   # measured DRAM bytes per launch of this kernel from the committed ncu capture (same cell count only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(kern)
+            if tj and tj["cells"] == local_cells:
+                traffic, traffic_src = tj["bytes"], tj["source"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": kern + " (finest MG level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_cell": bpc,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_cell": bpc,
                     "cells_per_launch": local_cells, "launches": cnt, "avg_launch_ms": tms / cnt,
                     "share_of_solve_kernel_time": tms / tot_ms if tot_ms > 0 else None}
     by_kernel = {}

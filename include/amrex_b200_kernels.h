@@ -113,6 +113,15 @@ int b200mg_gsrb2_poisson(int nblocks, const b200mg_tile* tiles, const b200mg_box
                          const b200mg_fab* phi_in, const b200mg_fab* phi_out, const b200mg_fab* rhs,
                          const b200mg_fab* f, const b200mg_ifab* m,
                          double dhx, double dhy, double dhz, int tx, int tile_y, int chunk_z, cudaStream_t s);
+/* Third-generation fused pass (same results): the descriptor tables are HOST arrays (one entry per local box; f / m:
+ * [box*6+face]); they travel to the device as kernel parameters, <= 64 boxes per launch.  abec == 0: Poisson.
+ * Requirements: every box has an even x extent with 4 <= nx <= 256, ny >= 2, (nx/2 rounded up to 32)*(tile_y+4) <= 1024;
+ * rhs and a share a layout. */
+int b200mg_gsrb3(int abec, int nboxes, const b200mg_box* h_vbox,
+                 const b200mg_fab* h_phi_in, const b200mg_fab* h_phi_out, const b200mg_fab* h_rhs, const b200mg_fab* h_a,
+                 const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
+                 const b200mg_fab* h_f, const b200mg_ifab* h_m,
+                 double alpha, double dhx, double dhy, double dhz, int tile_y, int chunk_z, cudaStream_t s);
 /* L2 prefetch distance (planes ahead of the loads) of the fused pass; 0 switches the prefetch off */
 void b200mg_set_gsrb2_prefetch(int planes);
 /* black (redblack=1) or red sweep restricted to the 1-cell surface shell of every box */

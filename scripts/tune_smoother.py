@@ -51,6 +51,9 @@ def kernel_ms(name):
         op.smooth(0, 0, x, b)
     rep = ab.profile_report()
     ab.profile_enable(False)
+    if name is None:
+        names = sorted(set(q[0] for q in rep))
+        return {nm: sum(q[3] for q in rep if q[0] == nm) / sum(q[2] for q in rep if q[0] == nm) for nm in names}
     r = [q for q in rep if q[0] == name]
     return (sum(q[3] for q in r) / sum(q[2] for q in r)) if r else None
 
@@ -71,14 +74,18 @@ if os.environ.get("TUNE_SKIP_FUSED"):
     sys.exit(0)
 
 op.setSmootherFusion(1)
-grid = list(itertools.product([4, 8, 12], [32, 128], [0, 2, 4]))
+ab.lib.b200mg_set_gsrb_lean_occupancy(4)
+grid = [(3, 4, 128), (3, 8, 128), (3, 12, 128), (3, 8, 32), (3, 8, 64), (2, 8, 128)]
 if os.environ.get("TUNE_GRID"):
     grid = [tuple(int(v) for v in g.split(",")) for g in os.environ["TUNE_GRID"].split(";")]
-for ty, cz, pf in grid:
-    op.setFusedPlan(ty, cz, pf)
+for ver, ty, cz in grid:
+    op.setFusedVersion(ver)
+    op.setFusedPlan(ty, cz, 0)
     ms = time_smooth()
-    k = kernel_ms("b200mg_gsrb2_abec")
+    km = kernel_ms(None)
+    k = km.get("b200mg_gsrb3" if ver >= 3 else "b200mg_gsrb2_abec")
+    sh = km.get("b200mg_gsrb_shell_abec")
     same = (x.norm0() == ref)
-    out.append(dict(variant=f"fused ty={ty} cz={cz} pf={pf}", ms_per_smooth=ms, kernel_ms=k,
+    out.append(dict(variant=f"fused v{ver} ty={ty} cz={cz}", ms_per_smooth=ms, kernel_ms=k, shell_ms=sh,
                     kernel_gbs_56=56.0 * cells / (k * 1e-3) / 1e9 if k else None, same_norm_as_pair=bool(same)))
     print(json.dumps(out[-1]), flush=True)
