@@ -146,7 +146,7 @@ k_gsrb2 (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ v
         }
     };
     auto store_plane = [&] (double* s, const double2& v, double vl, double vr) {
-        *reinterpret_cast<double2*>(s + srow) = v;
+        if (row_load) { *reinterpret_cast<double2*>(s + srow) = v; }   // idle lanes must not touch the ghost column
         if (gl) { s[srow - 1] = vl; }
         if (gr) { s[srow + 2] = vr; }
     };

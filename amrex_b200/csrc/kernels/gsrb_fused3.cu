@@ -162,7 +162,8 @@ fused_step (const FusedParams& P, const FusedBox& B, int kk, int k0, int k1, int
     }
 
     // ---- old plane kk+2 into the free buffer for the next step's red phase, rotate, advance
-    *reinterpret_cast<double2*>(sC + srow) = pp2;
+    // (only lanes that own cells store: with nx < 2*blockDim.x the first idle lane's pair would land on the ghost column)
+    if (row_load) { *reinterpret_cast<double2*>(sC + srow) = pp2; }
     if (first) { sC[srow - 1] = g2; }
     if (last) { sC[srow + 2] = g2; }
     pm1 = pk; pk = pp1; pp1 = pp2; pp2 = nq; g2 = gq;
@@ -229,7 +230,7 @@ k_gsrb3 (const __grid_constant__ FusedParams P)
     double g0, g1, g2;
     load_at(k0 - 2, pk, g0);
     load_at(k0 - 1, pp1, g1);
-    *reinterpret_cast<double2*>(sB + srow) = pp1;
+    if (row_load) { *reinterpret_cast<double2*>(sB + srow) = pp1; }
     if (first) { sB[srow - 1] = g1; }
     if (last) { sB[srow + 2] = g1; }
     load_at(k0, pp2, g2);
