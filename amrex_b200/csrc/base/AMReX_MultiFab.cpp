@@ -1,5 +1,6 @@
 #include "AMReX_MultiFab.H"
 #include <cstdio>
+#include <cstdlib>
 
 #include <cuda_runtime.h>
 #include <nccl.h>
@@ -447,6 +448,7 @@ struct CommPlan {
     long long snd_total = 0, rcv_total = 0;
     double *sndbuf = nullptr, *rcvbuf = nullptr;
     long long buf_ncomp = 0;
+    cudaEvent_t ev_packed = nullptr, ev_arrived = nullptr;
     ~CommPlan () { if (sndbuf) { The_Arena()->free(sndbuf); } if (rcvbuf) { The_Arena()->free(rcvbuf); } }
 };
 
@@ -483,10 +485,15 @@ void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc)
     P.rcv_total = off; P.nrcv = int(h.size()); P.d_rcv.assign(h);
 }
 
+// Halo exchange of one plan.  The NVLink transfer (grouped ncclSend/ncclRecv on the communication stream) runs concurrently
+// with the intra-GPU copies on the compute stream: pack -> [event] -> send/recv on commStream, local copies meanwhile on
+// gpuStream, then gpuStream waits for the transfer and unpacks (FillBoundary_nowait / FillBoundary_finish of the
+// reference, AMReX_FabArrayCommI.H:8-247, with the local copies in between as in FBEP_nowait :118-135).
 void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op)
 {
     cudaStream_t s = Gpu::gpuStream();
     const bool remote = (P.snd_total + P.rcv_total) > 0;
+    static const bool overlap = std::getenv("B200MG_NO_COMM_OVERLAP") == nullptr;
     if (remote) {
         if (P.buf_ncomp < ncomp) {
             Gpu::streamSynchronize();
@@ -496,27 +503,38 @@ void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, i
             P.buf_ncomp = ncomp;
         }
         AMREX_ALWAYS_ASSERT_WITH_MESSAGE(ncomp == 1, "remote halo exchange implemented for ncomp == 1");
+        if (!P.ev_packed) {
+            AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&P.ev_packed, cudaEventDisableTiming));
+            AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&P.ev_arrived, cudaEventDisableTiming));
+        }
         B200_KCALL(b200mg_copy_tags(P.nsnd, P.d_snd.data(), nullptr, src.d_fabs(), P.sndbuf, ncomp, scomp, dcomp, 0, s));
         ncclComm_t comm = static_cast<ncclComm_t>(ParallelDescriptor::Comm());
         AMREX_ALWAYS_ASSERT_WITH_MESSAGE(comm != nullptr, "multi-rank exchange without an NCCL communicator");
+        cudaStream_t cs = overlap ? Gpu::commStream() : s;
+        if (overlap) {
+            AMREX_CUDA_SAFE_CALL(cudaEventRecord(P.ev_packed, s));
+            AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(cs, P.ev_packed, 0));
+        }
         if (Gpu::debugSync()) {
             static long long opno = 0;
-            std::fprintf(stderr, "[comm %lld] rank %d ncomp %d op %d dst ba %llu (%ld boxes, ng %d, type %d%d%d) src ba %llu (%ld boxes): snd_total %lld rcv_total %lld sndbuf %p rcvbuf %p",
+            std::fprintf(stderr, "[comm %lld] rank %d ncomp %d op %d dst ba %llu (%ld boxes, ng %d, type %d%d%d) src ba %llu (%ld boxes): snd_total %lld rcv_total %lld",
                          opno++, ParallelDescriptor::MyProc(), ncomp, int(op), (unsigned long long)dst.boxArray().id(), long(dst.boxArray().size()), dst.nGrow(),
                          int(dst.ixType().test(0)), int(dst.ixType().test(1)), int(dst.ixType().test(2)),
-                         (unsigned long long)src.boxArray().id(), long(src.boxArray().size()), P.snd_total, P.rcv_total, (void*)P.sndbuf, (void*)P.rcvbuf);
+                         (unsigned long long)src.boxArray().id(), long(src.boxArray().size()), P.snd_total, P.rcv_total);
             for (auto const& p : P.rcv_peers) { std::fprintf(stderr, " | recv from %d off %lld n %lld", p.rank, p.offset, p.count); }
             for (auto const& p : P.snd_peers) { std::fprintf(stderr, " | send to %d off %lld n %lld", p.rank, p.offset, p.count); }
             std::fprintf(stderr, "\n");
         }
         ncclGroupStart();
-        for (auto const& p : P.rcv_peers) { ncclRecv(P.rcvbuf + p.offset * ncomp, p.count * ncomp, ncclDouble, p.rank, comm, s); }
-        for (auto const& p : P.snd_peers) { ncclSend(P.sndbuf + p.offset * ncomp, p.count * ncomp, ncclDouble, p.rank, comm, s); }
+        for (auto const& p : P.rcv_peers) { ncclRecv(P.rcvbuf + p.offset * ncomp, p.count * ncomp, ncclDouble, p.rank, comm, cs); }
+        for (auto const& p : P.snd_peers) { ncclSend(P.sndbuf + p.offset * ncomp, p.count * ncomp, ncclDouble, p.rank, comm, cs); }
         ncclGroupEnd();
+        if (overlap) { AMREX_CUDA_SAFE_CALL(cudaEventRecord(P.ev_arrived, cs)); }
         if (Gpu::debugSync()) { Gpu::check(Gpu::debugSyncNow(), "[B200MG_DEBUG_SYNC] ncclSend/ncclRecv group", __FILE__, __LINE__); }
     }
     B200_KCALL(b200mg_copy_tags(P.nloc, P.d_loc.data(), dst.d_fabs(), src.d_fabs(), nullptr, ncomp, scomp, dcomp, int(op), s));
     if (remote) {
+        if (overlap) { AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(s, P.ev_arrived, 0)); }
         B200_KCALL(b200mg_copy_tags(P.nrcv, P.d_rcv.data(), dst.d_fabs(), nullptr, P.rcvbuf, ncomp, scomp, dcomp, int(op), s));
     }
 }
