@@ -69,6 +69,7 @@ _SIGS = {
     "amrex_b200_linop_set_smoother_fusion": (None, [_P, _I]),
     "amrex_b200_linop_set_fused_plan": (None, [_P, _I, _I, _I]),
     "amrex_b200_linop_set_fused_version": (None, [_P, _I]),
+    "amrex_b200_set_fused4_plan": (_I, [_I, _I, _I]),
     "amrex_b200_linop_num_mg_levels": (_I, [_P, _I]), "amrex_b200_linop_prepare": (None, [_P]),
     "amrex_b200_linop_make": (None, [_P, _PP, _I, _I, _I]),
     "amrex_b200_linop_smooth": (None, [_P, _I, _I, _P, _P, _I]),

@@ -1049,6 +1049,19 @@ void MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiF
 {
     LevelData const& L = lev(amrlev, mglev);
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
+    if (m_fused_version >= 4 && L.fused4_ok != 0) {
+        auto const& ac = m_a_coeffs[amrlev][mglev]; auto const& bc = m_b_coeffs[amrlev][mglev];
+        int e;
+        {
+            Gpu::KernelScope ks__("b200mg_gsrb4(abec)");
+            e = b200mg_gsrb4(1, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), &ac.desc(0),
+                             &bc[0].desc(0), &bc[1].desc(0), &bc[2].desc(0), L.undrrelxr.h_table(), L.mask.h_table(),
+                             m_a_scalar, dh[0], dh[1], dh[2], Gpu::gpuStream());
+        }
+        if (e == 0) { return; }
+        if (e != int(cudaErrorInvalidValue)) { Gpu::check(e, "b200mg_gsrb4", __FILE__, __LINE__); }
+        L.fused4_ok = 0;                                // layout not eligible for the bulk-copy pass: generation 3 from now on
+    }
     if (m_fused_version >= 3) {
         auto const& ac = m_a_coeffs[amrlev][mglev]; auto const& bc = m_b_coeffs[amrlev][mglev];
         B200_KCALL(b200mg_gsrb3(1, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), &ac.desc(0),
@@ -1118,6 +1131,18 @@ void MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab con
 {
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    if (m_fused_version >= 4 && L.fused4_ok != 0) {
+        int e;
+        {
+            Gpu::KernelScope ks__("b200mg_gsrb4(poisson)");
+            e = b200mg_gsrb4(0, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), nullptr,
+                             nullptr, nullptr, nullptr, L.undrrelxr.h_table(), L.mask.h_table(),
+                             0.0, dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream());
+        }
+        if (e == 0) { return; }
+        if (e != int(cudaErrorInvalidValue)) { Gpu::check(e, "b200mg_gsrb4", __FILE__, __LINE__); }
+        L.fused4_ok = 0;
+    }
     if (m_fused_version >= 3) {
         B200_KCALL(b200mg_gsrb3(0, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), nullptr,
                                 nullptr, nullptr, nullptr, L.undrrelxr.h_table(), L.mask.h_table(),

@@ -136,7 +136,9 @@ void amrex_b200_new_linop(MLLinOp** linop, int kind /*0 abeclap, 1 poisson*/, in
 void amrex_b200_linop_set_smoother_fusion(MLLinOp* linop, int fuse);   /* 0: reference schedule, 1: fused colours */
 /* launch plan of the fused smoother: rows / planes per CTA tile (<= 0: automatic), L2 prefetch distance in planes (< 0: keep) */
 void amrex_b200_linop_set_fused_plan(MLLinOp* linop, int tile_y, int chunk_z, int prefetch_planes);
-void amrex_b200_linop_set_fused_version(MLLinOp* linop, int version);   /* 2: tile-table kernel, 3 (default): kernel-parameter descriptors */
+void amrex_b200_linop_set_fused_version(MLLinOp* linop, int version);   /* 2: tile-table kernel, 3: kernel-parameter descriptors, 4: bulk-async-copy staged pass */
+/* launch plan of the generation-4 fused pass (process-wide): rows per CTA tile, EARLY / LATE ring depths; 0 = accepted */
+int amrex_b200_set_fused4_plan(int tile_y, int early_stages, int late_stages);
 /* primitives of the operator on (amrlev 0, mglev), exposed for parity tests (MLCellLinOp::smooth/apply/...) */
 int  amrex_b200_linop_num_mg_levels(const MLLinOp* linop, int amrlev);
 void amrex_b200_linop_prepare(MLLinOp* linop);

@@ -122,6 +122,19 @@ int b200mg_gsrb3(int abec, int nboxes, const b200mg_box* h_vbox,
                  const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
                  const b200mg_fab* h_f, const b200mg_ifab* h_m,
                  double alpha, double dhx, double dhy, double dhz, int tile_y, int chunk_z, cudaStream_t s);
+/* Fourth-generation fused pass (same results, same descriptor tables as b200mg_gsrb3): every operand plane is staged
+ * into a shared-memory ring by 1-D bulk async copies (TMA engine, mbarrier transaction counts) several planes ahead of
+ * its use by a dedicated producer warp; compute warps read shared memory only.  Whole-z CTAs of (all x) x tile_y rows.
+ * Requirements: even x extent, 4 <= nx <= 128, ny >= 2, rows 16-byte aligned at the first valid cell, even strides,
+ * phi rows readable on [lo-2, hi+2], bx rows nx+2 doubles long (all guaranteed by the FabArray allocator);
+ * cudaErrorInvalidValue otherwise (the caller falls back to b200mg_gsrb3). */
+int b200mg_gsrb4(int abec, int nboxes, const b200mg_box* h_vbox,
+                 const b200mg_fab* h_phi_in, const b200mg_fab* h_phi_out, const b200mg_fab* h_rhs, const b200mg_fab* h_a,
+                 const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
+                 const b200mg_fab* h_f, const b200mg_ifab* h_m,
+                 double alpha, double dhx, double dhy, double dhz, cudaStream_t s);
+/* launch plan of b200mg_gsrb4: rows per CTA tile and ring depths; (8,4,3) default, (8,5,2), (8,4,2), (4,6,4), (4,5,3), (4,4,2) */
+int b200mg_set_gsrb4_plan(int tile_y, int early_stages, int late_stages);
 /* L2 prefetch distance (planes ahead of the loads) of the fused pass; 0 switches the prefetch off */
 void b200mg_set_gsrb2_prefetch(int planes);
 /* black (redblack=1) or red sweep restricted to the 1-cell surface shell of every box */
