@@ -153,13 +153,38 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
        int prow, int crow, int xrow, int& out_cur,
        double& zlo_b, double2& pk, double2& pp1, double& bzm_b, double2& bz1, Carry& cb, int& xmk, double& xf)
 {
-    // x-face relaxation coefficient of this step's red cell (first / last lane only), fetched during the previous step;
-    // fetch the next step's (pair position 1-C: low face for 1-C == 0) now so the global load never sits on the critical path
+    // The arithmetic below is straight-line code executed by EVERY thread (threads without a cell to update compute on
+    // whatever their in-range shared-memory addresses hold and only their stores are predicated): the two dependent
+    // chains of a step - the black cell's divide and partial sums, which do not depend on this step's red result, and
+    // the red update - then sit in the same scheduling region and overlap.
+    const bool do_red = row_red && (t + 1 <= nz);
+    const bool do_black = row_black && (t >= 1);
+
+    // ---- rare, warp-uniform: face relaxation coefficients (AMReX_MLABecLap_3D_K.H:228-245) of red cells on the y / z
+    //      box surface, global slab lookups; the x faces (first / last lane of every row) are fetched one step ahead
     const int xmk_now = xmk; const double xf_now = xf;
     if (((C == 1) ? first : last) && row_red && t + 2 <= nz) {
         const int xs = jrel + (t + 1) * (B.hi[1] - B.lo[1] + 1);         // x slabs: 1 x ny x nz
         xmk = B.m[C ? 0 : 3][xs]; xf = B.f[C ? 0 : 3][xs];
     }
+    const int kr_rel = t;                                                // red plane - lo_z
+    const bool klo = (kr_rel == 0), khi = (kr_rel == nz - 1);
+    const bool yz_surface = do_red && (jlo || jhi || klo || khi);
+    double cf1 = 0.0, cf2 = 0.0, cf4 = 0.0, cf5 = 0.0;
+    if (yz_surface) {
+        const int nx = B.hi[0] - B.lo[0] + 1;
+        const int ys = tx2 + C + kr_rel * nx;                            // y slabs: nx x 1 x nz
+        if (jlo) { const int mk = B.m[1][ys]; const double f = B.f[1][ys]; cf1 = (mk > 0) ? f : 0.0; }
+        if (jhi) { const int mk = B.m[4][ys]; const double f = B.f[4][ys]; cf4 = (mk > 0) ? f : 0.0; }
+        if (klo || khi) {
+            const int zo = (tx2 + C) + jrel * nx;
+            if (klo) { const int mk = B.m[2][zo]; const double f = B.f[2][zo]; cf2 = (mk > 0) ? f : 0.0; }
+            if (khi) { const int mk = B.m[5][zo]; const double f = B.f[5][zo]; cf5 = (mk > 0) ? f : 0.0; }
+        }
+    }
+    double cf0 = 0.0, cf3 = 0.0;
+    if (C == 0) { cf0 = (first && xmk_now > 0) ? xf_now : 0.0; } else { cf3 = (last && xmk_now > 0) ? xf_now : 0.0; }
+
     // ---- operands that land during this step's first use
     const uint32_t s0 = R.s0(t), s1 = R.s1(t), s2 = R.s2(t), sl = R.l(t);
     if (t + 2 <= nz + 1) { mbar_wait(barE + 8u * s2, R.par2(t)); }
@@ -169,121 +194,109 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
     double* __restrict__ e0 = smE + s0 * Y.e_size;
     const double* __restrict__ l1 = smL + sl * Y.l_size;
 
-    // plane t+2: the red update needs the cell above it and the z face above it now; the full pairs are read at the
-    // end of the step (shorter live ranges: the CTA runs at the register limit)
-    double zhi_r = 0.0, bzp_r = 0.0;
-    const bool have2 = row_load && (t + 2 <= nz + 1);
-    if (have2) {
-        zhi_r = e2[Y.e_phi + prow + C];
-        if constexpr (ABEC) { if (row_red) { bzp_r = e2[Y.e_bz + crow + C]; } }
-    }
-    const bool do_red = row_red && (t + 1 <= nz);
-    const bool do_black = row_black && (t >= 1);
-    Carry nb = cb;
-
-    // ---- red update of plane t+1, in place in EARLY[t+1].phi and pp1
-    if (do_red) {
-        double r_rhs, r_a = 0, r_bxm = 0, r_bxp = 0, r_bym = 0, r_byp = 0, r_bzm = 0, r_bzp = 0;
-        {
-            const double2 v = *reinterpret_cast<const double2*>(l1 + Y.l_rhs + crow);
-            r_rhs = C ? v.y : v.x; nb.rhs = C ? v.x : v.y;
-        }
+    // ---- black cell of plane t, part 1: everything that does not need the red value above it (computed below).
+    //      New red values on five sides: EARLY[t].phi in x / y (written during step t-1), zlo_b below.
+    const double pb = C ? pk.y : pk.x;
+    double b_q, b_part, b_w = 0.0, b_gp = 0.0, b_bzp = 0.0;
+    const double b_rhs = cb.rhs;
+    {
+        const double* sb = e0 + Y.e_phi + prow + C;
+        const double xm = C ? pk.x : sb[-1];
+        const double xp = C ? sb[1] : pk.y;
+        const double ym = sb[-Y.PS], yp = sb[Y.PS];
         if constexpr (ABEC) {
+            const double b_bzm = bzm_b;
+            b_bzp = C ? bz1.y : bz1.x;
+            const double gamma = P.alpha * cb.a + P.dhx * (cb.bxm + cb.bxp) + P.dhy * (cb.bym + cb.byp) + P.dhz * (b_bzm + b_bzp);
+            b_q = kOmega / gamma;
+            b_part = P.dhx * (cb.bxm * xm + cb.bxp * xp) + P.dhy * (cb.bym * ym + cb.byp * yp);
+            b_w = b_bzm * zlo_b;
+            b_gp = gamma * pb;
+        } else {
+            const double gamma = -2.0 * (P.dhx + P.dhy + P.dhz);
+            b_q = kOmega / gamma;
+            b_part = b_rhs - gamma * pb - P.dhx * (xm + xp) - P.dhy * (ym + yp);
+        }
+    }
+
+    // ---- red update of plane t+1, in place in EARLY[t+1].phi and pp1; the coefficient pairs are read once, the black
+    //      halves are carried to the next step
+    const double zhi_r = e2[Y.e_phi + prow + C];
+    double* sr = e1 + Y.e_phi + prow + C;
+    const double pr = C ? pp1.y : pp1.x;
+    double vr;
+    {
+        const double xm = C ? pp1.x : sr[-1];
+        const double xp = C ? sr[1] : pp1.y;
+        const double ym = sr[-Y.PS], yp = sr[Y.PS];
+        const double zlo = C ? pk.y : pk.x;
+        const double2 vrhs = *reinterpret_cast<const double2*>(l1 + Y.l_rhs + crow);
+        const double r_rhs = C ? vrhs.y : vrhs.x;
+        const double n_rhs = C ? vrhs.x : vrhs.y;
+        if constexpr (ABEC) {
+            const double bzp_r = e2[Y.e_bz + crow + C];
             const double2 va = *reinterpret_cast<const double2*>(l1 + Y.l_a + crow);
             const double2 vx = *reinterpret_cast<const double2*>(l1 + Y.l_bx + xrow);
             const double vx2 = l1[Y.l_bx + xrow + 2];
             const double2 vy0 = *reinterpret_cast<const double2*>(l1 + Y.l_by + crow);
             const double2 vy1 = *reinterpret_cast<const double2*>(l1 + Y.l_by + crow + Y.NX);
-            r_a = C ? va.y : va.x;       nb.a = C ? va.x : va.y;
-            r_bxm = C ? vx.y : vx.x;     r_bxp = C ? vx2 : vx.y;
-            nb.bxm = C ? vx.x : vx.y;    nb.bxp = C ? vx.y : vx2;
-            r_bym = C ? vy0.y : vy0.x;   nb.bym = C ? vy0.x : vy0.y;
-            r_byp = C ? vy1.y : vy1.x;   nb.byp = C ? vy1.x : vy1.y;
-            r_bzm = C ? bz1.y : bz1.x;   r_bzp = bzp_r;
-        }
-        double* s = e1 + Y.e_phi + prow + C;
-        const double p = C ? pp1.y : pp1.x;
-        const double xm = C ? pp1.x : s[-1];
-        const double xp = C ? s[1] : pp1.y;
-        const double ym = s[-Y.PS], yp = s[Y.PS];
-        const double zlo = C ? pk.y : pk.x, zhi = zhi_r;
-        // face relaxation coefficients (AMReX_MLABecLap_3D_K.H:228-245), global slab lookups on the box surface only
-        const int kr_rel = t;                                    // red plane - lo_z
-        const int nx = B.hi[0] - B.lo[0] + 1;
-        double cf0 = 0.0, cf3 = 0.0;
-        if ((C == 0) ? first : last) {
-            if (C == 0) { cf0 = (xmk_now > 0) ? xf_now : 0.0; } else { cf3 = (xmk_now > 0) ? xf_now : 0.0; }
-        }
-        const bool klo = (kr_rel == 0), khi = (kr_rel == nz - 1);
-        const bool yz_surface = jlo || jhi || klo || khi;        // warp-uniform
-        double cf1 = 0.0, cf2 = 0.0, cf4 = 0.0, cf5 = 0.0;
-        if (yz_surface) {
-            const int ys = tx2 + C + kr_rel * nx;                // y slabs: nx x 1 x nz
-            if (jlo) { const int mk = B.m[1][ys]; const double f = B.f[1][ys]; cf1 = (mk > 0) ? f : 0.0; }
-            if (jhi) { const int mk = B.m[4][ys]; const double f = B.f[4][ys]; cf4 = (mk > 0) ? f : 0.0; }
-            if (klo || khi) {
-                const int zo = (tx2 + C) + jrel * nx;
-                if (klo) { const int mk = B.m[2][zo]; const double f = B.f[2][zo]; cf2 = (mk > 0) ? f : 0.0; }
-                if (khi) { const int mk = B.m[5][zo]; const double f = B.f[5][zo]; cf5 = (mk > 0) ? f : 0.0; }
-            }
-        }
-        double v;
-        if constexpr (ABEC) {
+            const double r_a = C ? va.y : va.x;
+            const double r_bxm = C ? vx.y : vx.x, r_bxp = C ? vx2 : vx.y;
+            const double r_bym = C ? vy0.y : vy0.x, r_byp = C ? vy1.y : vy1.x;
+            const double r_bzm = C ? bz1.y : bz1.x, r_bzp = bzp_r;
             const double gamma = P.alpha * r_a + P.dhx * (r_bxm + r_bxp) + P.dhy * (r_bym + r_byp) + P.dhz * (r_bzm + r_bzp);
             double corr = P.dhx * (r_bxm * cf0 + r_bxp * cf3);
             if (yz_surface) { corr = corr + P.dhy * (r_bym * cf1 + r_byp * cf4) + P.dhz * (r_bzm * cf2 + r_bzp * cf5); }
             const double g_m_d = gamma - corr;
-            const double rho = P.dhx * (r_bxm * xm + r_bxp * xp) + P.dhy * (r_bym * ym + r_byp * yp) + P.dhz * (r_bzm * zlo + r_bzp * zhi);
-            const double res = r_rhs - (gamma * p - rho);
-            v = p + kOmega / g_m_d * res;
+            const double rho = P.dhx * (r_bxm * xm + r_bxp * xp) + P.dhy * (r_bym * ym + r_byp * yp) + P.dhz * (r_bzm * zlo + r_bzp * zhi_r);
+            const double res = r_rhs - (gamma * pr - rho);
+            vr = pr + kOmega / g_m_d * res;
+            if (do_red) {
+                cb.rhs = n_rhs; cb.a = C ? va.x : va.y;
+                cb.bxm = C ? vx.x : vx.y; cb.bxp = C ? vx.y : vx2;
+                cb.bym = C ? vy0.x : vy0.y; cb.byp = C ? vy1.x : vy1.y;
+            }
         } else {
             const double gamma = -2.0 * (P.dhx + P.dhy + P.dhz);
             double g_m_d = gamma + P.dhx * (cf0 + cf3);
             if (yz_surface) { g_m_d = g_m_d + P.dhy * (cf1 + cf4) + P.dhz * (cf2 + cf5); }
-            const double res = r_rhs - gamma * p - P.dhx * (xm + xp) - P.dhy * (ym + yp) - P.dhz * (zlo + zhi);
-            v = p + kOmega / g_m_d * res;
+            const double res = r_rhs - gamma * pr - P.dhx * (xm + xp) - P.dhy * (ym + yp) - P.dhz * (zlo + zhi_r);
+            vr = pr + kOmega / g_m_d * res;
+            if (do_red) { cb.rhs = n_rhs; }
         }
-        if (C) { pp1.y = v; } else { pp1.x = v; }
-        s[0] = v;
+    }
+    if (do_red) {
+        if (C) { pp1.y = vr; } else { pp1.x = vr; }
+        sr[0] = vr;
     }
 
-    // ---- black update of plane t (new red values on all six sides: EARLY[t].phi in x / y, pm1 / pp1 in z); box-surface
-    //      cells pass through unchanged and are finished by the shell kernel after the second halo refresh
+    // ---- black cell of plane t, part 2 (needs the red value above: pp1); box-surface cells pass through unchanged and
+    //      are finished by the shell kernel after the second halo refresh
     if (do_black) {
-        double2 out = pk;
         const int kb_rel = t - 1;                                // black plane - lo_z
         const bool surf_b = jlo || jhi || (C ? last : first) || (kb_rel == 0) || (kb_rel == nz - 1);
-        if (!surf_b) {
-            const double* s = e0 + Y.e_phi + prow + C;
-            const double p = C ? pk.y : pk.x;
-            const double xm = C ? pk.x : s[-1];
-            const double xp = C ? s[1] : pk.y;
-            const double ym = s[-Y.PS], yp = s[Y.PS];
-            const double zlo = zlo_b, zhi = C ? pp1.y : pp1.x;
-            double v;
-            if constexpr (ABEC) {
-                const double b_bzm = bzm_b, b_bzp = C ? bz1.y : bz1.x;
-                const double gamma = P.alpha * cb.a + P.dhx * (cb.bxm + cb.bxp) + P.dhy * (cb.bym + cb.byp) + P.dhz * (b_bzm + b_bzp);
-                const double rho = P.dhx * (cb.bxm * xm + cb.bxp * xp) + P.dhy * (cb.bym * ym + cb.byp * yp) + P.dhz * (b_bzm * zlo + b_bzp * zhi);
-                const double res = cb.rhs - (gamma * p - rho);
-                v = p + kOmega / gamma * res;
-            } else {
-                const double gamma = -2.0 * (P.dhx + P.dhy + P.dhz);
-                const double res = cb.rhs - gamma * p - P.dhx * (xm + xp) - P.dhy * (ym + yp) - P.dhz * (zlo + zhi);
-                v = p + kOmega / gamma * res;
-            }
-            if (C) { out.y = v; } else { out.x = v; }
+        const double zhi = C ? pp1.y : pp1.x;
+        double vb;
+        if constexpr (ABEC) {
+            const double rho = b_part + P.dhz * (b_w + b_bzp * zhi);
+            const double res = b_rhs - (b_gp - rho);
+            vb = pb + b_q * res;
+        } else {
+            const double res = b_part - P.dhz * (zlo_b + zhi);
+            vb = pb + b_q * res;
         }
+        double2 out = pk;
+        if (!surf_b) { if (C) { out.y = vb; } else { out.x = vb; } }
         *reinterpret_cast<double2*>(B.pout.p + out_cur) = out;
         out_cur += B.pout.ks;
     }
 
-    // ---- rotate, advance; generic-proxy accesses of the slots freed by this step are ordered before the producer's refill
+    // ---- rotate, advance; generic-proxy accesses of the slots freed by this step are ordered before the refill
     // (the next step works at pair position 1-C: its black cell needs the red value below it and the z face below it)
     zlo_b = C ? pk.x : pk.y; bzm_b = C ? bz1.x : bz1.y;
-    pk = pp1; cb = nb;
+    pk = pp1;
     pp1 = make_double2(0.0, 0.0); bz1 = pp1;
-    if (have2) {
+    if (row_load && (t + 2 <= nz + 1)) {
         pp1 = *reinterpret_cast<const double2*>(e2 + Y.e_phi + prow);
         if constexpr (ABEC) { if (row_red) { bz1 = *reinterpret_cast<const double2*>(e2 + Y.e_bz + crow); } }
     }
@@ -370,9 +383,10 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
     const bool row_black = xact && (ty >= 1) && (j <= j1);
     const bool first = (tx == 0), last = (i0 + 1 == B.hi[0]);
     const bool jlo = (j == B.lo[1]), jhi = (j == B.hi[1]);
-    const int prow = (ty + 1) * Y.PS + 2 * tx + 2;                 // own pair inside a phi plane
-    const int crow = ty * Y.NX + 2 * tx;                           // ... inside rhs / a / by / bz planes
-    const int xrow = ty * Y.XS + 2 * tx;                           // ... inside a bx plane
+    const int txe = xact ? tx : 0;                                 // idle lanes compute on in-range addresses (see step4)
+    const int prow = (ty + 1) * Y.PS + 2 * txe + 2;                // own pair inside a phi plane
+    const int crow = ty * Y.NX + 2 * txe;                          // ... inside rhs / a / by / bz planes
+    const int xrow = ty * Y.XS + 2 * txe;                          // ... inside a bx plane
 
     int out_cur = (i0 - B.glo_out[0]) + (j - B.glo_out[1]) * B.pout.js + (B.lo[2] - B.glo_out[2]) * B.pout.ks;
     const int tx2 = 2 * tx, jrel = j - B.lo[1];
@@ -406,7 +420,7 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
 #undef B200MG_STEP4
 }
 
-int g_plan_ty = 8, g_plan_se = 4, g_plan_sl = 3;                   // launch plan (b200mg_set_gsrb4_plan)
+int g_plan_ty = 8, g_plan_se = 4, g_plan_sl = 2;                   // launch plan (b200mg_set_gsrb4_plan)
 
 template <bool ABEC, int TY, int SE, int SL>
 int launch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
@@ -461,7 +475,7 @@ bool aligned16 (const double* p) { return (reinterpret_cast<uintptr_t>(p) & 15u)
 extern "C" {
 
 // launch plan of the fourth-generation fused pass: rows per CTA tile (4 or 8) and ring depths (EARLY, LATE);
-// supported: (8,4,3) default, (8,4,2), (6,5,3), (6,4,4), (6,4,2), (4,6,4), (4,4,4).  Returns 0 when the combination exists.
+// supported: (8,4,2) default, (8,4,3), (6,5,3), (6,4,4), (6,4,2), (4,6,4), (4,4,4).  Returns 0 when the combination exists.
 int b200mg_set_gsrb4_plan (int tile_y, int early_stages, int late_stages)
 {
     const int key = tile_y * 100 + early_stages * 10 + late_stages;

@@ -109,7 +109,9 @@ k_gsrb_poisson (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restr
 // Surface shell sweep: blockIdx.x = box*6 + face, blockIdx.y = chunk of the face; every shell cell belongs to exactly one
 // face (x faces own their edges/corners, y faces exclude the x extremes, z faces exclude x and y extremes).  Threads run
 // along the face's fastest-varying tangential direction (x for y/z faces: coalesced).
-constexpr int kShellChunks = 8;
+constexpr int kShellThreads = 256;
+// blockIdx.y chunks so that every thread owns ONE cell of the swept colour (the launch is latency bound otherwise)
+inline int shell_chunks (int face_cells) { const int c = (face_cells / 2 + kShellThreads - 1) / kShellThreads; return c < 1 ? 1 : (c > 64 ? 64 : c); }
 
 template <class F>
 __device__ __forceinline__ void shell_loop (const b200mg_box& vb, int face, int redblack, F&& f)
@@ -124,12 +126,16 @@ __device__ __forceinline__ void shell_loop (const b200mg_box& vb, int face, int 
     const int du = (d == 0) ? 1 : 0, dv = (d == 2) ? 1 : 2;     // tangential directions, u fastest in memory
     const int nu = hi[du] - lo[du] + 1, nv = hi[dv] - lo[dv] + 1;
     if (nu <= 0 || nv <= 0) { return; }
-    const unsigned n = unsigned(nu) * unsigned(nv);
+    // only cells of the swept colour are enumerated: row v holds them at u = 2*uu + (parity of the row's first cell)
+    const unsigned nuh = unsigned(nu + 1) / 2u;
+    const unsigned n = nuh * unsigned(nv);
     for (unsigned t = threadIdx.x + blockIdx.y * blockDim.x; t < n; t += blockDim.x * gridDim.y) {
-        const unsigned v = t / unsigned(nu), u = t - v * unsigned(nu);
+        const unsigned v = t / nuh, uu = t - v * nuh;
         int idx[3];
-        idx[d] = fix; idx[du] = lo[du] + int(u); idx[dv] = lo[dv] + int(v);
-        if (((idx[0] + idx[1] + idx[2] + redblack) & 1) == 0) { f(idx[0], idx[1], idx[2]); }
+        idx[d] = fix; idx[du] = lo[du]; idx[dv] = lo[dv] + int(v);
+        const int u = 2 * int(uu) + ((idx[0] + idx[1] + idx[2] + redblack) & 1);
+        idx[du] += u;
+        if (u < nu) { f(idx[0], idx[1], idx[2]); }
     }
 }
 
@@ -387,22 +393,22 @@ int b200mg_gsrb_shell_abec (int nboxes, const b200mg_box* vbox,
                             const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,
                             const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
                             const b200mg_fab* f, const b200mg_ifab* m,
-                            double alpha, double dhx, double dhy, double dhz, int redblack, cudaStream_t s)
+                            double alpha, double dhx, double dhy, double dhz, int redblack, int max_face_cells, cudaStream_t s)
 {
     if (nboxes <= 0) { return 0; }
     AbecArgs A{phi, rhs, a, bx, by, bz, f, m, alpha, dhx, dhy, dhz};
-    k_gsrb_shell_abec<<<dim3(nboxes * 6, kShellChunks), 256, 0, s>>>(vbox, A, redblack);
+    k_gsrb_shell_abec<<<dim3(nboxes * 6, shell_chunks(max_face_cells)), kShellThreads, 0, s>>>(vbox, A, redblack);
     return last_error();
 }
 
 int b200mg_gsrb_shell_poisson (int nboxes, const b200mg_box* vbox,
                                const b200mg_fab* phi, const b200mg_fab* rhs,
                                const b200mg_fab* f, const b200mg_ifab* m,
-                               double dhx, double dhy, double dhz, int redblack, cudaStream_t s)
+                               double dhx, double dhy, double dhz, int redblack, int max_face_cells, cudaStream_t s)
 {
     if (nboxes <= 0) { return 0; }
     PoisArgs A{phi, rhs, f, m, dhx, dhy, dhz};
-    k_gsrb_shell_poisson<<<dim3(nboxes * 6, kShellChunks), 256, 0, s>>>(vbox, A, redblack);
+    k_gsrb_shell_poisson<<<dim3(nboxes * 6, shell_chunks(max_face_cells)), kShellThreads, 0, s>>>(vbox, A, redblack);
     return last_error();
 }
 

@@ -526,9 +526,12 @@ bool MLLinOp::planFused (LevelData const& L) const
             for (int j = b.smallEnd(1); j <= b.bigEnd(1); j += tile_y) { ht.push_back(b200mg_tile{li, j, k, chunk_z}); }
     }
     L.h_vbox.resize(nl);
+    L.max_face_cells = 1;
     for (int li = 0; li < nl; ++li) {
         Box const& b = L.layout->box(li);
         for (int d = 0; d < 3; ++d) { L.h_vbox[li].lo[d] = b.smallEnd(d); L.h_vbox[li].hi[d] = b.bigEnd(d); }
+        const int n0 = b.length(0), n1 = b.length(1), n2 = b.length(2);
+        L.max_face_cells = std::max(L.max_face_cells, std::max(n0 * n1, std::max(n0 * n2, n1 * n2)));
     }
     L.fused_tx = tx; L.fused_tile_y = tile_y; L.fused_chunk_z = chunk_z; L.fused_nblocks = int(ht.size());
     L.fused_tiles.assign(ht);
@@ -1081,7 +1084,7 @@ void MLABecLaplacian::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiF
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
     B200_KCALL(b200mg_gsrb_shell_abec(L.layout->numLocal(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), m_a_coeffs[amrlev][mglev].d_fabs(),
                                       m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(), m_b_coeffs[amrlev][mglev][2].d_fabs(),
-                                      L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, Gpu::gpuStream()));
+                                      L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, L.max_face_cells, Gpu::gpuStream()));
 }
 
 // ============================================================================================ MLPoisson
@@ -1159,7 +1162,7 @@ void MLPoisson::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab con
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
     B200_KCALL(b200mg_gsrb_shell_poisson(L.layout->numLocal(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
-                                         dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, Gpu::gpuStream()));
+                                         dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, L.max_face_cells, Gpu::gpuStream()));
 }
 
 } // namespace amrex

@@ -133,20 +133,21 @@ int b200mg_gsrb4(int abec, int nboxes, const b200mg_box* h_vbox,
                  const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
                  const b200mg_fab* h_f, const b200mg_ifab* h_m,
                  double alpha, double dhx, double dhy, double dhz, cudaStream_t s);
-/* launch plan of b200mg_gsrb4: rows per CTA tile and ring depths; (8,4,3) default, (8,5,2), (8,4,2), (4,6,4), (4,5,3), (4,4,2) */
+/* launch plan of b200mg_gsrb4: rows per CTA tile and ring depths; (8,4,2) default, (8,4,3), (6,5,3), (6,4,4), (6,4,2), (4,6,4), (4,4,4) */
 int b200mg_set_gsrb4_plan(int tile_y, int early_stages, int late_stages);
 /* L2 prefetch distance (planes ahead of the loads) of the fused pass; 0 switches the prefetch off */
 void b200mg_set_gsrb2_prefetch(int planes);
-/* black (redblack=1) or red sweep restricted to the 1-cell surface shell of every box */
+/* black (redblack=1) or red sweep restricted to the 1-cell surface shell of every box; max_face_cells = cells of the
+ * largest box face of the level (sizes the grid: one thread per swept cell) */
 int b200mg_gsrb_shell_abec(int nboxes, const b200mg_box* vbox,
                            const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,
                            const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
                            const b200mg_fab* f, const b200mg_ifab* m,
-                           double alpha, double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+                           double alpha, double dhx, double dhy, double dhz, int redblack, int max_face_cells, cudaStream_t s);
 int b200mg_gsrb_shell_poisson(int nboxes, const b200mg_box* vbox,
                               const b200mg_fab* phi, const b200mg_fab* rhs,
                               const b200mg_fab* f, const b200mg_ifab* m,
-                              double dhx, double dhy, double dhz, int redblack, cudaStream_t s);
+                              double dhx, double dhy, double dhz, int redblack, int max_face_cells, cudaStream_t s);
 
 /* ---- operator apply / residual (K4 mlabeclap_adotx AMReX_MLABecLap_3D_K.H:9-28, K5 mlpoisson_adotx
  *      AMReX_MLPoisson_3D_K.H:9-16).  If rhs != NULL writes y = rhs - L(x)  (== Xpay(y,-1,rhs),
