@@ -70,6 +70,7 @@ _SIGS = {
     "amrex_b200_linop_set_fused_plan": (None, [_P, _I, _I, _I]),
     "amrex_b200_linop_set_fused_version": (None, [_P, _I]),
     "amrex_b200_set_fused4_plan": (_I, [_I, _I, _I]),
+    "amrex_b200_linop_set_fused_min_box_cells": (None, [_P, C.c_longlong]),
     "amrex_b200_linop_num_mg_levels": (_I, [_P, _I]), "amrex_b200_linop_prepare": (None, [_P]),
     "amrex_b200_linop_make": (None, [_P, _PP, _I, _I, _I]),
     "amrex_b200_linop_smooth": (None, [_P, _I, _I, _P, _P, _I]),
@@ -405,6 +406,9 @@ class MLLinOp(_Obj):
 
     def setFusedVersion(self, v):
         lib.amrex_b200_linop_set_fused_version(self.ptr, int(v))
+
+    def setFusedMinBoxCells(self, n):
+        lib.amrex_b200_linop_set_fused_min_box_cells(self.ptr, int(n))
 
     def setFusedPlan(self, tile_y=0, chunk_z=0, prefetch=-1):
         lib.amrex_b200_linop_set_fused_plan(self.ptr, int(tile_y), int(chunk_z), int(prefetch))

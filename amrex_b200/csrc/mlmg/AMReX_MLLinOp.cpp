@@ -1,6 +1,7 @@
 // MG hierarchy, boundary bookkeeping and level operations of the cell-centred operators.
 #include "AMReX_MLMG.H"
 
+#include <cstring>
 #include <cuda_runtime.h>
 
 namespace amrex {
@@ -502,7 +503,9 @@ bool MLLinOp::planFused (LevelData const& L) const
     if (L.fused_state >= 0) { return L.fused_state == 1; }
     L.fused_state = 0;
     const int nl = L.layout->numLocal();
-    if (nl == 0 || L.layout->localCells() < 32768 * Long(nl)) { return false; }
+    // measured (profiles/r01_s25_kernel_times_per_level_1gpu_fused4.txt): the z-marching fused pass pays from 64^3 boxes up;
+    // on 32^3 boxes (few short-lived CTAs) two colour sweeps are faster
+    if (nl == 0 || L.layout->localCells() < m_fused_min_box_cells * Long(nl)) { return false; }
     int nxmax = 0, nymax = 0, nzmax = 0;
     for (int li = 0; li < nl; ++li) {
         Box const& b = L.layout->box(li);
@@ -539,6 +542,32 @@ bool MLLinOp::planFused (LevelData const& L) const
     return true;
 }
 
+
+namespace {
+inline void hash_mix (std::size_t& h, std::size_t v) { h ^= v; h *= 1099511628211ull; }
+inline std::size_t bits_of (Real v) { std::size_t b = 0; std::memcpy(&b, &v, sizeof(Real) < sizeof(b) ? sizeof(Real) : sizeof(b)); return b; }
+}
+
+std::size_t MLLinOp::graphKey (int amrlev, int mglev) const
+{
+    LevelData const& L = lev(amrlev, mglev);
+    std::size_t h = 1469598103934665603ull;
+    hash_mix(h, reinterpret_cast<std::size_t>(L.mask.d_table()));
+    hash_mix(h, reinterpret_cast<std::size_t>(L.undrrelxr.d_table()));
+    hash_mix(h, reinterpret_cast<std::size_t>(L.layout.get()));
+    hash_mix(h, std::size_t(m_fuse_colors)); hash_mix(h, std::size_t(m_fused_version)); hash_mix(h, std::size_t(m_use_gauss_seidel));
+    hash_mix(h, std::size_t(maxorder));
+    return h;
+}
+
+std::size_t MLABecLaplacian::graphKey (int amrlev, int mglev) const
+{
+    std::size_t h = MLLinOp::graphKey(amrlev, mglev);
+    hash_mix(h, reinterpret_cast<std::size_t>(m_a_coeffs[amrlev][mglev].dataPtr()));
+    for (int d = 0; d < 3; ++d) { hash_mix(h, reinterpret_cast<std::size_t>(m_b_coeffs[amrlev][mglev][d].dataPtr())); }
+    hash_mix(h, bits_of(m_a_scalar)); hash_mix(h, bits_of(m_b_scalar));
+    return h;
+}
 
 void MLLinOp::setFusedPlan (int tile_y, int chunk_z, int prefetch_planes)
 {

@@ -3,6 +3,8 @@
 // MLCGSolverT (AMReX_MLCGSolver.H:98-410).
 #include "AMReX_MLMG.H"
 
+#include <cuda_runtime.h>
+#include <cstdlib>
 #include <iomanip>
 #include <iostream>
 #include <sstream>
@@ -141,7 +143,80 @@ int MLCGSolver::solve_cg (MultiFab& sol, MultiFab const& rhs, Real eps_rel, Real
 }
 
 // ================================================================================================ MLMG
-MLMG::MLMG (MLLinOp& a_lp) : linop(a_lp), namrlevs(a_lp.NAMRLevels()), finest_amr_lev(a_lp.NAMRLevels() - 1) {}
+MLMG::MLMG (MLLinOp& a_lp) : linop(a_lp), namrlevs(a_lp.NAMRLevels()), finest_amr_lev(a_lp.NAMRLevels() - 1)
+{
+    if (const char* e = std::getenv("B200MG_GRAPHS")) { m_use_graphs = (e[0] != '0'); }
+}
+
+MLMG::~MLMG ()
+{
+    for (auto* m : {&m_graph_down, &m_graph_up}) {
+        for (auto& kv : *m) { if (kv.second.exec) { cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(kv.second.exec)); } }
+    }
+}
+
+// ---- CUDA graphs of the coarse V-cycle legs (see AMReX_MLMG.H)
+namespace { constexpr Long kGraphLevelCells = Long(128) * 128 * 128; }
+
+// first MG level (>= mglev_top) from which every level down to the bottom has <= 128^3 cells and uses the plain colour
+// sweeps (the fused pass ping-pongs arrays: their addresses would alternate under the graph); mglev_bottom if none
+int MLMG::graphFirstLevel (int amrlev, int mglev_top, int mglev_bottom) const
+{
+    int g = mglev_bottom;
+    for (int m = mglev_bottom - 1; m >= mglev_top; --m) {
+        if (linop.Grids(amrlev, m).numPts() > kGraphLevelCells || linop.usesFusedSmoother(amrlev, m)) { break; }
+        g = m;
+    }
+    return g;
+}
+
+// every device address a captured leg bakes in: the cycle's work arrays on levels lev0..lev1 (+ schedule parameters)
+std::size_t MLMG::graphKey (int amrlev, int lev0, int lev1) const
+{
+    std::size_t h = 1469598103934665603ull;
+    auto mix = [&] (std::size_t v) { h ^= v; h *= 1099511628211ull; };
+    for (int m = lev0; m <= lev1; ++m) {
+        mix(reinterpret_cast<std::size_t>(cor[amrlev][m].dataPtr()));
+        mix(reinterpret_cast<std::size_t>(res[amrlev][m].dataPtr()));
+        mix(reinterpret_cast<std::size_t>(rescor[amrlev][m].dataPtr()));
+        if (m < int(cfine_mg.size()) && cfine_mg[m]) { mix(reinterpret_cast<std::size_t>(cfine_mg[m]->dataPtr())); }
+    }
+    for (int m = lev0; m <= lev1; ++m) { mix(linop.graphKey(amrlev, m)); }
+    mix(std::size_t(nu1)); mix(std::size_t(nu2)); mix(reinterpret_cast<std::size_t>(&linop));
+    return h;
+}
+
+template <class F>
+void MLMG::runGraphed (CycleGraph& g, std::size_t key, bool warm, F&& body)
+{
+    const bool usable = m_use_graphs && !m_graphs_broken && warm && ParallelDescriptor::NProcs() == 1
+        && !Gpu::profiling() && !Gpu::debugSync();
+    if (!usable) { body(); return; }
+    cudaStream_t s = Gpu::gpuStream();
+    if (g.exec && g.key == key) {
+        AMREX_CUDA_SAFE_CALL(cudaGraphLaunch(static_cast<cudaGraphExec_t>(g.exec), s));
+        Gpu::countLaunch(int(g.launches));
+        return;
+    }
+    if (g.exec) { cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(g.exec)); g.exec = nullptr; }
+    const long long l0 = Gpu::launchCount();
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); m_graphs_broken = true; body(); return; }
+    body();                                              // records the launches of the leg, executes nothing
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (e == cudaSuccess && graph) { e = cudaGraphInstantiate(&exec, graph, 0); }
+    if (graph) { cudaGraphDestroy(graph); }
+    const long long nk = Gpu::launchCount() - l0;        // kernels in the leg
+    if (e != cudaSuccess || !exec) {                     // not capturable here: stay eager from now on
+        cudaGetLastError(); m_graphs_broken = true;
+        Gpu::countLaunch(-int(nk));
+        body();
+        return;
+    }
+    g.exec = exec; g.key = key; g.launches = nk;
+    AMREX_CUDA_SAFE_CALL(cudaGraphLaunch(exec, s));      // the launches counted during the capture stand for this replay
+}
 
 Real MLMG::solve (Vector<MultiFab*> const& a_sol, Vector<MultiFab const*> const& a_rhs, Real a_tol_rel, Real a_tol_abs)
 {
@@ -300,16 +375,31 @@ void MLMG::oneIter (int iter)
 void MLMG::mgVcycle (int amrlev, int mglev_top)
 {
     const int mglev_bottom = linop.NMGLevels(amrlev) - 1;
-    for (int mglev = mglev_top; mglev < mglev_bottom; ++mglev) {
-        Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
-        cor[amrlev][mglev].setVal(0.0);
-        bool skip_fillboundary = true;
-        for (int i = 0; i < nu1; ++i) {
-            linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev], skip_fillboundary);
-            skip_fillboundary = false;
+    auto down = [&] (int m0, int m1) {                   // levels [m0, m1): pre-smooth, residual, restriction
+        for (int mglev = m0; mglev < m1; ++mglev) {
+            Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
+            cor[amrlev][mglev].setVal(0.0);
+            bool skip_fillboundary = true;
+            for (int i = 0; i < nu1; ++i) {
+                linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev], skip_fillboundary);
+                skip_fillboundary = false;
+            }
+            computeResOfCorrection(amrlev, mglev);
+            linop.restriction(amrlev, mglev + 1, res[amrlev][mglev + 1], rescor[amrlev][mglev]);
         }
-        computeResOfCorrection(amrlev, mglev);
-        linop.restriction(amrlev, mglev + 1, res[amrlev][mglev + 1], rescor[amrlev][mglev]);
+    };
+    auto up = [&] (int m1, int m0) {                     // levels m1 down to m0: prolongation-add, post-smooth
+        for (int mglev = m1; mglev >= m0; --mglev) {
+            Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
+            addInterpCorrection(amrlev, mglev);
+            for (int i = 0; i < nu2; ++i) { linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev]); }
+        }
+    };
+    // the launch-bound small levels [g, bottom) replay as CUDA graphs (see AMReX_MLMG.H); the big ones run eagerly
+    const int g = graphFirstLevel(amrlev, mglev_top, mglev_bottom);
+    down(mglev_top, g);
+    if (g < mglev_bottom) {
+        runGraphed(m_graph_down[amrlev * 1000 + g], graphKey(amrlev, g, mglev_bottom), m_cycles_done[amrlev] >= 1, [&] { down(g, mglev_bottom); });
     }
     if (amrlev == 0) { bottomSolve(); }
     else {
@@ -320,11 +410,11 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
             skip_fillboundary = false;
         }
     }
-    for (int mglev = mglev_bottom - 1; mglev >= mglev_top; --mglev) {
-        Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
-        addInterpCorrection(amrlev, mglev);
-        for (int i = 0; i < nu2; ++i) { linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev]); }
+    if (g < mglev_bottom) {
+        runGraphed(m_graph_up[amrlev * 1000 + g], graphKey(amrlev, g, mglev_bottom), m_cycles_done[amrlev] >= 1, [&] { up(mglev_bottom - 1, g); });
     }
+    up(g - 1, mglev_top);
+    ++m_cycles_done[amrlev];
 }
 
 void MLMG::mgFcycle ()

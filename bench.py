@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-cell", type=int, default=512)
     ap.add_argument("--max-grid-size", type=int, default=128)
-    ap.add_argument("--fusion", type=int, default=0)
+    ap.add_argument("--fusion", type=int, default=1, help="1: fused red+black pass (generation 4, bulk-async-copy staged) + surface shell; 0: one kernel per colour")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-(kernel, MG level) device-time table of one solve to this file")
@@ -259,7 +259,7 @@ def b200_arm(args):
             fh.write(f"# one MLMG solve, {n}^3, {world} GPU(s), rank 0: kernel, scope (amrlev*100+mglev), launches, total ms, min ms, max ms\n")
             for r in sorted(rep, key=lambda q: (q[1], -q[3])):
                 fh.write(f"{r[0]:36s} {r[1]:5d} {r[2]:6d} {r[3]:10.3f} {r[4]:9.4f} {r[5]:9.4f}\n")
-    kern = "b200mg_gsrb2_abec" if args.fusion else "b200mg_gsrb_abec_pairs_lean"
+    kern = "b200mg_gsrb4" if args.fusion else "b200mg_gsrb_abec_pairs_lean"
     top = [r for r in rep if r[0] == kern and r[1] == 0]
     peak, peak_src = measured_peak_gbs()
     roofline = None

@@ -102,6 +102,8 @@ def build_problem(ab, prob_type, n_cell, max_grid_size, dump, maxorder=2, agg_gr
         op.setLevelBC(0, sol)
     if fusion is not None:
         op.setSmootherFusion(fusion)
+        if fusion:
+            op.setFusedMinBoxCells(32 ** 3)     # tests exercise the fused pass on small boxes too (default: 64^3 and up)
     return dict(geom=geom, ba=ba, dm=dm, sol=sol, rhs=rhs, op=op, keep=keep, n=n_cell)
 
 
@@ -160,6 +162,8 @@ def build_problem_amr(ab, prob_type, n_cell, max_grid_size, dump, max_level=1, m
             op.setLevelBC(l, sols[l])
     if fusion is not None:
         op.setSmootherFusion(fusion)
+        if fusion:
+            op.setFusedMinBoxCells(32 ** 3)     # tests exercise the fused pass on small boxes too (default: 64^3 and up)
     return dict(geom=geoms, ba=bas, dm=dms, sol=sols, rhs=rhss, op=op, keep=keep, n=n_cell)
 
 
@@ -259,5 +263,7 @@ def synth_abeclap(ab, n, mgs, maxorder=2, fusion=None, a=1.e-3, b=1.0, keep_host
     op.setBCoeffs(0, faces)
     if fusion is not None:
         op.setSmootherFusion(fusion)
+        if fusion:
+            op.setFusedMinBoxCells(32 ** 3)     # tests exercise the fused pass on small boxes too (default: 64^3 and up)
     return dict(geom=geom, ba=ba, dm=dm, sol=sol, sol0=sol0, rhs=rhs, op=op, keep=[acoef, bcc] + faces, n=n, host=host,
                 pmap=pmap, me=me)
