@@ -1,6 +1,7 @@
 // MG hierarchy, boundary bookkeeping and level operations of the cell-centred operators.
 #include "AMReX_MLMG.H"
 
+#include <cmath>
 #include <cstring>
 #include <cuda_runtime.h>
 
@@ -503,9 +504,29 @@ bool MLLinOp::planFused (LevelData const& L) const
     if (L.fused_state >= 0) { return L.fused_state == 1; }
     L.fused_state = 0;
     const int nl = L.layout->numLocal();
-    // measured (profiles/r01_s25_kernel_times_per_level_1gpu_fused4.txt): the z-marching fused pass pays from 64^3 boxes up;
-    // on 32^3 boxes (few short-lived CTAs) two colour sweeps are faster
-    if (nl == 0 || L.layout->localCells() < m_fused_min_box_cells * Long(nl)) { return false; }
+    if (nl == 0 || L.layout->localCells() < Long(32768) * Long(nl)) { return false; }
+    if (m_fused_min_box_cells > 0) {
+        // explicit threshold (tests): fused wherever the average local box has at least this many cells
+        if (L.layout->localCells() < m_fused_min_box_cells * Long(nl)) { return false; }
+    } else {
+        // Cost model fitted to the measured launches (profiles/r01_s25_kernel_times_per_level_1gpu_fused4.txt, 512^3 on
+        // 1 / 2 GPUs): the fused pass (generation 4) runs ceil(CTAs / resident CTAs) rounds of (nz+1) barrier-separated
+        // steps of ~1.8 us (one 640-thread CTA per SM at nx = 128) or ~2.5 us (two CTAs per SM at nx <= 64) + the surface
+        // shell; a colour sweep takes cells x 44 B / 4.65 TB/s + ~40 us of ramp and tail.  Few boxes per GPU or short boxes favour the sweeps.
+        int nx0 = 0, ny0 = 0, nz0 = 0; Long surf = 0;
+        for (int li = 0; li < nl; ++li) {
+            Box const& b = L.layout->box(li);
+            nx0 = std::max(nx0, b.length(0)); ny0 = std::max(ny0, b.length(1)); nz0 = std::max(nz0, b.length(2));
+            surf += 2 * (Long(b.length(0)) * b.length(1) + Long(b.length(0)) * b.length(2) + Long(b.length(1)) * b.length(2));
+        }
+        if (nx0 > 128 || nx0 < 64) { return false; }
+        const int per_sm = (nx0 > 64) ? 1 : 2;
+        const double ctas = double(nl) * double((ny0 + 7) / 8);
+        const double rounds = std::ceil(ctas / (148.0 * per_sm));
+        const double fused_us = rounds * (nz0 + 1) * (per_sm == 1 ? 1.8 : 2.5) + 320.0 * double(surf) / 6.3e6 + 5.0;
+        const double pairs_us = 2.0 * (double(L.layout->localCells()) * 44.0 / 4.65e6 + 40.0);
+        if (fused_us > 0.95 * pairs_us) { return false; }
+    }
     int nxmax = 0, nymax = 0, nzmax = 0;
     for (int li = 0; li < nl; ++li) {
         Box const& b = L.layout->box(li);
