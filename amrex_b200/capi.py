@@ -70,6 +70,7 @@ _SIGS = {
     "amrex_b200_linop_set_fused_plan": (None, [_P, _I, _I, _I]),
     "amrex_b200_linop_set_fused_version": (None, [_P, _I]),
     "amrex_b200_set_fused4_plan": (_I, [_I, _I, _I]),
+    "b200mg_set_gsrb4_sync": (None, [_I]),
     "amrex_b200_linop_set_fused_min_box_cells": (None, [_P, C.c_longlong]),
     "amrex_b200_linop_num_mg_levels": (_I, [_P, _I]), "amrex_b200_linop_prepare": (None, [_P]),
     "amrex_b200_linop_make": (None, [_P, _PP, _I, _I, _I]),
@@ -82,6 +83,8 @@ _SIGS = {
     "amrex_b200_linop_level_nboxes": (_I, [_P, _I, _I]), "amrex_b200_linop_level_boxes": (None, [_P, _I, _I, _IP, _IP, _IP]),
     "amrex_fi_new_multigrid": (None, [_PP, _P]), "amrex_fi_delete_multigrid": (None, [_P]),
     "amrex_fi_multigrid_solve": (_D, [_P, _PP, _PP, _D, _D]),
+    "amrex_fi_multigrid_comp_residual": (None, [_P, _PP, _PP, _PP]),
+    "amrex_fi_multigrid_get_grad_solution": (None, [_P, _PP]), "amrex_fi_multigrid_get_fluxes": (None, [_P, _PP]),
     "amrex_fi_multigrid_set_verbose": (None, [_P, _I]), "amrex_fi_multigrid_set_max_iter": (None, [_P, _I]),
     "amrex_fi_multigrid_set_max_fmg_iter": (None, [_P, _I]), "amrex_fi_multigrid_set_fixed_iter": (None, [_P, _I]),
     "amrex_fi_multigrid_set_bottom_solver": (None, [_P, _I]), "amrex_fi_multigrid_set_bottom_verbose": (None, [_P, _I]),
@@ -503,6 +506,15 @@ class MLMG(_Obj):
         r = lib.amrex_fi_multigrid_solve(self.ptr, _ptr_array(sol), _ptr_array(rhs), float(tol_rel), float(tol_abs))
         check()
         return r
+
+    def getGradSolution(self, grads):
+        """grads: per AMR level a list of 3 face-centred MultiFabs"""
+        lib.amrex_fi_multigrid_get_grad_solution(self.ptr, _ptr_array([m for lev in grads for m in lev]))
+        check()
+
+    def getFluxes(self, fluxes):
+        lib.amrex_fi_multigrid_get_fluxes(self.ptr, _ptr_array([m for lev in fluxes for m in lev]))
+        check()
 
     def compResidual(self, res, sol, rhs):
         lib.amrex_fi_multigrid_comp_residual(self.ptr, _ptr_array(res), _ptr_array(sol), _ptr_array(rhs))

@@ -305,6 +305,25 @@ void amrex_fi_multigrid_comp_residual (MLMG* mlmg, MultiFab* a_res[], MultiFab* 
     FI_VOID( const int n = mlmg->numAMRLevels();
              mlmg->compResidual(Vector<MultiFab*>(a_res, a_res + n), Vector<MultiFab*>(a_sol, a_sol + n), Vector<const MultiFab*>(a_rhs, a_rhs + n)); )
 }
+// a_grad_sol / a_fluxes: [level*3 + dir], face-centred MultiFabs (AMReX_multigrid_fi.cpp:27-51)
+void amrex_fi_multigrid_get_grad_solution (MLMG* mlmg, MultiFab* a_grad_sol[])
+{
+    FI_TRY
+        const int n = mlmg->numAMRLevels();
+        Vector<Array<MultiFab*, 3>> g(n);
+        for (int l = 0; l < n; ++l) { for (int d = 0; d < 3; ++d) { g[l][d] = a_grad_sol[l * 3 + d]; } }
+        mlmg->getGradSolution(g);
+    FI_CATCH(return)
+}
+void amrex_fi_multigrid_get_fluxes (MLMG* mlmg, MultiFab* a_fluxes[])
+{
+    FI_TRY
+        const int n = mlmg->numAMRLevels();
+        Vector<Array<MultiFab*, 3>> f(n);
+        for (int l = 0; l < n; ++l) { for (int d = 0; d < 3; ++d) { f[l][d] = a_fluxes[l * 3 + d]; } }
+        mlmg->getFluxes(f);
+    FI_CATCH(return)
+}
 void amrex_fi_multigrid_set_verbose (MLMG* mlmg, int v) { mlmg->setVerbose(v); }
 void amrex_fi_multigrid_set_max_iter (MLMG* mlmg, int n) { mlmg->setMaxIter(n); }
 void amrex_fi_multigrid_set_max_fmg_iter (MLMG* mlmg, int n) { mlmg->setMaxFmgIter(n); }

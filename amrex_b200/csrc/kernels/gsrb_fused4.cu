@@ -79,6 +79,10 @@ __device__ __forceinline__ void bulk_g2s (uint32_t dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive (uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async () { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // CTA-wide barrier reached from two different code paths (compute warps inside step4, the producer warp in its loop)
 __device__ __forceinline__ void cta_sync () { asm volatile("bar.sync 1, %0;" :: "r"(int(blockDim.x)) : "memory"); }
@@ -145,10 +149,10 @@ produce (const Header* H, int d0, int d1, uint32_t bar, uint32_t stage_base, int
     }
 }
 
-template <bool ABEC, int TY, int SE, int SL, int C>
+template <bool ABEC, int TY, int SE, int SL, bool DEC, int C>
 __device__ __forceinline__ void
 step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double* __restrict__ smE, double* __restrict__ smL,
-       const Header* H, uint32_t barE, uint32_t barL, Ring<SE, SL>& R, int t, int nz,
+       const Header* H, uint32_t barE, uint32_t barL, uint32_t barS, Ring<SE, SL>& R, int t, int nz,
        bool row_load, bool row_red, bool row_black, bool first, bool last, bool jlo, bool jhi, int tx2, int jrel,
        int prow, int crow, int xrow, int& out_cur,
        double& zlo_b, double2& pk, double2& pp1, double& bzm_b, double2& bz1, Carry& cb, int& xmk, double& xf)
@@ -193,6 +197,9 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
     double* __restrict__ e1 = smE + s1 * Y.e_size;
     double* __restrict__ e0 = smE + s0 * Y.e_size;
     const double* __restrict__ l1 = smL + sl * Y.l_size;
+
+    // decoupled warps: the red x / y neighbours in EARLY[t].phi were written by other warps during THEIR step t-1
+    if constexpr (DEC) { if (t >= 1) { mbar_wait(barS + 8u * uint32_t((t - 1) & 1), uint32_t(((t - 1) >> 1) & 1)); } }
 
     // ---- black cell of plane t, part 1: everything that does not need the red value above it (computed below).
     //      New red values on five sides: EARLY[t].phi in x / y (written during step t-1), zlo_b below.
@@ -269,6 +276,10 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
         if (C) { pp1.y = vr; } else { pp1.x = vr; }
         sr[0] = vr;
     }
+    if constexpr (DEC) {                                 // this warp's red cells of plane t+1 are in shared memory
+        __syncwarp();
+        if ((threadIdx.x & 31u) == 0u) { mbar_arrive(barS + 8u * uint32_t(t & 1)); }
+    }
 
     // ---- black cell of plane t, part 2 (needs the red value above: pp1); box-surface cells pass through unchanged and
     //      are finished by the shell kernel after the second halo refresh
@@ -301,7 +312,15 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
         if constexpr (ABEC) { if (row_red) { bz1 = *reinterpret_cast<const double2*>(e2 + Y.e_bz + crow); } }
     }
     fence_proxy_async();
-    cta_sync();
+    if constexpr (DEC) {
+        // No CTA barrier: warps drift by up to a step.  Every warp reports the end of its step; only the issuing thread
+        // waits for all of them before it hands the freed slots back to the copy engine.
+        __syncwarp();
+        if ((threadIdx.x & 31u) == 0u) { mbar_arrive(barS + 16u + 8u * uint32_t(t & 1)); }
+        if (threadIdx.x == 0) { mbar_wait(barS + 16u + 8u * uint32_t(t & 1), uint32_t((t >> 1) & 1)); }
+    } else {
+        cta_sync();
+    }
     // ---- EARLY[t] and LATE[t+1] are free: refill them with planes t+SE and t+1+SL, then rotate the ring
     if (threadIdx.x == 0) {
         if (t + SE <= nz + 1) {
@@ -314,7 +333,7 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
     R.advance();
 }
 
-template <bool ABEC, int TY, int SE, int SL, int MAXT>
+template <bool ABEC, int TY, int SE, int SL, bool DEC, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 k_gsrb4 (const __grid_constant__ FusedParams4 P)
 {
@@ -329,12 +348,14 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
     double* smE = reinterpret_cast<double*>(sm_raw + kHdrBytes);
     double* smL = smE + SE * Y.e_size;
     const uint32_t barE = smem_u32(sm_raw), barL = barE + 8u * SE;
-    static_assert(8 * (SE + SL) <= kBarBytes, "too many stages for the mbarrier block");
+    const uint32_t barS = barL + 8u * SL;                           // red-done [2], step-done [2] (decoupled warps)
+    static_assert(8 * (SE + SL + 4) <= kBarBytes, "too many stages for the mbarrier block");
     static_assert(SE >= 4 && SL >= 2, "ring depths: EARLY planes live three steps, LATE planes one");
 
     const int tid = int(threadIdx.x);
     if (tid == 0) {
         for (int s = 0; s < SE + SL; ++s) { mbar_init(barE + 8u * s, 1u); }
+        for (int s = 0; s < 4; ++s) { mbar_init(barS + 8u * s, blockDim.x / 32u); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // rows this tile needs (clipped to what exists); one contiguous range per array and plane
         const int pj_lo = max(j0 - 2, B.lo[1] - 1), pj_hi = min(j1 + 2, B.hi[1] + 1);    // phi rows (ghost rows exist)
@@ -407,7 +428,7 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
     const int c_first = (i0 + j + B.lo[2]) & 1;                    // pair position of the red cell of plane lo_z (step 0)
     int xmk = 0; double xf = 0.0;                                  // x-face slab values of step 0 (see step4)
     if ((c_first ? last : first) && row_red) { xmk = B.m[c_first ? 3 : 0][jrel]; xf = B.f[c_first ? 3 : 0][jrel]; }
-#define B200MG_STEP4(CC, TT) step4<ABEC, TY, SE, SL, CC>(P, B, Y, smE, smL, H, barE, barL, R, TT, nz, row_load, row_red, row_black, first, last, \
+#define B200MG_STEP4(CC, TT) step4<ABEC, TY, SE, SL, DEC, CC>(P, B, Y, smE, smL, H, barE, barL, barS, R, TT, nz, row_load, row_red, row_black, first, last, \
                                                          jlo, jhi, tx2, jrel, prow, crow, xrow, out_cur, zlo_b, pk, pp1, bzm_b, bz1, cb, xmk, xf)
     int t = 0;
     if (c_first) {
@@ -421,8 +442,9 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
 }
 
 int g_plan_ty = 8, g_plan_se = 4, g_plan_sl = 2;                   // launch plan (b200mg_set_gsrb4_plan)
+int g_plan_dec = 0;                                                 // 1: decoupled warps (mbarrier arrive / wait instead of the CTA barrier)
 
-template <bool ABEC, int TY, int SE, int SL>
+template <bool ABEC, int TY, int SE, int SL, bool DEC>
 int launch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
 {
     const Lay<ABEC, TY> Y(P.nxs, P.ps, P.cs, P.xs);
@@ -432,17 +454,17 @@ int launch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
     const dim3 grid(P.nty, nboxes, 1);
     cudaError_t e = cudaSuccess;
     if (nthreads <= 384) {
-        auto kern = k_gsrb4<ABEC, TY, SE, SL, 384>;
+        auto kern = k_gsrb4<ABEC, TY, SE, SL, DEC, 384>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) { return int(e); }
         kern<<<grid, nthreads, smem, s>>>(P);
     } else if (nthreads <= 512) {
-        auto kern = k_gsrb4<ABEC, TY, SE, SL, 512>;
+        auto kern = k_gsrb4<ABEC, TY, SE, SL, DEC, 512>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) { return int(e); }
         kern<<<grid, nthreads, smem, s>>>(P);
     } else {
-        auto kern = k_gsrb4<ABEC, TY, SE, SL, 640>;
+        auto kern = k_gsrb4<ABEC, TY, SE, SL, DEC, 640>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) { return int(e); }
         kern<<<grid, nthreads, smem, s>>>(P);
@@ -454,16 +476,16 @@ template <bool ABEC>
 int dispatch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
 {
     const int key = g_plan_ty * 100 + g_plan_se * 10 + g_plan_sl;
+#define B200MG_PLAN4(K, TYv, SEv, SLv) case K: return g_plan_dec ? launch4<ABEC, TYv, SEv, SLv, true>(P, nboxes, s) : launch4<ABEC, TYv, SEv, SLv, false>(P, nboxes, s)
     switch (key) {
-        case 843: return launch4<ABEC, 8, 4, 3>(P, nboxes, s);
-        case 842: return launch4<ABEC, 8, 4, 2>(P, nboxes, s);
-        case 653: return launch4<ABEC, 6, 5, 3>(P, nboxes, s);
-        case 644: return launch4<ABEC, 6, 4, 4>(P, nboxes, s);
-        case 642: return launch4<ABEC, 6, 4, 2>(P, nboxes, s);
-        case 464: return launch4<ABEC, 4, 6, 4>(P, nboxes, s);
-        case 444: return launch4<ABEC, 4, 4, 4>(P, nboxes, s);
+        B200MG_PLAN4(842, 8, 4, 2);
+        B200MG_PLAN4(843, 8, 4, 3);
+        B200MG_PLAN4(653, 6, 5, 3);
+        B200MG_PLAN4(642, 6, 4, 2);
+        B200MG_PLAN4(444, 4, 4, 4);
         default: return int(cudaErrorInvalidValue);
     }
+#undef B200MG_PLAN4
 }
 
 FArr4 farr4 (const b200mg_fab& f) { return FArr4{f.p, int(f.jstride), int(f.kstride)}; }
@@ -475,14 +497,17 @@ bool aligned16 (const double* p) { return (reinterpret_cast<uintptr_t>(p) & 15u)
 extern "C" {
 
 // launch plan of the fourth-generation fused pass: rows per CTA tile (4 or 8) and ring depths (EARLY, LATE);
-// supported: (8,4,2) default, (8,4,3), (6,5,3), (6,4,4), (6,4,2), (4,6,4), (4,4,4).  Returns 0 when the combination exists.
+// supported: (8,4,2) default, (8,4,3), (6,5,3), (6,4,2), (4,4,4).  Returns 0 when the combination exists.
 int b200mg_set_gsrb4_plan (int tile_y, int early_stages, int late_stages)
 {
     const int key = tile_y * 100 + early_stages * 10 + late_stages;
-    if (key != 843 && key != 842 && key != 653 && key != 644 && key != 642 && key != 464 && key != 444) { return int(cudaErrorInvalidValue); }
+    if (key != 843 && key != 842 && key != 653 && key != 642 && key != 444) { return int(cudaErrorInvalidValue); }
     g_plan_ty = tile_y; g_plan_se = early_stages; g_plan_sl = late_stages;
     return 0;
 }
+
+// synchronisation inside the CTA: 0 = one CTA barrier per plane, 1 = decoupled warps (mbarrier arrive / wait)
+void b200mg_set_gsrb4_sync (int decoupled) { g_plan_dec = decoupled ? 1 : 0; }
 
 // HOST descriptor tables as in b200mg_gsrb3.  abec == 0: Poisson (a, bx, by, bz ignored).
 int b200mg_gsrb4 (int abec, int nboxes, const b200mg_box* h_vbox,

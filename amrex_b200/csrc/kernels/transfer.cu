@@ -123,9 +123,48 @@ k_cc_to_face (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restric
     tile_for(t, fb, 0, [&] (int i, int j, int k) { fc(i, j, k) = 0.5 * (cc(i - di, j - dj, k - dk) + cc(i, j, k)); });
 }
 
+// Face-centred difference of a cell-centred field along dir on the FACE boxes of that direction:
+//   mode 0  grad  : out = fac*(s(i) - s(i-e))                        compGrad,          AMReX_MLCellLinOp.H:1421-1436
+//   mode 1  abec  : out = -fac*b(i)*(s(i) - s(i-e))   [* post]       mlabeclap_flux_*,  AMReX_MLABecLap_3D_K.H:79-135
+//   mode 2  poiss : out =  fac*(s(i) - s(i-e))        [* post]       mlpoisson_flux_*,  AMReX_MLPoisson_3D_K.H:36-98
+// post (= 1/b_scalar) is applied as a separate multiplication when != 1, as MLCellABecLap::getFluxes does (:279-288).
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_face_flux (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ fbox,
+             const b200mg_fab* of, const b200mg_fab* sf, const b200mg_fab* bf, double fac, double post, int dir, int mode)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box fb = fbox[t.box];
+    const auto o = view(of[t.box]); const auto s = view(sf[t.box]);
+    const int di = (dir == 0), dj = (dir == 1), dk = (dir == 2);
+    if (mode == 1) {
+        const auto b = view(bf[t.box]);
+        tile_for(t, fb, 0, [&] (int i, int j, int k) {
+            double v = -fac * b(i, j, k) * (s(i, j, k) - s(i - di, j - dj, k - dk));
+            if (post != 1.0) { v = v * post; }
+            o(i, j, k) = v;
+        });
+    } else {
+        tile_for(t, fb, 0, [&] (int i, int j, int k) {
+            double v = fac * (s(i, j, k) - s(i - di, j - dj, k - dk));
+            if (mode == 2 && post != 1.0) { v = v * post; }
+            o(i, j, k) = v;
+        });
+    }
+}
+
 } // namespace
 
 extern "C" {
+
+int b200mg_face_flux (int ntiles, const b200mg_tile* tiles, const b200mg_box* fbox,
+                      const b200mg_fab* out, const b200mg_fab* sol, const b200mg_fab* b,
+                      double fac, double post, int dir, int mode, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    if (mode == 1 && b == nullptr) { return int(cudaErrorInvalidValue); }
+    k_face_flux<<<ntiles, tile_block(), 0, s>>>(tiles, fbox, out, sol, b, fac, post, dir, mode);
+    return last_error();
+}
 
 int b200mg_cc_to_face (int ntiles, const b200mg_tile* tiles, const b200mg_box* fbox,
                        const b200mg_fab* face, const b200mg_fab* cc, int dir, cudaStream_t s)

@@ -638,6 +638,51 @@ void MLLinOp::correctionResidual (int amrlev, int mglev, MultiFab& resid, MultiF
     Fapply(amrlev, mglev, resid, x, &b);
 }
 
+// ---- post-solve API: face-centred gradient and flux of the solution
+void MLLinOp::compGrad (int amrlev, Array<MultiFab*, 3> const& grad, MultiFab& sol)
+{
+    Gpu::ProfScope prof_scope__(amrlev * 100 + 0);
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(sol.nGrow() >= 1, "compGrad: the solution needs one ghost cell");
+    applyBC(amrlev, 0, sol, BCMode::Inhomogeneous, StateMode::Solution, m_bndry_sol[amrlev].get());
+    const Real* dxi = H.geom[amrlev][0].InvCellSize();
+    for (int d = 0; d < 3; ++d) {
+        MultiFab& g = *grad[d];
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(g.boxArray() == amrex::convert(sol.boxArray(), IntVect::TheDimensionVector(d))
+                                         && g.DistributionMap() == sol.DistributionMap(), "compGrad: grad[d] must live on the faces of sol's grids");
+        auto const& T = g.layout().tiles(0);
+        B200_KCALL(b200mg_face_flux(T.n, T.d.data(), g.layout().d_vbox(), g.d_fabs(), sol.d_fabs(), nullptr, dxi[d], 1.0, d, 0, Gpu::gpuStream()));
+    }
+}
+
+void MLLinOp::compFlux (int amrlev, Array<MultiFab*, 3> const& fluxes, MultiFab& sol)
+{
+    Gpu::ProfScope prof_scope__(amrlev * 100 + 0);
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(sol.nGrow() >= 1, "compFlux: the solution needs one ghost cell");
+    applyBC(amrlev, 0, sol, BCMode::Inhomogeneous, StateMode::Solution, m_bndry_sol[amrlev].get());
+    Array<MultiFab const*, 3> b; Real bscalar;
+    getFluxCoeffs(amrlev, b, bscalar);
+    const Real betainv = Real(1.0) / bscalar;
+    const Real* dxi = H.geom[amrlev][0].InvCellSize();
+    for (int d = 0; d < 3; ++d) {
+        MultiFab& f = *fluxes[d];
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(f.boxArray() == amrex::convert(sol.boxArray(), IntVect::TheDimensionVector(d))
+                                         && f.DistributionMap() == sol.DistributionMap(), "compFlux: fluxes[d] must live on the faces of sol's grids");
+        auto const& T = f.layout().tiles(0);
+        if (b[d]) {   // ABecLap: fac = b_scalar * dxinv (MLABecLaplacianT::FFlux, AMReX_MLABecLaplacian.H:1149-1180)
+            B200_KCALL(b200mg_face_flux(T.n, T.d.data(), f.layout().d_vbox(), f.d_fabs(), sol.d_fabs(), b[d]->d_fabs(),
+                                        bscalar * dxi[d], betainv, d, 1, Gpu::gpuStream()));
+        } else {      // Poisson: dxinv * (s - s^-), then * (1 / -1) (AMReX_MLPoisson.H:859-930, AMReX_MLCellABecLap.H:279-288)
+            B200_KCALL(b200mg_face_flux(T.n, T.d.data(), f.layout().d_vbox(), f.d_fabs(), sol.d_fabs(), nullptr,
+                                        dxi[d], betainv, d, 2, Gpu::gpuStream()));
+        }
+    }
+}
+
+void MLLinOp::getFluxes (Vector<Array<MultiFab*, 3>> const& a_flux, Vector<MultiFab*> const& a_sol)
+{
+    for (int alev = 0; alev < H.num_amr_levels; ++alev) { compFlux(alev, a_flux[alev], *a_sol[alev]); }
+}
+
 void MLLinOp::restriction (int amrlev, int cmglev, MultiFab& crse, MultiFab& fine) const
 {
     Gpu::ProfScope prof_scope__(amrlev * 100 + (cmglev - 1));

@@ -417,6 +417,20 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
     ++m_cycles_done[amrlev];
 }
 
+void MLMG::getGradSolution (Vector<Array<MultiFab*, 3>> const& a_grad_sol)
+{
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(int(sol.size()) == namrlevs && int(a_grad_sol.size()) == namrlevs, "getGradSolution: call solve first; one entry per AMR level");
+    for (int alev = 0; alev <= finest_amr_lev; ++alev) { linop.compGrad(alev, a_grad_sol[alev], sol[alev]); }
+}
+
+void MLMG::getFluxes (Vector<Array<MultiFab*, 3>> const& a_flux)
+{
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(int(sol.size()) == namrlevs && int(a_flux.size()) == namrlevs, "getFluxes: call solve first; one entry per AMR level");
+    Vector<MultiFab*> ps(namrlevs);
+    for (int alev = 0; alev < namrlevs; ++alev) { ps[alev] = &sol[alev]; }
+    linop.getFluxes(a_flux, ps);
+}
+
 void MLMG::mgFcycle ()
 {
     const int amrlev = 0;

@@ -160,6 +160,10 @@ void amrex_fi_new_multigrid(MLMG** mlmg, MLLinOp* lp);
 void amrex_fi_delete_multigrid(MLMG* mlmg);
 Real amrex_fi_multigrid_solve(MLMG* mlmg, MultiFab* a_sol[], MultiFab* a_rhs[], Real a_tol_rel, Real a_tol_abs);
 void amrex_fi_multigrid_comp_residual(MLMG* mlmg, MultiFab* a_res[], MultiFab* a_sol[], MultiFab* a_rhs[]);
+/* post-solve: face-centred grad(phi) / fluxes -b*grad(phi) of the solution of the last solve, arrays [level*3 + dir] of
+ * MultiFabs on the faces of the level's grids (reference: AMReX_multigrid_fi.cpp:27-51, MLMG::getGradSolution / getFluxes) */
+void amrex_fi_multigrid_get_grad_solution(MLMG* mlmg, MultiFab* a_grad_sol[]);
+void amrex_fi_multigrid_get_fluxes(MLMG* mlmg, MultiFab* a_fluxes[]);
 void amrex_fi_multigrid_set_verbose(MLMG* mlmg, int v);
 void amrex_fi_multigrid_set_max_iter(MLMG* mlmg, int n);
 void amrex_fi_multigrid_set_max_fmg_iter(MLMG* mlmg, int n);

@@ -133,8 +133,10 @@ int b200mg_gsrb4(int abec, int nboxes, const b200mg_box* h_vbox,
                  const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
                  const b200mg_fab* h_f, const b200mg_ifab* h_m,
                  double alpha, double dhx, double dhy, double dhz, cudaStream_t s);
-/* launch plan of b200mg_gsrb4: rows per CTA tile and ring depths; (8,4,2) default, (8,4,3), (6,5,3), (6,4,4), (6,4,2), (4,6,4), (4,4,4) */
+/* launch plan of b200mg_gsrb4: rows per CTA tile and ring depths; (8,4,2) default, (8,4,3), (6,5,3), (6,4,2), (4,4,4) */
 int b200mg_set_gsrb4_plan(int tile_y, int early_stages, int late_stages);
+/* synchronisation inside a CTA of b200mg_gsrb4: 0 = one CTA barrier per plane, 1 = decoupled warps (mbarrier arrive / wait) */
+void b200mg_set_gsrb4_sync(int decoupled);
 /* L2 prefetch distance (planes ahead of the loads) of the fused pass; 0 switches the prefetch off */
 void b200mg_set_gsrb2_prefetch(int planes);
 /* black (redblack=1) or red sweep restricted to the 1-cell surface shell of every box; max_face_cells = cells of the
@@ -214,6 +216,14 @@ int b200mg_reflux_fine(int npatches, const b200mg_fab* cfpatch, const b200mg_box
                        const b200mg_fab* mask, const b200mg_fab* fine_sol,
                        const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
                        double facx, double facy, double facz, double dtdx, double dtdy, double dtdz, int ratio, cudaStream_t s);
+
+/* face-centred fluxes / gradients of a cell-centred solution (post-solve API: MLMG::getFluxes / getGradSolution).
+ * fbox / tiles: FACE boxes of direction dir; sol needs one filled ghost cell.  mode 0: fac*(s-s^-) (compGrad,
+ * AMReX_MLCellLinOp.H:1421-1436); 1: -fac*b*(s-s^-) (mlabeclap_flux_*, AMReX_MLABecLap_3D_K.H:79-135); 2: fac*(s-s^-)
+ * (mlpoisson_flux_*, AMReX_MLPoisson_3D_K.H:36-98); modes 1, 2 multiply by post afterwards when post != 1. */
+int b200mg_face_flux(int ntiles, const b200mg_tile* tiles, const b200mg_box* fbox,
+                     const b200mg_fab* out, const b200mg_fab* sol, const b200mg_fab* b,
+                     double fac, double post, int dir, int mode, cudaStream_t s);
 
 /* arithmetic cell-centre -> face average (amrex::average_cellcenter_to_face, AMReX_MultiFabUtil_3D_C.H:81-89) */
 int b200mg_cc_to_face(int ntiles, const b200mg_tile* tiles, const b200mg_box* fbox,

@@ -302,6 +302,22 @@ int run_solve (Params const& p)
         times.push_back(std::chrono::duration<double>(t1-t0).count());
         iters = mlmg.getNumIters(); hist = mlmg.getResidualHistory();
         rhs0 = mlmg.getInitRHS(); res0 = mlmg.getInitResidual(); cgit = mlmg.getNumCGIters();
+        if (!p.dump_dir.empty() && is == p.nsolve - 1) {
+            // post-solve API of the reference (MLMG::getFluxes / getGradSolution, face-centred): AMReX_MLMG.H:556-640
+            Vector<Array<MultiFab,3>> flux(p.max_level+1), grad(p.max_level+1);
+            Vector<Array<MultiFab*,3>> pf(p.max_level+1), pg(p.max_level+1);
+            for (int l = 0; l <= p.max_level; ++l) for (int d = 0; d < 3; ++d) {
+                BoxArray fba = amrex::convert(P.grids[l], IntVect::TheDimensionVector(d));
+                flux[l][d].define(fba, P.dmap[l], 1, 0); grad[l][d].define(fba, P.dmap[l], 1, 0);
+                pf[l][d] = &flux[l][d]; pg[l][d] = &grad[l][d];
+            }
+            mlmg.getFluxes(pf);
+            mlmg.getGradSolution(pg);
+            for (int l = 0; l <= p.max_level; ++l) for (int d = 0; d < 3; ++d) {
+                dump_mf(p.dump_dir, "flux"+std::to_string(d)+"_lev"+std::to_string(l), flux[l][d], 0, man);
+                dump_mf(p.dump_dir, "grad"+std::to_string(d)+"_lev"+std::to_string(l), grad[l][d], 0, man);
+            }
+        }
     }
     std::vector<double> err; Long ncells = 0;
     for (int l = 0; l <= p.max_level; ++l) {

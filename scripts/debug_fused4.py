@@ -11,7 +11,7 @@ import amrex_b200 as ab  # noqa: E402
 from common import build_problem, run_ref  # noqa: E402
 
 ab.init(0)
-PLANS = [(8, 4, 3), (8, 4, 2), (6, 5, 3), (6, 4, 4), (6, 4, 2), (4, 6, 4), (4, 4, 4)]
+PLANS = [(8, 4, 2, 0), (8, 4, 2, 1), (8, 4, 3, 1), (6, 5, 3, 1), (6, 4, 2, 1), (4, 4, 4, 1)]   # (tile_y, EARLY, LATE, decoupled warps)
 cases = ((2, 64, 32), (1, 64, 32), (2, 128, 64), (2, 256, 128), (1, 96, 40))
 if len(sys.argv) > 1:
     cases = cases[:int(sys.argv[1])]
@@ -24,7 +24,9 @@ for prob, n, mgs in cases:
         op = P["op"]
         if plan is not None:
             op.setFusedVersion(4)
-            assert ab.lib.amrex_b200_set_fused4_plan(*plan) == 0
+            assert ab.lib.amrex_b200_set_fused4_plan(*plan[:3]) == 0
+            ab.lib.b200mg_set_gsrb4_sync(plan[3])
+            op.setFusedMinBoxCells(32 ** 3)
         op.prepareForSolve()
         for mglev in (0, 1):
             x = op.make(0, mglev, 1)
@@ -53,5 +55,6 @@ for prob, n, mgs in cases:
                 for ax in range(3):
                     vals, cnt = np.unique(bad[:, ax] % (mgs >> mglev), return_counts=True)
                     print(f"   axis {ax} (index mod box size) histogram:", dict(zip(vals.tolist()[:12], cnt.tolist()[:12])))
+ab.lib.b200mg_set_gsrb4_sync(0)
 print("TOTAL differing cells", nbad)
 sys.exit(1 if nbad else 0)

@@ -61,19 +61,21 @@ k = km.get("b200mg_gsrb_abec_pairs_lean")
 print(json.dumps(dict(variant="lean pair sweeps", ms_per_smooth=ms, kernel_ms=k, kernel_gbs_44=44.0 * cells / (k * 1e-3) / 1e9)), flush=True)
 
 op.setSmootherFusion(1)
-plans = [(3, 8, 0, 0), (4, 8, 4, 3), (4, 8, 4, 2), (4, 6, 5, 3), (4, 6, 4, 4), (4, 6, 4, 2), (4, 4, 6, 4), (4, 4, 4, 4)]
+plans = [(3, 8, 0, 0, 0), (4, 8, 4, 2, 0), (4, 8, 4, 2, 1), (4, 8, 4, 3, 1), (4, 6, 5, 3, 1), (4, 6, 4, 2, 1)]   # (version, tile_y, EARLY, LATE, decoupled)
 if os.environ.get("TUNE_PLANS"):
     plans = [tuple(int(v) for v in g.split(",")) for g in os.environ["TUNE_PLANS"].split(";")]
-for ver, ty, se, sl in plans:
+for ver, ty, se, sl, dec in plans:
     op.setFusedVersion(ver)
+    op.setFusedMinBoxCells(32 ** 3)
     if ver >= 4:
         assert ab.lib.amrex_b200_set_fused4_plan(ty, se, sl) == 0
+        ab.lib.b200mg_set_gsrb4_sync(dec)
     else:
         op.setFusedPlan(ty, 128, 0)
     ms = time_smooth()
     km = kernel_ms()
     k = km.get("b200mg_gsrb4") if ver >= 4 else km.get("b200mg_gsrb3")
     sh = km.get("b200mg_gsrb_shell_abec")
-    print(json.dumps(dict(variant=f"fused v{ver} ty={ty} stages={se},{sl}", ms_per_smooth=ms, kernel_ms=k, shell_ms=sh,
+    print(json.dumps(dict(variant=f"fused v{ver} ty={ty} stages={se},{sl} decoupled={dec}", ms_per_smooth=ms, kernel_ms=k, shell_ms=sh,
                           kernel_gbs_56=56.0 * cells / (k * 1e-3) / 1e9 if k else None, same_norm_as_pair=bool(x.norm0() == ref),
                           kernels={a: round(v, 4) for a, v in km.items()})), flush=True)

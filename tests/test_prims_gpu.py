@@ -105,7 +105,7 @@ def test_prims_vs_live_reference(ab, kw, fusion):
 
 # ---- fused smoother, generation 4 (bulk-async-copy staged pass): every compiled launch plan must reproduce the
 #      reference schedule (one kernel per colour) BIT FOR BIT, on both MG levels that are eligible (64^3 and 32^3 boxes)
-FUSED4_PLANS = [(8, 4, 2), (8, 4, 3), (6, 5, 3), (6, 4, 4), (6, 4, 2), (4, 6, 4), (4, 4, 4)]
+FUSED4_PLANS = [(8, 4, 2, 0), (8, 4, 3, 0), (6, 5, 3, 0), (6, 4, 2, 0), (4, 4, 4, 0), (8, 4, 2, 1), (6, 5, 3, 1)]   # (tile_y, EARLY, LATE, decoupled warps)
 
 
 def _two_smooths(ab, op, n, mglev, seed):
@@ -137,7 +137,8 @@ def test_fused4_abeclap_bitwise(ab, plan):
     P = synth_abeclap(ab, n, mgs, fusion=1)
     op = P["op"]
     op.setFusedVersion(4)
-    assert ab.lib.amrex_b200_set_fused4_plan(*plan) == 0
+    assert ab.lib.amrex_b200_set_fused4_plan(*plan[:3]) == 0
+    ab.lib.b200mg_set_gsrb4_sync(plan[3])
     try:
         op.prepareForSolve()
         for mglev in (0, 1):
@@ -146,6 +147,7 @@ def test_fused4_abeclap_bitwise(ab, plan):
             assert np.array_equal(got, want[mglev]), f"plan {plan} mglev {mglev}: max|diff| {np.abs(got - want[mglev]).max():.3e}"
     finally:
         ab.lib.amrex_b200_set_fused4_plan(8, 4, 2)
+        ab.lib.b200mg_set_gsrb4_sync(0)
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref/ref_driver not built")

@@ -102,3 +102,32 @@ def test_two_level_composite(ab, prob_type, n, mgs, maxorder):
         refv = refsol[1:-1, 1:-1, 1:-1]
         mine = P["sol"][lev].download(tuple(v + 1 for v in lo), refv.shape)
         assert rel_maxdiff(mine, refv) <= SOL_TOL
+
+
+@pytest.mark.parametrize("prob_type,n,mgs", [(2, 64, 32), (1, 64, 32)])
+def test_post_solve_fluxes_and_gradients(ab, prob_type, n, mgs):
+    """MLMG::getFluxes / getGradSolution (face-centred, amrex_fi_multigrid_get_fluxes / _get_grad_solution) against the
+    reference's own post-solve output.  The two solutions agree to 1e-10 relative, a face difference divides by h."""
+    ref, dump = run_ref(dump=True, mode="solve", prob_type=prob_type, n_cell=n, max_grid_size=mgs, linop_maxorder=2, agg_grid_size=32)
+    P = build_problem(ab, prob_type, n, mgs, dump, maxorder=2)
+    mlmg = ab.MLMG(P["op"])
+    mlmg.setVerbose(0)
+    mlmg.solve([P["sol"]], [P["rhs"]], 1e-10, 0.0)
+    faces = [ab.MultiFab(P["ba"].clone().convert(tuple(1 if a == d else 0 for a in range(3))), P["dm"], 1, 0) for d in range(3)]
+    for kind, call in (("flux", mlmg.getFluxes), ("grad", mlmg.getGradSolution)):
+        for f in faces:
+            f.setVal(1.e300)
+        call([faces])
+        for d in range(3):
+            shape = tuple(n + (1 if a == d else 0) for a in range(3))
+            mine = faces[d].download((0, 0, 0), shape)
+            lo, want = dump[f"{kind}{d}_lev0"]
+            assert want.shape == shape
+            assert rel_maxdiff(mine, want) <= 1e-7, (kind, d)
+    # the flux is -b_scalar*b*grad: for the Poisson operator (b_scalar = -1, getFluxes divides by it) flux == -grad
+    if prob_type == 1:
+        mlmg.getFluxes([faces])
+        fx = faces[0].download((0, 0, 0), (n + 1, n, n))
+        mlmg.getGradSolution([faces])
+        gx = faces[0].download((0, 0, 0), (n + 1, n, n))
+        assert np.array_equal(fx, -gx)
