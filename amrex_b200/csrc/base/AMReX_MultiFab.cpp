@@ -443,6 +443,7 @@ struct CommPlan {
     CommMetaData meta;
     DeviceTable<b200mg_copytag> d_loc, d_snd, d_rcv;
     int nloc = 0, nsnd = 0, nrcv = 0;
+    int maxloc = 0, maxsnd = 0, maxrcv = 0;              // points of the largest tag of each list (grid sizing)
     struct Peer { int rank; long long offset, count; };
     std::vector<Peer> snd_peers, rcv_peers;
     long long snd_total = 0, rcv_total = 0;
@@ -466,20 +467,21 @@ b200mg_copytag make_tag (CopyComTag const& t, int dst_fab, int src_fab, long lon
 void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc)
 {
     std::vector<b200mg_copytag> h;
-    for (auto const& t : P.meta.LocTags) { h.push_back(make_tag(t, ldst.localIndex(t.dstIndex), lsrc.localIndex(t.srcIndex), 0)); }
+    auto npts = [] (CopyComTag const& t) { return int(std::min<Long>(t.dbox.numPts(), Long(1) << 30)); };
+    for (auto const& t : P.meta.LocTags) { h.push_back(make_tag(t, ldst.localIndex(t.dstIndex), lsrc.localIndex(t.srcIndex), 0)); P.maxloc = std::max(P.maxloc, npts(t)); }
     P.nloc = int(h.size()); P.d_loc.assign(h);
     h.clear();
     long long off = 0;
     for (auto const& kv : P.meta.SndTags) {
         const long long start = off;
-        for (auto const& t : kv.second) { h.push_back(make_tag(t, -1, lsrc.localIndex(t.srcIndex), off)); off += t.dbox.numPts(); }
+        for (auto const& t : kv.second) { h.push_back(make_tag(t, -1, lsrc.localIndex(t.srcIndex), off)); off += t.dbox.numPts(); P.maxsnd = std::max(P.maxsnd, npts(t)); }
         P.snd_peers.push_back({kv.first, start, off - start});
     }
     P.snd_total = off; P.nsnd = int(h.size()); P.d_snd.assign(h);
     h.clear(); off = 0;
     for (auto const& kv : P.meta.RcvTags) {
         const long long start = off;
-        for (auto const& t : kv.second) { h.push_back(make_tag(t, ldst.localIndex(t.dstIndex), -1, off)); off += t.dbox.numPts(); }
+        for (auto const& t : kv.second) { h.push_back(make_tag(t, ldst.localIndex(t.dstIndex), -1, off)); off += t.dbox.numPts(); P.maxrcv = std::max(P.maxrcv, npts(t)); }
         P.rcv_peers.push_back({kv.first, start, off - start});
     }
     P.rcv_total = off; P.nrcv = int(h.size()); P.d_rcv.assign(h);
@@ -507,7 +509,7 @@ void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, i
             AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&P.ev_packed, cudaEventDisableTiming));
             AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&P.ev_arrived, cudaEventDisableTiming));
         }
-        B200_KCALL(b200mg_copy_tags(P.nsnd, P.d_snd.data(), nullptr, src.d_fabs(), P.sndbuf, ncomp, scomp, dcomp, 0, s));
+        B200_KCALL(b200mg_copy_tags(P.nsnd, P.d_snd.data(), nullptr, src.d_fabs(), P.sndbuf, ncomp, scomp, dcomp, 0, P.maxsnd, s));
         ncclComm_t comm = static_cast<ncclComm_t>(ParallelDescriptor::Comm());
         AMREX_ALWAYS_ASSERT_WITH_MESSAGE(comm != nullptr, "multi-rank exchange without an NCCL communicator");
         cudaStream_t cs = overlap ? Gpu::commStream() : s;
@@ -532,10 +534,10 @@ void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, i
         if (overlap) { AMREX_CUDA_SAFE_CALL(cudaEventRecord(P.ev_arrived, cs)); }
         if (Gpu::debugSync()) { Gpu::check(Gpu::debugSyncNow(), "[B200MG_DEBUG_SYNC] ncclSend/ncclRecv group", __FILE__, __LINE__); }
     }
-    B200_KCALL(b200mg_copy_tags(P.nloc, P.d_loc.data(), dst.d_fabs(), src.d_fabs(), nullptr, ncomp, scomp, dcomp, int(op), s));
+    B200_KCALL(b200mg_copy_tags(P.nloc, P.d_loc.data(), dst.d_fabs(), src.d_fabs(), nullptr, ncomp, scomp, dcomp, int(op), P.maxloc, s));
     if (remote) {
         if (overlap) { AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(s, P.ev_arrived, 0)); }
-        B200_KCALL(b200mg_copy_tags(P.nrcv, P.d_rcv.data(), dst.d_fabs(), nullptr, P.rcvbuf, ncomp, scomp, dcomp, int(op), s));
+        B200_KCALL(b200mg_copy_tags(P.nrcv, P.d_rcv.data(), dst.d_fabs(), nullptr, P.rcvbuf, ncomp, scomp, dcomp, int(op), P.maxrcv, s));
     }
 }
 

@@ -443,10 +443,13 @@ int b200mg_normalize_abec (int ntiles, const b200mg_tile* tiles, const b200mg_bo
 
 int b200mg_apply_bc (int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
                      const b200mg_fab* phi, const b200mg_ifab* m, const b200mg_fab* bcval,
-                     int maxorder, double dxinv0, double dxinv1, double dxinv2, int inhomog, cudaStream_t s)
+                     int maxorder, double dxinv0, double dxinv1, double dxinv2, int inhomog, int max_face_cells, cudaStream_t s)
 {
     if (nfaces <= 0) { return 0; }
-    k_apply_bc<<<dim3(nfaces, 8), 128, 0, s>>>(faces, vbox, phi, m, bcval, maxorder, dxinv0, dxinv1, dxinv2, inhomog);
+    // blockIdx.y chunks: 2 ghost cells per thread on the largest face (latency bound otherwise); <= 0: unknown, 8 chunks
+    int chunks = 8;
+    if (max_face_cells > 0) { chunks = (max_face_cells + 255) / 256; chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks); }
+    k_apply_bc<<<dim3(nfaces, chunks), 128, 0, s>>>(faces, vbox, phi, m, bcval, maxorder, dxinv0, dxinv1, dxinv2, inhomog);
     return last_error();
 }
 

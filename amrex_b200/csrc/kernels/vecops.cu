@@ -222,10 +222,14 @@ int b200mg_sum (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, co
 }
 
 int b200mg_copy_tags (int ntags, const b200mg_copytag* tags, const b200mg_fab* dst, const b200mg_fab* src,
-                      double* buf, int ncomp, int scomp, int dcomp, int op, cudaStream_t s)
+                      double* buf, int ncomp, int scomp, int dcomp, int op, int max_pts, cudaStream_t s)
 {
     if (ntags <= 0) { return 0; }
-    k_copy_tags<<<dim3(ntags, 4), 256, 0, s>>>(tags, dst, src, buf, ncomp, scomp, dcomp, op);
+    // blockIdx.y chunks: ~2 points per thread on the largest tag (these launches are latency bound: few tags on a GPU that
+    // owns few boxes), one chunk for the small tags of coarse levels; max_pts <= 0: unknown, 4 chunks
+    int chunks = 4;
+    if (max_pts > 0) { chunks = (max_pts + 511) / 512; chunks = chunks < 1 ? 1 : (chunks > 32 ? 32 : chunks); }
+    k_copy_tags<<<dim3(ntags, chunks), 256, 0, s>>>(tags, dst, src, buf, ncomp, scomp, dcomp, op);
     return last_error();
 }
 

@@ -428,7 +428,7 @@ void MLLinOp::setLevelBC (int amrlev, const MultiFab* levelbcdata)
         }
         if (!tags.empty()) {
             DeviceTable<b200mg_copytag> dt(tags);
-            B200_KCALL(b200mg_copy_tags(int(tags.size()), dt.data(), B.d_table(), levelbcdata->d_fabs(), nullptr, 1, 0, 0, 0, Gpu::gpuStream()));
+            B200_KCALL(b200mg_copy_tags(int(tags.size()), dt.data(), B.d_table(), levelbcdata->d_fabs(), nullptr, 1, 0, 0, 0, 0, Gpu::gpuStream()));
             Gpu::streamSynchronize();
         }
     }
@@ -483,7 +483,7 @@ void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, Stat
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
     const int flagbc = (bc_mode == BCMode::Inhomogeneous);
     B200_KCALL(b200mg_apply_bc(nf, L.bcfaces.data(), L.layout->d_vbox(), in.d_fabs(), L.mask.d_table(),
-                               bndry ? bndry->d_table() : nullptr, maxorder, dxi[0], dxi[1], dxi[2], flagbc, Gpu::gpuStream()));
+                               bndry ? bndry->d_table() : nullptr, maxorder, dxi[0], dxi[1], dxi[2], flagbc, maxFaceCells(L), Gpu::gpuStream()));
 }
 
 void MLLinOp::apply (int amrlev, int mglev, MultiFab& out, MultiFab& in, BCMode bc_mode, StateMode s_mode, const BndrySlabs<double>* bndry) const
@@ -499,6 +499,21 @@ void MLLinOp::apply (int amrlev, int mglev, MultiFab& out, MultiFab& in, BCMode 
 // sweep on the 1-cell surface shell runs after the second halo refresh.
 // Tile table of the fused smoother for one level.  Eligible: every local box has an even x extent <= 256 and the level
 // is big enough for the tiling to pay (small levels are launch-latency bound either way).
+// cells of the largest face of the level's local boxes (grid sizing of the O(n^2) kernels: BC fill, surface shell)
+int MLLinOp::maxFaceCells (LevelData const& L) const
+{
+    if (L.max_face_cells < 0) {
+        int m = 1;
+        for (int li = 0; li < L.layout->numLocal(); ++li) {
+            Box const& b = L.layout->box(li);
+            const int n0 = b.length(0), n1 = b.length(1), n2 = b.length(2);
+            m = std::max(m, std::max(n0 * n1, std::max(n0 * n2, n1 * n2)));
+        }
+        L.max_face_cells = m;
+    }
+    return L.max_face_cells;
+}
+
 bool MLLinOp::planFused (LevelData const& L) const
 {
     if (L.fused_state >= 0) { return L.fused_state == 1; }
@@ -550,12 +565,9 @@ bool MLLinOp::planFused (LevelData const& L) const
             for (int j = b.smallEnd(1); j <= b.bigEnd(1); j += tile_y) { ht.push_back(b200mg_tile{li, j, k, chunk_z}); }
     }
     L.h_vbox.resize(nl);
-    L.max_face_cells = 1;
     for (int li = 0; li < nl; ++li) {
         Box const& b = L.layout->box(li);
         for (int d = 0; d < 3; ++d) { L.h_vbox[li].lo[d] = b.smallEnd(d); L.h_vbox[li].hi[d] = b.bigEnd(d); }
-        const int n0 = b.length(0), n1 = b.length(1), n2 = b.length(2);
-        L.max_face_cells = std::max(L.max_face_cells, std::max(n0 * n1, std::max(n0 * n2, n1 * n2)));
     }
     L.fused_tx = tx; L.fused_tile_y = tile_y; L.fused_chunk_z = chunk_z; L.fused_nblocks = int(ht.size());
     L.fused_tiles.assign(ht);
@@ -1179,7 +1191,7 @@ void MLABecLaplacian::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiF
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
     B200_KCALL(b200mg_gsrb_shell_abec(L.layout->numLocal(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), m_a_coeffs[amrlev][mglev].d_fabs(),
                                       m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(), m_b_coeffs[amrlev][mglev][2].d_fabs(),
-                                      L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, L.max_face_cells, Gpu::gpuStream()));
+                                      L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, maxFaceCells(L), Gpu::gpuStream()));
 }
 
 // ============================================================================================ MLPoisson
@@ -1257,7 +1269,7 @@ void MLPoisson::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab con
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
     B200_KCALL(b200mg_gsrb_shell_poisson(L.layout->numLocal(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
-                                         dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, L.max_face_cells, Gpu::gpuStream()));
+                                         dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, maxFaceCells(L), Gpu::gpuStream()));
 }
 
 } // namespace amrex

@@ -163,6 +163,7 @@ def b200_arm(args):
         ab.comm_init_from_torch()
     n, mgs = args.n_cell, args.max_grid_size
     P = synth_abeclap(ab, n, mgs, fusion=args.fusion, keep_host=True)
+    P["op"].setFusedMinBoxCells(0)     # the product default: the per-level cost model picks fused pass or colour sweeps (tests force fusion)
     mlmg = ab.MLMG(P["op"])
     mlmg.setVerbose(0)
     stream = torch.cuda.ExternalStream(ab.lib.amrex_b200_stream(), device=torch.device("cuda", local))

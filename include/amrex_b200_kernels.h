@@ -177,10 +177,11 @@ int b200mg_normalize_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box
                           double alpha, double dhx, double dhy, double dhz, cudaStream_t s);
 
 /* ---- boundary conditions (K9 mllinop_apply_bc_* AMReX_MLLinOp_K.H:14-327; K11 comp_interp_coef0 :329-571).
- *      m, f, bcval: [box*6+face] tables.  bcval may be NULL (homogeneous). */
+ *      m, f, bcval: [box*6+face] tables.  bcval may be NULL (homogeneous).  max_face_cells: cells of the largest box face
+ *      (sizes the grid: 2 ghost cells per thread; <= 0 if unknown). */
 int b200mg_apply_bc(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
                     const b200mg_fab* phi, const b200mg_ifab* m, const b200mg_fab* bcval,
-                    int maxorder, double dxinv0, double dxinv1, double dxinv2, int inhomog, cudaStream_t s);
+                    int maxorder, double dxinv0, double dxinv1, double dxinv2, int inhomog, int max_face_cells, cudaStream_t s);
 int b200mg_comp_interp_coef0(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
                              const b200mg_fab* f, const b200mg_ifab* m,
                              int maxorder, double dxinv0, double dxinv1, double dxinv2, cudaStream_t s);
@@ -256,9 +257,10 @@ int b200mg_sum(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, con
 long long b200mg_reduce_scratch_doubles(int ntiles);
 
 /* ---- halo / redistribution copies (K10 fab_to_fab, pack, unpack; AMReX_FBI.H:53-70,272-328,729-893).
- *      op: 0 = copy, 1 = add.  buf: linear staging buffer (may be NULL when no tag uses it). */
+ *      op: 0 = copy, 1 = add.  buf: linear staging buffer (may be NULL when no tag uses it).
+ *      max_pts: points of the largest tag (sizes the grid: ~2 points per thread; <= 0 if unknown). */
 int b200mg_copy_tags(int ntags, const b200mg_copytag* tags, const b200mg_fab* dst, const b200mg_fab* src,
-                     double* buf, int ncomp, int scomp, int dcomp, int op, cudaStream_t s);
+                     double* buf, int ncomp, int scomp, int dcomp, int op, int max_pts, cudaStream_t s);
 
 /* library identification */
 const char* b200mg_version(void);

@@ -113,7 +113,7 @@ def test_post_solve_fluxes_and_gradients(ab, prob_type, n, mgs):
     mlmg = ab.MLMG(P["op"])
     mlmg.setVerbose(0)
     mlmg.solve([P["sol"]], [P["rhs"]], 1e-10, 0.0)
-    faces = [ab.MultiFab(P["ba"].clone().convert(tuple(1 if a == d else 0 for a in range(3))), P["dm"], 1, 0) for d in range(3)]
+    faces = [ab.MultiFab(P["ba"], P["dm"], 1, 0, nodal=[1 if a == d else 0 for a in range(3)]) for d in range(3)]
     for kind, call in (("flux", mlmg.getFluxes), ("grad", mlmg.getGradSolution)):
         for f in faces:
             f.setVal(1.e300)
