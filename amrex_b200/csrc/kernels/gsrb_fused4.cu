@@ -472,14 +472,21 @@ int launch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
     return last_error();
 }
 
+// rows per CTA tile actually used: boxes of nx <= 64 under the default 8-row plan take 16 rows, so that a CTA keeps the
+// footprint it has at nx = 128 (18 warps, one CTA per SM) instead of two half-size CTAs per SM paying the per-plane
+// overheads twice
+int effective_tile_y (int nxmax) { return (g_plan_ty == 8 && nxmax <= 64) ? 16 : g_plan_ty; }
+
 template <bool ABEC>
 int dispatch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
 {
-    const int key = g_plan_ty * 100 + g_plan_se * 10 + g_plan_sl;
+    const int key = effective_tile_y(P.nxs) * 100 + g_plan_se * 10 + g_plan_sl;
 #define B200MG_PLAN4(K, TYv, SEv, SLv) case K: return g_plan_dec ? launch4<ABEC, TYv, SEv, SLv, true>(P, nboxes, s) : launch4<ABEC, TYv, SEv, SLv, false>(P, nboxes, s)
     switch (key) {
         B200MG_PLAN4(842, 8, 4, 2);
         B200MG_PLAN4(843, 8, 4, 3);
+        B200MG_PLAN4(1642, 16, 4, 2);
+        B200MG_PLAN4(1643, 16, 4, 3);
         B200MG_PLAN4(653, 6, 5, 3);
         B200MG_PLAN4(642, 6, 4, 2);
         B200MG_PLAN4(444, 4, 4, 4);
@@ -528,7 +535,8 @@ int b200mg_gsrb4 (int abec, int nboxes, const b200mg_box* h_vbox,
     P.txp = ((nxmax / 2 + 31) / 32) * 32;
     P.nxs = nxmax;
     P.ps = int(h_phi_in[0].jstride); P.cs = int(h_rhs[0].jstride); P.xs = abec ? int(h_bx[0].jstride) : 0;
-    P.nty = (nymax + g_plan_ty - 1) / g_plan_ty;
+    const int ty = effective_tile_y(nxmax);
+    P.nty = (nymax + ty - 1) / ty;
     for (int b0 = 0; b0 < nboxes; b0 += kMaxBoxes4) {
         const int nb = (nboxes - b0 < kMaxBoxes4) ? nboxes - b0 : kMaxBoxes4;
         for (int n = 0; n < nb; ++n) {

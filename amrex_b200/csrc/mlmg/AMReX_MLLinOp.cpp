@@ -526,7 +526,7 @@ bool MLLinOp::planFused (LevelData const& L) const
     } else {
         // Cost model fitted to the measured launches (profiles/r01_s25_kernel_times_per_level_1gpu_fused4.txt, 512^3 on
         // 1 / 2 GPUs): the fused pass (generation 4) runs ceil(CTAs / resident CTAs) rounds of (nz+1) barrier-separated
-        // steps of ~1.8 us (one 640-thread CTA per SM at nx = 128) or ~2.5 us (two CTAs per SM at nx <= 64) + the surface
+        // steps of ~1.8 us (one 576..640-thread CTA per SM: 8 rows at nx = 128, 16 rows at nx = 64) + the surface
         // shell; a colour sweep takes cells x 44 B / 4.65 TB/s + ~40 us of ramp and tail.  Few boxes per GPU or short boxes favour the sweeps.
         int nx0 = 0, ny0 = 0, nz0 = 0; Long surf = 0;
         for (int li = 0; li < nl; ++li) {
@@ -535,10 +535,11 @@ bool MLLinOp::planFused (LevelData const& L) const
             surf += 2 * (Long(b.length(0)) * b.length(1) + Long(b.length(0)) * b.length(2) + Long(b.length(1)) * b.length(2));
         }
         if (nx0 > 128 || nx0 < 64) { return false; }
-        const int per_sm = (nx0 > 64) ? 1 : 2;
-        const double ctas = double(nl) * double((ny0 + 7) / 8);
-        const double rounds = std::ceil(ctas / (148.0 * per_sm));
-        const double fused_us = rounds * (nz0 + 1) * (per_sm == 1 ? 1.8 : 2.5) + 320.0 * double(surf) / 6.3e6 + 5.0;
+        // one CTA per SM: 8 rows x 128 cells, or 16 rows x 64 cells (b200mg_gsrb4 picks the tile from nx)
+        const int tile_y = (nx0 > 64) ? 8 : 16;
+        const double ctas = double(nl) * double((ny0 + tile_y - 1) / tile_y);
+        const double rounds = std::ceil(ctas / 148.0);
+        const double fused_us = rounds * (nz0 + 1) * 1.8 + 320.0 * double(surf) / 6.3e6 + 5.0;
         const double pairs_us = 2.0 * (double(L.layout->localCells()) * 44.0 / 4.65e6 + 40.0);
         if (fused_us > 0.95 * pairs_us) { return false; }
     }

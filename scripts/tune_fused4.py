@@ -1,7 +1,7 @@
 """Times one finest-level smooth of the benchmark workload with the lean pair sweeps, the generation-3 fused pass and the
 generation-4 (bulk-async-copy staged) fused pass for every compiled (tile_y, EARLY, LATE) plan.  One line per variant.
 
-  python scripts/tune_fused4.py [n_cell] [reps]
+  python scripts/tune_fused4.py [n_cell] [reps] [max_grid_size]
 """
 import json
 import os
@@ -16,8 +16,9 @@ from common import synth_abeclap  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+mgs = int(sys.argv[3]) if len(sys.argv) > 3 else (128 if n >= 128 else n)
 ab.init(0)
-P = synth_abeclap(ab, n, 128 if n >= 128 else n, fusion=0)
+P = synth_abeclap(ab, n, mgs, fusion=0)
 op = P["op"]
 op.prepareForSolve()
 x = op.make(0, 0, 1)
