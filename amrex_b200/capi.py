@@ -429,8 +429,8 @@ class MLLinOp(_Obj):
         check()
         return MultiFab(ptr=p)
 
-    def smooth(self, amrlev, mglev, sol, rhs, skip_fillboundary=False):
-        lib.amrex_b200_linop_smooth(self.ptr, amrlev, mglev, sol.ptr, rhs.ptr, int(skip_fillboundary))
+    def smooth(self, amrlev, mglev, sol, rhs, skip_fillboundary=False, zero_input=False):
+        lib.amrex_b200_linop_smooth(self.ptr, amrlev, mglev, sol.ptr, rhs.ptr, int(bool(skip_fillboundary)) | (2 if zero_input else 0))
         check()
 
     def apply(self, amrlev, mglev, out, inp):

@@ -21,7 +21,7 @@ namespace {
     ncclComm_t g_comm = nullptr;
     bool g_gpu_init = false;
     int g_device = -1;
-    cudaStream_t g_stream = nullptr, g_comm_stream = nullptr, g_override = nullptr;
+    cudaStream_t g_stream = nullptr, g_comm_stream = nullptr, g_aux_stream = nullptr, g_override = nullptr;
     long long g_launches = 0;
     double* g_red_dev = nullptr;     // staging for scalar all-reduces
     double* g_red_pin = nullptr;
@@ -54,6 +54,7 @@ void Initialize (int device_id)
     AMREX_CUDA_SAFE_CALL(cudaSetDevice(g_device));
     AMREX_CUDA_SAFE_CALL(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     AMREX_CUDA_SAFE_CALL(cudaStreamCreateWithFlags(&g_comm_stream, cudaStreamNonBlocking));
+    AMREX_CUDA_SAFE_CALL(cudaStreamCreateWithFlags(&g_aux_stream, cudaStreamNonBlocking));
     AMREX_CUDA_SAFE_CALL(cudaMalloc(&g_red_dev, kRedMax * sizeof(double)));
     AMREX_CUDA_SAFE_CALL(cudaMallocHost(&g_red_pin, kRedMax * sizeof(double)));
     g_gpu_init = true;
@@ -65,8 +66,8 @@ void Finalize ()
     cudaDeviceSynchronize();
     The_Arena()->freeUnused();
     cudaFree(g_red_dev); cudaFreeHost(g_red_pin);
-    cudaStreamDestroy(g_stream); cudaStreamDestroy(g_comm_stream);
-    g_stream = g_comm_stream = nullptr;
+    cudaStreamDestroy(g_stream); cudaStreamDestroy(g_comm_stream); cudaStreamDestroy(g_aux_stream);
+    g_stream = g_comm_stream = g_aux_stream = nullptr;
     g_gpu_init = false;
 }
 
@@ -76,6 +77,7 @@ int debugSyncNow () noexcept { return int(cudaDeviceSynchronize()); }
 int deviceId () noexcept { return g_device; }
 cudaStream_t gpuStream () noexcept { return g_override ? g_override : g_stream; }
 cudaStream_t commStream () noexcept { return g_comm_stream; }
+cudaStream_t auxStream () noexcept { return g_aux_stream; }
 void setStream (cudaStream_t s) noexcept { g_override = s; }
 void streamSynchronize () { AMREX_CUDA_SAFE_CALL(cudaStreamSynchronize(gpuStream())); }
 void synchronize () { AMREX_CUDA_SAFE_CALL(cudaDeviceSynchronize()); }

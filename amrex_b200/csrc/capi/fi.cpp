@@ -244,7 +244,7 @@ void amrex_b200_linop_prepare (MLLinOp* linop) { FI_VOID( linop->prepareForSolve
 void amrex_b200_linop_make (MLLinOp* linop, MultiFab** mf, int amrlev, int mglev, int ng) { FI_VOID( *mf = new MultiFab(linop->make(amrlev, mglev, ng)); ) }
 void amrex_b200_linop_smooth (MLLinOp* linop, int amrlev, int mglev, MultiFab* sol, const MultiFab* rhs, int skip)
 {
-    FI_VOID( linop->smooth(amrlev, mglev, *sol, *rhs, skip != 0); )
+    FI_VOID( linop->smooth(amrlev, mglev, *sol, *rhs, (skip & 1) != 0, (skip & 2) != 0); )   // bit 1: zero_input
 }
 void amrex_b200_linop_apply (MLLinOp* linop, int amrlev, int mglev, MultiFab* out, MultiFab* in, int inhomog)
 {

@@ -53,6 +53,8 @@ struct FusedParams4 {
     int txp;                                            // compute threads per row (multiple of 32)
     int nxs;                                            // longest row (max nx, even)
     int ps, cs, xs;                                     // row pitches (elements) of phi, of rhs / a / by / bz, and of bx
+    int phi_zero;                                       // 1: the input is identically zero (first smooth of a V-cycle): it is
+                                                        // not read from HBM, the shared-memory planes are zero-filled instead
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -122,6 +124,7 @@ template <int SE, int SL>
 struct Ring {
     static constexpr bool pe = (SE & (SE - 1)) == 0, pl = (SL & (SL - 1)) == 0;
     uint32_t c2 = 2u, cp2 = 0u, cl = 0u, cpl = 0u;
+    __device__ __forceinline__ uint32_t sm1 (int t) const { return pe ? uint32_t(t - 1) & (SE - 1) : (c2 >= 3u ? c2 - 3u : c2 + SE - 3u); }
     __device__ __forceinline__ uint32_t s0 (int t) const { return pe ? uint32_t(t) & (SE - 1) : (c2 >= 2u ? c2 - 2u : c2 + SE - 2u); }
     __device__ __forceinline__ uint32_t s1 (int t) const { return pe ? uint32_t(t + 1) & (SE - 1) : (c2 >= 1u ? c2 - 1u : c2 + SE - 1u); }
     __device__ __forceinline__ uint32_t s2 (int t) const { return pe ? uint32_t(t + 2) & (SE - 1) : c2; }
@@ -197,6 +200,10 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
     double* __restrict__ e1 = smE + s1 * Y.e_size;
     double* __restrict__ e0 = smE + s0 * Y.e_size;
     const double* __restrict__ l1 = smL + sl * Y.l_size;
+
+    // zero input: the red value this thread left in plane t-1 two steps ago (last read during step t-1) is cleared before
+    // the slot is used again - the copy engine does not touch the phi part of the planes in this mode
+    if (P.phi_zero && t >= 2) { smE[R.sm1(t) * Y.e_size + Y.e_phi + prow + C] = 0.0; }
 
     // decoupled warps: the red x / y neighbours in EARLY[t].phi were written by other warps during THEIR step t-1
     if constexpr (DEC) { if (t >= 1) { mbar_wait(barS + 8u * uint32_t((t - 1) & 1), uint32_t(((t - 1) >> 1) & 1)); } }
@@ -353,6 +360,10 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
     static_assert(SE >= 4 && SL >= 2, "ring depths: EARLY planes live three steps, LATE planes one");
 
     const int tid = int(threadIdx.x);
+    if (P.phi_zero) {                                               // phi part of every EARLY slot := 0 (see FusedParams4)
+        const int nphi = Y.e_bz - Y.e_phi;
+        for (int i = tid; i < SE * nphi; i += int(blockDim.x)) { smE[(i / nphi) * Y.e_size + Y.e_phi + (i % nphi)] = 0.0; }
+    }
     if (tid == 0) {
         for (int s = 0; s < SE + SL; ++s) { mbar_init(barE + 8u * s, 1u); }
         for (int s = 0; s < 4; ++s) { mbar_init(barS + 8u * s, blockDim.x / 32u); }
@@ -367,7 +378,7 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
             H->d[d].bytes = uint32_t(8 * nelem); H->d[d].qmin = qmin; H->d[d].qmax = qmax;
         };
         set(0, B.pin.p + ((B.lo[0] - 2 - B.glo_in[0]) + (long long)(pj_lo - B.glo_in[1]) * B.pin.js + (long long)(kbase - B.glo_in[2]) * B.pin.ks),
-            B.pin.ks, Y.e_phi + (pj_lo - (j0 - 2)) * Y.PS, (pj_hi - pj_lo) * Y.PS + nx + 4, 0, nz + 1);
+            B.pin.ks, Y.e_phi + (pj_lo - (j0 - 2)) * Y.PS, P.phi_zero ? 0 : (pj_hi - pj_lo) * Y.PS + nx + 4, 0, nz + 1);
         const int ccn = (cj_hi - cj_lo) * Y.NX + nx, ccoff = (cj_lo - (j0 - 1)) * Y.NX;
         set(2, B.rhs.p + ((long long)(cj_lo - B.lo[1]) * B.rhs.js + (long long)(kbase - B.lo[2]) * B.rhs.ks), B.rhs.ks, Y.l_rhs + ccoff, ccn, 1, nz);
         if constexpr (ABEC) {
@@ -481,7 +492,8 @@ template <bool ABEC>
 int dispatch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
 {
     const int key = effective_tile_y(P.nxs) * 100 + g_plan_se * 10 + g_plan_sl;
-#define B200MG_PLAN4(K, TYv, SEv, SLv) case K: return g_plan_dec ? launch4<ABEC, TYv, SEv, SLv, true>(P, nboxes, s) : launch4<ABEC, TYv, SEv, SLv, false>(P, nboxes, s)
+    // (the zero-input mode clears consumed red values behind the CTA barrier of the previous step: lock-step kernel only)
+#define B200MG_PLAN4(K, TYv, SEv, SLv) case K: return (g_plan_dec && !P.phi_zero) ? launch4<ABEC, TYv, SEv, SLv, true>(P, nboxes, s) : launch4<ABEC, TYv, SEv, SLv, false>(P, nboxes, s)
     switch (key) {
         B200MG_PLAN4(842, 8, 4, 2);
         B200MG_PLAN4(843, 8, 4, 3);
@@ -521,10 +533,11 @@ int b200mg_gsrb4 (int abec, int nboxes, const b200mg_box* h_vbox,
                   const b200mg_fab* h_phi_in, const b200mg_fab* h_phi_out, const b200mg_fab* h_rhs, const b200mg_fab* h_a,
                   const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
                   const b200mg_fab* h_f, const b200mg_ifab* h_m,
-                  double alpha, double dhx, double dhy, double dhz, cudaStream_t s)
+                  double alpha, double dhx, double dhy, double dhz, int phi_zero, cudaStream_t s)
 {
     if (nboxes <= 0) { return 0; }
     static FusedParams4 P;                              // kept off the stack; copied by value at every launch
+    P.phi_zero = phi_zero ? 1 : 0;
     P.alpha = alpha; P.dhx = dhx; P.dhy = dhy; P.dhz = dhz;
     int nxmax = 0, nymax = 0;
     for (int b = 0; b < nboxes; ++b) {

@@ -199,18 +199,24 @@ k_adotx_poisson (const b200mg_tile* __restrict__ tiles, const b200mg_box* __rest
 // z-marching operator apply / residual: each thread owns the cell pair (i0, i0+1) of one row and streams through the
 // planes of its tile; the x pair of planes k-1, k, k+1 and the z-face coefficient stay in registers, everything is read with
 // 16-byte loads (x/y neighbour loads hit L1).  Requires even x extents (16-byte aligned pairs); nx <= 2 * blockDim.x.
-template <bool ABEC>
+// NORM: max |y| over the launch is folded into *norm (which the host zeroes ahead of the launch) - the residual and its
+// inf-norm (MLMGT::ResNormInf, AMReX_MLMG.H:1808-1812) in ONE pass: per-thread running maximum, warp shuffles, one atomic
+// per warp.  max is order independent, so the result is the same bits as the separate reduction kernel.
+template <bool ABEC, bool NORM>
 __global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y, 4)
 k_adotx_pair (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox,
               const b200mg_fab* yf, const b200mg_fab* xf, const b200mg_fab* rf, const b200mg_fab* af,
               const b200mg_fab* bxf, const b200mg_fab* byf, const b200mg_fab* bzf,
-              double alpha, double dhx, double dhy, double dhz)
+              double alpha, double dhx, double dhy, double dhz, double* __restrict__ norm)
 {
     const b200mg_tile t = tiles[blockIdx.x];
     const b200mg_box vb = vbox[t.box];
     const int i0 = vb.lo[0] + 2 * int(threadIdx.x);
     const int j = t.j0 + int(threadIdx.y);
-    if (i0 >= vb.hi[0] || j > vb.hi[1]) { return; }
+    const bool idle = (i0 >= vb.hi[0] || j > vb.hi[1]);
+    if (!NORM && idle) { return; }
+    double nrm = 0.0;
+    if (!idle) {
     const int k0 = t.k0, k1 = min(t.k0 + tile_nk(t) - 1, vb.hi[2]);
     const auto x = view(xf[t.box]); const auto y = view(yf[t.box]);
     const int x_js = int(x.js), x_ks = int(x.ks), y_ks = int(y.ks);
@@ -257,8 +263,18 @@ k_adotx_pair (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restric
             pr += r_ks;
         }
         *reinterpret_cast<double2*>(py) = v;
+        if constexpr (NORM) { nrm = fmax(nrm, fmax(fabs(v.x), fabs(v.y))); }
         xm = xc; xc = xp;
         px += x_ks; py += y_ks;
+    }
+    }
+    if constexpr (NORM) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, o)); }
+        // non-negative doubles order like their bit patterns
+        if (((threadIdx.x + threadIdx.y * blockDim.x) & 31u) == 0u && nrm > 0.0) {
+            atomicMax(reinterpret_cast<unsigned long long*>(norm), static_cast<unsigned long long>(__double_as_longlong(nrm)));
+        }
     }
 }
 
@@ -465,19 +481,23 @@ int b200mg_comp_interp_coef0 (int nfaces, const b200mg_bcface* faces, const b200
 int b200mg_adotx_abec_pairs (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
                              const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs, const b200mg_fab* a,
                              const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
-                             double alpha, double dhx, double dhy, double dhz, cudaStream_t s)
+                             double alpha, double dhx, double dhy, double dhz, double* norminf, cudaStream_t s)
 {
+    if (norminf) { const cudaError_t e = cudaMemsetAsync(norminf, 0, sizeof(double), s); if (e != cudaSuccess) { return int(e); } }
     if (ntiles <= 0) { return 0; }
-    k_adotx_pair<true><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, a, bx, by, bz, alpha, dhx, dhy, dhz);
+    if (norminf) { k_adotx_pair<true, true><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, a, bx, by, bz, alpha, dhx, dhy, dhz, norminf); }
+    else { k_adotx_pair<true, false><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, a, bx, by, bz, alpha, dhx, dhy, dhz, nullptr); }
     return last_error();
 }
 
 int b200mg_adotx_poisson_pairs (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
                                 const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs,
-                                double dhx, double dhy, double dhz, cudaStream_t s)
+                                double dhx, double dhy, double dhz, double* norminf, cudaStream_t s)
 {
+    if (norminf) { const cudaError_t e = cudaMemsetAsync(norminf, 0, sizeof(double), s); if (e != cudaSuccess) { return int(e); } }
     if (ntiles <= 0) { return 0; }
-    k_adotx_pair<false><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, nullptr, nullptr, nullptr, nullptr, 0.0, dhx, dhy, dhz);
+    if (norminf) { k_adotx_pair<false, true><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, nullptr, nullptr, nullptr, nullptr, 0.0, dhx, dhy, dhz, norminf); }
+    else { k_adotx_pair<false, false><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, nullptr, nullptr, nullptr, nullptr, 0.0, dhx, dhy, dhz, nullptr); }
     return last_error();
 }
 

@@ -476,12 +476,36 @@ void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, Stat
     Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     AMREX_ALWAYS_ASSERT(mglev == 0 || bc_mode == BCMode::Homogeneous);
     AMREX_ALWAYS_ASSERT(bndry != nullptr || bc_mode == BCMode::Homogeneous);
-    if (!skip_fillboundary) { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
     LevelData const& L = lev(amrlev, mglev);
     const int nf = int(L.bcfaces_h.size());
-    if (nf == 0) { return; }
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
     const int flagbc = (bc_mode == BCMode::Inhomogeneous);
+    // The physical-boundary fill reads valid cells only and writes ghost cells outside the domain; the halo exchange
+    // writes ghost cells inside it: the two are independent (cross stencil) and both are latency-bound O(n^2) launches,
+    // so on big levels the BC kernel runs on a second stream next to the halo copies (fork / join through events).
+    bool concurrent = false;
+    if (!skip_fillboundary && nf > 0 && m_bc_overlap && maxFaceCells(L) >= 4096 && !Gpu::profiling() && !Gpu::debugSync()) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        concurrent = (cudaStreamIsCapturing(Gpu::gpuStream(), &cs) == cudaSuccess) && cs == cudaStreamCaptureStatusNone;
+    }
+    if (concurrent) {
+        static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        if (!ev_fork) {
+            AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
+        cudaStream_t s = Gpu::gpuStream(), aux = Gpu::auxStream();
+        AMREX_CUDA_SAFE_CALL(cudaEventRecord(ev_fork, s));
+        AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(aux, ev_fork, 0));
+        B200_KCALL(b200mg_apply_bc(nf, L.bcfaces.data(), L.layout->d_vbox(), in.d_fabs(), L.mask.d_table(),
+                                   bndry ? bndry->d_table() : nullptr, maxorder, dxi[0], dxi[1], dxi[2], flagbc, maxFaceCells(L), aux));
+        AMREX_CUDA_SAFE_CALL(cudaEventRecord(ev_join, aux));
+        in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true);
+        AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(s, ev_join, 0));
+        return;
+    }
+    if (!skip_fillboundary) { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
+    if (nf == 0) { return; }
     B200_KCALL(b200mg_apply_bc(nf, L.bcfaces.data(), L.layout->d_vbox(), in.d_fabs(), L.mask.d_table(),
                                bndry ? bndry->d_table() : nullptr, maxorder, dxi[0], dxi[1], dxi[2], flagbc, maxFaceCells(L), Gpu::gpuStream()));
 }
@@ -610,11 +634,14 @@ void MLLinOp::setFusedPlan (int tile_y, int chunk_z, int prefetch_planes)
     for (auto& av : m_lev) { for (auto& L : av) { L->fused_state = -1; } }
 }
 
-void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, bool skip_fillboundary) const
+void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, bool skip_fillboundary, bool zero_input) const
 {
     Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     LevelData const& L = lev(amrlev, mglev);
     const bool fuse = m_fuse_colors && m_use_gauss_seidel && planFused(L);
+    // zero input without a prior setVal: only the bulk-copy fused pass can do without reading sol
+    const bool zero4 = zero_input && fuse && m_zero_input_opt && m_fused_version >= 4 && L.fused4_ok != 0;
+    if (zero_input && !zero4) { sol.setVal(0.0); skip_fillboundary = true; }
     if (!fuse) {
         for (int redblack = 0; redblack < 2; ++redblack) {
             applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary);
@@ -624,19 +651,28 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
         return;
     }
     if (!L.scratch) { L.scratch = std::make_unique<MultiFab>(sol.boxArray(), sol.DistributionMap(), 1, sol.nGrow()); }
-    applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary);
-    Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs);
+    // (homogeneous BCs of a zero field are zero ghost cells: nothing to fill, and the pass does not read them)
+    if (!zero4) { applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary); }
+    Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs, zero4);
     sol.swap(*L.scratch);
     applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false);
     FsmoothShell(amrlev, mglev, sol, rhs, 1);
 }
 
-void MLLinOp::solutionResidual (int amrlev, MultiFab& resid, MultiFab& x, MultiFab const& b, const MultiFab* crse_bcdata)
+bool MLLinOp::solutionResidual (int amrlev, MultiFab& resid, MultiFab& x, MultiFab const& b, const MultiFab* crse_bcdata, Real* resnorm)
 {
     Gpu::ProfScope prof_scope__(amrlev * 100 + 0);
     if (crse_bcdata != nullptr) { updateSolBC(amrlev, *crse_bcdata); }
     applyBC(amrlev, 0, x, BCMode::Inhomogeneous, StateMode::Solution, m_bndry_sol[amrlev].get());
-    Fapply(amrlev, 0, resid, x, &b);    // resid = b - L(x), fused (== Fapply + Xpay(resid,-1,b))
+    // resid = b - L(x), fused (== Fapply + Xpay(resid,-1,b)); the unmasked inf-norm rides along when asked for
+    const bool want = resnorm != nullptr && m_fuse_resnorm && amrlev == H.num_amr_levels - 1;
+    const bool got = Fapply(amrlev, 0, resid, x, &b, want ? reduce_result_slot(1) : nullptr);
+    if (got) {
+        double r = fetch_reduce_result(1);
+        ParallelDescriptor::ReduceRealMax(&r, 1);
+        *resnorm = r;
+    }
+    return got;
 }
 
 void MLLinOp::correctionResidual (int amrlev, int mglev, MultiFab& resid, MultiFab& x, MultiFab const& b, BCMode bc_mode, const MultiFab* crse_bcdata)
@@ -1114,7 +1150,7 @@ void MLABecLaplacian::normalize (int amrlev, int mglev, MultiFab& mf) const
                                      m_a_scalar, m_b_scalar * dxi[0] * dxi[0], m_b_scalar * dxi[1] * dxi[1], m_b_scalar * dxi[2] * dxi[2], Gpu::gpuStream()));
 }
 
-void MLABecLaplacian::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab const& in, const MultiFab* rhs) const
+bool MLABecLaplacian::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab const& in, const MultiFab* rhs, Real* norm_dev) const
 {
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();   // dh = beta*dxinv^2 (AMReX_MLABecLap_3D_K.H:18-20)
     auto const& T = out.layout().tiles(0);
@@ -1122,13 +1158,14 @@ void MLABecLaplacian::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab con
         B200_KCALL(b200mg_adotx_abec_pairs(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
                                            m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(),
                                            m_b_coeffs[amrlev][mglev][2].d_fabs(), m_a_scalar, m_b_scalar * dxi[0] * dxi[0], m_b_scalar * dxi[1] * dxi[1],
-                                           m_b_scalar * dxi[2] * dxi[2], Gpu::gpuStream()));
-        return;
+                                           m_b_scalar * dxi[2] * dxi[2], norm_dev, Gpu::gpuStream()));
+        return norm_dev != nullptr;
     }
     B200_KCALL(b200mg_adotx_abec(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
                                  m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(),
                                  m_b_coeffs[amrlev][mglev][2].d_fabs(), m_a_scalar, m_b_scalar * dxi[0] * dxi[0], m_b_scalar * dxi[1] * dxi[1],
                                  m_b_scalar * dxi[2] * dxi[2], Gpu::gpuStream()));
+    return false;
 }
 
 namespace { inline void gsrb_dh (Geometry const& g, Real b, Real dh[3]) { const Real* h = g.CellSize(); for (int d = 0; d < 3; ++d) { dh[d] = b / (h[d] * h[d]); } } }
@@ -1156,7 +1193,7 @@ void MLABecLaplacian::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab co
                                 L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, Gpu::gpuStream()));
 }
 
-void MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab const& sol_in, MultiFab const& rhs) const
+void MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& sol_in, MultiFab const& rhs, bool zero_input) const
 {
     LevelData const& L = lev(amrlev, mglev);
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
@@ -1167,12 +1204,13 @@ void MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiF
             Gpu::KernelScope ks__("b200mg_gsrb4(abec)");
             e = b200mg_gsrb4(1, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), &ac.desc(0),
                              &bc[0].desc(0), &bc[1].desc(0), &bc[2].desc(0), L.undrrelxr.h_table(), L.mask.h_table(),
-                             m_a_scalar, dh[0], dh[1], dh[2], Gpu::gpuStream());
+                             m_a_scalar, dh[0], dh[1], dh[2], zero_input ? 1 : 0, Gpu::gpuStream());
         }
         if (e == 0) { return; }
         if (e != int(cudaErrorInvalidValue)) { Gpu::check(e, "b200mg_gsrb4", __FILE__, __LINE__); }
         L.fused4_ok = 0;                                // layout not eligible for the bulk-copy pass: generation 3 from now on
     }
+    if (zero_input) { sol_in.setVal(0.0); }             // the older generations read their input
     if (m_fused_version >= 3) {
         auto const& ac = m_a_coeffs[amrlev][mglev]; auto const& bc = m_b_coeffs[amrlev][mglev];
         B200_KCALL(b200mg_gsrb3(1, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), &ac.desc(0),
@@ -1205,17 +1243,18 @@ void MLPoisson::prepareForSolve ()
     if (no_dirichlet) { for (int alev = 0; alev < H.num_amr_levels; ++alev) { if (H.domain_covered[alev]) { m_is_singular[alev] = 1; } } }
 }
 
-void MLPoisson::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab const& in, const MultiFab* rhs) const
+bool MLPoisson::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab const& in, const MultiFab* rhs, Real* norm_dev) const
 {
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
     auto const& T = out.layout().tiles(0);
     if (out.layout().pairable()) {
         B200_KCALL(b200mg_adotx_poisson_pairs(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
-                                              dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream()));
-        return;
+                                              dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], norm_dev, Gpu::gpuStream()));
+        return norm_dev != nullptr;
     }
     B200_KCALL(b200mg_adotx_poisson(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
                                     dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream()));
+    return false;
 }
 
 void MLPoisson::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
@@ -1238,7 +1277,7 @@ void MLPoisson::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& r
                                    dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, Gpu::gpuStream()));
 }
 
-void MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab const& sol_in, MultiFab const& rhs) const
+void MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& sol_in, MultiFab const& rhs, bool zero_input) const
 {
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
@@ -1248,12 +1287,13 @@ void MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab con
             Gpu::KernelScope ks__("b200mg_gsrb4(poisson)");
             e = b200mg_gsrb4(0, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), nullptr,
                              nullptr, nullptr, nullptr, L.undrrelxr.h_table(), L.mask.h_table(),
-                             0.0, dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream());
+                             0.0, dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], zero_input ? 1 : 0, Gpu::gpuStream());
         }
         if (e == 0) { return; }
         if (e != int(cudaErrorInvalidValue)) { Gpu::check(e, "b200mg_gsrb4", __FILE__, __LINE__); }
         L.fused4_ok = 0;
     }
+    if (zero_input) { sol_in.setVal(0.0); }
     if (m_fused_version >= 3) {
         B200_KCALL(b200mg_gsrb3(0, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), nullptr,
                                 nullptr, nullptr, nullptr, L.undrrelxr.h_table(), L.mask.h_table(),

@@ -253,8 +253,10 @@ Real MLMG::solve (Vector<MultiFab*> const& a_sol, Vector<MultiFab const*> const&
         for (int iter = 0; iter < niters; ++iter) {
             oneIter(iter);
             converged = false;
-            computeResidual(finest_amr_lev);
-            const Real fine_norminf = ResNormInf(finest_amr_lev);
+            // the finest level's residual and its (unmasked) norm come out of one kernel where the operator can do that
+            Real fused_norm = 0.0;
+            const bool have_norm = computeResidual(finest_amr_lev, &fused_norm);
+            const Real fine_norminf = have_norm ? fused_norm : ResNormInf(finest_amr_lev);
             m_iter_fine_resnorm0.push_back(fine_norminf);
             composite_norminf = fine_norminf;
             if (verbose >= 2) { Print0(cat("MLMG: Iteration ", std::setw(3), iter + 1, " Fine resid/", norm_name, " = ", fine_norminf / max_norm, "\n")); }
@@ -378,10 +380,12 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
     auto down = [&] (int m0, int m1) {                   // levels [m0, m1): pre-smooth, residual, restriction
         for (int mglev = m0; mglev < m1; ++mglev) {
             Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
-            cor[amrlev][mglev].setVal(0.0);
+            // cor = 0, then nu1 smooths: the zeroing is handed to the first smooth (the fused pass needs neither the
+            // setVal nor the read of its zero input; every other path zeroes inside smooth)
+            if (nu1 <= 0) { cor[amrlev][mglev].setVal(0.0); }
             bool skip_fillboundary = true;
             for (int i = 0; i < nu1; ++i) {
-                linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev], skip_fillboundary);
+                linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev], skip_fillboundary, i == 0);
                 skip_fillboundary = false;
             }
             computeResOfCorrection(amrlev, mglev);
@@ -505,10 +509,10 @@ void MLMG::computeMLResidual (int amrlevmax)
     }
 }
 
-void MLMG::computeResidual (int alev)
+bool MLMG::computeResidual (int alev, Real* resnorm)
 {
     const MultiFab* crse_bcdata = (alev > 0) ? &sol[alev - 1] : nullptr;
-    linop.solutionResidual(alev, res[alev][0], sol[alev], rhs[alev], crse_bcdata);
+    return linop.solutionResidual(alev, res[alev][0], sol[alev], rhs[alev], crse_bcdata, resnorm);
 }
 
 void MLMG::computeResOfCorrection (int amrlev, int mglev)

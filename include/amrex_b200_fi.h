@@ -145,7 +145,9 @@ int amrex_b200_set_fused4_plan(int tile_y, int early_stages, int late_stages);
 int  amrex_b200_linop_num_mg_levels(const MLLinOp* linop, int amrlev);
 void amrex_b200_linop_prepare(MLLinOp* linop);
 void amrex_b200_linop_make(MLLinOp* linop, MultiFab** mf, int amrlev, int mglev, int ng);
-void amrex_b200_linop_smooth(MLLinOp* linop, int amrlev, int mglev, MultiFab* sol, const MultiFab* rhs, int skip_fillboundary);
+/* flags: bit 0 = skip_fillboundary (AMReX_MLCellLinOp.H:1206), bit 1 = zero_input (sol is taken as identically zero
+ * without being read: MLMG's cor.setVal(0) + first pre-smooth in one pass) */
+void amrex_b200_linop_smooth(MLLinOp* linop, int amrlev, int mglev, MultiFab* sol, const MultiFab* rhs, int flags);
 void amrex_b200_linop_apply(MLLinOp* linop, int amrlev, int mglev, MultiFab* out, MultiFab* in, int inhomog);
 void amrex_b200_linop_residual(MLLinOp* linop, int amrlev, int mglev, MultiFab* resid, MultiFab* x, const MultiFab* b, int inhomog);
 void amrex_b200_linop_restriction(MLLinOp* linop, int amrlev, int cmglev, MultiFab* crse, MultiFab* fine);

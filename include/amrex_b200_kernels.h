@@ -127,12 +127,15 @@ int b200mg_gsrb3(int abec, int nboxes, const b200mg_box* h_vbox,
  * its use by a dedicated producer warp; compute warps read shared memory only.  Whole-z CTAs of (all x) x tile_y rows.
  * Requirements: even x extent, 4 <= nx <= 128, ny >= 2, rows 16-byte aligned at the first valid cell, even strides,
  * phi rows readable on [lo-2, hi+2], bx rows nx+2 doubles long (all guaranteed by the FabArray allocator);
- * cudaErrorInvalidValue otherwise (the caller falls back to b200mg_gsrb3). */
+ * cudaErrorInvalidValue otherwise (the caller falls back to b200mg_gsrb3).
+ * phi_zero != 0: the input is identically zero INCLUDING its ghost cells (first smooth after cor.setVal(0),
+ * AMReX_MLMG.H:1318-1326): h_phi_in is not read at all - the shared-memory planes are zero-filled instead - so the
+ * caller may skip the setVal; the output is the same bits as with a zeroed input. */
 int b200mg_gsrb4(int abec, int nboxes, const b200mg_box* h_vbox,
                  const b200mg_fab* h_phi_in, const b200mg_fab* h_phi_out, const b200mg_fab* h_rhs, const b200mg_fab* h_a,
                  const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
                  const b200mg_fab* h_f, const b200mg_ifab* h_m,
-                 double alpha, double dhx, double dhy, double dhz, cudaStream_t s);
+                 double alpha, double dhx, double dhy, double dhz, int phi_zero, cudaStream_t s);
 /* launch plan of b200mg_gsrb4: rows per CTA tile and ring depths; (8,4,2) default, (8,4,3), (6,5,3), (6,4,2), (4,4,4) */
 int b200mg_set_gsrb4_plan(int tile_y, int early_stages, int late_stages);
 /* synchronisation inside a CTA of b200mg_gsrb4: 0 = one CTA barrier per plane, 1 = decoupled warps (mbarrier arrive / wait) */
@@ -162,14 +165,16 @@ int b200mg_adotx_poisson(int ntiles, const b200mg_tile* tiles, const b200mg_box*
                          const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs,
                          double dhx, double dhy, double dhz, cudaStream_t s);
 /* Same operators for levels whose boxes all have an even x extent <= 128: one thread per cell PAIR, streaming along z with
- * 16-byte loads (the fast path; results are bit-identical to the entries above). */
+ * 16-byte loads (the fast path; results are bit-identical to the entries above).
+ * norminf != NULL (device pointer): *norminf = max |y| over the launch, computed in the same pass (residual + ResNormInf,
+ * AMReX_MLMG.H:1808-1812, without re-reading y); NULL: not computed. */
 int b200mg_adotx_abec_pairs(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
                             const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs, const b200mg_fab* a,
                             const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
-                            double alpha, double dhx, double dhy, double dhz, cudaStream_t s);
+                            double alpha, double dhx, double dhy, double dhz, double* norminf, cudaStream_t s);
 int b200mg_adotx_poisson_pairs(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
                                const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs,
-                               double dhx, double dhy, double dhz, cudaStream_t s);
+                               double dhx, double dhy, double dhz, double* norminf, cudaStream_t s);
 /* K13 mlabeclap_normalize AMReX_MLABecLap_3D_K.H:60-75 */
 int b200mg_normalize_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
                           const b200mg_fab* x, const b200mg_fab* a,

@@ -267,3 +267,24 @@ def synth_abeclap(ab, n, mgs, maxorder=2, fusion=None, a=1.e-3, b=1.0, keep_host
             op.setFusedMinBoxCells(32 ** 3)     # tests exercise the fused pass on small boxes too (default: 64^3 and up)
     return dict(geom=geom, ba=ba, dm=dm, sol=sol, sol0=sol0, rhs=rhs, op=op, keep=[acoef, bcc] + faces, n=n, host=host,
                 pmap=pmap, me=me)
+
+
+def synth_poisson(ab, n, mgs, maxorder=2, fusion=None):
+    """MLPoisson on an n^3 unit cube chopped into mgs^3 boxes, homogeneous Dirichlet on every face (prob_type 1 BCs);
+    fields are supplied by the caller.  Returns dict with geom/ba/dm/sol0/op."""
+    ab.Geometry.setup((0., 0., 0.), (1., 1., 1.), (0, 0, 0))
+    geom = ab.Geometry((0, 0, 0), (n - 1,) * 3)
+    ba = ab.BoxArray((0, 0, 0), (n - 1,) * 3).maxSize(mgs)
+    dm = ab.DistributionMapping(ba)
+    sol0 = ab.MultiFab(ba, dm, 1, 1)
+    sol0.setVal(0.0, ng=1)
+    D = ab.LinOpBCType.Dirichlet
+    op = ab.MLPoisson([geom], [ba], [dm])
+    op.setMaxOrder(maxorder)
+    op.setDomainBC((D, D, D), (D, D, D))
+    op.setLevelBC(0, sol0)
+    if fusion is not None:
+        op.setSmootherFusion(fusion)
+        if fusion:
+            op.setFusedMinBoxCells(32 ** 3)
+    return dict(geom=geom, ba=ba, dm=dm, sol0=sol0, op=op, n=n)

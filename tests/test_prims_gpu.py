@@ -150,6 +150,48 @@ def test_fused4_abeclap_bitwise(ab, plan):
         ab.lib.b200mg_set_gsrb4_sync(0)
 
 
+@pytest.mark.parametrize("plan", [(8, 4, 2), (6, 5, 3), (4, 4, 4)])
+@pytest.mark.parametrize("kind", ["abeclap", "poisson"])
+def test_fused4_zero_input_bitwise(ab, kind, plan):
+    """smooth(zero_input) - MLMG's cor.setVal(0) + first pre-smooth as ONE pass that never reads cor - must give the bits
+    of setVal(0) followed by the ordinary smooth, also when cor holds garbage (NaN) on entry; a second smooth follows to
+    show that the ghost cells the pass leaves behind are handled."""
+    from common import synth_abeclap, synth_poisson
+    n, mgs = 128, 64
+    synth = synth_abeclap if kind == "abeclap" else synth_poisson
+    assert ab.lib.amrex_b200_set_fused4_plan(*plan) == 0
+    try:
+        out = {}
+        for zero_input in (False, True):
+            P = synth(ab, n, mgs, fusion=1)
+            op = P["op"]
+            op.setFusedVersion(4)
+            op.prepareForSolve()
+            for mglev in (0, 1):
+                nn = n >> mglev
+                x = op.make(0, mglev, 1)
+                b = op.make(0, mglev, 0)
+                b.upload(np.random.default_rng(5 + mglev).standard_normal((nn, nn, nn)), (0, 0, 0))
+                x.setVal(float("nan") if zero_input else 0.0, ng=1)
+                ab.profile_enable(True)
+                if zero_input:
+                    op.smooth(0, mglev, x, b, zero_input=True)
+                else:
+                    op.smooth(0, mglev, x, b, skip_fillboundary=True)
+                op.smooth(0, mglev, x, b)
+                names = set(q[0] for q in ab.profile_report())
+                ab.profile_enable(False)
+                assert "b200mg_gsrb4" in names, names
+                if zero_input:
+                    assert "b200mg_setval" not in names, names      # the zeroing really was skipped
+                out[(zero_input, mglev)] = x.download((0, 0, 0), (nn, nn, nn))
+        for mglev in (0, 1):
+            assert np.isfinite(out[(True, mglev)]).all()
+            assert np.array_equal(out[(False, mglev)], out[(True, mglev)]), f"mglev {mglev}"
+    finally:
+        ab.lib.amrex_b200_set_fused4_plan(8, 4, 2)
+
+
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref/ref_driver not built")
 @pytest.mark.parametrize("prob,n,mgs", [(1, 64, 32), (1, 96, 40), (2, 64, 32)])
 def test_fused4_vs_pairs_reference_problems(ab, prob, n, mgs):

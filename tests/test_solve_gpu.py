@@ -131,3 +131,36 @@ def test_post_solve_fluxes_and_gradients(ab, prob_type, n, mgs):
         mlmg.getGradSolution([faces])
         gx = faces[0].download((0, 0, 0), (n + 1, n, n))
         assert np.array_equal(fx, -gx)
+
+
+@pytest.mark.parametrize("kind", ["abeclap", "poisson"])
+def test_b200_schedule_switches_are_bit_neutral(ab, kind, monkeypatch):
+    """The B200-only schedule changes - residual + inf-norm in one kernel, first pre-smooth without zeroing / reading the
+    correction, BC fill on a second stream next to the halo copies - must not change a single bit of the solve: same
+    residual history and same solution as with all three switched off (environment read when the operator is built)."""
+    import os
+    from common import synth_abeclap, synth_poisson
+    n, mgs = 128, 64
+    out = {}
+    for off in (True, False):
+        for v in ("B200MG_NO_FUSED_RESNORM", "B200MG_NO_ZERO_INPUT", "B200MG_NO_BC_OVERLAP"):
+            if off:
+                monkeypatch.setenv(v, "1")
+            else:
+                monkeypatch.delenv(v, raising=False)
+        if kind == "abeclap":
+            P = synth_abeclap(ab, n, mgs, fusion=1)
+            sol, rhs = P["sol"], P["rhs"]
+        else:
+            P = synth_poisson(ab, n, mgs, fusion=1)
+            sol = ab.MultiFab(P["ba"], P["dm"], 1, 1)
+            rhs = ab.MultiFab(P["ba"], P["dm"], 1, 0)
+            sol.setVal(0.0, ng=1)
+            rhs.upload(np.random.default_rng(3).standard_normal((n, n, n)), (0, 0, 0))
+        mlmg = ab.MLMG(P["op"])
+        mlmg.setVerbose(0)
+        mlmg.solve([sol], [rhs], 1e-10, 0.0)
+        out[off] = (mlmg.numIters(), list(mlmg.residualHistory()), sol.download((0, 0, 0), (n, n, n)))
+    assert out[True][0] == out[False][0]
+    assert out[True][1] == out[False][1]
+    assert np.array_equal(out[True][2], out[False][2])
