@@ -67,6 +67,7 @@ _SIGS = {
     "amrex_fi_abeclap_set_scalars": (None, [_P, _D, _D]), "amrex_fi_abeclap_set_acoeffs": (None, [_P, _I, _P]),
     "amrex_fi_abeclap_set_bcoeffs": (None, [_P, _I, _PP]),
     "amrex_b200_linop_set_smoother_fusion": (None, [_P, _I]),
+    "amrex_b200_linop_set_gauss_seidel": (None, [_P, _I]),
     "amrex_b200_linop_set_fused_plan": (None, [_P, _I, _I, _I]),
     "amrex_b200_linop_set_fused_version": (None, [_P, _I]),
     "amrex_b200_set_fused4_plan": (_I, [_I, _I, _I]),
@@ -92,6 +93,14 @@ _SIGS = {
     "amrex_b200_multigrid_num_iters": (_I, [_P]), "amrex_b200_multigrid_residual_history": (_I, [_P, _DP, _I]),
     "amrex_b200_multigrid_init_rhs": (_D, [_P]), "amrex_b200_multigrid_init_residual": (_D, [_P]),
     "amrex_b200_multigrid_cg_iters": (_I, [_P, _IP, _I]), "amrex_b200_multigrid_timers": (None, [_P, _DP]),
+    "amrex_b200_new_gmres_mlmg": (None, [_PP, _P]), "amrex_b200_delete_gmres_mlmg": (None, [_P]),
+    "amrex_b200_gmres_mlmg_solve": (None, [_P, _P, _P, _D, _D]),
+    "amrex_b200_gmres_mlmg_set_verbose": (None, [_P, _I]), "amrex_b200_gmres_mlmg_set_max_iters": (None, [_P, _I]),
+    "amrex_b200_gmres_mlmg_set_restart_length": (None, [_P, _I]), "amrex_b200_gmres_mlmg_use_precond": (None, [_P, _I]),
+    "amrex_b200_gmres_mlmg_set_precond_num_iters": (None, [_P, _I]),
+    "amrex_b200_gmres_mlmg_set_property_of_zero": (None, [_P, _I]),
+    "amrex_b200_gmres_mlmg_num_iters": (_I, [_P]), "amrex_b200_gmres_mlmg_status": (_I, [_P]),
+    "amrex_b200_gmres_mlmg_residual_norm": (_D, [_P]), "amrex_b200_gmres_mlmg_residual_history": (_I, [_P, _DP, _I]),
     "amrex_b200_hierarchy_new": (_P, [_I, _PP, _PP, _PP, _I, _I, _I, _I, _I, _I]),
     "amrex_b200_hierarchy_delete": (None, [_P]), "amrex_b200_hierarchy_num_mg_levels": (_I, [_P, _I]),
     "amrex_b200_hierarchy_nboxes": (_I, [_P, _I, _I]), "amrex_b200_hierarchy_level": (None, [_P, _I, _I, _IP, _IP, _IP]),
@@ -407,6 +416,9 @@ class MLLinOp(_Obj):
     def setSmootherFusion(self, f):
         lib.amrex_b200_linop_set_smoother_fusion(self.ptr, int(f))
 
+    def setGaussSeidel(self, flag):
+        lib.amrex_b200_linop_set_gauss_seidel(self.ptr, int(bool(flag)))
+
     def setFusedVersion(self, v):
         lib.amrex_b200_linop_set_fused_version(self.ptr, int(v))
 
@@ -593,3 +605,38 @@ def cpc_tags(ba_dst, dm_dst, ng_dst, ba_src, dm_src, ng_src, period, myproc, kin
     buf = (C.c_int * (15 * max(n, 1)))()
     lib.amrex_b200_cpc_tags(ba_dst.ptr, dm_dst.ptr, ng_dst, ba_src.ptr, dm_src.ptr, ng_src, _i3(period), myproc, kind, buf, n)
     return _tags(n, buf)
+
+
+class GMRESMLMG(_Obj):
+    """GMRES preconditioned by MLMG V-cycles (amrex::GMRESMLMG, LinearSolvers/AMReX_GMRES_MLMG.H)."""
+    _deleter = "amrex_b200_delete_gmres_mlmg"
+
+    def __init__(self, mlmg):
+        p = C.c_void_p()
+        self._mlmg = mlmg
+        lib.amrex_b200_new_gmres_mlmg(C.byref(p), mlmg.ptr)
+        check()
+        super().__init__(p)
+
+    def setVerbose(self, v): lib.amrex_b200_gmres_mlmg_set_verbose(self.ptr, v)
+    def setMaxIters(self, n): lib.amrex_b200_gmres_mlmg_set_max_iters(self.ptr, n)
+    def usePrecond(self, f): lib.amrex_b200_gmres_mlmg_use_precond(self.ptr, int(bool(f)))
+    def setPrecondNumIters(self, n): lib.amrex_b200_gmres_mlmg_set_precond_num_iters(self.ptr, n)
+    def setPropertyOfZero(self, f): lib.amrex_b200_gmres_mlmg_set_property_of_zero(self.ptr, int(bool(f)))
+
+    def setRestartLength(self, n):
+        lib.amrex_b200_gmres_mlmg_set_restart_length(self.ptr, n)
+        check()
+
+    def solve(self, sol, rhs, tol_rel, tol_abs):
+        lib.amrex_b200_gmres_mlmg_solve(self.ptr, sol.ptr, rhs.ptr, float(tol_rel), float(tol_abs))
+        check()
+
+    def numIters(self): return lib.amrex_b200_gmres_mlmg_num_iters(self.ptr)
+    def status(self): return lib.amrex_b200_gmres_mlmg_status(self.ptr)
+    def residualNorm(self): return lib.amrex_b200_gmres_mlmg_residual_norm(self.ptr)
+
+    def residualHistory(self):
+        a = (C.c_double * 4096)()
+        n = lib.amrex_b200_gmres_mlmg_residual_history(self.ptr, a, 4096)
+        return list(a)[:min(n, 4096)]

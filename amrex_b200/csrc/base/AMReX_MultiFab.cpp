@@ -404,6 +404,52 @@ Real MultiFab::Dot (MultiFab const& x, MultiFab const& y, bool local)
     return r;
 }
 
+void MultiFab::MultiDot (MultiFab const& x, Vector<MultiFab const*> const& v, Real* out, bool local)
+{
+    const int nv = int(v.size());
+    if (nv == 0) { return; }
+    auto const& T = x.layout().tiles(0);
+    static double* d_res = nullptr; static double* h_res = nullptr;
+    static double* d_scr = nullptr; static long long scr_n = 0;
+    if (!d_res) {
+        d_res = static_cast<double*>(The_Arena()->alloc(B200MG_KRYLOV_GROUP * sizeof(double)));
+        h_res = static_cast<double*>(pinned_alloc(B200MG_KRYLOV_GROUP * sizeof(double)));
+    }
+    const long long need = b200mg_multi_dot_scratch_doubles(T.n);
+    if (need > scr_n) {
+        if (d_scr) { Gpu::streamSynchronize(); The_Arena()->free(d_scr); }
+        scr_n = need; d_scr = static_cast<double*>(The_Arena()->alloc(scr_n * sizeof(double)));
+    }
+    for (int n0 = 0; n0 < nv; n0 += B200MG_KRYLOV_GROUP) {
+        const int g = std::min(B200MG_KRYLOV_GROUP, nv - n0);
+        const b200mg_fab* tabs[B200MG_KRYLOV_GROUP];
+        for (int n = 0; n < g; ++n) {
+            AMREX_ALWAYS_ASSERT(v[n0 + n]->layoutPtr() == x.layoutPtr() || (v[n0 + n]->boxArray() == x.boxArray() && v[n0 + n]->DistributionMap() == x.DistributionMap()));
+            tabs[n] = v[n0 + n]->d_fabs();
+        }
+        B200_KCALL(b200mg_multi_dot(T.n, T.d.data(), x.layout().d_vbox(), x.d_fabs(), g, tabs, d_res, d_scr, Gpu::gpuStream()));
+        Gpu::dtoh_memcpy_async(h_res, d_res, g * sizeof(double));
+        Gpu::streamSynchronize();
+        for (int n = 0; n < g; ++n) { out[n0 + n] = h_res[n]; }
+    }
+    if (!local) { ParallelDescriptor::ReduceRealSum(out, nv); }
+}
+
+void MultiFab::MultiSaxpy (MultiFab& w, Vector<MultiFab const*> const& v, const Real* a)
+{
+    const int nv = int(v.size());
+    auto const& T = w.layout().tiles(0);
+    for (int n0 = 0; n0 < nv; n0 += B200MG_KRYLOV_GROUP) {
+        const int g = std::min(B200MG_KRYLOV_GROUP, nv - n0);
+        const b200mg_fab* tabs[B200MG_KRYLOV_GROUP];
+        for (int n = 0; n < g; ++n) {
+            AMREX_ALWAYS_ASSERT(v[n0 + n]->layoutPtr() == w.layoutPtr() || (v[n0 + n]->boxArray() == w.boxArray() && v[n0 + n]->DistributionMap() == w.DistributionMap()));
+            tabs[n] = v[n0 + n]->d_fabs();
+        }
+        B200_KCALL(b200mg_multi_axpy(T.n, T.d.data(), w.layout().d_vbox(), w.d_fabs(), g, tabs, a + n0, Gpu::gpuStream()));
+    }
+}
+
 namespace {
 void check_same (MultiFab const& a, MultiFab const& b, int scomp, int dcomp, int ncomp, int ng)
 {

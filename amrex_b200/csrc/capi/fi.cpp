@@ -1,5 +1,6 @@
 // extern "C" boundary: see include/amrex_b200_fi.h for the contract and the reference citations.
 #include "../mlmg/AMReX_MLMG.H"
+#include "../mlmg/AMReX_GMRESMLMG.H"
 #include "amrex_b200_fi.h"
 
 #include <cstring>
@@ -235,6 +236,7 @@ void amrex_fi_abeclap_set_bcoeffs (MLLinOp* linop, int amrlev, const MultiFab* b
     FI_VOID( dynamic_cast<MLABecLaplacian&>(*linop).setBCoeffs(amrlev, {beta[0], beta[1], beta[2]}); )
 }
 void amrex_b200_linop_set_smoother_fusion (MLLinOp* linop, int fuse) { linop->setSmootherFusion(fuse); }
+void amrex_b200_linop_set_gauss_seidel (MLLinOp* linop, int flag) { linop->setGaussSeidel(flag != 0); }   // MLCellLinOpT::setGaussSeidel, AMReX_MLCellLinOp.H:58
 void amrex_b200_linop_set_fused_plan (MLLinOp* linop, int tile_y, int chunk_z, int prefetch_planes) { linop->setFusedPlan(tile_y, chunk_z, prefetch_planes); }
 void amrex_b200_linop_set_fused_version (MLLinOp* linop, int version) { linop->setFusedVersion(version); }
 void amrex_b200_linop_set_fused_min_box_cells (MLLinOp* linop, long long n) { linop->setFusedMinBoxCells(Long(n)); }
@@ -355,6 +357,31 @@ int amrex_b200_multigrid_cg_iters (const MLMG* mlmg, int* iters, int capacity)
     return int(h.size());
 }
 void amrex_b200_multigrid_timers (const MLMG* mlmg, double t[3]) { auto a = mlmg->getTimers(); t[0] = a[0]; t[1] = a[1]; t[2] = a[2]; }
+
+// --------------------------------------------------------------------------------------------- GMRES + MLMG
+// The reference has no Fortran/C interface for GMRESMLMG (AMReX_GMRES_MLMG.H:19-110 is C++ only); these entries expose
+// the same members one to one.
+void amrex_b200_new_gmres_mlmg (GMRESMLMG** g, MLMG* mlmg) { FI_VOID( *g = new GMRESMLMG(*mlmg); ) }
+void amrex_b200_delete_gmres_mlmg (GMRESMLMG* g) { FI_VOID( delete g; ) }
+void amrex_b200_gmres_mlmg_solve (GMRESMLMG* g, MultiFab* sol, const MultiFab* rhs, Real tol_rel, Real tol_abs)
+{
+    FI_VOID( g->solve(*sol, *rhs, tol_rel, tol_abs); )
+}
+void amrex_b200_gmres_mlmg_set_verbose (GMRESMLMG* g, int v) { g->setVerbose(v); }
+void amrex_b200_gmres_mlmg_set_max_iters (GMRESMLMG* g, int n) { g->setMaxIters(n); }
+void amrex_b200_gmres_mlmg_set_restart_length (GMRESMLMG* g, int n) { FI_VOID( g->setRestartLength(n); ) }
+void amrex_b200_gmres_mlmg_use_precond (GMRESMLMG* g, int f) { g->usePrecond(f != 0); }
+void amrex_b200_gmres_mlmg_set_precond_num_iters (GMRESMLMG* g, int n) { g->setPrecondNumIters(n); }
+void amrex_b200_gmres_mlmg_set_property_of_zero (GMRESMLMG* g, int f) { g->setPropertyOfZero(f != 0); }
+int amrex_b200_gmres_mlmg_num_iters (const GMRESMLMG* g) { return g->getNumIters(); }
+int amrex_b200_gmres_mlmg_status (const GMRESMLMG* g) { return g->getStatus(); }
+Real amrex_b200_gmres_mlmg_residual_norm (const GMRESMLMG* g) { return g->getResidualNorm(); }
+int amrex_b200_gmres_mlmg_residual_history (const GMRESMLMG* g, Real* hist, int capacity)
+{
+    auto const& h = g->getResidualHistory();
+    for (int i = 0; i < capacity && i < int(h.size()); ++i) { hist[i] = h[i]; }
+    return int(h.size());
+}
 
 // ------------------------------------------------------------------------------- host-only metadata
 void* amrex_b200_hierarchy_new (int nlevels, const Geometry* geom[], const BoxArray* ba[], const DistributionMapping* dm[],

@@ -106,6 +106,64 @@ k_gsrb_poisson (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restr
     }
 }
 
+// Damped Jacobi sweep (abec_jacobi AMReX_MLABecLap_3D_K.H:332-375, mlpoisson_jacobi AMReX_MLPoisson_3D_K.H:250-281): the
+// reference first stores Ax = L(phi) (Fapply, AMReX_MLABecLaplacian.H:866-871) and then updates every cell; here both
+// happen in one out-of-place pass (phi_in -> phi_out), so Ax is never written.  ad*: the apply's beta*dxinv^2
+// (AMReX_MLABecLap_3D_K.H:18-20), dh*: the smoother's beta/h^2 (AMReX_MLABecLaplacian.H:907-909).
+struct JacobiDh { double adx, ady, adz; };
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_jacobi_abec (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* outf, AbecArgs A, JacobiDh D)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const AbecViews V(A, t.box);
+    const auto out = view(outf[t.box]);
+    const int js = int(V.phi.js), ks = int(V.phi.ks);
+    tile_for(t, vb, 0, [&] (int i, int j, int k) {
+        const double* pc = V.phi.ptr(i, j, k);
+        const double p = *pc;
+        const double* pbx = V.bx.ptr(i, j, k); const double* pby = V.by.ptr(i, j, k); const double* pbz = V.bz.ptr(i, j, k);
+        const double a = V.a(i, j, k);
+        const double bxm = pbx[0], bxp = pbx[1], bym = pby[0], byp = pby[V.by.js], bzm = pbz[0], bzp = pbz[V.bz.ks];
+        const double ax = adotx_abec_cell(p, pc[-1], pc[1], pc[-js], pc[js], pc[-ks], pc[ks], a, bxm, bxp, bym, byp, bzm, bzp,
+                                          V.alpha, D.adx, D.ady, D.adz);
+        FaceCoefs cf;
+        if (on_surface(i, j, k, vb)) { cf = face_coefs(i, j, k, vb, V.f6, V.m6); }
+        else {
+#pragma unroll
+            for (int n = 0; n < 6; ++n) { cf.c[n] = 0.0; }
+        }
+        const double gamma = V.alpha * a + V.dhx * (bxm + bxp) + V.dhy * (bym + byp) + V.dhz * (bzm + bzp);
+        const double g_m_d = gamma - (V.dhx * (bxm * cf.c[0] + bxp * cf.c[3]) + V.dhy * (bym * cf.c[1] + byp * cf.c[4]) + V.dhz * (bzm * cf.c[2] + bzp * cf.c[5]));
+        out(i, j, k) = p + (2.0 / 3.0) * (V.rhs(i, j, k) - ax) / g_m_d;
+    });
+}
+
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_jacobi_poisson (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* outf, PoisArgs A)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const PoisViews V(A, t.box);
+    const auto out = view(outf[t.box]);
+    const int js = int(V.phi.js), ks = int(V.phi.ks);
+    tile_for(t, vb, 0, [&] (int i, int j, int k) {
+        const double* pc = V.phi.ptr(i, j, k);
+        const double p = *pc;
+        const double ax = adotx_poisson_cell(p, pc[-1], pc[1], pc[-js], pc[js], pc[-ks], pc[ks], V.dhx, V.dhy, V.dhz);
+        FaceCoefs cf;
+        if (on_surface(i, j, k, vb)) { cf = face_coefs(i, j, k, vb, V.f6, V.m6); }
+        else {
+#pragma unroll
+            for (int n = 0; n < 6; ++n) { cf.c[n] = 0.0; }
+        }
+        const double gamma = -2.0 * (V.dhx + V.dhy + V.dhz);
+        const double g_m_d = gamma + V.dhx * (cf.c[0] + cf.c[3]) + V.dhy * (cf.c[1] + cf.c[4]) + V.dhz * (cf.c[2] + cf.c[5]);
+        out(i, j, k) = p + (2.0 / 3.0) * (V.rhs(i, j, k) - ax) / g_m_d;
+    });
+}
+
 // Surface shell sweep: blockIdx.x = box*6 + face, blockIdx.y = chunk of the face; every shell cell belongs to exactly one
 // face (x faces own their edges/corners, y faces exclude the x extremes, z faces exclude x and y extremes).  Threads run
 // along the face's fastest-varying tangential direction (x for y/z faces: coalesced).
@@ -498,6 +556,28 @@ int b200mg_adotx_poisson_pairs (int ntiles, const b200mg_tile* tiles, const b200
     if (ntiles <= 0) { return 0; }
     if (norminf) { k_adotx_pair<false, true><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, nullptr, nullptr, nullptr, nullptr, 0.0, dhx, dhy, dhz, norminf); }
     else { k_adotx_pair<false, false><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, nullptr, nullptr, nullptr, nullptr, 0.0, dhx, dhy, dhz, nullptr); }
+    return last_error();
+}
+
+int b200mg_jacobi_abec (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                        const b200mg_fab* phi_out, const b200mg_fab* phi_in, const b200mg_fab* rhs, const b200mg_fab* a,
+                        const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                        const b200mg_fab* f, const b200mg_ifab* m, double alpha, double dhx, double dhy, double dhz,
+                        double adx, double ady, double adz, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    const AbecArgs A{phi_in, rhs, a, bx, by, bz, f, m, alpha, dhx, dhy, dhz};
+    k_jacobi_abec<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, phi_out, A, JacobiDh{adx, ady, adz});
+    return last_error();
+}
+
+int b200mg_jacobi_poisson (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                           const b200mg_fab* phi_out, const b200mg_fab* phi_in, const b200mg_fab* rhs,
+                           const b200mg_fab* f, const b200mg_ifab* m, double dhx, double dhy, double dhz, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    const PoisArgs A{phi_in, rhs, f, m, dhx, dhy, dhz};
+    k_jacobi_poisson<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, phi_out, A);
     return last_error();
 }
 

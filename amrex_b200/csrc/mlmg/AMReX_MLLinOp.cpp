@@ -642,6 +642,18 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
     // zero input without a prior setVal: only the bulk-copy fused pass can do without reading sol
     const bool zero4 = zero_input && fuse && m_zero_input_opt && m_fused_version >= 4 && L.fused4_ok != 0;
     if (zero_input && !zero4) { sol.setVal(0.0); skip_fillboundary = true; }
+    if (!m_use_gauss_seidel) {
+        // Jacobi: the reference's two "colour" calls are two full damped sweeps (AMReX_MLCellLinOp.H:1206-1217 with
+        // Fsmooth ignoring redblack); each is one out-of-place pass that ping-pongs with the level's scratch field
+        if (!L.scratch) { L.scratch = std::make_unique<MultiFab>(sol.boxArray(), sol.DistributionMap(), 1, sol.nGrow()); }
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary);
+            Fjacobi(amrlev, mglev, *L.scratch, sol, rhs);
+            sol.swap(*L.scratch);
+            skip_fillboundary = false;
+        }
+        return;
+    }
     if (!fuse) {
         for (int redblack = 0; redblack < 2; ++redblack) {
             applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary);
@@ -1172,7 +1184,6 @@ namespace { inline void gsrb_dh (Geometry const& g, Real b, Real dh[3]) { const 
 
 void MLABecLaplacian::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
 {
-    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_use_gauss_seidel, "Jacobi smoothing is not implemented (setGaussSeidel(false))");
     LevelData const& L = lev(amrlev, mglev);
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);   // dh = beta/h^2 (AMReX_MLABecLaplacian.H:907-909)
     auto const& T = sol.layout().tiles(0);
@@ -1224,6 +1235,18 @@ void MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiF
                                  m_a_scalar, dh[0], dh[1], dh[2], L.fused_tx, L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));
 }
 
+void MLABecLaplacian::Fjacobi (int amrlev, int mglev, MultiFab& sol_out, MultiFab const& sol_in, MultiFab const& rhs) const
+{
+    LevelData const& L = lev(amrlev, mglev);
+    Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    auto const& T = sol_in.layout().tiles(0);
+    B200_KCALL(b200mg_jacobi_abec(T.n, T.d.data(), L.layout->d_vbox(), sol_out.d_fabs(), sol_in.d_fabs(), rhs.d_fabs(),
+                                  m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(),
+                                  m_b_coeffs[amrlev][mglev][2].d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2],
+                                  m_b_scalar * dxi[0] * dxi[0], m_b_scalar * dxi[1] * dxi[1], m_b_scalar * dxi[2] * dxi[2], Gpu::gpuStream()));
+}
+
 void MLABecLaplacian::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
 {
     LevelData const& L = lev(amrlev, mglev);
@@ -1259,7 +1282,6 @@ bool MLPoisson::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab const& in
 
 void MLPoisson::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
 {
-    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_use_gauss_seidel, "Jacobi smoothing is not implemented (setGaussSeidel(false))");
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
     auto const& T = sol.layout().tiles(0);
@@ -1303,6 +1325,15 @@ void MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& so
     B200_KCALL(b200mg_gsrb2_poisson(L.fused_nblocks, L.fused_tiles.data(), L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
                                     L.undrrelxr.d_table(), L.mask.d_table(), dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2],
                                     L.fused_tx, L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));
+}
+
+void MLPoisson::Fjacobi (int amrlev, int mglev, MultiFab& sol_out, MultiFab const& sol_in, MultiFab const& rhs) const
+{
+    LevelData const& L = lev(amrlev, mglev);
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    auto const& T = sol_in.layout().tiles(0);
+    B200_KCALL(b200mg_jacobi_poisson(T.n, T.d.data(), L.layout->d_vbox(), sol_out.d_fabs(), sol_in.d_fabs(), rhs.d_fabs(),
+                                     L.undrrelxr.d_table(), L.mask.d_table(), dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream()));
 }
 
 void MLPoisson::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const

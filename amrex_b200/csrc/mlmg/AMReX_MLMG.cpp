@@ -301,27 +301,16 @@ void MLMG::prepareForSolve (Vector<MultiFab*> const& a_sol, Vector<MultiFab cons
 {
     AMREX_ALWAYS_ASSERT(namrlevs <= int(a_sol.size()) && namrlevs <= int(a_rhs.size()));
     timer[0] = timer[1] = timer[2] = 0.0;
-    if (!linop_prepared) { linop.prepareForSolve(); linop_prepared = true; }
-    else if (linop.needsUpdate()) { linop.update(); }
-
-    if (!solve_called) {
+    prepareLinOp();
+    if (sol.empty()) {
         sol.resize(namrlevs); rhs.resize(namrlevs);
-        res.resize(namrlevs); rescor.resize(namrlevs); cor.resize(namrlevs); cor_hold.resize(std::max(namrlevs - 1, 1));
         for (int alev = 0; alev < namrlevs; ++alev) {
             sol[alev] = linop.make(alev, 0, 1);
             rhs[alev] = linop.make(alev, 0, 0);
-            const int nmg = linop.NMGLevels(alev);
-            res[alev].resize(nmg); rescor[alev].resize(nmg); cor[alev].resize(nmg);
-            for (int m = 0; m < nmg; ++m) {
-                res[alev][m] = linop.make(alev, m, 0); rescor[alev][m] = linop.make(alev, m, 0); cor[alev][m] = linop.make(alev, m, 1);
-            }
         }
-        const int nmg0 = linop.NMGLevels(0);
-        cor_hold[0].resize(nmg0);
-        for (int m = 0; m < nmg0 - 1; ++m) { cor_hold[0][m] = linop.make(0, m, 1); }
-        for (int alev = 1; alev < finest_amr_lev; ++alev) { cor_hold[alev].resize(1); cor_hold[alev][0] = linop.make(alev, 0, 1); }
-        cfine_mg.resize(nmg0);
     }
+    const bool cycle_data_fresh = res.empty();
+    prepareMGcycle();
     for (int alev = 0; alev < namrlevs; ++alev) {
         AMREX_ALWAYS_ASSERT_WITH_MESSAGE(a_sol[alev]->boxArray() == linop.Grids(alev) && a_sol[alev]->DistributionMap() == linop.DMap(alev),
                                          "MLMG::solve: sol must live on the operator's grids");
@@ -334,13 +323,7 @@ void MLMG::prepareForSolve (Vector<MultiFab*> const& a_sol, Vector<MultiFab cons
         average_down(rhs[falev], rhs[falev - 1], 0, 1, linop.AMRRefRatio(falev - 1));
     }
     if (linop.isSingular(0) && linop.getEnforceSingularSolvable()) { makeSolvable(); }
-    for (int alev = 0; alev <= finest_amr_lev; ++alev) {
-        for (int m = 0; m < linop.NMGLevels(alev); ++m) {
-            res[alev][m].setVal(0.0); rescor[alev][m].setVal(0.0); cor[alev][m].setVal(0.0);
-            if (alev == 0 && m < linop.NMGLevels(0) - 1) { cor_hold[0][m].setVal(0.0); }
-        }
-    }
-    for (int alev = 1; alev < finest_amr_lev; ++alev) { cor_hold[alev][0].setVal(0.0); }
+    if (!cycle_data_fresh) { zeroCycleData(); }
     if (verbose >= 2) {
         Print0(cat("MLMG: # of AMR levels: ", namrlevs, "\n", "      # of MG levels on the coarsest AMR level: ", linop.NMGLevels(0), "\n"));
     }
@@ -348,6 +331,43 @@ void MLMG::prepareForSolve (Vector<MultiFab*> const& a_sol, Vector<MultiFab cons
 
 // MLMGT::oneIter (AMReX_MLMG.H:1228-1293): down the AMR hierarchy (fine smooth, coarse composite residual), MG cycle on
 // level 0, then back up (interpolate the coarse correction, fine residual with coarse BC, fine smooth).
+void MLMG::prepareLinOp ()
+{
+    if (!linop_prepared) { linop.prepareForSolve(); linop_prepared = true; }
+    else if (linop.needsUpdate()) { linop.update(); }
+}
+
+// MLMGT::prepareMGcycle (AMReX_MLMG.H:1138-1190): the fields of the V-cycle, allocated once and zeroed
+void MLMG::prepareMGcycle ()
+{
+    if (!res.empty()) { return; }
+    res.resize(namrlevs); rescor.resize(namrlevs); cor.resize(namrlevs); cor_hold.resize(std::max(namrlevs - 1, 1));
+    for (int alev = 0; alev < namrlevs; ++alev) {
+        const int nmg = linop.NMGLevels(alev);
+        res[alev].resize(nmg); rescor[alev].resize(nmg); cor[alev].resize(nmg);
+        for (int m = 0; m < nmg; ++m) {
+            res[alev][m] = linop.make(alev, m, 0); rescor[alev][m] = linop.make(alev, m, 0); cor[alev][m] = linop.make(alev, m, 1);
+        }
+    }
+    const int nmg0 = linop.NMGLevels(0);
+    cor_hold[0].resize(nmg0);
+    for (int m = 0; m < nmg0 - 1; ++m) { cor_hold[0][m] = linop.make(0, m, 1); }
+    for (int alev = 1; alev < finest_amr_lev; ++alev) { cor_hold[alev].resize(1); cor_hold[alev][0] = linop.make(alev, 0, 1); }
+    cfine_mg.resize(nmg0);
+    zeroCycleData();
+}
+
+void MLMG::zeroCycleData ()
+{
+    for (int alev = 0; alev <= finest_amr_lev; ++alev) {
+        for (int m = 0; m < linop.NMGLevels(alev); ++m) {
+            res[alev][m].setVal(0.0); rescor[alev][m].setVal(0.0); cor[alev][m].setVal(0.0);
+            if (alev == 0 && m < linop.NMGLevels(0) - 1) { cor_hold[0][m].setVal(0.0); }
+        }
+    }
+    for (int alev = 1; alev < finest_amr_lev; ++alev) { cor_hold[alev][0].setVal(0.0); }
+}
+
 void MLMG::oneIter (int iter)
 {
     for (int alev = finest_amr_lev; alev > 0; --alev) {

@@ -22,12 +22,12 @@
 extern "C" {
 #define B200_OPAQUE(T) namespace amrex { class T; } typedef amrex::T T
 B200_OPAQUE(BoxArray); B200_OPAQUE(DistributionMapping); B200_OPAQUE(Geometry); B200_OPAQUE(MultiFab);
-B200_OPAQUE(MLLinOp); B200_OPAQUE(MLMG);
+B200_OPAQUE(MLLinOp); B200_OPAQUE(MLMG); B200_OPAQUE(GMRESMLMG);
 #undef B200_OPAQUE
 #else
 typedef struct BoxArray BoxArray; typedef struct DistributionMapping DistributionMapping;
 typedef struct Geometry Geometry; typedef struct MultiFab MultiFab;
-typedef struct MLLinOp MLLinOp; typedef struct MLMG MLMG;
+typedef struct MLLinOp MLLinOp; typedef struct MLMG MLMG; typedef struct GMRESMLMG GMRESMLMG;
 #endif
 typedef double Real;
 
@@ -134,6 +134,8 @@ void amrex_b200_new_linop(MLLinOp** linop, int kind /*0 abeclap, 1 poisson*/, in
                           const BoxArray* ba[], const DistributionMapping* dm[], int agglomeration, int consolidation,
                           int max_coarsening_level, int agg_grid_size, int con_grid_size);
 void amrex_b200_linop_set_smoother_fusion(MLLinOp* linop, int fuse);   /* 0: reference schedule, 1: fused colours */
+/* MLCellLinOpT::setGaussSeidel (AMReX_MLCellLinOp.H:58): 1 red-black Gauss-Seidel (default), 0 damped Jacobi */
+void amrex_b200_linop_set_gauss_seidel(MLLinOp* linop, int flag);
 /* launch plan of the fused smoother: rows / planes per CTA tile (<= 0: automatic), L2 prefetch distance in planes (< 0: keep) */
 void amrex_b200_linop_set_fused_plan(MLLinOp* linop, int tile_y, int chunk_z, int prefetch_planes);
 void amrex_b200_linop_set_fused_version(MLLinOp* linop, int version);   /* 2: tile-table kernel, 3: kernel-parameter descriptors, 4: bulk-async-copy staged pass */
@@ -181,6 +183,22 @@ Real amrex_b200_multigrid_init_rhs(const MLMG* mlmg);
 Real amrex_b200_multigrid_init_residual(const MLMG* mlmg);
 int  amrex_b200_multigrid_cg_iters(const MLMG* mlmg, int* iters, int capacity);
 void amrex_b200_multigrid_timers(const MLMG* mlmg, double t[3]);   /* solve, iter, bottom wall seconds */
+
+/* ---- GMRES preconditioned by MLMG V-cycles: amrex::GMRESMLMG (LinearSolvers/AMReX_GMRES_MLMG.H:19-236; the reference has
+ *      no C interface for it, members are exposed one to one).  Single AMR level; the MLMG object must outlive it. */
+void amrex_b200_new_gmres_mlmg(GMRESMLMG** g, MLMG* mlmg);
+void amrex_b200_delete_gmres_mlmg(GMRESMLMG* g);
+void amrex_b200_gmres_mlmg_solve(GMRESMLMG* g, MultiFab* sol, const MultiFab* rhs, Real tol_rel, Real tol_abs);
+void amrex_b200_gmres_mlmg_set_verbose(GMRESMLMG* g, int v);
+void amrex_b200_gmres_mlmg_set_max_iters(GMRESMLMG* g, int n);
+void amrex_b200_gmres_mlmg_set_restart_length(GMRESMLMG* g, int n);
+void amrex_b200_gmres_mlmg_use_precond(GMRESMLMG* g, int f);
+void amrex_b200_gmres_mlmg_set_precond_num_iters(GMRESMLMG* g, int n);
+void amrex_b200_gmres_mlmg_set_property_of_zero(GMRESMLMG* g, int f);
+int  amrex_b200_gmres_mlmg_num_iters(const GMRESMLMG* g);
+int  amrex_b200_gmres_mlmg_status(const GMRESMLMG* g);             /* 0 converged, 1 iteration limit, -1 not run */
+Real amrex_b200_gmres_mlmg_residual_norm(const GMRESMLMG* g);      /* 2-norm estimate of the last iteration */
+int  amrex_b200_gmres_mlmg_residual_history(const GMRESMLMG* g, Real* hist, int capacity);
 
 /* ---- host-only metadata (no device): bit-exact parity targets ---- */
 /* MG hierarchy as MLLinOpT::defineGrids would build it for `nprocs` ranks (AMReX_MLLinOp.H:795-1165).

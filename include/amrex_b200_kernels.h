@@ -154,6 +154,19 @@ int b200mg_gsrb_shell_poisson(int nboxes, const b200mg_box* vbox,
                               const b200mg_fab* f, const b200mg_ifab* m,
                               double dhx, double dhy, double dhz, int redblack, int max_face_cells, cudaStream_t s);
 
+/* ---- damped Jacobi sweep (abec_jacobi AMReX_MLABecLap_3D_K.H:332-375, mlpoisson_jacobi AMReX_MLPoisson_3D_K.H:250-281):
+ *      phi_out = phi_in + 2/3 * (rhs - L(phi_in)) / (gamma - face terms) on every valid cell, out of place, with L(phi_in)
+ *      evaluated in the same pass (the reference stores it first).  dh*: beta/h^2 of the smoother, ad*: beta*dxinv^2 of
+ *      the apply (Poisson: both are dxinv^2).  The PoisArgs mirror b200mg_gsrb_poisson. */
+int b200mg_jacobi_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                       const b200mg_fab* phi_out, const b200mg_fab* phi_in, const b200mg_fab* rhs, const b200mg_fab* a,
+                       const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                       const b200mg_fab* f, const b200mg_ifab* m, double alpha, double dhx, double dhy, double dhz,
+                       double adx, double ady, double adz, cudaStream_t s);
+int b200mg_jacobi_poisson(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                          const b200mg_fab* phi_out, const b200mg_fab* phi_in, const b200mg_fab* rhs,
+                          const b200mg_fab* f, const b200mg_ifab* m, double dhx, double dhy, double dhz, cudaStream_t s);
+
 /* ---- operator apply / residual (K4 mlabeclap_adotx AMReX_MLABecLap_3D_K.H:9-28, K5 mlpoisson_adotx
  *      AMReX_MLPoisson_3D_K.H:9-16).  If rhs != NULL writes y = rhs - L(x)  (== Xpay(y,-1,rhs),
  *      AMReX_MLCellLinOp.H:1234), else y = L(x).  dx*: beta*dxinv^2 (abec) or dxinv^2 (poisson). */
@@ -260,6 +273,19 @@ int b200mg_sum(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, con
                double* result, double* scratch, cudaStream_t s);
 /* scratch must hold b200mg_reduce_scratch_doubles(ntiles) doubles */
 long long b200mg_reduce_scratch_doubles(int ntiles);
+
+/* ---- batched Krylov vector kernels (GMRES Gram-Schmidt: the dotProduct / increment loops of
+ *      GMRES::gram_schmidt_orthogonalization, AMReX_GMRES.H:322-348).  v: HOST array of nv <= B200MG_KRYLOV_GROUP device
+ *      fab tables living on the same layout as x / w.
+ *      multi_dot : result[n] = sum_valid x * v[n]  (device array of nv doubles; deterministic two-stage reduction,
+ *                  scratch >= b200mg_multi_dot_scratch_doubles(ntiles) doubles), x is read once.
+ *      multi_axpy: w = a[nv-1]*v[nv-1] + (... (a[0]*v[0] + w)), one pass, the roundings of nv successive Saxpy calls. */
+#define B200MG_KRYLOV_GROUP 8
+long long b200mg_multi_dot_scratch_doubles(int ntiles);
+int b200mg_multi_dot(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x,
+                     int nv, const b200mg_fab* const* v, double* result, double* scratch, cudaStream_t s);
+int b200mg_multi_axpy(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* w,
+                      int nv, const b200mg_fab* const* v, const double* a, cudaStream_t s);
 
 /* ---- halo / redistribution copies (K10 fab_to_fab, pack, unpack; AMReX_FBI.H:53-70,272-328,729-893).
  *      op: 0 = copy, 1 = add.  buf: linear staging buffer (may be NULL when no tag uses it).

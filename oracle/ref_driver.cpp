@@ -19,6 +19,7 @@
 #include <AMReX_MLMG.H>
 #include <AMReX_MLABecLaplacian.H>
 #include <AMReX_MLPoisson.H>
+#include <AMReX_GMRES_MLMG.H>
 #include <AMReX_Print.H>
 
 #include <chrono>
@@ -39,6 +40,8 @@ struct Params {
     int nsolve = 1, max_coarsening_level = 30, agglomeration = 1, consolidation = 1;
     int nprocs = 1;           // meta: rank count for the SFC map dump
     int prim_mglev = 0;       // prim: MG level on which primitives run
+    int use_gmres = 0, gmres_precond = 1, gmres_precond_iters = 1;   // solve: GMRESMLMG instead of MLMG::solve
+    int gauss_seidel = 1;     // 0: damped Jacobi smoother (MLCellLinOp::setGaussSeidel(false))
     std::string bottom = "default";
     std::string dump_dir;     // empty: no dump
     Real tol_rel = 1.e-10, tol_abs = 0.0, ascalar = 1.e-3, bscalar = 1.0;
@@ -57,6 +60,8 @@ Params read_params ()
     pp.query("nprocs", p.nprocs); pp.query("prim_mglev", p.prim_mglev);
     pp.query("bottom", p.bottom); pp.query("dump_dir", p.dump_dir);
     pp.query("tol_rel", p.tol_rel); pp.query("tol_abs", p.tol_abs);
+    pp.query("gauss_seidel", p.gauss_seidel);
+    pp.query("use_gmres", p.use_gmres); pp.query("gmres_precond", p.gmres_precond); pp.query("gmres_precond_iters", p.gmres_precond_iters);
     return p;
 }
 
@@ -230,6 +235,7 @@ LPInfo make_info (Params const& p)
 void setup_abec (Params const& p, Problem& P, MLABecLaplacian& op)
 {
     op.setMaxOrder(p.maxorder);
+    op.setGaussSeidel(p.gauss_seidel != 0);
     op.setDomainBC({LinOpBCType::Dirichlet, LinOpBCType::Neumann, LinOpBCType::Neumann},
                    {LinOpBCType::Neumann, LinOpBCType::Dirichlet, LinOpBCType::Neumann});
     for (int l = 0; l <= p.max_level; ++l) { op.setLevelBC(l, &P.sol[l]); }
@@ -243,6 +249,7 @@ void setup_abec (Params const& p, Problem& P, MLABecLaplacian& op)
 void setup_poisson (Params const& p, Problem& P, MLPoisson& op)
 {
     op.setMaxOrder(p.maxorder);
+    op.setGaussSeidel(p.gauss_seidel != 0);
     const auto t = (p.prob_type == 5) ? LinOpBCType::Periodic : LinOpBCType::Dirichlet;
     op.setDomainBC({t,t,t},{t,t,t});
     for (int l = 0; l <= p.max_level; ++l) { op.setLevelBC(l, &P.sol[l]); }
@@ -296,6 +303,20 @@ int run_solve (Params const& p)
         mlmg.setMaxIter(p.max_iter); mlmg.setMaxFmgIter(p.max_fmg_iter);
         mlmg.setVerbose(p.verbose); mlmg.setBottomVerbose(p.bottom_verbose);
         set_bottom(p, mlmg);
+        if (p.use_gmres) {
+            // GMRES preconditioned by one MLMG V-cycle (Tests/LinearSolvers/ABecLaplacian_C/MyTest.cpp:466-532, inputs.gmres)
+            AMREX_ALWAYS_ASSERT(p.max_level == 0);
+            GMRESMLMG gm(mlmg);
+            gm.usePrecond(p.gmres_precond != 0);
+            gm.setPrecondNumIters(p.gmres_precond_iters);
+            gm.setVerbose(p.verbose);
+            auto t0 = std::chrono::steady_clock::now();
+            gm.solve(P.sol[0], P.rhs[0], p.tol_rel, p.tol_abs);
+            auto t1 = std::chrono::steady_clock::now();
+            times.push_back(std::chrono::duration<double>(t1-t0).count());
+            iters = gm.getNumIters(); fin = gm.getResidualNorm(); hist.clear();
+            continue;
+        }
         auto t0 = std::chrono::steady_clock::now();
         fin = mlmg.solve(GetVecOfPtrs(P.sol), GetVecOfConstPtrs(P.rhs), p.tol_rel, p.tol_abs);
         auto t1 = std::chrono::steady_clock::now();

@@ -17,6 +17,8 @@ def solve_case(ab, prob_type, n_cell, mgs, maxorder=2, fusion=None, bottom=None,
     ref, dump = run_ref(dump=True, mode="solve", prob_type=prob_type, n_cell=n_cell, max_grid_size=mgs,
                         linop_maxorder=maxorder, agg_grid_size=32, **refkw)
     P = build_problem(ab, prob_type, n_cell, mgs, dump, maxorder=maxorder, fusion=fusion)
+    if not refkw.get("gauss_seidel", 1):
+        P["op"].setGaussSeidel(False)
     mlmg = ab.MLMG(P["op"])
     mlmg.setVerbose(0)
     mlmg.setMaxIter(100)
@@ -164,3 +166,47 @@ def test_b200_schedule_switches_are_bit_neutral(ab, kind, monkeypatch):
     assert out[True][0] == out[False][0]
     assert out[True][1] == out[False][1]
     assert np.array_equal(out[True][2], out[False][2])
+
+
+# ---- GMRES preconditioned by MLMG: Tests/LinearSolvers/ABecLaplacian_C inputs.gmres, MyTest.cpp:466-532
+@pytest.mark.parametrize("prob_type,n,mgs,precond", [(2, 64, 32, 1), (2, 128, 64, 1), (1, 64, 32, 1), (2, 32, 16, 0)])
+def test_gmres_mlmg(ab, prob_type, n, mgs, precond):
+    """Same GMRES iteration count as the reference's GMRESMLMG on identical inputs, same final residual estimate
+    (1e-5 relative: the Krylov recurrences amplify last-bit differences of the reductions), solution within 1e-10."""
+    kw = dict(gmres_precond=precond)
+    if not precond:
+        kw["tol_rel"] = 1e-4     # unpreconditioned GMRES(30) crawls; a loose tolerance keeps the test short
+    ref, dump = run_ref(dump=True, mode="solve", prob_type=prob_type, n_cell=n, max_grid_size=mgs, linop_maxorder=2,
+                        agg_grid_size=32, use_gmres=1, **kw)
+    P = build_problem(ab, prob_type, n, mgs, dump, maxorder=2)
+    mlmg = ab.MLMG(P["op"])
+    gm = ab.GMRESMLMG(mlmg)
+    gm.usePrecond(bool(precond))
+    gm.setVerbose(0)
+    gm.solve(P["sol"], P["rhs"], kw.get("tol_rel", 1e-10), 0.0)
+    assert gm.status() == 0
+    h = gm.residualHistory()
+    assert len(h) == gm.numIters() + 1 and all(h[i + 1] <= h[i] * (1 + 1e-8) for i in range(len(h) - 1))
+    lo, refsol = dump["sol_lev0"]
+    diff = rel_maxdiff(P["sol"].download((0, 0, 0), (n, n, n)), refsol[1:-1, 1:-1, 1:-1])
+    if precond:
+        assert gm.numIters() == ref["iters"]
+        assert gm.residualNorm() == pytest.approx(ref["final_resnorm"], rel=1e-5)
+        assert diff <= SOL_TOL
+    else:
+        # 79 iterations with two restarts: the stopping iteration may move by one when a reduction rounds differently
+        assert ref["iters"] > 60 and abs(gm.numIters() - ref["iters"]) <= 1
+        if gm.numIters() == ref["iters"]:
+            assert gm.residualNorm() == pytest.approx(ref["final_resnorm"], rel=1e-3)
+            assert diff <= 1e-6
+
+
+# ---- damped Jacobi smoother (SURVEY 8f row 4): MLCellLinOp::setGaussSeidel(false), abec_jacobi / mlpoisson_jacobi
+@pytest.mark.parametrize("prob_type,n,mgs", [(1, 64, 32), (2, 64, 32), (2, 128, 64)])
+def test_jacobi_smoother(ab, prob_type, n, mgs):
+    ref, mlmg, diff = solve_case(ab, prob_type, n, mgs, gauss_seidel=0)
+    assert ref["iters"] > 12                                    # Jacobi needs about twice the V-cycles of GSRB
+    assert mlmg.numIters() == ref["iters"]
+    for a, b in zip(mlmg.residualHistory(), ref["history"]):
+        assert a == pytest.approx(b, rel=1e-6)
+    assert diff <= SOL_TOL
