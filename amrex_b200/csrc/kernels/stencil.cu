@@ -406,6 +406,43 @@ k_apply_bc (const b200mg_bcface* __restrict__ faces, const b200mg_box* __restric
     }
 }
 
+// Inhomogeneous Neumann data (ghost cell = d(phi)/dn on the domain face).  mode 0: the boundary flux moves into the right-hand
+// side of the cell inside the face (mllinop_apply_innu_*, AMReX_MLLinOp_K.H:930-1075: rhs -= fac*b*bcval on low faces,
+// += on high faces, fac = beta*dxinv); mode 1: the face value of a flux / gradient array is overwritten by fac*b*bcval
+// (MLCellABecLapT::addInhomogNeumannFlux, AMReX_MLCellABecLap.H:517-620).  Only faces flagged in on_face[] whose ghost
+// cells are outside the domain (mask == 2) take part.  out3 / b3: per-direction fab tables (mode 0 passes rhs three times).
+struct Innu { const b200mg_fab* out[3]; const b200mg_fab* b[3]; double fac[3]; int on_face[6]; int mode; };
+
+__global__ void __launch_bounds__(128)
+k_apply_innu (const b200mg_bcface* __restrict__ faces, const b200mg_box* __restrict__ vbox,
+              const b200mg_ifab* mf, const b200mg_fab* bvf, Innu P)
+{
+    const b200mg_bcface fc = faces[blockIdx.x];
+    if (!P.on_face[fc.face] || fc.bctype != kBcNeumann) { return; }
+    const b200mg_box vb = vbox[fc.box];
+    const int d = fc.face % 3;
+    const bool low = fc.face < 3;
+    const auto mask = view(mf[fc.box * 6 + fc.face]);
+    const auto bv = view(bvf[fc.box * 6 + fc.face]);
+    const auto out = view(P.out[d][fc.box]);
+    const bool has_b = (P.b[d] != nullptr);
+    View<double> bc = out;
+    if (has_b) { bc = view(P.b[d][fc.box]); }
+    const double fac = P.fac[d];
+    face_loop(vb, fc.face, [&] (int i, int j, int k) {
+        if (mask(i, j, k) != 2) { return; }
+        // face index of the domain face = first valid cell (low side) or the ghost cell itself (high side)
+        const int fi = i + ((low && d == 0) ? 1 : 0), fj = j + ((low && d == 1) ? 1 : 0), fk = k + ((low && d == 2) ? 1 : 0);
+        const double b = has_b ? bc(fi, fj, fk) : 1.0;
+        if (P.mode == 0) {
+            if (low) { out(fi, fj, fk) -= fac * b * bv(i, j, k); }
+            else { out(i - (d == 0), j - (d == 1), k - (d == 2)) += fac * b * bv(i, j, k); }
+        } else {
+            out(fi, fj, fk) = fac * b * bv(i, j, k);
+        }
+    });
+}
+
 __global__ void __launch_bounds__(128)
 k_comp_interp_coef0 (const b200mg_bcface* __restrict__ faces, const b200mg_box* __restrict__ vbox,
                      const b200mg_fab* ff, const b200mg_ifab* mf,
@@ -524,6 +561,19 @@ int b200mg_apply_bc (int nfaces, const b200mg_bcface* faces, const b200mg_box* v
     int chunks = 8;
     if (max_face_cells > 0) { chunks = (max_face_cells + 255) / 256; chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks); }
     k_apply_bc<<<dim3(nfaces, chunks), 128, 0, s>>>(faces, vbox, phi, m, bcval, maxorder, dxinv0, dxinv1, dxinv2, inhomog);
+    return last_error();
+}
+
+int b200mg_apply_innu (int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
+                       const b200mg_fab* const out3[3], const b200mg_fab* const b3[3],
+                       const b200mg_ifab* m, const b200mg_fab* bcval, const double fac[3], const int on_face[6], int mode, cudaStream_t s)
+{
+    if (nfaces <= 0) { return 0; }
+    Innu P;
+    for (int d = 0; d < 3; ++d) { P.out[d] = out3[d]; P.b[d] = b3 ? b3[d] : nullptr; P.fac[d] = fac[d]; }
+    for (int f = 0; f < 6; ++f) { P.on_face[f] = on_face[f]; }
+    P.mode = mode;
+    k_apply_innu<<<dim3(nfaces, 8), 128, 0, s>>>(faces, vbox, m, bcval, P);
     return last_error();
 }
 

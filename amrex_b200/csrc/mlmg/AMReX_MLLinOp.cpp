@@ -350,9 +350,73 @@ void MLLinOp::setDomainBC (Array<BCType, 3> const& a_lobc, Array<BCType, 3> cons
         } else {
             AMREX_ALWAYS_ASSERT(m_lobc[d] != BCType::Periodic && m_hibc[d] != BCType::Periodic);
         }
-        if (m_lobc[d] == BCType::inhomogNeumann || m_lobc[d] == BCType::Robin) { Abort("inhomogeneous Neumann / Robin BC not supported yet"); }
-        if (m_hibc[d] == BCType::inhomogNeumann || m_hibc[d] == BCType::Robin) { Abort("inhomogeneous Neumann / Robin BC not supported yet"); }
+        if (m_lobc[d] == BCType::Robin || m_hibc[d] == BCType::Robin) { Abort("Robin BC not supported"); }
+        // inhomogeneous Neumann acts as Neumann inside the cycle; its data moves into the right-hand side
+        // (MLLinOpT::setDomainBC, AMReX_MLLinOp.H:1211-1221)
+        if (m_lobc[d] == BCType::inhomogNeumann) { m_lobc[d] = BCType::Neumann; }
+        if (m_hibc[d] == BCType::inhomogNeumann) { m_hibc[d] = BCType::Neumann; }
     }
+}
+
+bool MLLinOp::hasInhomogNeumannBC () const noexcept
+{
+    for (int d = 0; d < 3; ++d) { if (m_lobc_orig[d] == BCType::inhomogNeumann || m_hibc_orig[d] == BCType::inhomogNeumann) { return true; } }
+    return false;
+}
+
+namespace {
+void innu_faces (Array<LinOpBCType, 3> const& lo, Array<LinOpBCType, 3> const& hi, int on_face[6])
+{
+    for (int d = 0; d < 3; ++d) {
+        on_face[d] = (lo[d] == LinOpBCType::inhomogNeumann); on_face[d + 3] = (hi[d] == LinOpBCType::inhomogNeumann);
+    }
+}
+}
+
+// MLCellABecLapT::applyInhomogNeumannTerm (AMReX_MLCellABecLap.H:295-513)
+void MLLinOp::applyInhomogNeumannTerm (int amrlev, MultiFab& rhs) const
+{
+    if (!hasInhomogNeumannBC()) { return; }
+    LevelData const& L = lev(amrlev, 0);
+    const int nf = int(L.bcfaces_h.size());
+    if (nf == 0) { return; }
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_bndry_sol[amrlev] != nullptr, "inhomogeneous Neumann BC: setLevelBC must supply the boundary data");
+    Array<MultiFab const*, 3> b; Real bscalar;
+    getFluxCoeffs(amrlev, b, bscalar);
+    const Real* dxi = H.geom[amrlev][0].InvCellSize();
+    const b200mg_fab* out3[3] = {rhs.d_fabs(), rhs.d_fabs(), rhs.d_fabs()};
+    const b200mg_fab* b3[3] = {b[0] ? b[0]->d_fabs() : nullptr, b[1] ? b[1]->d_fabs() : nullptr, b[2] ? b[2]->d_fabs() : nullptr};
+    const double fac[3] = {bscalar * dxi[0], bscalar * dxi[1], bscalar * dxi[2]};
+    int on_face[6]; innu_faces(m_lobc_orig, m_hibc_orig, on_face);
+    // a cell on a domain edge or corner collects the terms of two or three faces: one launch per face orientation, in the
+    // reference's order (x low, x high, y low, ...), keeps the updates race free and the roundings identical
+    for (int d = 0; d < 3; ++d) {
+        for (int side = 0; side < 2; ++side) {
+            const int f = d + 3 * side;
+            if (!on_face[f]) { continue; }
+            int only[6] = {0, 0, 0, 0, 0, 0}; only[f] = 1;
+            B200_KCALL(b200mg_apply_innu(nf, L.bcfaces.data(), L.layout->d_vbox(), out3, b3, L.mask.d_table(), m_bndry_sol[amrlev]->d_table(),
+                                         fac, only, 0, Gpu::gpuStream()));
+        }
+    }
+}
+
+// MLCellABecLapT::addInhomogNeumannFlux (AMReX_MLCellABecLap.H:517-620): mult_bcoef: grad holds -b grad(phi), else grad(phi)
+void MLLinOp::addInhomogNeumannFlux (int amrlev, Array<MultiFab*, 3> const& grad, bool mult_bcoef) const
+{
+    if (!hasInhomogNeumannBC()) { return; }
+    LevelData const& L = lev(amrlev, 0);
+    const int nf = int(L.bcfaces_h.size());
+    if (nf == 0) { return; }
+    Array<MultiFab const*, 3> b{{nullptr, nullptr, nullptr}}; Real bscalar = 1.0;
+    if (mult_bcoef) { getFluxCoeffs(amrlev, b, bscalar); }
+    const b200mg_fab* out3[3] = {grad[0]->d_fabs(), grad[1]->d_fabs(), grad[2]->d_fabs()};
+    const b200mg_fab* b3[3] = {b[0] ? b[0]->d_fabs() : nullptr, b[1] ? b[1]->d_fabs() : nullptr, b[2] ? b[2]->d_fabs() : nullptr};
+    const double f = mult_bcoef ? -1.0 : 1.0;
+    const double fac[3] = {f, f, f};
+    int on_face[6]; innu_faces(m_lobc_orig, m_hibc_orig, on_face);
+    B200_KCALL(b200mg_apply_innu(nf, L.bcfaces.data(), L.layout->d_vbox(), out3, b3, L.mask.d_table(), m_bndry_sol[amrlev]->d_table(),
+                                 fac, on_face, 1, Gpu::gpuStream()));
 }
 
 void MLLinOp::setCoarseFineBC (const MultiFab* crse, int crse_ratio, LinOpBCType bc_type)
@@ -713,6 +777,7 @@ void MLLinOp::compGrad (int amrlev, Array<MultiFab*, 3> const& grad, MultiFab& s
         auto const& T = g.layout().tiles(0);
         B200_KCALL(b200mg_face_flux(T.n, T.d.data(), g.layout().d_vbox(), g.d_fabs(), sol.d_fabs(), nullptr, dxi[d], 1.0, d, 0, Gpu::gpuStream()));
     }
+    addInhomogNeumannFlux(amrlev, grad, false);              // AMReX_MLCellLinOp.H:1441
 }
 
 void MLLinOp::compFlux (int amrlev, Array<MultiFab*, 3> const& fluxes, MultiFab& sol)
@@ -741,7 +806,10 @@ void MLLinOp::compFlux (int amrlev, Array<MultiFab*, 3> const& fluxes, MultiFab&
 
 void MLLinOp::getFluxes (Vector<Array<MultiFab*, 3>> const& a_flux, Vector<MultiFab*> const& a_sol)
 {
-    for (int alev = 0; alev < H.num_amr_levels; ++alev) { compFlux(alev, a_flux[alev], *a_sol[alev]); }
+    for (int alev = 0; alev < H.num_amr_levels; ++alev) {
+        compFlux(alev, a_flux[alev], *a_sol[alev]);
+        addInhomogNeumannFlux(alev, a_flux[alev], true);     // AMReX_MLCellABecLap.H:289
+    }
 }
 
 void MLLinOp::restriction (int amrlev, int cmglev, MultiFab& crse, MultiFab& fine) const
@@ -777,12 +845,25 @@ void MLLinOp::interpolation (int amrlev, int fmglev, MultiFab& fine, MultiFab co
 }
 
 // trilinear interpolation used by the F-cycle (AMReX_MLCellLinOp.H:1003-1092)
+// The reference takes the direct path only when the two levels' BoxArrays share their box list (amrex::isMFIterSafe ->
+// BoxArray::SameRefs, AMReX_MLCellLinOp.H:1014): true for levels made by coarsening the user's grids, never for levels
+// rebuilt by agglomeration (AMReX_MLLinOp.H:996-1020, each a fresh BoxArray).  For restriction / prolongation the two
+// paths give the same bits and the geometric test (isMFIterSafe) picks the cheaper one; the trilinear F-cycle
+// interpolation however reads ghost cells, and the temporary's ghost cells outside the domain are ZERO while the
+// coarse field's own hold stale boundary fills - so here the reference's criterion decides.
+bool MLLinOp::sharesBoxList (int amrlev, int mglev1, int mglev2) const
+{
+    if (!(H.dmap[amrlev][mglev1] == H.dmap[amrlev][mglev2])) { return false; }
+    if (amrlev > 0 || !H.agged) { return true; }
+    return mglev1 < H.agg_lev && mglev2 < H.agg_lev;
+}
+
 void MLLinOp::interpAssign (int amrlev, int fmglev, MultiFab& fine, MultiFab& crse) const
 {
     Gpu::ProfScope prof_scope__(amrlev * 100 + fmglev);
     Geometry const& cgeom = H.geom[amrlev][fmglev + 1];
     const MultiFab* cmf = &crse;
-    if (isMFIterSafe(amrlev, fmglev, fmglev + 1)) {
+    if (isMFIterSafe(amrlev, fmglev, fmglev + 1) && sharesBoxList(amrlev, fmglev, fmglev + 1)) {
         crse.FillBoundary(0, 1, IntVect(crse.nGrow()), cgeom.periodicity(), false);
     } else {
         LevelData const& L = lev(amrlev, fmglev);

@@ -317,6 +317,7 @@ void MLMG::prepareForSolve (Vector<MultiFab*> const& a_sol, Vector<MultiFab cons
         MultiFab::Copy(sol[alev], *a_sol[alev], 0, 0, 1, 0);
         sol[alev].setBndry(0.0);
         MultiFab::Copy(rhs[alev], *a_rhs[alev], 0, 0, 1, 0);
+        linop.applyInhomogNeumannTerm(alev, rhs[alev]);          // AMReX_MLMG.H:1009
     }
     for (int falev = finest_amr_lev; falev > 0; --falev) {
         average_down(sol[falev], sol[falev - 1], 0, 1, linop.AMRRefRatio(falev - 1));
@@ -630,9 +631,16 @@ void MLMG::compResidual (Vector<MultiFab*> const& a_res, Vector<MultiFab*> const
         s[alev] = linop.make(alev, 0, 1);
         MultiFab::Copy(s[alev], *a_sol[alev], 0, 0, 1, 0);
     }
+    const bool innu = linop.hasInhomogNeumannBC();
     for (int alev = finest_amr_lev; alev >= 0; --alev) {
         const MultiFab* crse_bcdata = (alev > 0) ? &s[alev - 1] : nullptr;
-        linop.solutionResidual(alev, *a_res[alev], s[alev], *a_rhs[alev], crse_bcdata);
+        MultiFab rhstmp;                                         // AMReX_MLMG.H:825-835: the Neumann data enters through the rhs
+        if (innu) {
+            rhstmp = linop.make(alev, 0, 0);
+            MultiFab::Copy(rhstmp, *a_rhs[alev], 0, 0, 1, 0);
+            linop.applyInhomogNeumannTerm(alev, rhstmp);
+        }
+        linop.solutionResidual(alev, *a_res[alev], s[alev], innu ? rhstmp : *a_rhs[alev], crse_bcdata);
         if (alev < finest_amr_lev) {
             linop.reflux(alev, *a_res[alev], s[alev], s[alev + 1]);
             average_down(*a_res[alev + 1], *a_res[alev], 0, 1, linop.AMRRefRatio(alev));
@@ -647,6 +655,15 @@ void MLMG::apply (Vector<MultiFab*> const& out, Vector<MultiFab*> const& in)
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(namrlevs == 1, "apply: single level only for now");
     MultiFab s = linop.make(0, 0, 1);
     MultiFab::Copy(s, *in[0], 0, 0, 1, 0);
+    if (linop.hasInhomogNeumannBC()) {
+        // AMReX_MLMG.H:866-932: out = -(rh - L(in)) with rh = 0 + the Neumann boundary term
+        MultiFab rh = linop.make(0, 0, 0);
+        rh.setVal(0.0);
+        linop.applyInhomogNeumannTerm(0, rh);
+        linop.solutionResidual(0, *out[0], s, rh);
+        out[0]->mult(-1.0);
+        return;
+    }
     linop.apply(0, 0, *out[0], s, MLLinOp::BCMode::Inhomogeneous, MLLinOp::StateMode::Solution, linop.m_bndry_sol[0].get());
 }
 

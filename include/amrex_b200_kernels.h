@@ -200,6 +200,17 @@ int b200mg_normalize_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box
 int b200mg_apply_bc(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
                     const b200mg_fab* phi, const b200mg_ifab* m, const b200mg_fab* bcval,
                     int maxorder, double dxinv0, double dxinv1, double dxinv2, int inhomog, int max_face_cells, cudaStream_t s);
+/* Inhomogeneous Neumann data, stored as d(phi)/dn in the ghost cells of the BC values (bcval, [box*6+face]).
+ *   mode 0 (mllinop_apply_innu_*, AMReX_MLLinOp_K.H:930-1075): rhs of the cell inside a flagged domain face
+ *          -= (low) / += (high) fac[d]*b*bcval, fac = beta*dxinv; out3 = {rhs, rhs, rhs};
+ *   mode 1 (MLCellABecLapT::addInhomogNeumannFlux, AMReX_MLCellABecLap.H:517-620): the domain-face value of the
+ *          face-centred array out3[d] := fac[d]*b*bcval.
+ * b3: face coefficients per direction (NULL or NULL entries: b = 1); on_face[6]: which domain faces (orientation values)
+ * carry inhomogeneous Neumann data; only ghost cells with mask == 2 (outside the domain) take part.  Mode 0 updates are
+ * plain read-modify-writes: flag ONE face orientation per launch (edge / corner cells belong to several faces). */
+int b200mg_apply_innu(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
+                      const b200mg_fab* const out3[3], const b200mg_fab* const b3[3],
+                      const b200mg_ifab* m, const b200mg_fab* bcval, const double fac[3], const int on_face[6], int mode, cudaStream_t s);
 int b200mg_comp_interp_coef0(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
                              const b200mg_fab* f, const b200mg_ifab* m,
                              int maxorder, double dxinv0, double dxinv1, double dxinv2, cudaStream_t s);

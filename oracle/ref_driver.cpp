@@ -86,7 +86,7 @@ void build_problem (Params const& p, Problem& P)
     const int nlev = p.max_level+1;
     P.geom.resize(nlev); P.grids.resize(nlev); P.dmap.resize(nlev);
     P.sol.resize(nlev); P.rhs.resize(nlev); P.exact.resize(nlev);
-    const bool abec = (p.prob_type == 2);
+    const bool abec = (p.prob_type == 2 || p.prob_type == 3);   // 3: the fields of 2 with inhomogeneous Neumann data on every face
     if (abec) { P.acoef.resize(nlev); P.bcoef.resize(nlev); P.bface.resize(nlev); }
 
     RealBox rb({0.,0.,0.},{1.,1.,1.});
@@ -153,6 +153,12 @@ void build_problem (Params const& p, Problem& P)
                                               + pi*std::cos(fpi*x)*std::cos(fpi*y)*std::sin(fpi*z)))
                             + a*(std::cos(tpi*x)*std::cos(tpi*y)*std::cos(tpi*z)
                                  + 0.25*std::cos(fpi*x)*std::cos(fpi*y)*std::cos(fpi*z));
+                    } else if (p.prob_type == 3) {
+                        // inhomogeneous Neumann: the ghost cell holds d(phi)/dn on the boundary face (the reference's
+                        // convention, Tests/LinearSolvers/ABecLaplacian_C/initProb.cpp:105-143); any smooth data will do
+                        double xb = std::min(std::max(x,0.0),1.0), yb = std::min(std::max(y,0.0),1.0),
+                               zb = std::min(std::max(z,0.0),1.0);
+                        s(i,j,k) = 0.5*std::sin(tpi*(xb + 2.0*yb))*std::cos(tpi*zb) + 0.1;
                     } else {
                         double xb = std::min(std::max(x,0.0),1.0), yb = std::min(std::max(y,0.0),1.0),
                                zb = std::min(std::max(z,0.0),1.0);
@@ -236,8 +242,13 @@ void setup_abec (Params const& p, Problem& P, MLABecLaplacian& op)
 {
     op.setMaxOrder(p.maxorder);
     op.setGaussSeidel(p.gauss_seidel != 0);
-    op.setDomainBC({LinOpBCType::Dirichlet, LinOpBCType::Neumann, LinOpBCType::Neumann},
-                   {LinOpBCType::Neumann, LinOpBCType::Dirichlet, LinOpBCType::Neumann});
+    if (p.prob_type == 3) {
+        const auto t = LinOpBCType::inhomogNeumann;
+        op.setDomainBC({t,t,t},{t,t,t});
+    } else {
+        op.setDomainBC({LinOpBCType::Dirichlet, LinOpBCType::Neumann, LinOpBCType::Neumann},
+                       {LinOpBCType::Neumann, LinOpBCType::Dirichlet, LinOpBCType::Neumann});
+    }
     for (int l = 0; l <= p.max_level; ++l) { op.setLevelBC(l, &P.sol[l]); }
     op.setScalars(p.ascalar, p.bscalar);
     for (int l = 0; l <= p.max_level; ++l) {
@@ -269,7 +280,7 @@ void dump_inputs (Params const& p, Problem& P, std::ostream& man)
         dump_mf(p.dump_dir, "sol0"+s, P.sol[l], 1, man);
         dump_mf(p.dump_dir, "rhs"+s, P.rhs[l], 0, man);
         dump_mf(p.dump_dir, "exact"+s, P.exact[l], 0, man);
-        if (p.prob_type == 2) {
+        if (p.prob_type == 2 || p.prob_type == 3) {
             dump_mf(p.dump_dir, "acoef"+s, P.acoef[l], 0, man);
             dump_mf(p.dump_dir, "bx"+s, P.bface[l][0], 0, man);
             dump_mf(p.dump_dir, "by"+s, P.bface[l][1], 0, man);
@@ -287,7 +298,7 @@ int run_solve (Params const& p)
 
     std::unique_ptr<MLLinOp> op;
     LPInfo info = make_info(p);
-    if (p.prob_type == 2) {
+    if (p.prob_type == 2 || p.prob_type == 3) {
         auto o = std::make_unique<MLABecLaplacian>(P.geom, P.grids, P.dmap, info); setup_abec(p, P, *o); op = std::move(o);
     } else {
         auto o = std::make_unique<MLPoisson>(P.geom, P.grids, P.dmap, info); setup_poisson(p, P, *o); op = std::move(o);
@@ -433,7 +444,7 @@ int run_amr (Params const& p)
     dump_inputs(p, P, man);
     std::unique_ptr<MLLinOp> op;
     LPInfo info = make_info(p);
-    if (p.prob_type == 2) {
+    if (p.prob_type == 2 || p.prob_type == 3) {
         auto o = std::make_unique<MLABecLaplacian>(P.geom, P.grids, P.dmap, info); setup_abec(p, P, *o); op = std::move(o);
     } else {
         auto o = std::make_unique<MLPoisson>(P.geom, P.grids, P.dmap, info); setup_poisson(p, P, *o); op = std::move(o);

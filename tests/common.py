@@ -72,11 +72,15 @@ def build_problem(ab, prob_type, n_cell, max_grid_size, dump, maxorder=2, agg_gr
     rhs.upload(a, lo)
     D, N, P = ab.LinOpBCType.Dirichlet, ab.LinOpBCType.Neumann, ab.LinOpBCType.Periodic
     keep = []
-    if prob_type == 2:
+    if prob_type in (2, 3):
         op = ab.MLABecLaplacian([geom], [ba], [dm], agg_grid_size=agg_grid_size, con_grid_size=agg_grid_size,
                                 max_coarsening_level=max_coarsening_level)
         op.setMaxOrder(maxorder)
-        op.setDomainBC((D, N, N), (N, D, N))
+        if prob_type == 3:     # the fields of problem 2 with inhomogeneous Neumann data (ghost cells of sol0) on every face
+            IN = ab.LinOpBCType.inhomogNeumann
+            op.setDomainBC((IN, IN, IN), (IN, IN, IN))
+        else:
+            op.setDomainBC((D, N, N), (N, D, N))
         op.setLevelBC(0, sol)
         op.setScalars(1.e-3, 1.0)
         acoef = ab.MultiFab(ba, dm, 1, 0)

@@ -106,7 +106,7 @@ def test_two_level_composite(ab, prob_type, n, mgs, maxorder):
         assert rel_maxdiff(mine, refv) <= SOL_TOL
 
 
-@pytest.mark.parametrize("prob_type,n,mgs", [(2, 64, 32), (1, 64, 32)])
+@pytest.mark.parametrize("prob_type,n,mgs", [(2, 64, 32), (1, 64, 32), (3, 64, 32)])
 def test_post_solve_fluxes_and_gradients(ab, prob_type, n, mgs):
     """MLMG::getFluxes / getGradSolution (face-centred, amrex_fi_multigrid_get_fluxes / _get_grad_solution) against the
     reference's own post-solve output.  The two solutions agree to 1e-10 relative, a face difference divides by h."""
@@ -210,3 +210,32 @@ def test_jacobi_smoother(ab, prob_type, n, mgs):
     for a, b in zip(mlmg.residualHistory(), ref["history"]):
         assert a == pytest.approx(b, rel=1e-6)
     assert diff <= SOL_TOL
+
+
+# ---- inhomogeneous Neumann boundary data: LinOpBCType::inhomogNeumann on every domain face, the data
+#      (d phi / dn in the ghost cells handed to setLevelBC) enters through the right-hand side (applyInhomogNeumannTerm)
+@pytest.mark.parametrize("n,mgs,fusion", [(64, 32, 0), (64, 32, 1), (128, 64, 1)])
+def test_inhomogeneous_neumann(ab, n, mgs, fusion):
+    ref, mlmg, diff = solve_case(ab, 3, n, mgs, fusion=fusion)
+    assert mlmg.numIters() == ref["iters"]
+    assert mlmg.initRHS() == pytest.approx(ref["rhsnorm0"], rel=1e-13)      # the norm of the MODIFIED right-hand side
+    for a, b in zip(mlmg.residualHistory(), ref["history"]):
+        assert a == pytest.approx(b, rel=1e-5)                             # as test_abeclap: 1e-9 of the rhs scale at the end
+    assert diff <= SOL_TOL
+
+
+# ---- F-cycles (max_fmg_iter > 0, MLMGT::mgFcycle AMReX_MLMG.H:1422-1457; the reference's inputs-rt-* regression inputs)
+@pytest.mark.parametrize("prob_type,n,mgs", [(1, 64, 32), (2, 64, 32)])
+def test_fcycle(ab, prob_type, n, mgs):
+    ref, dump = run_ref(dump=True, mode="solve", prob_type=prob_type, n_cell=n, max_grid_size=mgs, linop_maxorder=2,
+                        agg_grid_size=32, max_fmg_iter=2)
+    P = build_problem(ab, prob_type, n, mgs, dump, maxorder=2)
+    mlmg = ab.MLMG(P["op"])
+    mlmg.setVerbose(0)
+    mlmg.setMaxFmgIter(2)
+    mlmg.solve([P["sol"]], [P["rhs"]], 1e-10, 0.0)
+    assert mlmg.numIters() == ref["iters"]
+    for a, b in zip(mlmg.residualHistory(), ref["history"]):
+        assert a == pytest.approx(b, rel=1e-6)
+    lo, refsol = dump["sol_lev0"]
+    assert rel_maxdiff(P["sol"].download((0, 0, 0), (n, n, n)), refsol[1:-1, 1:-1, 1:-1]) <= SOL_TOL
