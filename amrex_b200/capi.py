@@ -58,6 +58,9 @@ _SIGS = {
     "amrex_b200_multifab_upload": (None, [_P, _P, _IP, _IP, _I, _I]),
     "amrex_b200_multifab_download": (None, [_P, _P, _IP, _IP, _I, _I]),
     "amrex_b200_average_cellcenter_to_face": (None, [_P, _P, _P, _P, _P]),
+    "amrex_fi_write_plotfile": (None, [C.c_char_p, _I, _PP, C.POINTER(C.c_char_p), _PP, _D, _IP, _IP]),
+    "amrex_b200_vismf_write": (None, [_P, C.c_char_p]),
+    "amrex_fi_multifab_subtract": (None, [_P, _P, _I, _I, _I, _IP]),
     "amrex_b200_new_linop": (None, [_PP, _I, _I, _PP, _PP, _PP, _I, _I, _I, _I, _I]),
     "amrex_fi_new_abeclaplacian": (None, [_PP, _I, _PP, _PP, _PP, _I, _I, _I, _I]),
     "amrex_fi_new_poisson": (None, [_PP, _I, _PP, _PP, _PP, _I, _I, _I, _I]),
@@ -346,8 +349,13 @@ class MultiFab(_Obj):
         check()
         return r
 
-    def copy_from(self, src, ng=0):
-        lib.amrex_fi_multifab_copy(self.ptr, src.ptr, 0, 0, 1, _i3((ng,) * 3))
+    def copy_from(self, src, ng=0, scomp=0, dcomp=0, ncomp=1):
+        lib.amrex_fi_multifab_copy(self.ptr, src.ptr, scomp, dcomp, ncomp, _i3((ng,) * 3))
+        check()
+
+    def subtract(self, src, scomp=0, dcomp=0, ncomp=1, ng=0):
+        """self(dcomp..) -= src(scomp..)"""
+        lib.amrex_fi_multifab_subtract(self.ptr, src.ptr, scomp, dcomp, ncomp, _i3((ng,) * 3))
         check()
 
     def fill_boundary(self, geom, cross=False):
@@ -640,3 +648,13 @@ class GMRESMLMG(_Obj):
         a = (C.c_double * 4096)()
         n = lib.amrex_b200_gmres_mlmg_residual_history(self.ptr, a, 4096)
         return list(a)[:min(n, 4096)]
+
+
+def write_plotfile(name, mfs, varnames, geoms, time=0.0, level_steps=None, ref_ratio=None):
+    """amrex::WriteMultiLevelPlotfile: mfs[lev] has one component per variable name."""
+    n = len(mfs)
+    names = (C.c_char_p * len(varnames))(*[v.encode() for v in varnames])
+    steps = (C.c_int * n)(*(level_steps or [0] * n))
+    rr = (C.c_int * max(n - 1, 1))(*((ref_ratio or [2] * (n - 1)) + [0])[:max(n - 1, 1)])
+    lib.amrex_fi_write_plotfile(str(name).encode(), n, _ptr_array(mfs), names, _ptr_array(geoms), float(time), steps, rr)
+    check()

@@ -236,7 +236,13 @@ void FabArray<T>::define (BoxArray const& ba, DistributionMapping const& dm, int
         Gpu::memset_async(m_data, 0, total * sizeof(T));
     }
     for (int li = 0; li < nl; ++li) { m_hdesc[li].p = m_data + offs[li]; }
-    m_ddesc.assign(m_hdesc);
+    // device table: [comp][local fab]; the entries of component c point at that component's first element, so the
+    // single-component kernels work on any component of a multi-component array (d_fabs(c))
+    std::vector<Desc> all(std::size_t(nl) * std::max(ncomp, 1));
+    for (int c = 0; c < std::max(ncomp, 1); ++c) {
+        for (int li = 0; li < nl; ++li) { Desc d = m_hdesc[li]; if (d.p) { d.p += std::size_t(c) * d.nstride; } all[std::size_t(c) * nl + li] = d; }
+    }
+    m_ddesc.assign(all);
 }
 
 template <class T>
@@ -296,6 +302,16 @@ void FabArray<T>::copyToHost (T* h, Box const& region, int comp, int ng, bool va
             if (isect.ok()) { copy3d(m_hdesc[li], h, region, isect, comp, true); }
         }
     }
+    Gpu::streamSynchronize();
+}
+
+// one local fab (its own valid + ng ghost cells, nothing from its neighbours), Fortran order over the grown box
+template <class T>
+void FabArray<T>::copyFabToHost (int li, T* h, int comp, int ng) const
+{
+    AMREX_ALWAYS_ASSERT(ng <= m_ngrow && li >= 0 && li < local_size() && comp >= 0 && comp < m_ncomp);
+    const Box g = amrex::grow(validbox(li), ng);
+    copy3d(m_hdesc[li], h, g, g, comp, true);
     Gpu::streamSynchronize();
 }
 
@@ -455,7 +471,8 @@ void check_same (MultiFab const& a, MultiFab const& b, int scomp, int dcomp, int
 {
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(a.layoutPtr() == b.layoutPtr() || (a.boxArray() == b.boxArray() && a.DistributionMap() == b.DistributionMap()),
                                      "MultiFab op: operands must share BoxArray and DistributionMapping");
-    AMREX_ALWAYS_ASSERT(scomp == 0 && dcomp == 0 && ncomp == 1 && ng <= a.nGrow() && ng <= b.nGrow());
+    AMREX_ALWAYS_ASSERT(scomp >= 0 && dcomp >= 0 && ncomp >= 1 && scomp + ncomp <= b.nComp() && dcomp + ncomp <= a.nComp()
+                        && ng <= a.nGrow() && ng <= b.nGrow());
 }
 }
 
@@ -463,24 +480,31 @@ void MultiFab::Copy (MultiFab& dst, MultiFab const& src, int scomp, int dcomp, i
 {
     check_same(dst, src, scomp, dcomp, ncomp, ng);
     auto const& T = dst.layout().tiles(ng);
-    B200_KCALL(b200mg_copy(T.n, T.d.data(), dst.layout().d_vbox(), dst.d_fabs(), src.d_fabs(), ng, Gpu::gpuStream()));
+    for (int n = 0; n < ncomp; ++n) {
+        B200_KCALL(b200mg_copy(T.n, T.d.data(), dst.layout().d_vbox(), dst.d_fabs(dcomp + n), src.d_fabs(scomp + n), ng, Gpu::gpuStream()));
+    }
 }
 
-void MultiFab::LinComb (MultiFab& dst, Real a, MultiFab const& x, Real b, int ng)
+// dst(dcomp..) = a * x(scomp..) + b * dst(dcomp..), component by component
+void MultiFab::LinComb (MultiFab& dst, Real a, MultiFab const& x, Real b, int scomp, int dcomp, int ncomp, int ng)
 {
-    check_same(dst, x, 0, 0, 1, ng);
+    check_same(dst, x, scomp, dcomp, ncomp, ng);
     auto const& T = dst.layout().tiles(ng);
-    B200_KCALL(b200mg_lincomb(T.n, T.d.data(), dst.layout().d_vbox(), dst.d_fabs(), a, x.d_fabs(), b, ng, Gpu::gpuStream()));
+    for (int n = 0; n < ncomp; ++n) {
+        B200_KCALL(b200mg_lincomb(T.n, T.d.data(), dst.layout().d_vbox(), dst.d_fabs(dcomp + n), a, x.d_fabs(scomp + n), b, ng, Gpu::gpuStream()));
+    }
 }
+
+void MultiFab::LinComb (MultiFab& dst, Real a, MultiFab const& x, Real b, int ng) { LinComb(dst, a, x, b, 0, 0, 1, ng); }
 
 void MultiFab::Add (MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, int ng)
-{ check_same(dst, src, scomp, dcomp, ncomp, ng); LinComb(dst, 1.0, src, 1.0, ng); }
+{ LinComb(dst, 1.0, src, 1.0, scomp, dcomp, ncomp, ng); }
 void MultiFab::Subtract (MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, int ng)
-{ check_same(dst, src, scomp, dcomp, ncomp, ng); LinComb(dst, -1.0, src, 1.0, ng); }
+{ LinComb(dst, -1.0, src, 1.0, scomp, dcomp, ncomp, ng); }
 void MultiFab::Saxpy (MultiFab& dst, Real a, MultiFab const& src, int scomp, int dcomp, int ncomp, int ng)
-{ check_same(dst, src, scomp, dcomp, ncomp, ng); LinComb(dst, a, src, 1.0, ng); }
+{ LinComb(dst, a, src, 1.0, scomp, dcomp, ncomp, ng); }
 void MultiFab::Xpay (MultiFab& dst, Real a, MultiFab const& src, int scomp, int dcomp, int ncomp, int ng)
-{ check_same(dst, src, scomp, dcomp, ncomp, ng); LinComb(dst, 1.0, src, a, ng); }
+{ LinComb(dst, 1.0, src, a, scomp, dcomp, ncomp, ng); }
 
 // ================================================================================== halo exchange plans
 namespace {

@@ -1,6 +1,7 @@
 // extern "C" boundary: see include/amrex_b200_fi.h for the contract and the reference citations.
 #include "../mlmg/AMReX_MLMG.H"
 #include "../mlmg/AMReX_GMRESMLMG.H"
+#include "../base/AMReX_PlotFileUtil.H"
 #include "amrex_b200_fi.h"
 
 #include <cstring>
@@ -183,6 +184,24 @@ void amrex_b200_average_cellcenter_to_face (MultiFab* fx, MultiFab* fy, MultiFab
 {
     FI_VOID( average_cellcenter_to_face({fx, fy, fz}, *cc, *geom); )
 }
+
+// --------------------------------------------------------------------------------- plotfile output
+// Src/F_Interfaces/Base/AMReX_plotfile_fi.cpp:8-26, same name and arguments
+void amrex_fi_write_plotfile (const char* name, int nlevs, const MultiFab* mf[], const char* varname[], const Geometry* geom[],
+                              Real time, const int level_steps[], const int ref_ratio[])
+{
+    FI_VOID(
+        Vector<const MultiFab*> mfarr(mf, mf + nlevs);
+        Vector<std::string> names(varname, varname + mf[0]->nComp());
+        Vector<Geometry> geomarr;
+        for (int lev = 0; lev < nlevs; ++lev) { geomarr.push_back(*geom[lev]); }
+        Vector<int> steps(level_steps, level_steps + nlevs);
+        Vector<IntVect> rr;
+        for (int lev = 0; lev < nlevs - 1; ++lev) { rr.push_back(IntVect(ref_ratio[lev])); }
+        WriteMultiLevelPlotfile(name, nlevs, mfarr, names, geomarr, time, steps, rr); )
+}
+// VisMF::Write (Src/Base/AMReX_VisMF.H:89): <name>_H + <name>_D_<rank>, ghost cells included
+void amrex_b200_vismf_write (const MultiFab* mf, const char* name) { FI_VOID( VisMF::Write(*mf, name); ) }
 
 // --------------------------------------------------------------------------------- linear operators
 namespace {

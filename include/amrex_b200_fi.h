@@ -112,6 +112,13 @@ void amrex_b200_multifab_upload(MultiFab* mf, const Real* h, const int lo[3], co
 void amrex_b200_multifab_download(const MultiFab* mf, Real* h, const int lo[3], const int hi[3], int comp, int ng);
 /* cell centres -> faces (amrex::average_cellcenter_to_face, Src/Base/AMReX_MultiFabUtil.cpp:226) */
 void amrex_b200_average_cellcenter_to_face(MultiFab* fx, MultiFab* fy, MultiFab* fz, const MultiFab* cc, const Geometry* geom);
+/* ---- plotfile output in the reference's on-disk format (readable by its Tools/Plotfile: fcompare, fextrema, ...)
+ *      amrex_fi_write_plotfile: Src/F_Interfaces/Base/AMReX_plotfile_fi.cpp:8-26 (same name and arguments); mf[lev] holds
+ *      one component per entry of varname[]; ref_ratio[lev] for lev < nlevs-1.  One data file per rank, rank 0 writes
+ *      the headers.  amrex_b200_vismf_write: amrex::VisMF::Write(mf, name) (ghost cells included). */
+void amrex_fi_write_plotfile(const char* name, int nlevs, const MultiFab* mf[], const char* varname[], const Geometry* geom[],
+                             Real time, const int level_steps[], const int ref_ratio[]);
+void amrex_b200_vismf_write(const MultiFab* mf, const char* name);
 
 /* ---- linear operators (Src/F_Interfaces/LinearSolvers/AMReX_abeclaplacian_fi.cpp:8-48, AMReX_poisson_fi.cpp:8,
  *      AMReX_linop_fi.cpp:8-40) ---- */

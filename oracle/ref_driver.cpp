@@ -20,6 +20,7 @@
 #include <AMReX_MLABecLaplacian.H>
 #include <AMReX_MLPoisson.H>
 #include <AMReX_GMRES_MLMG.H>
+#include <AMReX_PlotFileUtil.H>
 #include <AMReX_Print.H>
 
 #include <chrono>
@@ -44,6 +45,7 @@ struct Params {
     int gauss_seidel = 1;     // 0: damped Jacobi smoother (MLCellLinOp::setGaussSeidel(false))
     std::string bottom = "default";
     std::string dump_dir;     // empty: no dump
+    std::string plotfile;     // solve: write solution / rhs / exact_solution / error as the reference's test driver does
     Real tol_rel = 1.e-10, tol_abs = 0.0, ascalar = 1.e-3, bscalar = 1.0;
 };
 
@@ -60,7 +62,7 @@ Params read_params ()
     pp.query("nprocs", p.nprocs); pp.query("prim_mglev", p.prim_mglev);
     pp.query("bottom", p.bottom); pp.query("dump_dir", p.dump_dir);
     pp.query("tol_rel", p.tol_rel); pp.query("tol_abs", p.tol_abs);
-    pp.query("gauss_seidel", p.gauss_seidel);
+    pp.query("gauss_seidel", p.gauss_seidel); pp.query("plotfile", p.plotfile);
     pp.query("use_gmres", p.use_gmres); pp.query("gmres_precond", p.gmres_precond); pp.query("gmres_precond_iters", p.gmres_precond_iters);
     return p;
 }
@@ -360,6 +362,22 @@ int run_solve (Params const& p)
         }
         MultiFab::Subtract(d, P.exact[l], 0, 0, 1, 0);
         err.push_back(d.norminf()); ncells += P.grids[l].numPts();
+    }
+    if (!p.plotfile.empty()) {
+        // Tests/LinearSolvers/ABecLaplacian_C/MyTestPlotfile.cpp:52-84 (without the coefficient components)
+        const int nlevels = p.max_level + 1;
+        Vector<MultiFab> plotmf(nlevels);
+        for (int l = 0; l < nlevels; ++l) {
+            plotmf[l].define(P.grids[l], P.dmap[l], 4, 0);
+            MultiFab::Copy(plotmf[l], P.sol[l], 0, 0, 1, 0);
+            MultiFab::Copy(plotmf[l], P.rhs[l], 0, 1, 1, 0);
+            MultiFab::Copy(plotmf[l], P.exact[l], 0, 2, 1, 0);
+            MultiFab::Copy(plotmf[l], P.sol[l], 0, 3, 1, 0);
+            MultiFab::Subtract(plotmf[l], plotmf[l], 2, 3, 1, 0);
+        }
+        WriteMultiLevelPlotfile(p.plotfile, nlevels, amrex::GetVecOfConstPtrs(plotmf),
+                                {"solution", "rhs", "exact_solution", "error"}, P.geom, 0.0, Vector<int>(nlevels, 0),
+                                Vector<IntVect>(nlevels, IntVect(p.ref_ratio)));
     }
     if (!p.dump_dir.empty()) {
         for (int l = 0; l <= p.max_level; ++l) { dump_mf(p.dump_dir, "sol_lev"+std::to_string(l), P.sol[l], 1, man); }

@@ -239,3 +239,48 @@ def test_fcycle(ab, prob_type, n, mgs):
         assert a == pytest.approx(b, rel=1e-6)
     lo, refsol = dump["sol_lev0"]
     assert rel_maxdiff(P["sol"].download((0, 0, 0), (n, n, n)), refsol[1:-1, 1:-1, 1:-1]) <= SOL_TOL
+
+
+# ---- plotfile output: the reference's own comparison tool (Tools/Plotfile/fcompare, the judge of its
+#      regression suite) reads the plotfile this library writes and compares it with the one the reference wrote
+def test_plotfile_judged_by_reference_fcompare(ab, tmp_path):
+    import os
+    import subprocess
+    from common import REF_DRIVER
+    fcompare = os.path.join(os.path.dirname(REF_DRIVER), "fcompare")
+    if not os.access(fcompare, os.X_OK):
+        pytest.skip("oracle/_ref/fcompare not built")
+    n, mgs = 64, 32
+    ref_plt, my_plt = str(tmp_path / "plt_ref"), str(tmp_path / "plt_b200")
+    ref, dump = run_ref(dump=True, mode="solve", prob_type=2, n_cell=n, max_grid_size=mgs, linop_maxorder=2, agg_grid_size=32,
+                        plotfile=ref_plt)
+    P = build_problem(ab, 2, n, mgs, dump, maxorder=2)
+    mlmg = ab.MLMG(P["op"])
+    mlmg.setVerbose(0)
+    mlmg.solve([P["sol"]], [P["rhs"]], 1e-10, 0.0)
+    # the reference driver's plot variables (MyTestPlotfile.cpp:52-84): solution, rhs, exact_solution, error = solution - exact
+    exact = ab.MultiFab(P["ba"], P["dm"], 1, 0)
+    exact.upload(dump["exact_lev0"][1], dump["exact_lev0"][0])
+    plotmf = ab.MultiFab(P["ba"], P["dm"], 4, 0)
+    plotmf.copy_from(P["sol"], scomp=0, dcomp=0)
+    plotmf.copy_from(P["rhs"], scomp=0, dcomp=1)
+    plotmf.copy_from(exact, scomp=0, dcomp=2)
+    plotmf.copy_from(P["sol"], scomp=0, dcomp=3)
+    plotmf.subtract(plotmf, scomp=2, dcomp=3)
+    ab.write_plotfile(my_plt, [plotmf], ["solution", "rhs", "exact_solution", "error"], [P["geom"]])
+    # job header: identical text; VisMF header: same box list and file table
+    assert open(os.path.join(my_plt, "Header")).read() == open(os.path.join(ref_plt, "Header")).read()
+    mine = open(os.path.join(my_plt, "Level_0", "Cell_H")).read().split("\n\n")[0]
+    want = open(os.path.join(ref_plt, "Level_0", "Cell_H")).read().split("\n\n")[0]
+    assert mine == want
+    out = subprocess.run([fcompare, "-r", "1e-8", ref_plt, my_plt], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    rows = {ln.split()[0]: ln.split()[1:] for ln in out.stdout.splitlines() if ln.strip().startswith(("solution", "rhs", "exact_solution", "error"))}
+    assert float(rows["rhs"][0]) == 0.0 and float(rows["exact_solution"][0]) == 0.0      # bit-identical inputs
+    assert float(rows["solution"][1]) <= 1e-10                                            # ||A-B|| / ||A||
+    # exact zero difference with itself, and a perturbed copy must FAIL (the tool really reads our data)
+    assert subprocess.run([fcompare, my_plt, my_plt], capture_output=True, text=True, timeout=300).returncode == 0
+    plotmf.copy_from(P["rhs"], scomp=0, dcomp=0)
+    bad = str(tmp_path / "plt_bad")
+    ab.write_plotfile(bad, [plotmf], ["solution", "rhs", "exact_solution", "error"], [P["geom"]])
+    assert subprocess.run([fcompare, "-r", "1e-8", ref_plt, bad], capture_output=True, text=True, timeout=300).returncode != 0
