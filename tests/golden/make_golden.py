@@ -43,6 +43,17 @@ SOLVE = [
     ("p2_n64_g32_lev1_mo3", dict(prob_type=2, n_cell=64, max_grid_size=32, linop_maxorder=3, max_level=1)),
     ("p2_n128_g64_lev1_mo3", dict(prob_type=2, n_cell=128, max_grid_size=64, linop_maxorder=3, max_level=1)),
 ]
+# the options of section 8f: GMRES preconditioned by MLMG, damped Jacobi smoother, inhomogeneous Neumann data (prob_type 3:
+# the fields of problem 2 with d(phi)/dn prescribed on every face), F-cycles
+SOLVE += [
+    ("p2_n64_g32_gmres", dict(prob_type=2, n_cell=64, max_grid_size=32, linop_maxorder=2, use_gmres=1)),
+    ("p1_n64_g32_gmres", dict(prob_type=1, n_cell=64, max_grid_size=32, linop_maxorder=2, use_gmres=1)),
+    ("p2_n64_g32_jacobi", dict(prob_type=2, n_cell=64, max_grid_size=32, linop_maxorder=2, gauss_seidel=0)),
+    ("p1_n64_g32_jacobi", dict(prob_type=1, n_cell=64, max_grid_size=32, linop_maxorder=2, gauss_seidel=0)),
+    ("p3_n64_g32", dict(prob_type=3, n_cell=64, max_grid_size=32, linop_maxorder=2)),
+    ("p2_n64_g32_fmg2", dict(prob_type=2, n_cell=64, max_grid_size=32, linop_maxorder=2, max_fmg_iter=2)),
+    ("p1_n64_g32_fmg2", dict(prob_type=1, n_cell=64, max_grid_size=32, linop_maxorder=2, max_fmg_iter=2)),
+]
 BIG = [("p2_n512_g128", dict(prob_type=2, n_cell=512, max_grid_size=128, linop_maxorder=2))]
 PRIM = [
     ("p2_n16_g8_m0", dict(prob_type=2, n_cell=16, max_grid_size=8, linop_maxorder=2, prim_mglev=0, agg_grid_size=4)),
@@ -53,18 +64,21 @@ PRIM = [
 
 def main():
     big = "--big" in sys.argv
-    for name, kw in META:
+    for name, kw in ([] if any(a.startswith("--only=") for a in sys.argv) else META):
         res, _ = run_ref(mode="meta", agg_grid_size=32, **kw)
         res["_args"] = dict(kw, agg_grid_size=32)
         json.dump(res, open(os.path.join(HERE, f"meta_{name}.json"), "w"), separators=(",", ":"))
         print("meta", name, [len(l) for l in res["hierarchy"]])
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
     for name, kw in SOLVE + (BIG if big else []):
+        if only and not any(o in name for o in only):
+            continue
         res, _ = run_ref(mode="solve", agg_grid_size=32, **kw)
         res["_args"] = dict(kw, agg_grid_size=32)
         res.pop("solve_times", None)
         json.dump(res, open(os.path.join(HERE, f"solve_{name}.json"), "w"), indent=0)
         print("solve", name, res["iters"], res["err_inf"])
-    for name, kw in PRIM:
+    for name, kw in ([] if any(a.startswith("--only=") for a in sys.argv) else PRIM):
         res, dump = run_ref(dump=True, mode="prim", **kw)
         arrays = {}
         for k, (lo, a) in dump.items():

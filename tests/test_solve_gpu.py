@@ -220,7 +220,8 @@ def test_inhomogeneous_neumann(ab, n, mgs, fusion):
     assert mlmg.numIters() == ref["iters"]
     assert mlmg.initRHS() == pytest.approx(ref["rhsnorm0"], rel=1e-13)      # the norm of the MODIFIED right-hand side
     for a, b in zip(mlmg.residualHistory(), ref["history"]):
-        assert a == pytest.approx(b, rel=1e-5)                             # as test_abeclap: 1e-9 of the rhs scale at the end
+        # residuals within a few ulp of |A||x| (12 beta / h^2 * eps ~ 2e-10 at 128^3) are rounding noise of the reductions
+        assert a == pytest.approx(b, rel=1e-5, abs=1e-9)
     assert diff <= SOL_TOL
 
 
