@@ -499,6 +499,54 @@ void MLLinOp::setLevelBC (int amrlev, const MultiFab* levelbcdata)
     for (int m = 0; m < H.num_mg_levels[amrlev]; ++m) { buildBCFaces(amrlev, m); }
 }
 
+// ---- single-kernel BiCGStab bottom solve (kernels/bottom.cu)
+bool MLLinOp::bottomKernelEligible (int mglev) const
+{
+    if (!m_bottom_kernel || Gpu::debugSync()) { return false; }
+    BoxArray const& ba = H.grids[0][mglev];
+    Geometry const& geom = H.geom[0][mglev];
+    if (ba.size() != 1 || ba[0] != geom.Domain() || ba[0].numPts() > 32768) { return false; }
+    for (int d = 0; d < 3; ++d) { if (geom.isPeriodic(d)) { return false; } }
+    LevelData const& L = lev(0, mglev);
+    if (L.layout->numLocal() == 1) {
+        if (L.bcfaces_h.size() != 6) { return false; }
+        for (auto const& fc : L.bcfaces_h) { if (fc.box != 0 || fc.bctype < 101 || fc.bctype > 103) { return false; } }
+    }
+    return true;
+}
+
+int MLLinOp::bottomBiCGStabKernel (int mglev, MultiFab& sol, MultiFab const& rhs, MultiFab& r, MultiFab& p, MultiFab& v, MultiFab& t,
+                                   MultiFab& rh, Real eps_rel, Real eps_abs, int maxiter, int& iter) const
+{
+    Gpu::ProfScope prof_scope__(mglev);
+    LevelData const& L = lev(0, mglev);
+    double res[2] = {0.0, 0.0};                                      // return code, iterations (0 on ranks without the box)
+    if (L.layout->numLocal() == 1) {
+        static double* d_out = nullptr; static double* h_out = nullptr;
+        if (!d_out) {
+            d_out = static_cast<double*>(The_Arena()->alloc(4 * sizeof(double)));
+            h_out = static_cast<double*>(pinned_alloc(4 * sizeof(double)));
+        }
+        const MultiFab* a = nullptr; Array<MultiFab const*, 3> b{{nullptr, nullptr, nullptr}}; Real alpha = 0.0, beta = 1.0;
+        getLevelCoeffs(0, mglev, a, b, alpha, beta);
+        const bool abec = (a != nullptr);
+        const Real* dxi = H.geom[0][mglev].InvCellSize();
+        Box const& bx = L.layout->box(0);
+        b200mg_box vb; for (int d = 0; d < 3; ++d) { vb.lo[d] = bx.smallEnd(d); vb.hi[d] = bx.bigEnd(d); }
+        B200_KCALL(b200mg_bottom_bicgstab(abec ? 1 : 0, &vb, &sol.desc(0), &rhs.desc(0), &r.desc(0), &p.desc(0), &v.desc(0), &t.desc(0), &rh.desc(0),
+                                          abec ? &a->desc(0) : nullptr, abec ? &b[0]->desc(0) : nullptr, abec ? &b[1]->desc(0) : nullptr,
+                                          abec ? &b[2]->desc(0) : nullptr, alpha, beta * dxi[0] * dxi[0], beta * dxi[1] * dxi[1], beta * dxi[2] * dxi[2],
+                                          int(L.bcfaces_h.size()), L.bcfaces_h.data(), L.mask.d_table(), maxorder, dxi[0], dxi[1], dxi[2],
+                                          eps_rel, eps_abs, maxiter, d_out, Gpu::gpuStream()));
+        Gpu::dtoh_memcpy_async(h_out, d_out, 4 * sizeof(double));
+        Gpu::streamSynchronize();
+        res[0] = h_out[0]; res[1] = h_out[1];
+    }
+    ParallelDescriptor::ReduceRealMax(res, 2);                        // the owner's values reach every rank
+    iter = int(res[1]);
+    return int(res[0]);
+}
+
 bool MLLinOp::isMFIterSafe (int amrlev, int mglev1, int mglev2) const
 {
     if (!(H.dmap[amrlev][mglev1] == H.dmap[amrlev][mglev2])) { return false; }

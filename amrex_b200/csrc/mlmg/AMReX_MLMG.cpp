@@ -36,6 +36,10 @@ int MLCGSolver::solve_bicgstab (MultiFab& sol, MultiFab const& rhs, Real eps_rel
 {
     using BCMode = MLLinOp::BCMode; using StateMode = MLLinOp::StateMode;
     ensure_temps(sol);
+    if (initial_vec_zeroed && verbose <= 0 && sol.nGrow() >= 1 && Lp.bottomKernelEligible(mglev)) {
+        // B200: the whole solve below as one single-CTA kernel (kernels/bottom.cu), one host read-back instead of ~6 per iteration
+        return Lp.bottomBiCGStabKernel(mglev, sol, rhs, r, p, v, t, rh, eps_rel, eps_abs, maxiter, iter);
+    }
     p.setVal(0.0); r.setVal(0.0);
     if (initial_vec_zeroed) { MultiFab::Copy(r, rhs, 0, 0, 1, 0); }
     else {

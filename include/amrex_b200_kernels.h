@@ -285,6 +285,21 @@ int b200mg_sum(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, con
 /* scratch must hold b200mg_reduce_scratch_doubles(ntiles) doubles */
 long long b200mg_reduce_scratch_doubles(int ntiles);
 
+/* ---- whole BiCGStab bottom solve in one single-CTA kernel (MLCGSolverT::solve_bicgstab with a zeroed initial vector,
+ *      AMReX_MLCGSolver.H:98-273): for a bottom MG level that is ONE box (<= 32^3 cells) covering a non-periodic domain.
+ *      h_*: HOST descriptors of the box's fabs (sol, r, p with one ghost cell; sol zeroed by the caller; r, p, v, t, rh
+ *      scratch); abec == 0: Poisson (a, bx, by, bz ignored; dh* = dxinv^2), else dh* = beta*dxinv^2.  h_faces: the box's
+ *      physical faces (<= 6, box == 0), d_mask: DEVICE table of the box's 6 mask slabs.  d_out (device, 4 doubles):
+ *      return code of solve_bicgstab, iteration count, final and initial max-norm of the residual. */
+int b200mg_bottom_bicgstab(int abec, const b200mg_box* h_vbox,
+                           const b200mg_fab* h_sol, const b200mg_fab* h_rhs, const b200mg_fab* h_r, const b200mg_fab* h_p,
+                           const b200mg_fab* h_v, const b200mg_fab* h_t, const b200mg_fab* h_rh,
+                           const b200mg_fab* h_a, const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
+                           double alpha, double dhx, double dhy, double dhz,
+                           int nfaces, const b200mg_bcface* h_faces, const b200mg_ifab* d_mask, int maxorder,
+                           double dxinv0, double dxinv1, double dxinv2, double eps_rel, double eps_abs, int maxiter,
+                           double* d_out, cudaStream_t s);
+
 /* ---- batched Krylov vector kernels (GMRES Gram-Schmidt: the dotProduct / increment loops of
  *      GMRES::gram_schmidt_orthogonalization, AMReX_GMRES.H:322-348).  v: HOST array of nv <= B200MG_KRYLOV_GROUP device
  *      fab tables living on the same layout as x / w.

@@ -285,3 +285,33 @@ def test_plotfile_judged_by_reference_fcompare(ab, tmp_path):
     bad = str(tmp_path / "plt_bad")
     ab.write_plotfile(bad, [plotmf], ["solution", "rhs", "exact_solution", "error"], [P["geom"]])
     assert subprocess.run([fcompare, "-r", "1e-7", ref_plt, bad], capture_output=True, text=True, timeout=300).returncode != 0
+
+
+# ---- B200: the BiCGStab bottom solve as ONE single-CTA kernel (kernels/bottom.cu, the default; B200MG_NO_BOTTOM_KERNEL=1 switches it off) against the
+#      launch-per-operation schedule: same arithmetic per cell, only the summation order of the dot products differs
+@pytest.mark.parametrize("prob_type,n,mgs", [(2, 64, 32), (1, 64, 32), (2, 128, 64), (1, 128, 64)])
+def test_bottom_kernel_matches_launch_schedule(ab, prob_type, n, mgs, monkeypatch):
+    ref, dump = run_ref(dump=True, mode="solve", prob_type=prob_type, n_cell=n, max_grid_size=mgs, linop_maxorder=2, agg_grid_size=32)
+    out = {}
+    for on in (False, True):
+        if on:
+            monkeypatch.delenv("B200MG_NO_BOTTOM_KERNEL", raising=False)
+        else:
+            monkeypatch.setenv("B200MG_NO_BOTTOM_KERNEL", "1")
+        P = build_problem(ab, prob_type, n, mgs, dump, maxorder=2)
+        mlmg = ab.MLMG(P["op"])
+        mlmg.setVerbose(0)
+        ab.profile_enable(True)
+        mlmg.solve([P["sol"]], [P["rhs"]], 1e-10, 0.0)
+        names = set(q[0] for q in ab.profile_report())
+        ab.profile_enable(False)
+        assert ("b200mg_bottom_bicgstab" in names) == on, names
+        out[on] = (mlmg.numIters(), mlmg.residualHistory(), mlmg.cgIters(), P["sol"].download((0, 0, 0), (n, n, n)))
+    assert out[True][0] == out[False][0] == ref["iters"]
+    for a, b, c in zip(out[True][1], out[False][1], ref["history"]):
+        assert a == pytest.approx(b, rel=1e-6) and a == pytest.approx(c, rel=1e-5)
+    assert all(abs(a - b) <= 1 for a, b in zip(out[True][2], out[False][2])), (out[True][2], out[False][2])
+    assert out[True][2] == ref["cg_iters"] or all(abs(a - b) <= 1 for a, b in zip(out[True][2], ref["cg_iters"]))
+    lo, refsol = dump["sol_lev0"]
+    assert rel_maxdiff(out[True][3], out[False][3]) <= 1e-11
+    assert rel_maxdiff(out[True][3], refsol[1:-1, 1:-1, 1:-1]) <= SOL_TOL
