@@ -55,3 +55,31 @@ def test_product_does_not_reference_oracle():
                 if "oracle/" in s or "ref_driver" in s or "/root/reference" in s:
                     bad.append(os.path.join(root, f))
     assert not bad, bad
+
+
+def _header_prototypes():
+    """name -> number of parameters, for every function declared in include/*.h."""
+    import re
+    protos = {}
+    inc = os.path.join(REPO, "include")
+    for h in sorted(os.listdir(inc)):
+        if not h.endswith(".h"):
+            continue
+        src = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, h)).read(), flags=re.S)
+        src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+        for m in re.finditer(r"\b((?:amrex_fi|amrex_b200|b200mg)_\w+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+            args = m.group(2).strip()
+            protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return protos
+
+
+def test_ctypes_signatures_match_the_headers():
+    """Every ctypes signature of amrex_b200/capi.py has the parameter count of its C prototype: a changed C entry point
+    cannot silently keep a stale Python binding."""
+    from amrex_b200 import capi
+    protos = _header_prototypes()
+    assert len(protos) > 150
+    stale = {n: (len(sig[1]), protos[n]) for n, sig in capi._SIGS.items() if n in protos and len(sig[1]) != protos[n]}
+    unknown = [n for n in capi._SIGS if n not in protos]
+    assert not stale, stale
+    assert not unknown, unknown
