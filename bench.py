@@ -90,6 +90,23 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_sample(n, mgs, cores=None):
+    """The reference itself (oracle/_ref/ref_driver, all host cores) on a bounded sample of the workload: the second of two
+    full solves (warm caches, as the reference's own scaling test times it) of the workload itself when one solve is
+    expected to take <= ~20 s on this host (512^3: ~11 s on 16 threads), else of its 256^3 instance."""
+    cores = cores or os.cpu_count() or 1
+    try:
+        est = 36.0 * (n / 512.0) ** 3 * 8.0 / cores      # seconds per solve: 35 s on the 8 build-container cores, 11 s on 16 GPU-box threads
+        nb = n if est <= 20.0 else min(n, 256)
+        res = run_reference_solve(nb, min(mgs, nb), 2, cores)
+        t = res["solve_times"][-1]
+        return {"value": res["ncells"] / t, "unit": UNIT, "cores": res["omp_threads"], "kind": "reference",
+                "sample": f"second of two full solves of the {nb}^3 instance of the workload ({res['iters']} V-cycles, {t:.2f} s), "
+                          f"reference AMReX 24.10 CPU OpenMP build (oracle/_ref/ref_driver), {res['omp_threads']} threads"}
+    except Exception as e:  # the GPU number stands on its own
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+
+
 # ------------------------------------------------------------------------------------------------- helpers
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
@@ -289,15 +306,7 @@ def b200_arm(args):
     # ---- CPU baseline (rank 0, N = 1): the reference itself on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            cores = os.cpu_count() or 1
-            nb = min(n, 256)
-            res = run_reference_solve(nb, min(mgs, nb), 1, cores)
-            cpu = {"value": res["ncells"] / res["solve_times"][0], "unit": UNIT, "cores": res["omp_threads"], "kind": "reference",
-                   "sample": f"one full solve of the {nb}^3 instance of the workload ({res['iters']} V-cycles, {res['solve_times'][0]:.2f} s), "
-                             f"reference AMReX 24.10 CPU OpenMP build (oracle/_ref/ref_driver)"}
-        except Exception as e:  # the GPU number stands on its own
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        cpu = cpu_baseline_sample(n, mgs)
 
     if rank == 0:
         line = {
