@@ -107,6 +107,7 @@ _SIGS = {
     "amrex_b200_hierarchy_new": (_P, [_I, _PP, _PP, _PP, _I, _I, _I, _I, _I, _I]),
     "amrex_b200_hierarchy_delete": (None, [_P]), "amrex_b200_hierarchy_num_mg_levels": (_I, [_P, _I]),
     "amrex_b200_hierarchy_nboxes": (_I, [_P, _I, _I]), "amrex_b200_hierarchy_level": (None, [_P, _I, _I, _IP, _IP, _IP]),
+    "amrex_b200_hierarchy_shares_box_list": (_I, [_P, _I, _I, _I]),
     "amrex_b200_fb_tags": (_I, [_P, _P, _I, _I, _IP, _I, _I, _IP, _I]),
     "amrex_b200_cpc_tags": (_I, [_P, _P, _I, _P, _P, _I, _IP, _I, _I, _IP, _I]),
 }
@@ -576,7 +577,9 @@ def hierarchy(geom, ba, dm, nprocs, agglomeration=1, consolidation=1, max_coarse
             n = lib.amrex_b200_hierarchy_nboxes(h, a, m)
             boxes, pmap, dom = (C.c_int * (6 * n))(), (C.c_int * n)(), (C.c_int * 6)()
             lib.amrex_b200_hierarchy_level(h, a, m, boxes, pmap, dom)
-            levs.append({"boxes": [tuple(boxes[6 * i:6 * i + 6]) for i in range(n)], "dmap": list(pmap), "domain": tuple(dom)})
+            levs.append({"boxes": [tuple(boxes[6 * i:6 * i + 6]) for i in range(n)], "dmap": list(pmap), "domain": tuple(dom),
+                         "safe_with_next": bool(lib.amrex_b200_hierarchy_shares_box_list(h, a, m, m + 1))
+                         if m + 1 < lib.amrex_b200_hierarchy_num_mg_levels(h, a) else None})
         out.append(levs)
     lib.amrex_b200_hierarchy_delete(h)
     return out

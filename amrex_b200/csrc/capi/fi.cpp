@@ -419,6 +419,7 @@ void* amrex_b200_hierarchy_new (int nlevels, const Geometry* geom[], const BoxAr
 void amrex_b200_hierarchy_delete (void* h) { delete static_cast<MGHierarchy*>(h); }
 int amrex_b200_hierarchy_num_mg_levels (const void* h, int amrlev) { return static_cast<const MGHierarchy*>(h)->num_mg_levels[amrlev]; }
 int amrex_b200_hierarchy_nboxes (const void* h, int a, int m) { return int(static_cast<const MGHierarchy*>(h)->grids[a][m].size()); }
+int amrex_b200_hierarchy_shares_box_list (const void* h, int a, int m1, int m2) { return static_cast<const MGHierarchy*>(h)->sharesBoxList(a, m1, m2) ? 1 : 0; }
 void amrex_b200_hierarchy_level (const void* h, int a, int m, int* boxes6, int* pmap, int* domain6) { level_out(*static_cast<const MGHierarchy*>(h), a, m, boxes6, pmap, domain6); }
 
 namespace {

@@ -899,12 +899,7 @@ void MLLinOp::interpolation (int amrlev, int fmglev, MultiFab& fine, MultiFab co
 // paths give the same bits and the geometric test (isMFIterSafe) picks the cheaper one; the trilinear F-cycle
 // interpolation however reads ghost cells, and the temporary's ghost cells outside the domain are ZERO while the
 // coarse field's own hold stale boundary fills - so here the reference's criterion decides.
-bool MLLinOp::sharesBoxList (int amrlev, int mglev1, int mglev2) const
-{
-    if (!(H.dmap[amrlev][mglev1] == H.dmap[amrlev][mglev2])) { return false; }
-    if (amrlev > 0 || !H.agged) { return true; }
-    return mglev1 < H.agg_lev && mglev2 < H.agg_lev;
-}
+bool MLLinOp::sharesBoxList (int amrlev, int mglev1, int mglev2) const { return H.sharesBoxList(amrlev, mglev1, mglev2); }
 
 void MLLinOp::interpAssign (int amrlev, int fmglev, MultiFab& fine, MultiFab& crse) const
 {

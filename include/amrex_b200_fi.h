@@ -216,6 +216,8 @@ void* amrex_b200_hierarchy_new(int nlevels, const Geometry* geom[], const BoxArr
 void amrex_b200_hierarchy_delete(void* h);
 int  amrex_b200_hierarchy_num_mg_levels(const void* h, int amrlev);
 int  amrex_b200_hierarchy_nboxes(const void* h, int amrlev, int mglev);
+/* amrex::isMFIterSafe between MG levels m1, m2 of AMR level a (equal dmaps and shared box list, BoxArray::SameRefs) */
+int  amrex_b200_hierarchy_shares_box_list(const void* h, int a, int m1, int m2);
 void amrex_b200_hierarchy_level(const void* h, int amrlev, int mglev, int* boxes6, int* pmap, int* domain6);
 /* FillBoundary / ParallelCopy tag lists as rank `myproc` sees them (AMReX_FabArrayBase.cpp:658-877, 324-467).
  * kind: 0 LocTags, 1 SndTags, 2 RcvTags.  Each tag is written as 15 ints:

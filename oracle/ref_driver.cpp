@@ -408,6 +408,18 @@ void print_hierarchy (OP const& op, int namr)
         std::printf("]");
     }
     std::printf("],\n");
+    // amrex::isMFIterSafe between consecutive MG levels (AMReX_FabArrayBase.H: same DistributionMapping AND the two
+    // BoxArrays share their box list): decides direct vs temporary+ParallelCopy paths, e.g. in interpAssign
+    std::printf("\"mfiter_safe\": [");
+    for (int a = 0; a < namr; ++a) {
+        std::printf("%s[", a ? "," : "");
+        for (int m = 0; m + 1 < op.m_num_mg_levels[a]; ++m) {
+            const bool safe = (op.m_dmap[a][m] == op.m_dmap[a][m+1]) && BoxArray::SameRefs(op.m_grids[a][m], op.m_grids[a][m+1]);
+            std::printf("%s%d", m ? "," : "", safe ? 1 : 0);
+        }
+        std::printf("]");
+    }
+    std::printf("],\n");
 }
 
 void print_fb (const char* key, MultiFab const& mf, int ng, Periodicity const& per, bool cross)
