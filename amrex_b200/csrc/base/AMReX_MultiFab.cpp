@@ -358,11 +358,13 @@ double fetch_reduce_result (int which)
 }
 
 // ============================================================================================== MultiFab
-void MultiFab::setVal (Real v, int ng)
+void MultiFab::setVal (Real v, int comp, int ncomp, int ng)
 {
-    AMREX_ALWAYS_ASSERT(m_ncomp == 1 && ng <= m_ngrow);
+    AMREX_ALWAYS_ASSERT(comp >= 0 && ncomp >= 1 && comp + ncomp <= m_ncomp && ng <= m_ngrow);
     auto const& T = layout().tiles(ng);
-    B200_KCALL(b200mg_setval(T.n, T.d.data(), layout().d_vbox(), d_fabs(), v, ng, Gpu::gpuStream()));
+    for (int n = 0; n < ncomp; ++n) {
+        B200_KCALL(b200mg_setval(T.n, T.d.data(), layout().d_vbox(), d_fabs(comp + n), v, ng, Gpu::gpuStream()));
+    }
 }
 
 void MultiFab::setBndry (Real v)
@@ -384,13 +386,34 @@ void MultiFab::mult (Real v, int ng)
     B200_KCALL(b200mg_lincomb(T.n, T.d.data(), layout().d_vbox(), d_fabs(), 0.0, d_fabs(), v, ng, Gpu::gpuStream()));
 }
 
-Real MultiFab::norminf (bool local) const
+Real MultiFab::norminf (int comp, bool local) const
 {
+    AMREX_ALWAYS_ASSERT(comp >= 0 && comp < m_ncomp);
     auto const& T = layout().tiles(0);
-    B200_KCALL(b200mg_norminf(T.n, T.d.data(), layout().d_vbox(), d_fabs(), nullptr, reduce_result_slot(0), reduce_scratch(T.n), Gpu::gpuStream()));
+    B200_KCALL(b200mg_norminf(T.n, T.d.data(), layout().d_vbox(), d_fabs(comp), nullptr, reduce_result_slot(0), reduce_scratch(T.n), Gpu::gpuStream()));
     double r = fetch_reduce_result(0);
     if (!local) { ParallelDescriptor::ReduceRealMax(&r, 1); }
     return r;
+}
+
+Real MultiFab::norm1 (int comp, bool local) const
+{
+    AMREX_ALWAYS_ASSERT(comp >= 0 && comp < m_ncomp);
+    auto const& T = layout().tiles(0);
+    B200_KCALL(b200mg_asum(T.n, T.d.data(), layout().d_vbox(), d_fabs(comp), reduce_result_slot(0), reduce_scratch(T.n), Gpu::gpuStream()));
+    double r = fetch_reduce_result(0);
+    if (!local) { ParallelDescriptor::ReduceRealSum(&r, 1); }
+    return r;
+}
+
+Real MultiFab::norm2 (int comp) const
+{
+    AMREX_ALWAYS_ASSERT(comp >= 0 && comp < m_ncomp);
+    auto const& T = layout().tiles(0);
+    B200_KCALL(b200mg_dot(T.n, T.d.data(), layout().d_vbox(), d_fabs(comp), d_fabs(comp), reduce_result_slot(0), reduce_scratch(T.n), Gpu::gpuStream()));
+    double r = fetch_reduce_result(0);
+    ParallelDescriptor::ReduceRealSum(&r, 1);
+    return std::sqrt(r);
 }
 
 Real MultiFab::norminf (iMultiFab const& mask, bool local) const

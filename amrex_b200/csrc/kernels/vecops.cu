@@ -123,6 +123,16 @@ k_sum (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbo
     reduce_tiles<OpSum>(t, vb, result, scratch, [&] (int i, int j, int k) { return x(i, j, k); });
 }
 
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_asum (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* xf,
+        double* result, double* scratch)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto x = view(xf[t.box]);
+    reduce_tiles<OpSum>(t, vb, result, scratch, [&] (int i, int j, int k) { return fabs(x(i, j, k)); });
+}
+
 // fab_to_fab / pack / unpack (AMReX_FBI.H:53-70, 729-893).  blockIdx.x = tag; threads sweep the tag box,
 // x fastest, then y, z, component -- the order that also defines the linear buffer layout (AMReX_FBI.H:765-771).
 __global__ void __launch_bounds__(256)
@@ -218,6 +228,14 @@ int b200mg_sum (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, co
 {
     if (ntiles <= 0) { return int(cudaMemsetAsync(result, 0, sizeof(double), s)); }
     k_sum<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, x, result, scratch);
+    return last_error();
+}
+
+int b200mg_asum (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x,
+                 double* result, double* scratch, cudaStream_t s)
+{
+    if (ntiles <= 0) { return int(cudaMemsetAsync(result, 0, sizeof(double), s)); }
+    k_asum<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, x, result, scratch);
     return last_error();
 }
 

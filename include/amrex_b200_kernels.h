@@ -282,6 +282,9 @@ int b200mg_dot(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, con
                const b200mg_fab* y, double* result, double* scratch, cudaStream_t s);
 int b200mg_sum(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x,
                double* result, double* scratch, cudaStream_t s);
+/* sum of |x| over the valid cells (FabArray::norm1, AMReX_FabArray.H) */
+int b200mg_asum(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x,
+                double* result, double* scratch, cudaStream_t s);
 /* scratch must hold b200mg_reduce_scratch_doubles(ntiles) doubles */
 long long b200mg_reduce_scratch_doubles(int ntiles);
 
