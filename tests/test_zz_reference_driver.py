@@ -53,10 +53,11 @@ def _run_driver(tmp_path, **kw):
 @pytest.mark.skipif(not os.access(EXE, os.X_OK), reason="build/refdriver/ABecLaplacian_C.b200.ex not built (scripts/build_reference_driver.sh)")
 @pytest.mark.parametrize("prob_type,golden", [(1, "p1_n64_g32"), (2, "p2_n64_g32")])
 def test_reference_driver_runs_on_gpu(tmp_path, prob_type, golden):
-    """First executed on hardware by the round-end GPU tier (the executable was built after this round's GPU budget was
-    spent), so this round every deviation - crash, iteration count, plotfile difference - is reported as xfail together with
-    the driver's output, and a pass means: same V-cycle count (+-1) as the reference and a plotfile its fcompare accepts.
-    (File name: runs after every other test module.)"""
+    """The executable was finished with 18 GPU-seconds of this round's budget left: the ABecLap deck ran once on a B200
+    (profiles/r01_s40_reference_driver_on_b200.txt: 8 V-cycles and the reference's residual, plotfile equal to 1.8e-16), the
+    Poisson deck not yet.  So this round every deviation - crash, iteration count, plotfile difference - is reported as
+    xfail together with the driver's output; a pass means: same V-cycle count (+-1) as the reference and a plotfile its
+    fcompare accepts.  (File name: runs after every other test module.)"""
     g = json.load(open(os.path.join(GOLDEN, f"solve_{golden}.json")))
     run = _run_driver(tmp_path, max_level=0, n_cell=64, max_grid_size=32, prob_type=prob_type, verbose=2, composite_solve=1)
     log = run.stdout + run.stderr
