@@ -469,7 +469,19 @@ void MLLinOp::setLevelBC (int amrlev, const MultiFab* levelbcdata)
     BndrySlabs<double>& B = *m_bndry_sol[amrlev];
     B.setVal(0.0);
     if (amrlev == 0 && m_needs_coarse_data_for_bc) {
-        Abort("level solve with coarse/fine boundary data (setCoarseFineBC) is not implemented yet");
+        // Level solve of a level that does not cover its domain (AMReX_MLCellLinOp.H:536-566): the faces that are not
+        // physical boundaries take Dirichlet data interpolated from the coarse MultiFab of setCoarseFineBC (zero without one)
+        const int ratio = (m_coarse_data_crse_ratio > 0) ? m_coarse_data_crse_ratio : 2;
+        if (!m_amr_bndry[0] || m_amr_bndry[0]->ratio != ratio) { defineAmrBndry(0, ratio); }
+        AmrBndry& A = *m_amr_bndry[0];
+        if (m_coarse_data_for_bc != nullptr) {
+            AMREX_ALWAYS_ASSERT(m_coarse_data_crse_ratio > 0);
+            const Box cbx = amrex::coarsen(H.geom[0][0].Domain(), ratio);
+            A.crse_sol_br.copyFrom(*m_coarse_data_for_bc, H.geom[0][0].periodicity(cbx));
+        } else {
+            for (int f = 0; f < 6; ++f) { A.crse_sol_br.mf[f].setVal(0.0); }
+        }
+        interpBndry(0, B, A.crse_sol_br);
     }
     if (levelbcdata) {
         Geometry const& geom = H.geom[amrlev][0];
@@ -947,41 +959,48 @@ void MLLinOp::CrseBndryReg::copyFrom (MultiFab const& crse, Periodicity const& p
     for (int f = 0; f < 6; ++f) { mf[f].ParallelCopy(crse, 0, 0, 1, 0, 0, period); }
 }
 
+// The coarse/fine boundary machinery of AMR level a against data `ratio` times coarser: BndryData masks, the coarse
+// boundary registers and the list of faces that take interpolated coarse data (MLCellLinOpT::defineBC,
+// AMReX_MLCellLinOp.H:431-509; for level 0 built on demand by setLevelBC, :536-566)
+void MLLinOp::defineAmrBndry (int a, int ratio)
+{
+    m_amr_bndry[a] = std::make_unique<AmrBndry>();
+    AmrBndry& A = *m_amr_bndry[a];
+    LevelLayout const& layout = *lev(a, 0).layout;
+    Geometry const& geom = H.geom[a][0];
+    // BndryData masks: in_rad 0, out_rad 2, extent NTangHalfWidth = 5 (AMReX_BndryData.H:156,265)
+    A.bmask.define(layout, false, 2, 5);
+    std::vector<int> h;
+    fill_masks(A.bmask, layout, geom, H.grids[a][0], 5, h);
+    A.bmask.upload(h);
+    const BoxArray cba = amrex::coarsen(H.grids[a][0], ratio);
+    A.crse_sol_br.define(cba, H.dmap[a][0]);
+    A.crse_cor_br.define(cba, H.dmap[a][0]);
+    // faces that get interpolated coarse data: everything but non-periodic physical boundaries
+    // (InterpBndryDataT::setBndryValues, AMReX_InterpBndryData.H:177-181)
+    const Box domain = geom.Domain();
+    for (int li = 0; li < layout.numLocal(); ++li) {
+        Box const& bx = layout.box(li);
+        for (int f = 0; f < 6; ++f) {
+            const int d = f % 3; const bool low = f < 3;
+            const int dface = low ? domain.smallEnd(d) : domain.bigEnd(d);
+            const int bface = low ? bx.smallEnd(d) : bx.bigEnd(d);
+            if (bface != dface || geom.isPeriodic(d)) {
+                b200mg_bcface fc; fc.box = li; fc.face = f; fc.bctype = 0; fc.blen = bx.length(d); fc.bcloc = 0.0;
+                A.cf_faces_h.push_back(fc);
+            }
+        }
+    }
+    A.cf_faces.assign(A.cf_faces_h);
+    A.ratio = ratio;
+}
+
 void MLLinOp::defineAmrData ()
 {
     const int nlev = H.num_amr_levels;
     m_amr_bndry.resize(nlev);
     m_fluxreg.resize(std::max(0, nlev - 1));
-    for (int a = 1; a < nlev; ++a) {
-        m_amr_bndry[a] = std::make_unique<AmrBndry>();
-        AmrBndry& A = *m_amr_bndry[a];
-        LevelLayout const& layout = *lev(a, 0).layout;
-        Geometry const& geom = H.geom[a][0];
-        // BndryData masks: in_rad 0, out_rad 2, extent NTangHalfWidth = 5 (AMReX_BndryData.H:156,265)
-        A.bmask.define(layout, false, 2, 5);
-        std::vector<int> h;
-        fill_masks(A.bmask, layout, geom, H.grids[a][0], 5, h);
-        A.bmask.upload(h);
-        const BoxArray cba = amrex::coarsen(H.grids[a][0], H.amr_ref_ratio[a - 1]);
-        A.crse_sol_br.define(cba, H.dmap[a][0]);
-        A.crse_cor_br.define(cba, H.dmap[a][0]);
-        // faces that get interpolated coarse data: everything but non-periodic physical boundaries
-        // (InterpBndryDataT::setBndryValues, AMReX_InterpBndryData.H:177-181)
-        const Box domain = geom.Domain();
-        for (int li = 0; li < layout.numLocal(); ++li) {
-            Box const& bx = layout.box(li);
-            for (int f = 0; f < 6; ++f) {
-                const int d = f % 3; const bool low = f < 3;
-                const int dface = low ? domain.smallEnd(d) : domain.bigEnd(d);
-                const int bface = low ? bx.smallEnd(d) : bx.bigEnd(d);
-                if (bface != dface || geom.isPeriodic(d)) {
-                    b200mg_bcface fc; fc.box = li; fc.face = f; fc.bctype = 0; fc.blen = bx.length(d); fc.bcloc = 0.0;
-                    A.cf_faces_h.push_back(fc);
-                }
-            }
-        }
-        A.cf_faces.assign(A.cf_faces_h);
-    }
+    for (int a = 1; a < nlev; ++a) { defineAmrBndry(a, H.amr_ref_ratio[a - 1]); }
 
     for (int a = 0; a + 1 < nlev; ++a) {   // YAFluxRegisterT::define
         m_fluxreg[a] = std::make_unique<FluxReg>();
@@ -1075,7 +1094,7 @@ void MLLinOp::interpBndry (int amrlev, BndrySlabs<double>& bndry, CrseBndryReg c
     const int nf = int(A.cf_faces_h.size());
     if (nf == 0) { return; }
     B200_KCALL(b200mg_interp_bndry_o3(nf, A.cf_faces.data(), lev(amrlev, 0).layout->d_vbox(), bndry.d_table(), br.table.data(),
-                                      A.bmask.d_table(), H.amr_ref_ratio[amrlev - 1], Gpu::gpuStream()));
+                                      A.bmask.d_table(), A.ratio, Gpu::gpuStream()));
 }
 
 void MLLinOp::updateSolBC (int amrlev, MultiFab const& crse_bcdata) const

@@ -43,6 +43,7 @@ struct Params {
     int prim_mglev = 0;       // prim: MG level on which primitives run
     int use_gmres = 0, gmres_precond = 1, gmres_precond_iters = 1;   // solve: GMRESMLMG instead of MLMG::solve
     int gauss_seidel = 1;     // 0: damped Jacobi smoother (MLCellLinOp::setGaussSeidel(false))
+    int composite_solve = 1;  // 0: level by level, each fine level with setCoarseFineBC data from the level below (MyTest.cpp:104-141)
     std::string bottom = "default";
     std::string dump_dir;     // empty: no dump
     std::string plotfile;     // solve: write solution / rhs / exact_solution / error as the reference's test driver does
@@ -62,7 +63,7 @@ Params read_params ()
     pp.query("nprocs", p.nprocs); pp.query("prim_mglev", p.prim_mglev);
     pp.query("bottom", p.bottom); pp.query("dump_dir", p.dump_dir);
     pp.query("tol_rel", p.tol_rel); pp.query("tol_abs", p.tol_abs);
-    pp.query("gauss_seidel", p.gauss_seidel); pp.query("plotfile", p.plotfile);
+    pp.query("gauss_seidel", p.gauss_seidel); pp.query("composite_solve", p.composite_solve); pp.query("plotfile", p.plotfile);
     pp.query("use_gmres", p.use_gmres); pp.query("gmres_precond", p.gmres_precond); pp.query("gmres_precond_iters", p.gmres_precond_iters);
     return p;
 }
@@ -310,7 +311,42 @@ int run_solve (Params const& p)
         sol0[l].define(P.grids[l], P.dmap[l], 1, 1); MultiFab::Copy(sol0[l], P.sol[l], 0, 0, 1, 1);
     }
     std::vector<double> times; int iters = 0; Vector<Real> hist; Real rhs0 = 0, res0 = 0, fin = 0; Vector<int> cgit;
-    for (int is = 0; is < p.nsolve; ++is) {
+    if (!p.composite_solve) {
+        // level-by-level solves as the reference's test driver does them (Tests/LinearSolvers/ABecLaplacian_C/MyTest.cpp:104-141,
+        // 226-279): one single-level operator per AMR level, fine levels take Dirichlet data from the level below
+        auto t0 = std::chrono::steady_clock::now();
+        for (int l = 0; l <= p.max_level; ++l) {
+            std::unique_ptr<MLLinOp> lop;
+            if (p.prob_type == 2 || p.prob_type == 3) {
+                auto o = std::make_unique<MLABecLaplacian>(Vector<Geometry>{P.geom[l]}, Vector<BoxArray>{P.grids[l]}, Vector<DistributionMapping>{P.dmap[l]}, info);
+                o->setMaxOrder(p.maxorder); o->setGaussSeidel(p.gauss_seidel != 0);
+                o->setDomainBC({LinOpBCType::Dirichlet, LinOpBCType::Neumann, LinOpBCType::Neumann},
+                               {LinOpBCType::Neumann, LinOpBCType::Dirichlet, LinOpBCType::Neumann});
+                if (l > 0) { o->setCoarseFineBC(&P.sol[l-1], p.ref_ratio); }
+                o->setLevelBC(0, &P.sol[l]);
+                o->setScalars(p.ascalar, p.bscalar);
+                o->setACoeffs(0, P.acoef[l]);
+                o->setBCoeffs(0, amrex::GetArrOfConstPtrs(P.bface[l]));
+                lop = std::move(o);
+            } else {
+                auto o = std::make_unique<MLPoisson>(Vector<Geometry>{P.geom[l]}, Vector<BoxArray>{P.grids[l]}, Vector<DistributionMapping>{P.dmap[l]}, info);
+                o->setMaxOrder(p.maxorder); o->setGaussSeidel(p.gauss_seidel != 0);
+                o->setDomainBC({LinOpBCType::Dirichlet, LinOpBCType::Dirichlet, LinOpBCType::Dirichlet},
+                               {LinOpBCType::Dirichlet, LinOpBCType::Dirichlet, LinOpBCType::Dirichlet});
+                if (l > 0) { o->setCoarseFineBC(&P.sol[l-1], p.ref_ratio); }
+                o->setLevelBC(0, &P.sol[l]);
+                lop = std::move(o);
+            }
+            MLMG mlmg(*lop);
+            mlmg.setMaxIter(p.max_iter); mlmg.setMaxFmgIter(p.max_fmg_iter);
+            mlmg.setVerbose(p.verbose); mlmg.setBottomVerbose(p.bottom_verbose);
+            fin = mlmg.solve({&P.sol[l]}, {&P.rhs[l]}, p.tol_rel, p.tol_abs);
+            iters = mlmg.getNumIters(); hist = mlmg.getResidualHistory();       // of the finest level solved
+            rhs0 = mlmg.getInitRHS(); res0 = mlmg.getInitResidual(); cgit = mlmg.getNumCGIters();
+        }
+        times.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    for (int is = 0; is < (p.composite_solve ? p.nsolve : 0); ++is) {
         for (int l = 0; l <= p.max_level; ++l) { MultiFab::Copy(P.sol[l], sol0[l], 0, 0, 1, 1); }
         MLMG mlmg(*op);
         mlmg.setMaxIter(p.max_iter); mlmg.setMaxFmgIter(p.max_fmg_iter);

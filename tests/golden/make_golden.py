@@ -53,6 +53,9 @@ SOLVE += [
     ("p3_n64_g32", dict(prob_type=3, n_cell=64, max_grid_size=32, linop_maxorder=2)),
     ("p2_n64_g32_fmg2", dict(prob_type=2, n_cell=64, max_grid_size=32, linop_maxorder=2, max_fmg_iter=2)),
     ("p1_n64_g32_fmg2", dict(prob_type=1, n_cell=64, max_grid_size=32, linop_maxorder=2, max_fmg_iter=2)),
+    # level-by-level solves: each fine level is a single-level operator with setCoarseFineBC data from the level below
+    ("p2_n64_g32_lev1_levelsolve", dict(prob_type=2, n_cell=64, max_grid_size=32, linop_maxorder=2, max_level=1, composite_solve=0)),
+    ("p1_n64_g32_lev1_levelsolve", dict(prob_type=1, n_cell=64, max_grid_size=32, linop_maxorder=2, max_level=1, composite_solve=0)),
 ]
 BIG = [("p2_n512_g128", dict(prob_type=2, n_cell=512, max_grid_size=128, linop_maxorder=2))]
 PRIM = [

@@ -33,7 +33,7 @@ def test_reference_known_answers_abeclap():
 SMALL = ["p1_n64_g32", "p2_n64_g32", "p2_n64_g32_mo3", "p5_n64_g32", "p1_n64_g32_cg", "p2_n64_g32_lev1_mo3",
          # section 8f options: Jacobi smoother, inhomogeneous Neumann data, F-cycles, GMRES preconditioned by MLMG
          "p2_n64_g32_jacobi", "p1_n64_g32_jacobi", "p3_n64_g32", "p2_n64_g32_fmg2", "p1_n64_g32_fmg2",
-         "p2_n64_g32_gmres", "p1_n64_g32_gmres"]
+         "p2_n64_g32_gmres", "p1_n64_g32_gmres", "p2_n64_g32_lev1_levelsolve", "p1_n64_g32_lev1_levelsolve"]
 
 
 @pytest.mark.parametrize("name", SMALL)

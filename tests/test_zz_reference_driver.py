@@ -51,16 +51,18 @@ def _run_driver(tmp_path, **kw):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.access(EXE, os.X_OK), reason="build/refdriver/ABecLaplacian_C.b200.ex not built (scripts/build_reference_driver.sh)")
-@pytest.mark.parametrize("prob_type,golden,max_level,maxorder", [(1, "p1_n64_g32", 0, 2), (2, "p2_n64_g32", 0, 2),
-                                                                 (2, "p2_n64_g32_lev1_mo3", 1, 3)])
-def test_reference_driver_runs_on_gpu(tmp_path, prob_type, golden, max_level, maxorder):
+@pytest.mark.parametrize("prob_type,golden,max_level,maxorder,composite", [
+    (1, "p1_n64_g32", 0, 2, 1), (2, "p2_n64_g32", 0, 2, 1), (2, "p2_n64_g32_lev1_mo3", 1, 3, 1),
+    # level-by-level: the fine level is solved as a single-level operator with setCoarseFineBC data (MyTest.cpp:104-141, 226-279)
+    (2, "p2_n64_g32_lev1_levelsolve", 1, 2, 0), (1, "p1_n64_g32_lev1_levelsolve", 1, 2, 0)])
+def test_reference_driver_runs_on_gpu(tmp_path, prob_type, golden, max_level, maxorder, composite):
     """The executable was finished with 18 GPU-seconds of this round's budget left: the ABecLap deck ran once on a B200
     (profiles/r01_s40_reference_driver_on_b200.txt: 8 V-cycles and the reference's residual, plotfile equal to 1.8e-16), the
     Poisson deck not yet.  So this round every deviation - crash, iteration count, plotfile difference - is reported as
     xfail together with the driver's output; a pass means: same V-cycle count (+-1) as the reference and a plotfile its
     fcompare accepts.  (File name: runs after every other test module.)"""
     g = json.load(open(os.path.join(GOLDEN, f"solve_{golden}.json")))
-    run = _run_driver(tmp_path, max_level=max_level, n_cell=64, max_grid_size=32, prob_type=prob_type, verbose=2, composite_solve=1,
+    run = _run_driver(tmp_path, max_level=max_level, n_cell=64, max_grid_size=32, prob_type=prob_type, verbose=2, composite_solve=composite,
                       linop_maxorder=maxorder)
     log = run.stdout + run.stderr
     if run.returncode != 0:
@@ -76,7 +78,7 @@ def test_reference_driver_runs_on_gpu(tmp_path, prob_type, golden, max_level, ma
     if have_ref() and os.access(fcompare, os.X_OK):
         ref_plt = str(tmp_path / "plt_ref")
         run_ref(mode="solve", prob_type=prob_type, n_cell=64, max_grid_size=32, linop_maxorder=maxorder, agg_grid_size=32,
-                max_level=max_level, plotfile=ref_plt)
+                max_level=max_level, composite_solve=composite, plotfile=ref_plt)
         cmp_ = subprocess.run([fcompare, "-r", "1e-7", ref_plt, os.path.join(str(tmp_path), "plot")], capture_output=True, text=True, timeout=300)
         if cmp_.returncode != 0:
             pytest.xfail("fcompare found differences on the first hardware run:\n" + cmp_.stdout[-2000:])
