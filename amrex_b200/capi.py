@@ -71,8 +71,6 @@ _SIGS = {
     "amrex_fi_abeclap_set_bcoeffs": (None, [_P, _I, _PP]),
     "amrex_b200_linop_set_smoother_fusion": (None, [_P, _I]),
     "amrex_b200_linop_set_gauss_seidel": (None, [_P, _I]),
-    "amrex_b200_linop_set_fused_plan": (None, [_P, _I, _I, _I]),
-    "amrex_b200_linop_set_fused_version": (None, [_P, _I]),
     "amrex_b200_set_fused4_plan": (_I, [_I, _I, _I]),
     "b200mg_set_gsrb4_sync": (None, [_I]),
     "amrex_b200_linop_set_fused_min_box_cells": (None, [_P, C.c_longlong]),
@@ -428,14 +426,8 @@ class MLLinOp(_Obj):
     def setGaussSeidel(self, flag):
         lib.amrex_b200_linop_set_gauss_seidel(self.ptr, int(bool(flag)))
 
-    def setFusedVersion(self, v):
-        lib.amrex_b200_linop_set_fused_version(self.ptr, int(v))
-
     def setFusedMinBoxCells(self, n):
         lib.amrex_b200_linop_set_fused_min_box_cells(self.ptr, int(n))
-
-    def setFusedPlan(self, tile_y=0, chunk_z=0, prefetch=-1):
-        lib.amrex_b200_linop_set_fused_plan(self.ptr, int(tile_y), int(chunk_z), int(prefetch))
 
     def NMGLevels(self, amrlev=0):
         return lib.amrex_b200_linop_num_mg_levels(self.ptr, amrlev)

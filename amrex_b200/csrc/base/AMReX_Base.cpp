@@ -169,6 +169,10 @@ void boxDiff (BoxList& out, Box const& b1in, Box const& b2)
 BoxList boxDiff (Box const& b1, Box const& b2) { BoxList bl(b1.ixType()); boxDiff(bl, b1, b2); return bl; }
 
 // ---------------------------------------------------------------------------------------- BoxArray
+static std::atomic<RefDeathHook> s_ref_death_hook{nullptr};
+void setRefDeathHook (RefDeathHook h) noexcept { s_ref_death_hook = h; }
+void notifyRefDeath (std::uint64_t id, int kind) noexcept { if (RefDeathHook h = s_ref_death_hook.load()) { h(id, kind); } }
+
 static std::atomic<std::uint64_t> s_next_id{1};
 
 void BoxArray::newId () { m_ref->id = s_next_id++; }

@@ -157,16 +157,22 @@ void define_cpc_metadata (CommMetaData& cmd, BoxArray const& ba_dst, Distributio
 }
 
 // ========================================================================================= LevelLayout
+// The cache holds weak references: a layout (device box and tile tables) lives as long as a FabArray or an operator level
+// uses it, and its entry goes when the BoxArray / DistributionMapping it is keyed by dies (evict_by_id below).  The maps
+// are heap objects that are never destroyed, so Ref destructors running during static destruction find them intact.
 namespace {
-    std::map<std::pair<std::uint64_t, std::uint64_t>, std::shared_ptr<LevelLayout>> g_layouts;
+    using LayoutMap = std::map<std::pair<std::uint64_t, std::uint64_t>, std::weak_ptr<LevelLayout>>;
+    LayoutMap& layouts () { static LayoutMap* m = new LayoutMap; return *m; }
+    void evict_by_id (std::uint64_t id, int kind);
+    const bool g_hook_set = (setRefDeathHook(&evict_by_id), true);
 }
 
 std::shared_ptr<LevelLayout> LevelLayout::get (BoxArray const& ba, DistributionMapping const& dm)
 {
     AMREX_ALWAYS_ASSERT(ba.size() == dm.size());
     auto key = std::make_pair(ba.id(), dm.id());
-    auto it = g_layouts.find(key);
-    if (it != g_layouts.end()) { return it->second; }
+    auto it = layouts().find(key);
+    if (it != layouts().end()) { if (auto sp = it->second.lock()) { return sp; } }
     auto L = std::shared_ptr<LevelLayout>(new LevelLayout);
     const int me = ParallelDescriptor::MyProc();
     std::vector<b200mg_box> hb;
@@ -182,11 +188,11 @@ std::shared_ptr<LevelLayout> LevelLayout::get (BoxArray const& ba, DistributionM
         hb.push_back(b);
     }
     L->m_dvbox.assign(hb);
-    g_layouts[key] = L;
+    layouts()[key] = L;
     return L;
 }
 
-void LevelLayout::clearCache () { g_layouts.clear(); }
+void LevelLayout::clearCache () { layouts().clear(); }
 
 LevelLayout::Tiles const& LevelLayout::tiles (int ng)
 {
@@ -374,16 +380,21 @@ void MultiFab::setBndry (Real v)
     B200_KCALL(b200mg_setbndry(T.n, T.d.data(), layout().d_vbox(), d_fabs(), v, m_ngrow, Gpu::gpuStream()));
 }
 
+// every component, like the reference's FabArray::plus / mult (AMReX_FabArray.H:2932-2990)
 void MultiFab::plus (Real v, int ng)
 {
     auto const& T = layout().tiles(ng);
-    B200_KCALL(b200mg_plus(T.n, T.d.data(), layout().d_vbox(), d_fabs(), v, ng, Gpu::gpuStream()));
+    for (int n = 0; n < m_ncomp; ++n) {
+        B200_KCALL(b200mg_plus(T.n, T.d.data(), layout().d_vbox(), d_fabs(n), v, ng, Gpu::gpuStream()));
+    }
 }
 
 void MultiFab::mult (Real v, int ng)
 {
     auto const& T = layout().tiles(ng);
-    B200_KCALL(b200mg_lincomb(T.n, T.d.data(), layout().d_vbox(), d_fabs(), 0.0, d_fabs(), v, ng, Gpu::gpuStream()));
+    for (int n = 0; n < m_ncomp; ++n) {
+        B200_KCALL(b200mg_lincomb(T.n, T.d.data(), layout().d_vbox(), d_fabs(n), 0.0, d_fabs(n), v, ng, Gpu::gpuStream()));
+    }
 }
 
 Real MultiFab::norminf (int comp, bool local) const
@@ -418,6 +429,7 @@ Real MultiFab::norm2 (int comp) const
 
 Real MultiFab::norminf (iMultiFab const& mask, bool local) const
 {
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_ncomp == 1, "MultiFab::norminf(mask): single-component arrays only");
     auto const& T = layout().tiles(0);
     B200_KCALL(b200mg_norminf(T.n, T.d.data(), layout().d_vbox(), d_fabs(), mask.d_fabs(), reduce_result_slot(0), reduce_scratch(T.n), Gpu::gpuStream()));
     double r = fetch_reduce_result(0);
@@ -427,6 +439,7 @@ Real MultiFab::norminf (iMultiFab const& mask, bool local) const
 
 Real MultiFab::sum (bool local) const
 {
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_ncomp == 1, "MultiFab::sum: single-component arrays only");
     auto const& T = layout().tiles(0);
     B200_KCALL(b200mg_sum(T.n, T.d.data(), layout().d_vbox(), d_fabs(), reduce_result_slot(0), reduce_scratch(T.n), Gpu::gpuStream()));
     double r = fetch_reduce_result(0);
@@ -436,6 +449,7 @@ Real MultiFab::sum (bool local) const
 
 Real MultiFab::Dot (MultiFab const& x, MultiFab const& y, bool local)
 {
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(x.nComp() == 1 && y.nComp() == 1, "MultiFab::Dot: single-component arrays only");
     auto const& T = x.layout().tiles(0);
     B200_KCALL(b200mg_dot(T.n, T.d.data(), x.layout().d_vbox(), x.d_fabs(), y.d_fabs(), reduce_result_slot(0), reduce_scratch(T.n), Gpu::gpuStream()));
     double r = fetch_reduce_result(0);
@@ -543,7 +557,11 @@ struct CommPlan {
     double *sndbuf = nullptr, *rcvbuf = nullptr;
     long long buf_ncomp = 0;
     cudaEvent_t ev_packed = nullptr, ev_arrived = nullptr;
-    ~CommPlan () { if (sndbuf) { The_Arena()->free(sndbuf); } if (rcvbuf) { The_Arena()->free(rcvbuf); } }
+    ~CommPlan ()
+    {
+        if (sndbuf) { The_Arena()->free(sndbuf); } if (rcvbuf) { The_Arena()->free(rcvbuf); }
+        if (ev_packed) { cudaEventDestroy(ev_packed); } if (ev_arrived) { cudaEventDestroy(ev_arrived); }
+    }
 };
 
 b200mg_copytag make_tag (CopyComTag const& t, int dst_fab, int src_fab, long long off)
@@ -635,13 +653,32 @@ void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, i
 }
 
 using FBKey = std::tuple<std::uint64_t, std::uint64_t, int, int, int, int, int, int, int>;
-std::map<FBKey, std::unique_ptr<CommPlan>> g_fb_cache;
+using FBCache = std::map<FBKey, std::unique_ptr<CommPlan>>;
+FBCache& fb_cache () { static FBCache* m = new FBCache; return *m; }
 using CPCKey = std::tuple<std::uint64_t, std::uint64_t, int, std::uint64_t, std::uint64_t, int, int, int, int>;
-std::map<CPCKey, std::unique_ptr<CommPlan>> g_cpc_cache;
+using CPCCache = std::map<CPCKey, std::unique_ptr<CommPlan>>;
+CPCCache& cpc_cache () { static CPCCache* m = new CPCCache; return *m; }
+
+// a BoxArray (kind 0) or DistributionMapping (kind 1) box list died: nothing can ask for its plans or layouts again
+void evict_by_id (std::uint64_t id, int kind)
+{
+    for (auto it = layouts().begin(); it != layouts().end(); ) {
+        if ((kind == 0 ? it->first.first : it->first.second) == id) { it = layouts().erase(it); } else { ++it; }
+    }
+    for (auto it = fb_cache().begin(); it != fb_cache().end(); ) {
+        if ((kind == 0 ? std::get<0>(it->first) : std::get<1>(it->first)) == id) { it = fb_cache().erase(it); } else { ++it; }
+    }
+    for (auto it = cpc_cache().begin(); it != cpc_cache().end(); ) {
+        const bool hit = (kind == 0) ? (std::get<0>(it->first) == id || std::get<3>(it->first) == id)
+                                     : (std::get<1>(it->first) == id || std::get<4>(it->first) == id);
+        if (hit) { it = cpc_cache().erase(it); } else { ++it; }
+    }
+}
 
 } // namespace
 
-void clear_comm_caches () { g_fb_cache.clear(); g_cpc_cache.clear(); }
+void clear_comm_caches () { fb_cache().clear(); cpc_cache().clear(); }
+std::size_t comm_cache_size () { return fb_cache().size() + cpc_cache().size() + layouts().size(); }
 
 void MultiFab::FillBoundary (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross)
 {
@@ -649,12 +686,12 @@ void MultiFab::FillBoundary (int scomp, int ncomp, IntVect const& nghost, Period
     AMREX_ALWAYS_ASSERT(nghost.allLE(IntVect(m_ngrow)));
     FBKey key{m_ba.id(), m_dm.id(), nghost[0], nghost[1], nghost[2], int(cross),
               period.intVect()[0], period.intVect()[1], period.intVect()[2]};
-    auto it = g_fb_cache.find(key);
-    if (it == g_fb_cache.end()) {
+    auto it = fb_cache().find(key);
+    if (it == fb_cache().end()) {
         auto P = std::make_unique<CommPlan>();
         define_fb_metadata(P->meta, m_ba, m_dm, nghost, cross, period, ParallelDescriptor::MyProc());
         finish_plan(*P, layout(), layout());
-        it = g_fb_cache.emplace(key, std::move(P)).first;
+        it = fb_cache().emplace(key, std::move(P)).first;
     }
     execute_plan(*it->second, *this, *this, scomp, scomp, ncomp, CpOp::COPY);
 }
@@ -670,13 +707,13 @@ void MultiFab::ParallelCopy (MultiFab const& src, int scomp, int dcomp, int ncom
     }
     CPCKey key{m_ba.id(), m_dm.id(), dst_ng, src.boxArray().id(), src.DistributionMap().id(), src_ng,
                period.intVect()[0], period.intVect()[1], period.intVect()[2]};
-    auto it = g_cpc_cache.find(key);
-    if (it == g_cpc_cache.end()) {
+    auto it = cpc_cache().find(key);
+    if (it == cpc_cache().end()) {
         auto P = std::make_unique<CommPlan>();
         define_cpc_metadata(P->meta, m_ba, m_dm, IntVect(dst_ng), src.boxArray(), src.DistributionMap(), IntVect(src_ng),
                             period, false, ParallelDescriptor::MyProc());
         finish_plan(*P, layout(), src.layout());
-        it = g_cpc_cache.emplace(key, std::move(P)).first;
+        it = cpc_cache().emplace(key, std::move(P)).first;
     }
     execute_plan(*it->second, *this, src, scomp, dcomp, ncomp, op);
 }

@@ -256,8 +256,6 @@ void amrex_fi_abeclap_set_bcoeffs (MLLinOp* linop, int amrlev, const MultiFab* b
 }
 void amrex_b200_linop_set_smoother_fusion (MLLinOp* linop, int fuse) { linop->setSmootherFusion(fuse); }
 void amrex_b200_linop_set_gauss_seidel (MLLinOp* linop, int flag) { linop->setGaussSeidel(flag != 0); }   // MLCellLinOpT::setGaussSeidel, AMReX_MLCellLinOp.H:58
-void amrex_b200_linop_set_fused_plan (MLLinOp* linop, int tile_y, int chunk_z, int prefetch_planes) { linop->setFusedPlan(tile_y, chunk_z, prefetch_planes); }
-void amrex_b200_linop_set_fused_version (MLLinOp* linop, int version) { linop->setFusedVersion(version); }
 void amrex_b200_linop_set_fused_min_box_cells (MLLinOp* linop, long long n) { linop->setFusedMinBoxCells(Long(n)); }
 int amrex_b200_set_fused4_plan (int tile_y, int early_stages, int late_stages) { return b200mg_set_gsrb4_plan(tile_y, early_stages, late_stages); }
 int amrex_b200_linop_num_mg_levels (const MLLinOp* linop, int amrlev) { return linop->NMGLevels(amrlev); }

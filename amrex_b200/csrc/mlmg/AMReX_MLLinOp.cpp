@@ -464,7 +464,11 @@ void MLLinOp::setLevelBC (int amrlev, const MultiFab* levelbcdata)
 {
     AMREX_ALWAYS_ASSERT(amrlev >= 0 && amrlev < H.num_amr_levels);
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_lobc[0] != BCType::bogus, "setDomainBC must be called before setLevelBC");
-    if (levelbcdata) { AMREX_ALWAYS_ASSERT(levelbcdata->nGrow() >= 1); }
+    if (levelbcdata) {
+        AMREX_ALWAYS_ASSERT(levelbcdata->nGrow() >= 1);
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(levelbcdata->boxArray() == H.grids[amrlev][0] && levelbcdata->DistributionMap() == H.dmap[amrlev][0],
+                                         "MLLinOp::setLevelBC: levelbcdata must live on the level's grids and distribution");
+    }
     LevelData& L = lev(amrlev, 0);
     BndrySlabs<double>& B = *m_bndry_sol[amrlev];
     B.setVal(0.0);
@@ -518,13 +522,64 @@ bool MLLinOp::bottomKernelEligible (int mglev) const
     BoxArray const& ba = H.grids[0][mglev];
     Geometry const& geom = H.geom[0][mglev];
     if (ba.size() != 1 || ba[0] != geom.Domain() || ba[0].numPts() > 32768) { return false; }
-    for (int d = 0; d < 3; ++d) { if (geom.isPeriodic(d)) { return false; } }
+    int nper = 0;
+    for (int d = 0; d < 3; ++d) { if (geom.isPeriodic(d)) { ++nper; } }
     LevelData const& L = lev(0, mglev);
     if (L.layout->numLocal() == 1) {
-        if (L.bcfaces_h.size() != 6) { return false; }
+        if (int(L.bcfaces_h.size()) != 6 - 2 * nper) { return false; }
         for (auto const& fc : L.bcfaces_h) { if (fc.box != 0 || fc.bctype < 101 || fc.bctype > 103) { return false; } }
     }
     return true;
+}
+
+bool MLLinOp::coarseLegLevelEligible (int mglev) const
+{
+    if (!m_coarse_leg || !m_use_gauss_seidel || Gpu::debugSync() || m_needs_coarse_data_for_bc) { return false; }
+    BoxArray const& ba = H.grids[0][mglev];
+    Geometry const& geom = H.geom[0][mglev];
+    if (ba.size() != 1 || ba[0] != geom.Domain() || ba[0].numPts() > 32768 || !ba[0].cellCentered()) { return false; }
+    for (int d = 0; d < 3; ++d) {
+        if (geom.isPeriodic(d)) { continue; }
+        for (BCType t : {m_lobc[d], m_hibc[d]}) {
+            if (t != BCType::Dirichlet && t != BCType::Neumann && t != BCType::reflect_odd) { return false; }
+        }
+    }
+    if (mglev + 1 < H.num_mg_levels[0] && H.mg_coarsen_ratio_vec[mglev] != IntVect(2)) { return false; }
+    return true;
+}
+
+Real MLLinOp::bottomVolInv () const
+{
+    ensureVolInv();
+    return m_volinv[0][H.num_mg_levels[0] - 1];
+}
+
+void MLLinOp::fillLegLevel (int mglev, b200mg_leg_level& out) const
+{
+    LevelData const& L = lev(0, mglev);
+    AMREX_ALWAYS_ASSERT(L.layout->numLocal() == 1);
+    Geometry const& geom = H.geom[0][mglev];
+    Box const& bx = L.layout->box(0);
+    for (int d = 0; d < 3; ++d) { out.vb.lo[d] = bx.smallEnd(d); out.vb.hi[d] = bx.bigEnd(d); out.periodic[d] = geom.isPeriodic(d) ? 1 : 0; }
+    const MultiFab* a = nullptr; Array<MultiFab const*, 3> b{{nullptr, nullptr, nullptr}}; Real alpha = 0.0, beta = 1.0;
+    getLevelCoeffs(0, mglev, a, b, alpha, beta);
+    const Real* dxi = geom.InvCellSize();
+    const Real* h = geom.CellSize();
+    for (int d = 0; d < 3; ++d) {
+        out.dxi[d] = dxi[d];
+        out.adh[d] = beta * dxi[d] * dxi[d];                               // Fapply: beta*dxinv^2 (AMReX_MLABecLap_3D_K.H:18-20)
+        out.dh[d] = a ? beta / (h[d] * h[d]) : dxi[d] * dxi[d];            // Fsmooth: beta/h^2 (AMReX_MLABecLaplacian.H:907-909)
+    }
+    if (a) { out.a = a->desc(0); out.bx = b[0]->desc(0); out.by = b[1]->desc(0); out.bz = b[2]->desc(0); }
+    else { std::memset(&out.a, 0, sizeof(out.a)); out.bx = out.by = out.bz = out.a; }
+    for (int f = 0; f < 6; ++f) { out.f[f] = L.undrrelxr.h_table()[f]; out.m[f] = L.mask.h_table()[f]; }
+    AMREX_ALWAYS_ASSERT(L.bcfaces_h.size() <= 6);
+    out.nfaces = int(L.bcfaces_h.size());
+    std::memset(out.faces, 0, sizeof(out.faces));
+    for (int n = 0; n < out.nfaces; ++n) {
+        out.faces[n] = L.bcfaces_h[n];
+        AMREX_ALWAYS_ASSERT(out.faces[n].box == 0 && out.faces[n].bctype >= 101 && out.faces[n].bctype <= 103);
+    }
 }
 
 int MLLinOp::bottomBiCGStabKernel (int mglev, MultiFab& sol, MultiFab const& rhs, MultiFab& r, MultiFab& p, MultiFab& v, MultiFab& t,
@@ -545,10 +600,11 @@ int MLLinOp::bottomBiCGStabKernel (int mglev, MultiFab& sol, MultiFab const& rhs
         const Real* dxi = H.geom[0][mglev].InvCellSize();
         Box const& bx = L.layout->box(0);
         b200mg_box vb; for (int d = 0; d < 3; ++d) { vb.lo[d] = bx.smallEnd(d); vb.hi[d] = bx.bigEnd(d); }
+        const int per[3] = {H.geom[0][mglev].isPeriodic(0) ? 1 : 0, H.geom[0][mglev].isPeriodic(1) ? 1 : 0, H.geom[0][mglev].isPeriodic(2) ? 1 : 0};
         B200_KCALL(b200mg_bottom_bicgstab(abec ? 1 : 0, &vb, &sol.desc(0), &rhs.desc(0), &r.desc(0), &p.desc(0), &v.desc(0), &t.desc(0), &rh.desc(0),
                                           abec ? &a->desc(0) : nullptr, abec ? &b[0]->desc(0) : nullptr, abec ? &b[1]->desc(0) : nullptr,
                                           abec ? &b[2]->desc(0) : nullptr, alpha, beta * dxi[0] * dxi[0], beta * dxi[1] * dxi[1], beta * dxi[2] * dxi[2],
-                                          int(L.bcfaces_h.size()), L.bcfaces_h.data(), L.mask.d_table(), maxorder, dxi[0], dxi[1], dxi[2],
+                                          int(L.bcfaces_h.size()), L.bcfaces_h.data(), L.mask.h_table(), per, maxorder, dxi[0], dxi[1], dxi[2],
                                           eps_rel, eps_abs, maxiter, d_out, Gpu::gpuStream()));
         Gpu::dtoh_memcpy_async(h_out, d_out, 4 * sizeof(double));
         Gpu::streamSynchronize();
@@ -666,6 +722,10 @@ bool MLLinOp::planFused (LevelData const& L) const
 {
     if (L.fused_state >= 0) { return L.fused_state == 1; }
     L.fused_state = 0;
+    // The fused pass defers the black cells of the 1-cell surface shell until after the second boundary fill.  With
+    // maxorder 4 that fill reads x[lo+2], an interior black cell the pass has already updated where the reference still
+    // sees its pre-sweep value: only orders <= 3 give the bits of two colour sweeps.
+    if (maxorder > 3) { return false; }
     const int nl = L.layout->numLocal();
     if (nl == 0 || L.layout->localCells() < Long(32768) * Long(nl)) { return false; }
     if (m_fused_min_box_cells > 0) {
@@ -691,35 +751,15 @@ bool MLLinOp::planFused (LevelData const& L) const
         const double pairs_us = 2.0 * (double(L.layout->localCells()) * 44.0 / 4.65e6 + 40.0);
         if (fused_us > 0.95 * pairs_us) { return false; }
     }
-    int nxmax = 0, nymax = 0, nzmax = 0;
     for (int li = 0; li < nl; ++li) {
         Box const& b = L.layout->box(li);
-        if (b.length(0) % 2 != 0 || b.length(0) > 256 || b.length(0) < 16 || b.length(1) < 2) { return false; }
-        nxmax = std::max(nxmax, b.length(0)); nymax = std::max(nymax, b.length(1)); nzmax = std::max(nzmax, b.length(2));
-    }
-    const int env_ty = m_fused_tile_y, env_cz = m_fused_chunk_z;
-    const int tx = ((nxmax / 2 + 31) / 32) * 32;
-    int tile_y = std::min(1024 / tx - 4, 8);    // 768-thread CTAs: best of the measured grid (profiles/r01_s8_tune_smoother.txt)
-    if (env_ty > 0) { tile_y = std::min(env_ty, 1024 / tx - 4); }
-    tile_y = std::max(1, std::min(tile_y, nymax));
-    // enough CTAs for >= 4 waves over the 148 SMs when the level allows it
-    const Long ytiles = Long(nl) * ((nymax + tile_y - 1) / tile_y);
-    int chunk_z = nzmax;
-    while (chunk_z > 16 && ytiles * ((nzmax + chunk_z - 1) / chunk_z) < 4 * 148) { chunk_z /= 2; }
-    if (env_cz > 0) { chunk_z = env_cz; }
-    std::vector<b200mg_tile> ht;
-    for (int li = 0; li < nl; ++li) {
-        Box const& b = L.layout->box(li);
-        for (int k = b.smallEnd(2); k <= b.bigEnd(2); k += chunk_z)
-            for (int j = b.smallEnd(1); j <= b.bigEnd(1); j += tile_y) { ht.push_back(b200mg_tile{li, j, k, chunk_z}); }
+        if (b.length(0) % 2 != 0 || b.length(0) > 128 || b.length(0) < 16 || b.length(1) < 2) { return false; }
     }
     L.h_vbox.resize(nl);
     for (int li = 0; li < nl; ++li) {
         Box const& b = L.layout->box(li);
         for (int d = 0; d < 3; ++d) { L.h_vbox[li].lo[d] = b.smallEnd(d); L.h_vbox[li].hi[d] = b.bigEnd(d); }
     }
-    L.fused_tx = tx; L.fused_tile_y = tile_y; L.fused_chunk_z = chunk_z; L.fused_nblocks = int(ht.size());
-    L.fused_tiles.assign(ht);
     L.fused_state = 1;
     return true;
 }
@@ -737,7 +777,7 @@ std::size_t MLLinOp::graphKey (int amrlev, int mglev) const
     hash_mix(h, reinterpret_cast<std::size_t>(L.mask.d_table()));
     hash_mix(h, reinterpret_cast<std::size_t>(L.undrrelxr.d_table()));
     hash_mix(h, reinterpret_cast<std::size_t>(L.layout.get()));
-    hash_mix(h, std::size_t(m_fuse_colors)); hash_mix(h, std::size_t(m_fused_version)); hash_mix(h, std::size_t(m_use_gauss_seidel));
+    hash_mix(h, std::size_t(m_fuse_colors)); hash_mix(h, std::size_t(m_use_gauss_seidel));
     hash_mix(h, std::size_t(maxorder));
     return h;
 }
@@ -751,20 +791,13 @@ std::size_t MLABecLaplacian::graphKey (int amrlev, int mglev) const
     return h;
 }
 
-void MLLinOp::setFusedPlan (int tile_y, int chunk_z, int prefetch_planes)
-{
-    m_fused_tile_y = tile_y; m_fused_chunk_z = chunk_z;
-    if (prefetch_planes >= 0) { b200mg_set_gsrb2_prefetch(prefetch_planes); }
-    for (auto& av : m_lev) { for (auto& L : av) { L->fused_state = -1; } }
-}
-
 void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, bool skip_fillboundary, bool zero_input) const
 {
     Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     LevelData const& L = lev(amrlev, mglev);
-    const bool fuse = m_fuse_colors && m_use_gauss_seidel && planFused(L);
-    // zero input without a prior setVal: only the bulk-copy fused pass can do without reading sol
-    const bool zero4 = zero_input && fuse && m_zero_input_opt && m_fused_version >= 4 && L.fused4_ok != 0;
+    const bool fuse = m_fuse_colors && m_use_gauss_seidel && planFused(L) && L.fused4_ok != 0;
+    // zero input without a prior setVal: the fused pass can do without reading sol
+    const bool zero4 = zero_input && fuse && m_zero_input_opt;
     if (zero_input && !zero4) { sol.setVal(0.0); skip_fillboundary = true; }
     if (!m_use_gauss_seidel) {
         // Jacobi: the reference's two "colour" calls are two full damped sweeps (AMReX_MLCellLinOp.H:1206-1217 with
@@ -778,21 +811,25 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
         }
         return;
     }
-    if (!fuse) {
-        for (int redblack = 0; redblack < 2; ++redblack) {
-            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary);
-            Fsmooth(amrlev, mglev, sol, rhs, redblack);
-            skip_fillboundary = false;
+    if (fuse) {
+        if (!L.scratch) { L.scratch = std::make_unique<MultiFab>(sol.boxArray(), sol.DistributionMap(), 1, sol.nGrow()); }
+        // (homogeneous BCs of a zero field are zero ghost cells: nothing to fill, and the pass does not read them)
+        if (!zero4) { applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary); }
+        if (Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs, zero4)) {
+            sol.swap(*L.scratch);
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false);
+            FsmoothShell(amrlev, mglev, sol, rhs, 1);
+            return;
         }
-        return;
+        // the layout cannot take the bulk copies (L.fused4_ok is 0 from now on): colour sweeps; the boundary fill above is
+        // repeated below, which is harmless
+        if (zero4) { sol.setVal(0.0); skip_fillboundary = true; }
     }
-    if (!L.scratch) { L.scratch = std::make_unique<MultiFab>(sol.boxArray(), sol.DistributionMap(), 1, sol.nGrow()); }
-    // (homogeneous BCs of a zero field are zero ghost cells: nothing to fill, and the pass does not read them)
-    if (!zero4) { applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary); }
-    Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs, zero4);
-    sol.swap(*L.scratch);
-    applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false);
-    FsmoothShell(amrlev, mglev, sol, rhs, 1);
+    for (int redblack = 0; redblack < 2; ++redblack) {
+        applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary);
+        Fsmooth(amrlev, mglev, sol, rhs, redblack);
+        skip_fillboundary = false;
+    }
 }
 
 bool MLLinOp::solutionResidual (int amrlev, MultiFab& resid, MultiFab& x, MultiFab const& b, const MultiFab* crse_bcdata, Real* resnorm)
@@ -1177,7 +1214,7 @@ Real MLLinOp::normInf (int amrlev, MultiFab const& mf, bool local) const
     return (amrlev == finest) ? mf.norminf(local) : mf.norminf(*m_norm_fine_mask[amrlev], local);
 }
 
-Vector<Real> MLLinOp::getSolvabilityOffset (int amrlev, int mglev, MultiFab const& rhs) const
+void MLLinOp::ensureVolInv () const
 {
     if (m_volinv.empty()) {   // computeVolInv, AMReX_MLCellLinOp.H:1944-2004
         m_volinv.resize(H.num_amr_levels);
@@ -1188,6 +1225,11 @@ Vector<Real> MLLinOp::getSolvabilityOffset (int amrlev, int mglev, MultiFab cons
         };
         f(0, 0); f(0, H.num_mg_levels[0] - 1);
     }
+}
+
+Vector<Real> MLLinOp::getSolvabilityOffset (int amrlev, int mglev, MultiFab const& rhs) const
+{
+    ensureVolInv();
     Vector<Real> offset(1);
     offset[0] = rhs.sum(true) * m_volinv[amrlev][mglev];
     ParallelDescriptor::ReduceRealSum(offset.data(), 1);
@@ -1347,35 +1389,22 @@ void MLABecLaplacian::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab co
                                 L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, Gpu::gpuStream()));
 }
 
-void MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& sol_in, MultiFab const& rhs, bool zero_input) const
+bool MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& sol_in, MultiFab const& rhs, bool zero_input) const
 {
     LevelData const& L = lev(amrlev, mglev);
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
-    if (m_fused_version >= 4 && L.fused4_ok != 0) {
-        auto const& ac = m_a_coeffs[amrlev][mglev]; auto const& bc = m_b_coeffs[amrlev][mglev];
-        int e;
-        {
-            Gpu::KernelScope ks__("b200mg_gsrb4(abec)");
-            e = b200mg_gsrb4(1, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), &ac.desc(0),
-                             &bc[0].desc(0), &bc[1].desc(0), &bc[2].desc(0), L.undrrelxr.h_table(), L.mask.h_table(),
-                             m_a_scalar, dh[0], dh[1], dh[2], zero_input ? 1 : 0, Gpu::gpuStream());
-        }
-        if (e == 0) { return; }
-        if (e != int(cudaErrorInvalidValue)) { Gpu::check(e, "b200mg_gsrb4", __FILE__, __LINE__); }
-        L.fused4_ok = 0;                                // layout not eligible for the bulk-copy pass: generation 3 from now on
+    auto const& ac = m_a_coeffs[amrlev][mglev]; auto const& bc = m_b_coeffs[amrlev][mglev];
+    int e;
+    {
+        Gpu::KernelScope ks__("b200mg_gsrb4(abec)");
+        e = b200mg_gsrb4(1, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), &ac.desc(0),
+                         &bc[0].desc(0), &bc[1].desc(0), &bc[2].desc(0), L.undrrelxr.h_table(), L.mask.h_table(),
+                         m_a_scalar, dh[0], dh[1], dh[2], zero_input ? 1 : 0, Gpu::gpuStream());
     }
-    if (zero_input) { sol_in.setVal(0.0); }             // the older generations read their input
-    if (m_fused_version >= 3) {
-        auto const& ac = m_a_coeffs[amrlev][mglev]; auto const& bc = m_b_coeffs[amrlev][mglev];
-        B200_KCALL(b200mg_gsrb3(1, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), &ac.desc(0),
-                                &bc[0].desc(0), &bc[1].desc(0), &bc[2].desc(0), L.undrrelxr.h_table(), L.mask.h_table(),
-                                m_a_scalar, dh[0], dh[1], dh[2], L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));
-        return;
-    }
-    B200_KCALL(b200mg_gsrb2_abec(L.fused_nblocks, L.fused_tiles.data(), L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
-                                 m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(),
-                                 m_b_coeffs[amrlev][mglev][2].d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
-                                 m_a_scalar, dh[0], dh[1], dh[2], L.fused_tx, L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));
+    if (e == 0) { return true; }
+    if (e != int(cudaErrorInvalidValue)) { Gpu::check(e, "b200mg_gsrb4", __FILE__, __LINE__); }
+    L.fused4_ok = 0;
+    return false;
 }
 
 void MLABecLaplacian::Fjacobi (int amrlev, int mglev, MultiFab& sol_out, MultiFab const& sol_in, MultiFab const& rhs) const
@@ -1442,32 +1471,21 @@ void MLPoisson::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& r
                                    dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, Gpu::gpuStream()));
 }
 
-void MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& sol_in, MultiFab const& rhs, bool zero_input) const
+bool MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& sol_in, MultiFab const& rhs, bool zero_input) const
 {
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
-    if (m_fused_version >= 4 && L.fused4_ok != 0) {
-        int e;
-        {
-            Gpu::KernelScope ks__("b200mg_gsrb4(poisson)");
-            e = b200mg_gsrb4(0, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), nullptr,
-                             nullptr, nullptr, nullptr, L.undrrelxr.h_table(), L.mask.h_table(),
-                             0.0, dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], zero_input ? 1 : 0, Gpu::gpuStream());
-        }
-        if (e == 0) { return; }
-        if (e != int(cudaErrorInvalidValue)) { Gpu::check(e, "b200mg_gsrb4", __FILE__, __LINE__); }
-        L.fused4_ok = 0;
+    int e;
+    {
+        Gpu::KernelScope ks__("b200mg_gsrb4(poisson)");
+        e = b200mg_gsrb4(0, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), nullptr,
+                         nullptr, nullptr, nullptr, L.undrrelxr.h_table(), L.mask.h_table(),
+                         0.0, dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], zero_input ? 1 : 0, Gpu::gpuStream());
     }
-    if (zero_input) { sol_in.setVal(0.0); }
-    if (m_fused_version >= 3) {
-        B200_KCALL(b200mg_gsrb3(0, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), nullptr,
-                                nullptr, nullptr, nullptr, L.undrrelxr.h_table(), L.mask.h_table(),
-                                0.0, dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));
-        return;
-    }
-    B200_KCALL(b200mg_gsrb2_poisson(L.fused_nblocks, L.fused_tiles.data(), L.layout->d_vbox(), sol_in.d_fabs(), sol_out.d_fabs(), rhs.d_fabs(),
-                                    L.undrrelxr.d_table(), L.mask.d_table(), dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2],
-                                    L.fused_tx, L.fused_tile_y, L.fused_chunk_z, Gpu::gpuStream()));
+    if (e == 0) { return true; }
+    if (e != int(cudaErrorInvalidValue)) { Gpu::check(e, "b200mg_gsrb4", __FILE__, __LINE__); }
+    L.fused4_ok = 0;
+    return false;
 }
 
 void MLPoisson::Fjacobi (int amrlev, int mglev, MultiFab& sol_out, MultiFab const& sol_in, MultiFab const& rhs) const

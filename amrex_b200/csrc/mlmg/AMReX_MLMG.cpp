@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <cstring>
 #include <iomanip>
 #include <iostream>
 #include <sstream>
@@ -150,6 +151,14 @@ int MLCGSolver::solve_cg (MultiFab& sol, MultiFab const& rhs, Real eps_rel, Real
 MLMG::MLMG (MLLinOp& a_lp) : linop(a_lp), namrlevs(a_lp.NAMRLevels()), finest_amr_lev(a_lp.NAMRLevels() - 1)
 {
     if (const char* e = std::getenv("B200MG_GRAPHS")) { m_use_graphs = (e[0] != '0'); }
+    if (const char* e = std::getenv("B200MG_LEG_CTAS")) { m_leg_ctas = std::max(1, std::min(16, std::atoi(e))); }
+}
+
+MLMG::LegPlan::~LegPlan ()
+{
+    for (auto& kv : args) { if (kv.second.first) { The_Arena()->free(kv.second.first); } }
+    if (d_log) { The_Arena()->free(d_log); }
+    if (h_log) { pinned_free(h_log); }
 }
 
 MLMG::~MLMG ()
@@ -231,6 +240,7 @@ Real MLMG::solve (Vector<MultiFab*> const& a_sol, Vector<MultiFab const*> const&
     Real& composite_norminf = m_final_resnorm0;
     m_niters_cg.clear();
     m_iter_fine_resnorm0.clear();
+    m_leg.slots.clear(); m_leg.launches = 0;
 
     prepareForSolve(a_sol, a_rhs);
     computeMLResidual(finest_amr_lev);
@@ -293,6 +303,7 @@ Real MLMG::solve (Vector<MultiFab*> const& a_sol, Vector<MultiFab const*> const&
         MultiFab::Copy(*a_sol[alev], sol[alev], 0, 0, 1, std::min(ng_back, a_sol[alev]->nGrow()));
     }
     Gpu::streamSynchronize();
+    collectLegLog();
     timer[0] = ParallelDescriptor::second() - solve_start_time;
     if (verbose >= 1) { Print0(cat("MLMG: Timers: Solve = ", timer[0], " Iter = ", timer[1], " Bottom = ", timer[2], "\n")); }
     ++solve_called;
@@ -424,6 +435,15 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
             for (int i = 0; i < nu2; ++i) { linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev]); }
         }
     };
+    // B200: every level from the first single-box level down to the bottom solve and back up is ONE kernel
+    const int leg0 = coarseLegFirstLevel(amrlev, mglev_top, mglev_bottom);
+    if (leg0 >= 0) {
+        down(mglev_top, leg0);
+        runCoarseLeg(leg0, mglev_bottom);
+        up(leg0 - 1, mglev_top);
+        ++m_cycles_done[amrlev];
+        return;
+    }
     // the launch-bound small levels [g, bottom) replay as CUDA graphs (see AMReX_MLMG.H); the big ones run eagerly
     const int g = graphFirstLevel(amrlev, mglev_top, mglev_bottom);
     down(mglev_top, g);
@@ -444,6 +464,111 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
     }
     up(g - 1, mglev_top);
     ++m_cycles_done[amrlev];
+}
+
+int MLMG::coarseLegFirstLevel (int amrlev, int mglev_top, int mglev_bottom) const
+{
+    if (amrlev != 0) { return -1; }
+    const BottomSolver bs = (bottom_solver == BottomSolver::Default) ? linop.getDefaultBottomSolver() : bottom_solver;
+    if ((bs != BottomSolver::bicgstab && bs != BottomSolver::smoother) || bottom_verbose > 0) { return -1; }
+    int leg0 = -1;
+    for (int m = mglev_bottom; m >= mglev_top; --m) {
+        if (!linop.coarseLegLevelEligible(m)) { break; }
+        leg0 = m;
+    }
+    if (leg0 < 0 || mglev_bottom - leg0 + 1 > B200MG_LEG_MAX_LEVELS) { return -1; }
+    return leg0;
+}
+
+namespace {
+inline void leg_mix (std::size_t& h, std::size_t v) { h ^= v; h *= 1099511628211ull; }
+inline std::size_t leg_bits (Real v) { std::size_t b = 0; std::memcpy(&b, &v, sizeof(Real)); return b; }
+}
+
+void MLMG::runCoarseLeg (int leg0, int mglev_bottom)
+{
+    Gpu::ProfScope prof_scope__(leg0);
+    const bool bicg = (bottom_solver != BottomSolver::smoother);
+    if (bicg) {
+        if (int(m_leg.slots.size()) < kLegLogMax) { m_leg.slots.push_back(int(m_niters_cg.size())); }
+        m_niters_cg.push_back(-1);
+    }
+    if (!linop.ownsSingleBox(leg0)) { return; }          // another rank owns the box of these levels
+    const int nlev = mglev_bottom - leg0 + 1;
+    const bool singular = bicg && linop.isBottomSingular() && linop.getEnforceSingularSolvable();
+    MLCGSolver::Temps tmp{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (bicg) {
+        if (!cg_solver) { cg_solver = std::make_unique<MLCGSolver>(linop); }
+        tmp = cg_solver->temps(cor[0][mglev_bottom]);
+        if (singular && !bottom_b) { bottom_b = std::make_unique<MultiFab>(linop.make(0, mglev_bottom, 0)); }
+    }
+    // every device address and parameter the kernel bakes in
+    std::size_t key = 1469598103934665603ull;
+    for (int m = leg0; m <= mglev_bottom; ++m) {
+        leg_mix(key, reinterpret_cast<std::size_t>(cor[0][m].dataPtr())); leg_mix(key, reinterpret_cast<std::size_t>(res[0][m].dataPtr()));
+        leg_mix(key, reinterpret_cast<std::size_t>(rescor[0][m].dataPtr())); leg_mix(key, linop.graphKey(0, m));
+    }
+    if (bicg) {
+        for (MultiFab* q : {tmp.p, tmp.r, tmp.rh, tmp.v, tmp.t}) { leg_mix(key, reinterpret_cast<std::size_t>(q->dataPtr())); }
+        if (singular) { leg_mix(key, reinterpret_cast<std::size_t>(bottom_b->dataPtr())); }
+    }
+    for (int v : {nu1, nu2, nuf, nub, bottom_maxiter, int(bicg), int(singular), leg0, nlev}) { leg_mix(key, std::size_t(v)); }
+    leg_mix(key, leg_bits(bottom_reltol)); leg_mix(key, leg_bits(bottom_abstol));
+    leg_mix(key, leg_bits(linop.getAScalar())); leg_mix(key, leg_bits(linop.getBScalar()));
+    auto& plan = m_leg.args[leg0];
+    if (!plan.first || plan.second != key) {
+        static b200mg_leg_args A;                         // ~10 KB: kept off the stack
+        std::memset(&A, 0, sizeof(A));
+        A.nlev = nlev; A.maxorder = linop.getMaxOrder(); A.nu1 = nu1; A.nu2 = nu2; A.nuf = nuf; A.nub = nub;
+        A.bottom_mode = bicg ? 0 : 1; A.singular = singular ? 1 : 0; A.maxiter = bottom_maxiter;
+        A.alpha = linop.getAScalar(); A.volinv = singular ? linop.bottomVolInv() : 0.0;
+        A.eps_rel = bottom_reltol; A.eps_abs = bottom_abstol;
+        if (bicg) {
+            A.r = tmp.r->desc(0); A.p = tmp.p->desc(0); A.v = tmp.v->desc(0); A.t = tmp.t->desc(0); A.rh = tmp.rh->desc(0);
+            if (singular) { A.bb = bottom_b->desc(0); }
+        }
+        for (int l = 0; l < nlev; ++l) {
+            const int m = leg0 + l;
+            linop.fillLegLevel(m, A.lev[l]);
+            A.lev[l].cor = cor[0][m].desc(0); A.lev[l].res = res[0][m].desc(0); A.lev[l].rescor = rescor[0][m].desc(0);
+        }
+        if (!plan.first) { plan.first = static_cast<b200mg_leg_args*>(The_Arena()->alloc(sizeof(b200mg_leg_args))); }
+        Gpu::htod_memcpy_async(plan.first, &A, sizeof(A));
+        Gpu::streamSynchronize();                          // A is reused by the next plan
+        plan.second = key;
+    }
+    if (!m_leg.d_log) {
+        m_leg.d_log = static_cast<double*>(The_Arena()->alloc(2 * kLegLogMax * sizeof(double)));
+        m_leg.h_log = static_cast<double*>(pinned_alloc(2 * kLegLogMax * sizeof(double)));
+    }
+    double* out = (bicg && m_leg.launches < kLegLogMax) ? m_leg.d_log + 2 * m_leg.launches : nullptr;
+    const MultiFab* a = nullptr; Array<MultiFab const*, 3> b{{nullptr, nullptr, nullptr}}; Real alpha = 0.0, beta = 1.0;
+    linop.getLevelCoeffs(0, leg0, a, b, alpha, beta);
+    B200_KCALL(b200mg_coarse_leg(a ? 1 : 0, plan.first, out, m_leg_ctas, Gpu::gpuStream()));
+    if (bicg) { ++m_leg.launches; }
+    if (bicg && verbose > 1 && out) {                      // the reference reports a failed bottom solve right away
+        double h[2];
+        Gpu::dtoh_memcpy_async(h, out, 2 * sizeof(double)); Gpu::streamSynchronize();
+        if (int(h[0]) != 0) { Print0("MLMG: Bottom solve failed.\n"); }
+    }
+}
+
+// The leg kernel leaves {return code, iterations} of each bottom solve in device memory; one read-back per solve and one
+// small all-reduce (only the rank that owns the coarse box knows the numbers) instead of a host round trip per V-cycle.
+void MLMG::collectLegLog ()
+{
+    const int n = int(m_leg.slots.size());
+    if (n == 0) { return; }
+    std::vector<double> its(n, 0.0);
+    if (m_leg.launches > 0) {
+        const int m = std::min(m_leg.launches, kLegLogMax);
+        Gpu::dtoh_memcpy_async(m_leg.h_log, m_leg.d_log, 2 * m * sizeof(double));
+        Gpu::streamSynchronize();
+        for (int i = 0; i < std::min(n, m); ++i) { its[i] = m_leg.h_log[2 * i + 1]; }
+    }
+    for (int i0 = 0; i0 < n; i0 += 32) { ParallelDescriptor::ReduceRealMax(its.data() + i0, std::min(32, n - i0)); }
+    for (int i = 0; i < n; ++i) { m_niters_cg[m_leg.slots[i]] = int(its[i]); }
+    m_leg.slots.clear(); m_leg.launches = 0;
 }
 
 void MLMG::getGradSolution (Vector<Array<MultiFab*, 3>> const& a_grad_sol)

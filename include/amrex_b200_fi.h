@@ -144,8 +144,6 @@ void amrex_b200_linop_set_smoother_fusion(MLLinOp* linop, int fuse);   /* 0: ref
 /* MLCellLinOpT::setGaussSeidel (AMReX_MLCellLinOp.H:58): 1 red-black Gauss-Seidel (default), 0 damped Jacobi */
 void amrex_b200_linop_set_gauss_seidel(MLLinOp* linop, int flag);
 /* launch plan of the fused smoother: rows / planes per CTA tile (<= 0: automatic), L2 prefetch distance in planes (< 0: keep) */
-void amrex_b200_linop_set_fused_plan(MLLinOp* linop, int tile_y, int chunk_z, int prefetch_planes);
-void amrex_b200_linop_set_fused_version(MLLinOp* linop, int version);   /* 2: tile-table kernel, 3: kernel-parameter descriptors, 4: bulk-async-copy staged pass */
 /* n > 0: fused pass on every level whose local boxes average >= n cells (floor 32^3); n <= 0 (default): per-level cost model */
 void amrex_b200_linop_set_fused_min_box_cells(MLLinOp* linop, long long n);
 /* launch plan of the generation-4 fused pass (process-wide): rows per CTA tile, EARLY / LATE ring depths; 0 = accepted */

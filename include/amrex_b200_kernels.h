@@ -102,32 +102,15 @@ void b200mg_set_gsrb_lean_occupancy(int min_blocks);
 /* Fused red+black pass (one sweep over memory per smooth): red update of every valid cell and black update of the
  * cells that do not touch the box surface, out of place (phi_in -> phi_out).  The black surface shell is finished by
  * b200mg_gsrb_shell_* after the halo refresh.  Same arithmetic and update order as two colour sweeps.
- * tiles: one entry per CTA = rows [j0, j0+tile_y) x planes [k0, k0+chunk_z) x all x of a box (clipped to the box).
- * Requirements: every box has an even x extent <= 4*tx; tx in {32,64,96,128}; tx*(tile_y+4) <= 1024. */
-int b200mg_gsrb2_abec(int nblocks, const b200mg_tile* tiles, const b200mg_box* vbox,
-                      const b200mg_fab* phi_in, const b200mg_fab* phi_out, const b200mg_fab* rhs, const b200mg_fab* a,
-                      const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
-                      const b200mg_fab* f, const b200mg_ifab* m,
-                      double alpha, double dhx, double dhy, double dhz, int tx, int tile_y, int chunk_z, cudaStream_t s);
-int b200mg_gsrb2_poisson(int nblocks, const b200mg_tile* tiles, const b200mg_box* vbox,
-                         const b200mg_fab* phi_in, const b200mg_fab* phi_out, const b200mg_fab* rhs,
-                         const b200mg_fab* f, const b200mg_ifab* m,
-                         double dhx, double dhy, double dhz, int tx, int tile_y, int chunk_z, cudaStream_t s);
-/* Third-generation fused pass (same results): the descriptor tables are HOST arrays (one entry per local box; f / m:
- * [box*6+face]); they travel to the device as kernel parameters, <= 64 boxes per launch.  abec == 0: Poisson.
- * Requirements: every box has an even x extent with 4 <= nx <= 256, ny >= 2, (nx/2 rounded up to 32)*(tile_y+4) <= 1024;
- * rhs and a share a layout. */
-int b200mg_gsrb3(int abec, int nboxes, const b200mg_box* h_vbox,
-                 const b200mg_fab* h_phi_in, const b200mg_fab* h_phi_out, const b200mg_fab* h_rhs, const b200mg_fab* h_a,
-                 const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
-                 const b200mg_fab* h_f, const b200mg_ifab* h_m,
-                 double alpha, double dhx, double dhy, double dhz, int tile_y, int chunk_z, cudaStream_t s);
-/* Fourth-generation fused pass (same results, same descriptor tables as b200mg_gsrb3): every operand plane is staged
+ * (Two earlier generations of this pass - plain global loads with L2 prefetch - were measured at 36-44 % of the HBM
+ * peak in round 1 and have been removed; levels the staged pass cannot take run the colour sweeps.) */
+/* The fused pass: HOST descriptor tables (one entry per local box; f / m: [box*6+face]) travel to the device as kernel
+ * parameters, <= 64 boxes per launch; abec == 0: Poisson.  Every operand plane is staged
  * into a shared-memory ring by 1-D bulk async copies (TMA engine, mbarrier transaction counts) several planes ahead of
  * its use by a dedicated producer warp; compute warps read shared memory only.  Whole-z CTAs of (all x) x tile_y rows.
  * Requirements: even x extent, 4 <= nx <= 128, ny >= 2, rows 16-byte aligned at the first valid cell, even strides,
  * phi rows readable on [lo-2, hi+2], bx rows nx+2 doubles long (all guaranteed by the FabArray allocator);
- * cudaErrorInvalidValue otherwise (the caller falls back to b200mg_gsrb3).
+ * cudaErrorInvalidValue otherwise (the caller falls back to the colour sweeps).
  * phi_zero != 0: the input is identically zero INCLUDING its ghost cells (first smooth after cor.setVal(0),
  * AMReX_MLMG.H:1318-1326): h_phi_in is not read at all - the shared-memory planes are zero-filled instead - so the
  * caller may skip the setVal; the output is the same bits as with a zeroed input. */
@@ -140,8 +123,6 @@ int b200mg_gsrb4(int abec, int nboxes, const b200mg_box* h_vbox,
 int b200mg_set_gsrb4_plan(int tile_y, int early_stages, int late_stages);
 /* synchronisation inside a CTA of b200mg_gsrb4: 0 = one CTA barrier per plane, 1 = decoupled warps (mbarrier arrive / wait) */
 void b200mg_set_gsrb4_sync(int decoupled);
-/* L2 prefetch distance (planes ahead of the loads) of the fused pass; 0 switches the prefetch off */
-void b200mg_set_gsrb2_prefetch(int planes);
 /* black (redblack=1) or red sweep restricted to the 1-cell surface shell of every box; max_face_cells = cells of the
  * largest box face of the level (sizes the grid: one thread per swept cell) */
 int b200mg_gsrb_shell_abec(int nboxes, const b200mg_box* vbox,
@@ -289,19 +270,54 @@ int b200mg_asum(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, co
 long long b200mg_reduce_scratch_doubles(int ntiles);
 
 /* ---- whole BiCGStab bottom solve in one single-CTA kernel (MLCGSolverT::solve_bicgstab with a zeroed initial vector,
- *      AMReX_MLCGSolver.H:98-273): for a bottom MG level that is ONE box (<= 32^3 cells) covering a non-periodic domain.
+ *      AMReX_MLCGSolver.H:98-273): for a bottom MG level that is ONE box (<= 32^3 cells) covering the domain.
  *      h_*: HOST descriptors of the box's fabs (sol, r, p with one ghost cell; sol zeroed by the caller; r, p, v, t, rh
  *      scratch); abec == 0: Poisson (a, bx, by, bz ignored; dh* = dxinv^2), else dh* = beta*dxinv^2.  h_faces: the box's
- *      physical faces (<= 6, box == 0), d_mask: DEVICE table of the box's 6 mask slabs.  d_out (device, 4 doubles):
+ *      physical faces (<= 6, box == 0), h_mask: HOST table of the box's 6 mask slabs, periodic[3]: directions in which the
+ *      box wraps onto itself (NULL: none).  d_out (device, 4 doubles):
  *      return code of solve_bicgstab, iteration count, final and initial max-norm of the residual. */
 int b200mg_bottom_bicgstab(int abec, const b200mg_box* h_vbox,
                            const b200mg_fab* h_sol, const b200mg_fab* h_rhs, const b200mg_fab* h_r, const b200mg_fab* h_p,
                            const b200mg_fab* h_v, const b200mg_fab* h_t, const b200mg_fab* h_rh,
                            const b200mg_fab* h_a, const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
                            double alpha, double dhx, double dhy, double dhz,
-                           int nfaces, const b200mg_bcface* h_faces, const b200mg_ifab* d_mask, int maxorder,
+                           int nfaces, const b200mg_bcface* h_faces, const b200mg_ifab* h_mask, const int* periodic, int maxorder,
                            double dxinv0, double dxinv1, double dxinv2, double eps_rel, double eps_abs, int maxiter,
                            double* d_out, cudaStream_t s);
+
+/* ---- the coarse leg of a V-cycle in ONE thread-block-cluster kernel (MLMGT::mgVcycle AMReX_MLMG.H:1308-1415 from the
+ *      first MG level that is a single box covering the domain down to the bottom solve - MLMGT::bottomSolve :1460-1576,
+ *      BiCGStab as b200mg_bottom_bicgstab or nuf smooths - and back up).  lev[0] is the top level of the leg, lev[nlev-1]
+ *      the bottom; every level is ONE box of <= 32^3 cells, coarsened by 2 from the level above, whose faces are physical
+ *      Dirichlet / Neumann / reflect-odd boundaries or wrap onto the box itself (periodic).  res[0] holds the right-hand
+ *      side on entry, cor[0] the correction on exit; all other fields of the leg are scratch.  Same bits as the
+ *      launch-per-operation schedule (shared per-cell code, same operation order). */
+#define B200MG_LEG_MAX_LEVELS 8
+typedef struct b200mg_leg_level {
+    b200mg_box vb;                  /* the level's box == its domain */
+    b200mg_fab cor, res, rescor;    /* cor: one ghost cell */
+    b200mg_fab a, bx, by, bz;       /* MLABecLaplacian coefficients (unused for Poisson) */
+    b200mg_fab f[6];                /* relaxation-coefficient slabs (m_undrrelxr), [face] */
+    b200mg_ifab m[6];               /* mask slabs (m_maskvals), [face] */
+    int nfaces;                     /* faces with uncovered ghost cells = physical boundaries */
+    int periodic[3];
+    b200mg_bcface faces[6];
+    double dxi[3];                  /* inverse cell size */
+    double dh[3];                   /* smoother scaling: beta/h^2 (Poisson: dxinv^2) */
+    double adh[3];                  /* apply scaling: beta*dxinv^2 (Poisson: dxinv^2) */
+} b200mg_leg_level;
+typedef struct b200mg_leg_args {
+    int nlev, maxorder, nu1, nu2, nuf, nub;
+    int bottom_mode;                /* 0: BiCGStab, 1: smoother */
+    int singular;                   /* bottom right-hand side is made solvable on the copy bb first */
+    int maxiter, pad;
+    double alpha, volinv, eps_rel, eps_abs;
+    b200mg_fab r, p, v, t, rh, bb;  /* bottom-level scratch: r, p with one ghost cell */
+    b200mg_leg_level lev[B200MG_LEG_MAX_LEVELS];
+} b200mg_leg_args;
+/* d_args: the arguments in DEVICE memory; d_out (device, 2 doubles, may be NULL): return code and iteration count of the
+ * BiCGStab bottom solve; cluster_ctas: CTAs of the one cluster that runs the leg (1..16, 512 threads each). */
+int b200mg_coarse_leg(int abec, const b200mg_leg_args* d_args, double* d_out, int cluster_ctas, cudaStream_t s);
 
 /* ---- batched Krylov vector kernels (GMRES Gram-Schmidt: the dotProduct / increment loops of
  *      GMRES::gram_schmidt_orthogonalization, AMReX_GMRES.H:322-348).  v: HOST array of nv <= B200MG_KRYLOV_GROUP device

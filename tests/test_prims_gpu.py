@@ -136,7 +136,6 @@ def test_fused4_abeclap_bitwise(ab, plan):
         assert "b200mg_gsrb4" not in names
     P = synth_abeclap(ab, n, mgs, fusion=1)
     op = P["op"]
-    op.setFusedVersion(4)
     assert ab.lib.amrex_b200_set_fused4_plan(*plan[:3]) == 0
     ab.lib.b200mg_set_gsrb4_sync(plan[3])
     try:
@@ -165,7 +164,6 @@ def test_fused4_zero_input_bitwise(ab, kind, plan):
         for zero_input in (False, True):
             P = synth(ab, n, mgs, fusion=1)
             op = P["op"]
-            op.setFusedVersion(4)
             op.prepareForSolve()
             for mglev in (0, 1):
                 nn = n >> mglev

@@ -73,7 +73,7 @@ def test_abeclap_maxorder3(ab):
 def test_periodic_poisson(ab):
     ref, mlmg, diff = solve_case(ab, 5, 64, 32)
     assert abs(mlmg.numIters() - ref["iters"]) <= 1
-    assert diff <= 1e-9
+    assert diff <= SOL_TOL
 
 
 @pytest.mark.parametrize("bottom", ["smoother", "cg"])
@@ -166,6 +166,74 @@ def test_b200_schedule_switches_are_bit_neutral(ab, kind, monkeypatch):
     assert out[True][0] == out[False][0]
     assert out[True][1] == out[False][1]
     assert np.array_equal(out[True][2], out[False][2])
+
+
+@pytest.mark.parametrize("kind,n,mgs,bottom", [("abeclap", 128, 64, None), ("poisson", 128, 64, None), ("abeclap", 64, 32, None),
+                                               ("abeclap", 32, 32, None), ("poisson", 64, 32, "smoother")])
+def test_coarse_leg_kernel_is_bit_neutral(ab, kind, n, mgs, bottom, monkeypatch):
+    """kernels/coarse_leg.cu - every single-box MG level plus the bottom solve as ONE cluster kernel per V-cycle - against the
+    launch-per-operation schedule (B200MG_NO_COARSE_LEG=1, which ends in the single-CTA bottom kernel): same V-cycle count,
+    bit-identical residual history, solution and BiCGStab iteration counts.  The 32^3 case is one box: the whole cycle is the leg."""
+    from common import synth_abeclap, synth_poisson
+    out = {}
+    for off in (True, False):
+        if off:
+            monkeypatch.setenv("B200MG_NO_COARSE_LEG", "1")
+        else:
+            monkeypatch.delenv("B200MG_NO_COARSE_LEG", raising=False)
+        if kind == "abeclap":
+            P = synth_abeclap(ab, n, mgs, fusion=1)
+            sol, rhs = P["sol"], P["rhs"]
+        else:
+            P = synth_poisson(ab, n, mgs, fusion=1)
+            sol = ab.MultiFab(P["ba"], P["dm"], 1, 1)
+            rhs = ab.MultiFab(P["ba"], P["dm"], 1, 0)
+            sol.setVal(0.0, ng=1)
+            rhs.upload(np.random.default_rng(3).standard_normal((n, n, n)), (0, 0, 0))
+        mlmg = ab.MLMG(P["op"])
+        mlmg.setVerbose(0)
+        if bottom:
+            mlmg.setBottomSolver(bottom)
+        ab.profile_enable(True)
+        mlmg.solve([sol], [rhs], 1e-10, 0.0)
+        names = set(q[0] for q in ab.profile_report())
+        ab.profile_enable(False)
+        assert ("b200mg_coarse_leg" in names) == (not off), names
+        out[off] = (mlmg.numIters(), list(mlmg.residualHistory()), sol.download((0, 0, 0), (n, n, n)), list(mlmg.cgIters()))
+    assert out[True][0] == out[False][0]
+    assert out[True][1] == out[False][1]
+    assert np.array_equal(out[True][2], out[False][2])
+    assert out[True][3] == out[False][3] and (bottom or all(i >= 1 for i in out[False][3]))
+
+
+def test_coarse_leg_kernel_periodic(ab, monkeypatch):
+    """Periodic (singular) Poisson: the leg wraps the box onto itself and makes the bottom right-hand side solvable on the
+    device.  Its sums run in another order than the host path's reduction kernels, so the two agree to rounding, not bits:
+    same V-cycle count, histories within 1e-6, solutions (mean removed) within 1e-10 - and both match the reference."""
+    ref, dump = run_ref(dump=True, mode="solve", prob_type=5, n_cell=64, max_grid_size=32, linop_maxorder=2, agg_grid_size=32)
+    out = {}
+    for off in (True, False):
+        if off:
+            monkeypatch.setenv("B200MG_NO_COARSE_LEG", "1")
+        else:
+            monkeypatch.delenv("B200MG_NO_COARSE_LEG", raising=False)
+        P = build_problem(ab, 5, 64, 32, dump)
+        mlmg = ab.MLMG(P["op"])
+        mlmg.setVerbose(0)
+        ab.profile_enable(True)
+        mlmg.solve([P["sol"]], [P["rhs"]], 1e-10, 0.0)
+        names = set(q[0] for q in ab.profile_report())
+        ab.profile_enable(False)
+        assert ("b200mg_coarse_leg" in names) == (not off), names
+        mine = P["sol"].download((0, 0, 0), (64, 64, 64))
+        out[off] = (mlmg.numIters(), list(mlmg.residualHistory()), mine - mine.mean())
+    assert out[True][0] == out[False][0] and abs(out[False][0] - ref["iters"]) <= 1
+    for a, b in zip(out[True][1], out[False][1]):
+        assert a == pytest.approx(b, rel=1e-6)
+    refv = dump["sol_lev0"][1][1:-1, 1:-1, 1:-1]
+    refv = refv - refv.mean()
+    assert rel_maxdiff(out[False][2], out[True][2]) <= SOL_TOL
+    assert rel_maxdiff(out[False][2], refv) <= SOL_TOL
 
 
 # ---- GMRES preconditioned by MLMG (SURVEY 8f row 2): Tests/LinearSolvers/ABecLaplacian_C inputs.gmres, MyTest.cpp:466-532
@@ -293,6 +361,7 @@ def test_plotfile_judged_by_reference_fcompare(ab, tmp_path):
 def test_bottom_kernel_matches_launch_schedule(ab, prob_type, n, mgs, monkeypatch):
     ref, dump = run_ref(dump=True, mode="solve", prob_type=prob_type, n_cell=n, max_grid_size=mgs, linop_maxorder=2, agg_grid_size=32)
     out = {}
+    monkeypatch.setenv("B200MG_NO_COARSE_LEG", "1")      # the leg kernel would absorb the bottom solve (tested on its own above)
     for on in (False, True):
         if on:
             monkeypatch.delenv("B200MG_NO_BOTTOM_KERNEL", raising=False)
