@@ -532,12 +532,12 @@ bool MLLinOp::bottomKernelEligible (int mglev) const
     return true;
 }
 
-bool MLLinOp::coarseLegLevelEligible (int mglev) const
+bool MLLinOp::coarseLegLevelEligible (int mglev, Long max_cells) const
 {
     if (!m_coarse_leg || !m_use_gauss_seidel || Gpu::debugSync() || m_needs_coarse_data_for_bc) { return false; }
     BoxArray const& ba = H.grids[0][mglev];
     Geometry const& geom = H.geom[0][mglev];
-    if (ba.size() != 1 || ba[0] != geom.Domain() || ba[0].numPts() > 32768 || !ba[0].cellCentered()) { return false; }
+    if (ba.size() != 1 || ba[0] != geom.Domain() || ba[0].numPts() > max_cells || !ba[0].cellCentered()) { return false; }
     for (int d = 0; d < 3; ++d) {
         if (geom.isPeriodic(d)) { continue; }
         for (BCType t : {m_lobc[d], m_hibc[d]}) {
@@ -580,6 +580,59 @@ void MLLinOp::fillLegLevel (int mglev, b200mg_leg_level& out) const
         out.faces[n] = L.bcfaces_h[n];
         AMREX_ALWAYS_ASSERT(out.faces[n].box == 0 && out.faces[n].bctype >= 101 && out.faces[n].bctype <= 103);
     }
+}
+
+void MLLinOp::copyOptionsTo (MLLinOp& op) const
+{
+    op.setMaxOrder(maxorder);
+    op.setGaussSeidel(m_use_gauss_seidel);
+    op.setEnforceSingularSolvable(enforceSingularSolvable);
+    op.setSmootherFusion(m_fuse_colors);
+    op.setDomainBC(m_lobc, m_hibc);           // (inhomogeneous Neumann already acts as Neumann below the finest level)
+    op.m_domain_bloc_lo = m_domain_bloc_lo; op.m_domain_bloc_hi = m_domain_bloc_hi;
+    op.setLevelBC(0, nullptr);
+}
+
+void MLLinOp::buildMergedLeg ()
+{
+    m_merged.reset(); m_merged_lev = -1;
+    const bool off = std::getenv("B200MG_NO_MERGED_LEG") != nullptr;            // read per build: tests toggle it
+    if (off || m_is_merged_copy || !m_coarse_leg || !m_use_gauss_seidel || Gpu::debugSync() || m_needs_coarse_data_for_bc) { return; }
+    if (!H.domain_covered[0]) { return; }
+    for (int d = 0; d < 3; ++d) {
+        if (H.geom[0][0].isPeriodic(d)) { continue; }
+        for (BCType t : {m_lobc[d], m_hibc[d]}) {
+            if (t != BCType::Dirichlet && t != BCType::Neumann && t != BCType::reflect_odd) { return; }
+        }
+    }
+    const char* mc = std::getenv("B200MG_MERGED_MAX_CELLS");
+    const Long max_cells = mc ? Long(std::atoll(mc)) : (Long(1) << 21);
+    const int nm = H.num_mg_levels[0];
+    int m0 = -1;
+    for (int m = 0; m < nm; ++m) {
+        if (H.grids[0][m].size() == 1) { break; }                  // one box already: the leg kernel takes the level as it is
+        if (H.geom[0][m].Domain().numPts() <= max_cells && H.grids[0][m].ixType().cellCentered()) { m0 = m; break; }
+    }
+    if (m0 < 0) { return; }
+    for (int m = m0; m < nm; ++m) {
+        if (m + 1 < nm && H.mg_coarsen_ratio_vec[m] != IntVect(2)) { return; }
+        BoxArray const& ba = H.grids[0][m];
+        if (ba.numPts() != H.geom[0][m].Domain().numPts()) { return; }
+        if (ba.size() == 1) { continue; }
+        // the order of the Dirichlet ghost-value interpolation is min(box length + 1, maxorder): a chopped level and its
+        // one-box copy agree only where no box is shorter than that
+        for (int i = 0, N = int(ba.size()); i < N; ++i) {
+            for (int d = 0; d < 3; ++d) { if (ba[i].length(d) + 1 < maxorder) { return; } }
+        }
+    }
+    const int owner = (H.grids[0][nm - 1].size() == 1) ? H.dmap[0][nm - 1][0] : 0;
+    LPInfo inf;
+    inf.setAgglomeration(false).setConsolidation(false).setMaxCoarseningLevel(nm - 1 - m0);
+    std::unique_ptr<MLLinOp> op = makeMergedOp(H.geom[0][m0], BoxArray(H.geom[0][m0].Domain()), DistributionMapping(Vector<int>{owner}), inf, m0);
+    if (!op || op->NMGLevels(0) != nm - m0) { return; }
+    for (int l = 0; l < nm - m0; ++l) { if (op->Geom(0, l).Domain() != H.geom[0][m0 + l].Domain()) { return; } }
+    if (op->isBottomSingular() != isBottomSingular()) { return; }
+    m_merged = std::move(op); m_merged_lev = m0;
 }
 
 int MLLinOp::bottomBiCGStabKernel (int mglev, MultiFab& sol, MultiFab const& rhs, MultiFab& r, MultiFab& p, MultiFab& v, MultiFab& t,
@@ -1329,6 +1382,7 @@ void MLABecLaplacian::prepareForSolve ()
     averageDownCoeffs();
     update_singular_flags();
     m_needs_update = false;
+    buildMergedLeg();
 }
 
 void MLABecLaplacian::update ()
@@ -1336,6 +1390,21 @@ void MLABecLaplacian::update ()
     averageDownCoeffs();
     update_singular_flags();
     m_needs_update = false;
+    buildMergedLeg();
+}
+
+std::unique_ptr<MLLinOp> MLABecLaplacian::makeMergedOp (Geometry const& geom, BoxArray const& ba, DistributionMapping const& dm,
+                                                        LPInfo const& inf, int mglev) const
+{
+    auto op = std::make_unique<MLABecLaplacian>();
+    op->m_is_merged_copy = true;
+    op->define({geom}, {ba}, {dm}, inf);
+    copyOptionsTo(*op);
+    op->setScalars(m_a_scalar, m_b_scalar);
+    op->setACoeffs(0, m_a_coeffs[0][mglev]);                     // ParallelCopy onto the one box
+    op->setBCoeffs(0, {{&m_b_coeffs[0][mglev][0], &m_b_coeffs[0][mglev][1], &m_b_coeffs[0][mglev][2]}});
+    op->prepareForSolve();
+    return op;
 }
 
 void MLABecLaplacian::normalize (int amrlev, int mglev, MultiFab& mf) const
@@ -1436,6 +1505,18 @@ void MLPoisson::prepareForSolve ()
     bool no_dirichlet = true;
     for (int d = 0; d < 3; ++d) { if (m_lobc[d] == BCType::Dirichlet || m_hibc[d] == BCType::Dirichlet) { no_dirichlet = false; } }
     if (no_dirichlet) { for (int alev = 0; alev < H.num_amr_levels; ++alev) { if (H.domain_covered[alev]) { m_is_singular[alev] = 1; } } }
+    buildMergedLeg();
+}
+
+std::unique_ptr<MLLinOp> MLPoisson::makeMergedOp (Geometry const& geom, BoxArray const& ba, DistributionMapping const& dm,
+                                                  LPInfo const& inf, int) const
+{
+    auto op = std::make_unique<MLPoisson>();
+    op->m_is_merged_copy = true;
+    op->define({geom}, {ba}, {dm}, inf);
+    copyOptionsTo(*op);
+    op->prepareForSolve();
+    return op;
 }
 
 bool MLPoisson::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab const& in, const MultiFab* rhs, Real* norm_dev) const

@@ -151,7 +151,8 @@ int MLCGSolver::solve_cg (MultiFab& sol, MultiFab const& rhs, Real eps_rel, Real
 MLMG::MLMG (MLLinOp& a_lp) : linop(a_lp), namrlevs(a_lp.NAMRLevels()), finest_amr_lev(a_lp.NAMRLevels() - 1)
 {
     if (const char* e = std::getenv("B200MG_GRAPHS")) { m_use_graphs = (e[0] != '0'); }
-    if (const char* e = std::getenv("B200MG_LEG_CTAS")) { m_leg_ctas = std::max(1, std::min(16, std::atoi(e))); }
+    if (const char* e = std::getenv("B200MG_LEG_CTAS")) { m_leg_max_ctas = std::max(1, std::atoi(e)); }
+    if (const char* e = std::getenv("B200MG_LEG_NARROW")) { m_leg_narrow_cells = std::max(0, std::atoi(e)); }
 }
 
 MLMG::LegPlan::~LegPlan ()
@@ -439,7 +440,7 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
     const int leg0 = coarseLegFirstLevel(amrlev, mglev_top, mglev_bottom);
     if (leg0 >= 0) {
         down(mglev_top, leg0);
-        runCoarseLeg(leg0, mglev_bottom);
+        runCoarseLeg(leg0, mglev_bottom, legIsMerged(leg0));
         up(leg0 - 1, mglev_top);
         ++m_cycles_done[amrlev];
         return;
@@ -471,9 +472,22 @@ int MLMG::coarseLegFirstLevel (int amrlev, int mglev_top, int mglev_bottom) cons
     if (amrlev != 0) { return -1; }
     const BottomSolver bs = (bottom_solver == BottomSolver::Default) ? linop.getDefaultBottomSolver() : bottom_solver;
     if ((bs != BottomSolver::bicgstab && bs != BottomSolver::smoother) || bottom_verbose > 0) { return -1; }
+    constexpr Long kWideMax = Long(1) << 21, kBiCGMax = 32768;        // the bottom BiCGStab is one CTA's work
+    // the merged copy of the operator (every level from mergedLegLevel() down re-gridded as one box)
+    const int mm = linop.mergedLegLevel();
+    if (mm >= mglev_top && mm <= mglev_bottom && mglev_bottom - mm + 1 <= B200MG_LEG_MAX_LEVELS && mglev_bottom == linop.NMGLevels(0) - 1) {
+        MLLinOp const& op = linop.mergedOp();
+        bool ok = true;
+        for (int l = 0; l <= mglev_bottom - mm && ok; ++l) {
+            const bool bottom = (l == mglev_bottom - mm);
+            ok = op.coarseLegLevelEligible(l, (bottom && bs == BottomSolver::bicgstab) ? kBiCGMax : kWideMax);
+        }
+        if (ok) { return mm; }
+    }
     int leg0 = -1;
     for (int m = mglev_bottom; m >= mglev_top; --m) {
-        if (!linop.coarseLegLevelEligible(m)) { break; }
+        const bool bottom = (m == mglev_bottom);
+        if (!linop.coarseLegLevelEligible(m, (bottom && bs == BottomSolver::bicgstab) ? kBiCGMax : kWideMax)) { break; }
         leg0 = m;
     }
     if (leg0 < 0 || mglev_bottom - leg0 + 1 > B200MG_LEG_MAX_LEVELS) { return -1; }
@@ -485,7 +499,9 @@ inline void leg_mix (std::size_t& h, std::size_t v) { h ^= v; h *= 1099511628211
 inline std::size_t leg_bits (Real v) { std::size_t b = 0; std::memcpy(&b, &v, sizeof(Real)); return b; }
 }
 
-void MLMG::runCoarseLeg (int leg0, int mglev_bottom)
+// merged: the leg runs on linop.mergedOp() (level l of it == MG level leg0 + l here): the residual of level leg0 moves onto
+// the one box by ParallelCopy, the correction comes back the same way.
+void MLMG::runCoarseLeg (int leg0, int mglev_bottom, bool merged)
 {
     Gpu::ProfScope prof_scope__(leg0);
     const bool bicg = (bottom_solver != BottomSolver::smoother);
@@ -493,64 +509,90 @@ void MLMG::runCoarseLeg (int leg0, int mglev_bottom)
         if (int(m_leg.slots.size()) < kLegLogMax) { m_leg.slots.push_back(int(m_niters_cg.size())); }
         m_niters_cg.push_back(-1);
     }
-    if (!linop.ownsSingleBox(leg0)) { return; }          // another rank owns the box of these levels
+    MLLinOp& op = merged ? linop.mergedOp() : linop;
+    const int off = merged ? leg0 : 0;                       // MG level of op = MG level of linop - off
     const int nlev = mglev_bottom - leg0 + 1;
-    const bool singular = bicg && linop.isBottomSingular() && linop.getEnforceSingularSolvable();
-    MLCGSolver::Temps tmp{nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (bicg) {
-        if (!cg_solver) { cg_solver = std::make_unique<MLCGSolver>(linop); }
-        tmp = cg_solver->temps(cor[0][mglev_bottom]);
-        if (singular && !bottom_b) { bottom_b = std::make_unique<MultiFab>(linop.make(0, mglev_bottom, 0)); }
+    if (merged) {
+        if (m_leg.mop != &op) {                              // first use, or update() rebuilt the copy
+            m_leg.mcor.clear(); m_leg.mres.clear(); m_leg.mrescor.clear(); m_leg.mcg.reset(); m_leg.mbb.reset();
+            for (int l = 0; l < nlev; ++l) {
+                m_leg.mcor.push_back(op.make(0, l, 1)); m_leg.mres.push_back(op.make(0, l, 0)); m_leg.mrescor.push_back(op.make(0, l, 0));
+            }
+            m_leg.mop = &op;
+        }
+        m_leg.mres[0].ParallelCopy(res[0][leg0], 0, 0, 1);
     }
-    // every device address and parameter the kernel bakes in
-    std::size_t key = 1469598103934665603ull;
-    for (int m = leg0; m <= mglev_bottom; ++m) {
-        leg_mix(key, reinterpret_cast<std::size_t>(cor[0][m].dataPtr())); leg_mix(key, reinterpret_cast<std::size_t>(res[0][m].dataPtr()));
-        leg_mix(key, reinterpret_cast<std::size_t>(rescor[0][m].dataPtr())); leg_mix(key, linop.graphKey(0, m));
-    }
-    if (bicg) {
-        for (MultiFab* q : {tmp.p, tmp.r, tmp.rh, tmp.v, tmp.t}) { leg_mix(key, reinterpret_cast<std::size_t>(q->dataPtr())); }
-        if (singular) { leg_mix(key, reinterpret_cast<std::size_t>(bottom_b->dataPtr())); }
-    }
-    for (int v : {nu1, nu2, nuf, nub, bottom_maxiter, int(bicg), int(singular), leg0, nlev}) { leg_mix(key, std::size_t(v)); }
-    leg_mix(key, leg_bits(bottom_reltol)); leg_mix(key, leg_bits(bottom_abstol));
-    leg_mix(key, leg_bits(linop.getAScalar())); leg_mix(key, leg_bits(linop.getBScalar()));
-    auto& plan = m_leg.args[leg0];
-    if (!plan.first || plan.second != key) {
-        static b200mg_leg_args A;                         // ~10 KB: kept off the stack
-        std::memset(&A, 0, sizeof(A));
-        A.nlev = nlev; A.maxorder = linop.getMaxOrder(); A.nu1 = nu1; A.nu2 = nu2; A.nuf = nuf; A.nub = nub;
-        A.bottom_mode = bicg ? 0 : 1; A.singular = singular ? 1 : 0; A.maxiter = bottom_maxiter;
-        A.alpha = linop.getAScalar(); A.volinv = singular ? linop.bottomVolInv() : 0.0;
-        A.eps_rel = bottom_reltol; A.eps_abs = bottom_abstol;
+    auto Cor = [&] (int m) -> MultiFab& { return merged ? m_leg.mcor[m - off] : cor[0][m]; };
+    auto Res = [&] (int m) -> MultiFab& { return merged ? m_leg.mres[m - off] : res[0][m]; };
+    auto Rescor = [&] (int m) -> MultiFab& { return merged ? m_leg.mrescor[m - off] : rescor[0][m]; };
+    if (op.ownsSingleBox(leg0 - off)) {                      // else another rank owns the box of these levels
+        const bool singular = bicg && op.isBottomSingular() && op.getEnforceSingularSolvable();
+        MLCGSolver::Temps tmp{nullptr, nullptr, nullptr, nullptr, nullptr};
+        MultiFab* bb = nullptr;
         if (bicg) {
-            A.r = tmp.r->desc(0); A.p = tmp.p->desc(0); A.v = tmp.v->desc(0); A.t = tmp.t->desc(0); A.rh = tmp.rh->desc(0);
-            if (singular) { A.bb = bottom_b->desc(0); }
+            std::unique_ptr<MLCGSolver>& cg = merged ? m_leg.mcg : cg_solver;
+            if (!cg) { cg = std::make_unique<MLCGSolver>(op); }
+            tmp = cg->temps(Cor(mglev_bottom));
+            if (singular) {
+                std::unique_ptr<MultiFab>& b = merged ? m_leg.mbb : bottom_b;
+                if (!b) { b = std::make_unique<MultiFab>(op.make(0, mglev_bottom - off, 0)); }
+                bb = b.get();
+            }
         }
-        for (int l = 0; l < nlev; ++l) {
-            const int m = leg0 + l;
-            linop.fillLegLevel(m, A.lev[l]);
-            A.lev[l].cor = cor[0][m].desc(0); A.lev[l].res = res[0][m].desc(0); A.lev[l].rescor = rescor[0][m].desc(0);
+        Long top_cells = op.Geom(0, leg0 - off).Domain().numPts();
+        const int ctas = (top_cells <= Long(m_leg_narrow_cells)) ? 1
+                       : int(std::min<Long>(Long(m_leg_max_ctas), (top_cells / 2 + 511) / 512));
+        // every device address and parameter the kernel bakes in
+        std::size_t key = 1469598103934665603ull;
+        for (int m = leg0; m <= mglev_bottom; ++m) {
+            leg_mix(key, reinterpret_cast<std::size_t>(Cor(m).dataPtr())); leg_mix(key, reinterpret_cast<std::size_t>(Res(m).dataPtr()));
+            leg_mix(key, reinterpret_cast<std::size_t>(Rescor(m).dataPtr())); leg_mix(key, op.graphKey(0, m - off));
         }
-        if (!plan.first) { plan.first = static_cast<b200mg_leg_args*>(The_Arena()->alloc(sizeof(b200mg_leg_args))); }
-        Gpu::htod_memcpy_async(plan.first, &A, sizeof(A));
-        Gpu::streamSynchronize();                          // A is reused by the next plan
-        plan.second = key;
+        if (bicg) {
+            for (MultiFab* q : {tmp.p, tmp.r, tmp.rh, tmp.v, tmp.t}) { leg_mix(key, reinterpret_cast<std::size_t>(q->dataPtr())); }
+            if (singular) { leg_mix(key, reinterpret_cast<std::size_t>(bb->dataPtr())); }
+        }
+        for (int v : {nu1, nu2, nuf, nub, bottom_maxiter, int(bicg), int(singular), leg0, nlev, int(merged), m_leg_narrow_cells}) { leg_mix(key, std::size_t(v)); }
+        leg_mix(key, leg_bits(bottom_reltol)); leg_mix(key, leg_bits(bottom_abstol));
+        leg_mix(key, leg_bits(op.getAScalar())); leg_mix(key, leg_bits(op.getBScalar()));
+        auto& plan = m_leg.args[leg0];
+        if (!plan.first || plan.second != key) {
+            static b200mg_leg_args A;                         // ~10 KB: kept off the stack
+            std::memset(&A, 0, sizeof(A));
+            A.nlev = nlev; A.maxorder = op.getMaxOrder(); A.nu1 = nu1; A.nu2 = nu2; A.nuf = nuf; A.nub = nub;
+            A.bottom_mode = bicg ? 0 : 1; A.singular = singular ? 1 : 0; A.maxiter = bottom_maxiter; A.narrow_cells = m_leg_narrow_cells;
+            A.alpha = op.getAScalar(); A.volinv = singular ? op.bottomVolInv() : 0.0;
+            A.eps_rel = bottom_reltol; A.eps_abs = bottom_abstol;
+            if (bicg) {
+                A.r = tmp.r->desc(0); A.p = tmp.p->desc(0); A.v = tmp.v->desc(0); A.t = tmp.t->desc(0); A.rh = tmp.rh->desc(0);
+                if (singular) { A.bb = bb->desc(0); }
+            }
+            for (int l = 0; l < nlev; ++l) {
+                const int m = leg0 + l;
+                op.fillLegLevel(m - off, A.lev[l]);
+                A.lev[l].cor = Cor(m).desc(0); A.lev[l].res = Res(m).desc(0); A.lev[l].rescor = Rescor(m).desc(0);
+            }
+            if (!plan.first) { plan.first = static_cast<b200mg_leg_args*>(The_Arena()->alloc(sizeof(b200mg_leg_args))); }
+            Gpu::htod_memcpy_async(plan.first, &A, sizeof(A));
+            Gpu::streamSynchronize();                          // A is reused by the next plan
+            plan.second = key;
+        }
+        if (!m_leg.d_log) {
+            m_leg.d_log = static_cast<double*>(The_Arena()->alloc(2 * kLegLogMax * sizeof(double)));
+            m_leg.h_log = static_cast<double*>(pinned_alloc(2 * kLegLogMax * sizeof(double)));
+        }
+        double* out = (bicg && m_leg.launches < kLegLogMax) ? m_leg.d_log + 2 * m_leg.launches : nullptr;
+        const MultiFab* a = nullptr; Array<MultiFab const*, 3> b{{nullptr, nullptr, nullptr}}; Real alpha = 0.0, beta = 1.0;
+        op.getLevelCoeffs(0, leg0 - off, a, b, alpha, beta);
+        B200_KCALL(b200mg_coarse_leg(a ? 1 : 0, plan.first, out, ctas, Gpu::gpuStream()));
+        if (bicg) { ++m_leg.launches; }
+        if (bicg && verbose > 1 && out) {                      // the reference reports a failed bottom solve right away
+            double h[2];
+            Gpu::dtoh_memcpy_async(h, out, 2 * sizeof(double)); Gpu::streamSynchronize();
+            if (int(h[0]) != 0) { Print0("MLMG: Bottom solve failed.\n"); }
+        }
     }
-    if (!m_leg.d_log) {
-        m_leg.d_log = static_cast<double*>(The_Arena()->alloc(2 * kLegLogMax * sizeof(double)));
-        m_leg.h_log = static_cast<double*>(pinned_alloc(2 * kLegLogMax * sizeof(double)));
-    }
-    double* out = (bicg && m_leg.launches < kLegLogMax) ? m_leg.d_log + 2 * m_leg.launches : nullptr;
-    const MultiFab* a = nullptr; Array<MultiFab const*, 3> b{{nullptr, nullptr, nullptr}}; Real alpha = 0.0, beta = 1.0;
-    linop.getLevelCoeffs(0, leg0, a, b, alpha, beta);
-    B200_KCALL(b200mg_coarse_leg(a ? 1 : 0, plan.first, out, m_leg_ctas, Gpu::gpuStream()));
-    if (bicg) { ++m_leg.launches; }
-    if (bicg && verbose > 1 && out) {                      // the reference reports a failed bottom solve right away
-        double h[2];
-        Gpu::dtoh_memcpy_async(h, out, 2 * sizeof(double)); Gpu::streamSynchronize();
-        if (int(h[0]) != 0) { Print0("MLMG: Bottom solve failed.\n"); }
-    }
+    if (merged) { cor[0][leg0].ParallelCopy(m_leg.mcor[0], 0, 0, 1); }
 }
 
 // The leg kernel leaves {return code, iterations} of each bottom solve in device memory; one read-back per solve and one

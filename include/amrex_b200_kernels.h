@@ -285,13 +285,15 @@ int b200mg_bottom_bicgstab(int abec, const b200mg_box* h_vbox,
                            double dxinv0, double dxinv1, double dxinv2, double eps_rel, double eps_abs, int maxiter,
                            double* d_out, cudaStream_t s);
 
-/* ---- the coarse leg of a V-cycle in ONE thread-block-cluster kernel (MLMGT::mgVcycle AMReX_MLMG.H:1308-1415 from the
- *      first MG level that is a single box covering the domain down to the bottom solve - MLMGT::bottomSolve :1460-1576,
- *      BiCGStab as b200mg_bottom_bicgstab or nuf smooths - and back up).  lev[0] is the top level of the leg, lev[nlev-1]
- *      the bottom; every level is ONE box of <= 32^3 cells, coarsened by 2 from the level above, whose faces are physical
- *      Dirichlet / Neumann / reflect-odd boundaries or wrap onto the box itself (periodic).  res[0] holds the right-hand
- *      side on entry, cor[0] the correction on exit; all other fields of the leg are scratch.  Same bits as the
- *      launch-per-operation schedule (shared per-cell code, same operation order). */
+/* ---- the coarse leg of a V-cycle in ONE cooperative kernel (MLMGT::mgVcycle AMReX_MLMG.H:1308-1415 from the first MG
+ *      level that is - or has been merged into - a single box covering the domain down to the bottom solve,
+ *      MLMGT::bottomSolve :1460-1576, BiCGStab as b200mg_bottom_bicgstab or nuf smooths, and back up).  lev[0] is the top
+ *      level of the leg, lev[nlev-1] the bottom (<= 32^3 cells when solved by BiCGStab); every level is ONE box, coarsened
+ *      by 2 from the level above, whose faces are physical Dirichlet / Neumann / reflect-odd boundaries or wrap onto the
+ *      box itself (periodic).  Levels of more than narrow_cells cells are worked on by the whole grid (grid barrier between
+ *      phases), smaller ones by CTA 0 alone (block barriers).  res[0] holds the right-hand side on entry, cor[0] the
+ *      correction on exit; all other fields of the leg are scratch.  Same bits as the launch-per-operation schedule
+ *      (shared per-cell code, same operation order). */
 #define B200MG_LEG_MAX_LEVELS 8
 typedef struct b200mg_leg_level {
     b200mg_box vb;                  /* the level's box == its domain */
@@ -310,14 +312,14 @@ typedef struct b200mg_leg_args {
     int nlev, maxorder, nu1, nu2, nuf, nub;
     int bottom_mode;                /* 0: BiCGStab, 1: smoother */
     int singular;                   /* bottom right-hand side is made solvable on the copy bb first */
-    int maxiter, pad;
+    int maxiter, narrow_cells;
     double alpha, volinv, eps_rel, eps_abs;
     b200mg_fab r, p, v, t, rh, bb;  /* bottom-level scratch: r, p with one ghost cell */
     b200mg_leg_level lev[B200MG_LEG_MAX_LEVELS];
 } b200mg_leg_args;
 /* d_args: the arguments in DEVICE memory; d_out (device, 2 doubles, may be NULL): return code and iteration count of the
- * BiCGStab bottom solve; cluster_ctas: CTAs of the one cluster that runs the leg (1..16, 512 threads each). */
-int b200mg_coarse_leg(int abec, const b200mg_leg_args* d_args, double* d_out, int cluster_ctas, cudaStream_t s);
+ * BiCGStab bottom solve; ctas: CTAs of the cooperative grid (512 threads each; clamped to one per SM). */
+int b200mg_coarse_leg(int abec, const b200mg_leg_args* d_args, double* d_out, int ctas, cudaStream_t s);
 
 /* ---- batched Krylov vector kernels (GMRES Gram-Schmidt: the dotProduct / increment loops of
  *      GMRES::gram_schmidt_orthogonalization, AMReX_GMRES.H:322-348).  v: HOST array of nv <= B200MG_KRYLOV_GROUP device

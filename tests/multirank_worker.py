@@ -1,0 +1,111 @@
+"""One rank of a multi-GPU parity run (launched by tests/test_multirank_gpu.py through torch.distributed.run, one process
+per GPU, NCCL).  Every rank runs the reference (oracle/_ref/ref_driver, CPU) on the case to get bit-identical inputs and the
+reference's answer, builds the distributed problem through the C ABI (boxes spread by the SFC DistributionMapping, remote
+halos over ncclSend/ncclRecv, agglomerated MG levels reached by ParallelCopy), solves, and compares ITS boxes of the
+solution with the reference's.  Rank 0 writes the verdict as one JSON line to argv[2].
+
+    python -m torch.distributed.run --nproc-per-node N tests/multirank_worker.py <case> <out.json>
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+CASES = {
+    # name: (prob_type, n_cell, max_grid_size, max_level, maxorder)
+    "abeclap128": (2, 128, 32, 0, 2),        # 64 boxes: agglomeration / consolidation across ranks
+    "abeclap128_g64": (2, 128, 64, 0, 3),    # 8 boxes of 64^3: fused smoother + remote halos
+    "poisson_periodic64": (5, 64, 16, 0, 2),
+    "poisson128": (1, 128, 64, 0, 2),
+    "amr64": (2, 64, 32, 1, 3),              # two-level composite solve
+    "amr128": (1, 128, 32, 1, 3),
+}
+
+
+def main():
+    case, out_path = sys.argv[1], sys.argv[2]
+    prob_type, n, mgs, max_level, maxorder = CASES[case]
+    import torch
+    import torch.distributed as dist
+    import amrex_b200 as ab
+    from common import build_problem, build_problem_amr, rel_maxdiff, run_ref
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    ab.init(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ab.comm_init_from_torch()
+    kw = dict(mode="solve", prob_type=prob_type, n_cell=n, max_grid_size=mgs, linop_maxorder=maxorder, agg_grid_size=32)
+    if max_level:
+        kw["max_level"] = max_level
+    ref, dump = run_ref(dump=True, threads=max(1, (os.cpu_count() or 2) // max(world, 1)), **kw)
+    if max_level:
+        P = build_problem_amr(ab, prob_type, n, mgs, dump, max_level=max_level, maxorder=maxorder)
+        sols, rhss = P["sol"], P["rhs"]
+        bas, dms = P["ba"], P["dm"]
+    else:
+        P = build_problem(ab, prob_type, n, mgs, dump, maxorder=maxorder)
+        sols, rhss = [P["sol"]], [P["rhs"]]
+        bas, dms = [P["ba"]], [P["dm"]]
+    mlmg = ab.MLMG(P["op"])
+    mlmg.setVerbose(0)
+    mlmg.setMaxIter(100)
+    ab.profile_enable(True)
+    mlmg.solve(sols, rhss, 1e-10, 0.0)
+    names = sorted(set(q[0] for q in ab.profile_report()))
+    ab.profile_enable(False)
+    me = ab.lib.amrex_b200_myproc()
+    diff, refmax, nlocal = 0.0, 0.0, 0
+    means = []
+    for lev in range(max_level + 1):
+        lo, refsol = dump[f"sol_lev{lev}"]
+        pmap = dms[lev].pmap(bas[lev].size())
+        for g, b in enumerate(bas[lev].boxes()):
+            sl = tuple(slice(b[d] - lo[d], b[d + 3] - lo[d] + 1) for d in range(3))
+            r = refsol[sl]
+            refmax = max(refmax, float(np.max(np.abs(r))))
+            if pmap[g] != me:
+                continue
+            nlocal += 1
+            mine = P["sol"][lev].download(b[:3], r.shape) if max_level else P["sol"].download(b[:3], r.shape)
+            if prob_type == 5:          # singular: compare up to the constant (means gathered below)
+                means.append((float(mine.sum()), float(r.sum()), mine, r))
+            else:
+                diff = max(diff, float(np.max(np.abs(mine - r))))
+    if prob_type == 5:
+        t = torch.tensor([sum(m[0] for m in means), sum(m[1] for m in means)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        shift = (t[0].item() - t[1].item()) / float(n ** 3)
+        for _, _, mine, r in means:
+            diff = max(diff, float(np.max(np.abs(mine - shift - r))))
+    t = torch.tensor([diff, float(nlocal)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    hist, rh = list(mlmg.residualHistory()), ref["history"]
+    floor = 1e-13 * max(ref["rhsnorm0"], ref["resnorm0"])
+    hist_rel = max((abs(a - b) / max(abs(b), floor) for a, b in zip(hist, rh)), default=0.0)
+    res = dict(case=case, world=world, iters=mlmg.numIters(), ref_iters=ref["iters"], sol_rel_maxdiff=t[0].item() / max(refmax, 1e-300),
+               history_max_rel_diff=hist_rel, history=hist, ref_history=rh, cg_iters=list(mlmg.cgIters()), ref_cg_iters=ref.get("cg_iters"),
+               init_resnorm=mlmg.initResidual(), ref_init_resnorm=ref["resnorm0"], max_local_boxes=int(t[1].item()),
+               kernels=names, comm_nranks=int(ab.lib.amrex_b200_nprocs()))
+    if rank == 0:
+        with open(out_path, "w") as fh:
+            fh.write(json.dumps(res) + "\n")
+    if world > 1:
+        dist.barrier()
+        ab.lib.amrex_b200_comm_finalize()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,7 @@ def test_b200_schedule_switches_are_bit_neutral(ab, kind, monkeypatch):
     from common import synth_abeclap, synth_poisson
     n, mgs = 128, 64
     out = {}
+    monkeypatch.setenv("B200MG_NO_MERGED_LEG", "1")       # keep the 128^3 / 64^3 levels on the launch-per-operation path under test
     for off in (True, False):
         for v in ("B200MG_NO_FUSED_RESNORM", "B200MG_NO_ZERO_INPUT", "B200MG_NO_BC_OVERLAP"):
             if off:
@@ -169,18 +170,22 @@ def test_b200_schedule_switches_are_bit_neutral(ab, kind, monkeypatch):
 
 
 @pytest.mark.parametrize("kind,n,mgs,bottom", [("abeclap", 128, 64, None), ("poisson", 128, 64, None), ("abeclap", 64, 32, None),
-                                               ("abeclap", 32, 32, None), ("poisson", 64, 32, "smoother")])
+                                               ("abeclap", 32, 32, None), ("poisson", 64, 32, "smoother"), ("abeclap", 96, 32, None)])
 def test_coarse_leg_kernel_is_bit_neutral(ab, kind, n, mgs, bottom, monkeypatch):
-    """kernels/coarse_leg.cu - every single-box MG level plus the bottom solve as ONE cluster kernel per V-cycle - against the
+    """kernels/coarse_leg.cu - the small MG levels plus the bottom solve as ONE cooperative kernel per V-cycle - against the
     launch-per-operation schedule (B200MG_NO_COARSE_LEG=1, which ends in the single-CTA bottom kernel): same V-cycle count,
-    bit-identical residual history, solution and BiCGStab iteration counts.  The 32^3 case is one box: the whole cycle is the leg."""
+    bit-identical residual history, solution and BiCGStab iteration counts.  Three schedules: "off", "direct" (only levels
+    that are one box in the hierarchy, B200MG_NO_MERGED_LEG=1) and "merged" (default: every level of <= 128^3 cells runs on a
+    one-box copy of the operator; here that is the whole cycle).  The 32^3 case is one box: direct == merged."""
     from common import synth_abeclap, synth_poisson
     out = {}
-    for off in (True, False):
-        if off:
+    for mode in ("off", "direct", "merged"):
+        monkeypatch.delenv("B200MG_NO_COARSE_LEG", raising=False)
+        monkeypatch.delenv("B200MG_NO_MERGED_LEG", raising=False)
+        if mode == "off":
             monkeypatch.setenv("B200MG_NO_COARSE_LEG", "1")
-        else:
-            monkeypatch.delenv("B200MG_NO_COARSE_LEG", raising=False)
+        elif mode == "direct":
+            monkeypatch.setenv("B200MG_NO_MERGED_LEG", "1")
         if kind == "abeclap":
             P = synth_abeclap(ab, n, mgs, fusion=1)
             sol, rhs = P["sol"], P["rhs"]
@@ -198,12 +203,17 @@ def test_coarse_leg_kernel_is_bit_neutral(ab, kind, n, mgs, bottom, monkeypatch)
         mlmg.solve([sol], [rhs], 1e-10, 0.0)
         names = set(q[0] for q in ab.profile_report())
         ab.profile_enable(False)
-        assert ("b200mg_coarse_leg" in names) == (not off), names
-        out[off] = (mlmg.numIters(), list(mlmg.residualHistory()), sol.download((0, 0, 0), (n, n, n)), list(mlmg.cgIters()))
-    assert out[True][0] == out[False][0]
-    assert out[True][1] == out[False][1]
-    assert np.array_equal(out[True][2], out[False][2])
-    assert out[True][3] == out[False][3] and (bottom or all(i >= 1 for i in out[False][3]))
+        assert ("b200mg_coarse_leg" in names) == (mode != "off"), names
+        if mode == "merged":       # the whole cycle is the leg: no smoother launch outside it
+            assert not any(k.startswith("b200mg_gsrb") for k in names), names
+        elif n > mgs:
+            assert any(k.startswith("b200mg_gsrb") for k in names), names
+        out[mode] = (mlmg.numIters(), list(mlmg.residualHistory()), sol.download((0, 0, 0), (n, n, n)), list(mlmg.cgIters()))
+    for mode in ("direct", "merged"):
+        assert out["off"][0] == out[mode][0]
+        assert out["off"][1] == out[mode][1]
+        assert np.array_equal(out["off"][2], out[mode][2])
+        assert out["off"][3] == out[mode][3] and (bottom or all(i >= 1 for i in out[mode][3]))
 
 
 def test_coarse_leg_kernel_periodic(ab, monkeypatch):
@@ -212,11 +222,13 @@ def test_coarse_leg_kernel_periodic(ab, monkeypatch):
     same V-cycle count, histories within 1e-6, solutions (mean removed) within 1e-10 - and both match the reference."""
     ref, dump = run_ref(dump=True, mode="solve", prob_type=5, n_cell=64, max_grid_size=32, linop_maxorder=2, agg_grid_size=32)
     out = {}
-    for off in (True, False):
-        if off:
+    for mode in ("off", "direct", "merged"):
+        monkeypatch.delenv("B200MG_NO_COARSE_LEG", raising=False)
+        monkeypatch.delenv("B200MG_NO_MERGED_LEG", raising=False)
+        if mode == "off":
             monkeypatch.setenv("B200MG_NO_COARSE_LEG", "1")
-        else:
-            monkeypatch.delenv("B200MG_NO_COARSE_LEG", raising=False)
+        elif mode == "direct":
+            monkeypatch.setenv("B200MG_NO_MERGED_LEG", "1")
         P = build_problem(ab, 5, 64, 32, dump)
         mlmg = ab.MLMG(P["op"])
         mlmg.setVerbose(0)
@@ -224,16 +236,18 @@ def test_coarse_leg_kernel_periodic(ab, monkeypatch):
         mlmg.solve([P["sol"]], [P["rhs"]], 1e-10, 0.0)
         names = set(q[0] for q in ab.profile_report())
         ab.profile_enable(False)
-        assert ("b200mg_coarse_leg" in names) == (not off), names
+        assert ("b200mg_coarse_leg" in names) == (mode != "off"), names
         mine = P["sol"].download((0, 0, 0), (64, 64, 64))
-        out[off] = (mlmg.numIters(), list(mlmg.residualHistory()), mine - mine.mean())
-    assert out[True][0] == out[False][0] and abs(out[False][0] - ref["iters"]) <= 1
-    for a, b in zip(out[True][1], out[False][1]):
-        assert a == pytest.approx(b, rel=1e-6)
+        out[mode] = (mlmg.numIters(), list(mlmg.residualHistory()), mine - mine.mean())
     refv = dump["sol_lev0"][1][1:-1, 1:-1, 1:-1]
     refv = refv - refv.mean()
-    assert rel_maxdiff(out[False][2], out[True][2]) <= SOL_TOL
-    assert rel_maxdiff(out[False][2], refv) <= SOL_TOL
+    for mode in ("direct", "merged"):
+        assert out["off"][0] == out[mode][0] and abs(out[mode][0] - ref["iters"]) <= 1
+        for a, b in zip(out["off"][1], out[mode][1]):
+            assert a == pytest.approx(b, rel=1e-6)
+        assert rel_maxdiff(out[mode][2], out["off"][2]) <= SOL_TOL
+        assert rel_maxdiff(out[mode][2], refv) <= SOL_TOL
+    assert out["direct"][1] == out["merged"][1] and np.array_equal(out["direct"][2], out["merged"][2])   # same kernel, same bits
 
 
 # ---- GMRES preconditioned by MLMG: Tests/LinearSolvers/ABecLaplacian_C inputs.gmres, MyTest.cpp:466-532
