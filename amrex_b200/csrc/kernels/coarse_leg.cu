@@ -24,6 +24,15 @@ constexpr int kLegThreads = kBottomThreads;     // CTA size (the bottom solve's 
 
 struct Team { int tid, nth; };
 
+// phase time stamps (tuning aid): thread 0 of CTA 0 appends (id << 48 | clock) after a phase's barrier
+struct Stamps {
+    unsigned long long* buf; int n;
+    __device__ __forceinline__ void mark (int id)
+    {
+        if (buf != nullptr && n < B200MG_LEG_MAX_STAMPS) { buf[n++] = ((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xffffffffffffull); buf[0] = (unsigned long long)n; }
+    }
+};
+
 // WIDE: the team is the whole grid, else the calling CTA
 template <bool WIDE> __device__ __forceinline__ void team_sync ()
 {
@@ -47,12 +56,77 @@ __device__ __forceinline__ void zero_field (const b200mg_leg_level& L, const Tea
     for_box(L.vb, 1, T, [&] (int i, int j, int k) { x(i, j, k) = 0.0; });
 }
 
+// Boundary conditions of a one-box level by face orientation.  The leg never stores ghost values: a cell on the box surface
+// computes the value the boundary fill (bc_fill = mllinop_apply_bc_*, or the periodic wrap) would have left in the ghost
+// cell beyond its face, from the same operands in the same order - the same bits, with half the barriers per smooth and no
+// O(n^2) phases.  (The ghost cells of cor therefore hold stale values after the leg; nothing reads them: prolongation and
+// the copy back to a chopped level take valid cells only.)
+struct FaceBC {
+    int type[6];                            // kBcDirichletB / kBcNeumannB / kBcReflectOddB, or kPeriodicFace
+    int nx[6];                              // Dirichlet: interpolation nodes (ghost-side node included)
+    double coef[6][4];
+    double w[6][3];                         // the same fill as ONE expression: ghost = 0 + x0*w0 + x1*w1 + x2*w2 over the first
+                                            // three cells inside the face (Neumann 1,0,0; reflect-odd -1,0,0; Dirichlet coef[1..3],
+                                            // zeros beyond the order: adding x*0 changes no bit of a finite sum)
+};
+constexpr int kPeriodicFace = 200;
+
+__device__ __forceinline__ void make_face_bc (FaceBC& F, const BoxBC& B)
+{
+    for (int o = 0; o < 6; ++o) { F.type[o] = B.periodic[o % 3] ? kPeriodicFace : kBcNeumannB; F.nx[o] = 0; for (int m = 0; m < 4; ++m) { F.coef[o][m] = 0.0; } }
+    for (int n = 0; n < B.nfaces; ++n) {
+        const int o = B.faces[n].face;
+        F.type[o] = B.faces[n].bctype; F.nx[o] = B.nxo[n];
+        for (int m = 0; m < 4; ++m) { F.coef[o][m] = B.coef[n][m]; }
+    }
+    for (int o = 0; o < 6; ++o) {
+        F.w[o][0] = F.w[o][1] = F.w[o][2] = 0.0;
+        if (F.type[o] == kBcNeumannB) { F.w[o][0] = 1.0; }
+        else if (F.type[o] == kBcReflectOddB) { F.w[o][0] = -1.0; }
+        else if (F.type[o] == kBcDirichletB) { for (int m = 1; m < F.nx[o] && m < 4; ++m) { F.w[o][m - 1] = F.coef[o][m]; } }
+    }
+}
+
+// ghost value beyond face o next to the inside cell *pc; sst: signed stride from the ghost cell towards the inside,
+// n: cells of the box along that direction
+__device__ __forceinline__ double ghost_value (const FaceBC& F, int o, const double* pc, long long sst, int n)
+{
+    const int t = F.type[o];
+    if (t == kPeriodicFace) { return pc[(long long)(n - 1) * sst]; }
+    if (t == kBcNeumannB) { return *pc; }
+    if (t == kBcReflectOddB) { return -*pc; }
+    double tmp = 0.0;
+    for (int m = 1; m < F.nx[o]; ++m) { tmp += pc[(long long)(m - 1) * sst] * F.coef[o][m]; }
+    return tmp;
+}
+
+struct Nbrs { double c, xm, xp, ym, yp, zm, zp; };
+
+__device__ __forceinline__ Nbrs load_nbrs (const double* pc, int i, int j, int k, const b200mg_box& vb, const FaceBC& F, long long js, long long ks)
+{
+    Nbrs q;
+    q.c = *pc;
+    q.xm = (i > vb.lo[0]) ? pc[-1] : ghost_value(F, 0, pc, 1, vb.hi[0] - vb.lo[0] + 1);
+    q.xp = (i < vb.hi[0]) ? pc[1] : ghost_value(F, 3, pc, -1, vb.hi[0] - vb.lo[0] + 1);
+    q.ym = (j > vb.lo[1]) ? pc[-js] : ghost_value(F, 1, pc, js, vb.hi[1] - vb.lo[1] + 1);
+    q.yp = (j < vb.hi[1]) ? pc[js] : ghost_value(F, 4, pc, -js, vb.hi[1] - vb.lo[1] + 1);
+    q.zm = (k > vb.lo[2]) ? pc[-ks] : ghost_value(F, 2, pc, ks, vb.hi[2] - vb.lo[2] + 1);
+    q.zp = (k < vb.hi[2]) ? pc[ks] : ghost_value(F, 5, pc, -ks, vb.hi[2] - vb.lo[2] + 1);
+    return q;
+}
+
+// operands of one cell update, gathered before any store so that the loads of a batch of cells overlap
+template <bool ABEC>
+struct CellIn {
+    double* pc; Nbrs q; double rhs, a, bxm, bxp, bym, byp, bzm, bzp; int i, j, k; bool on;
+};
+
 // one colour of MLCellLinOpT::smooth's Fsmooth (abec_gsrb / mlpoisson_gsrb), cells with (i+j+k+redblack) even
 template <bool ABEC>
-__device__ __forceinline__ void sweep (const b200mg_leg_level& L, double alpha, int redblack, const Team& T)
+__device__ __noinline__ void sweep (const b200mg_leg_level& L, const FaceBC& F, double alpha, int redblack, const Team& T)
 {
     const auto phi = view(L.cor); const auto rhs = view(L.res);
-    const int js = int(phi.js), ks = int(phi.ks);
+    const long long js = phi.js, ks = phi.ks;
     const b200mg_box vb = L.vb;
     View<double> a = phi, bx = phi, by = phi, bz = phi;
     if constexpr (ABEC) { a = view(L.a); bx = view(L.bx); by = view(L.by); bz = view(L.bz); }
@@ -60,64 +134,232 @@ __device__ __forceinline__ void sweep (const b200mg_leg_level& L, double alpha, 
     const int nx = vb.hi[0] - vb.lo[0] + 1, ny = vb.hi[1] - vb.lo[1] + 1, nz = vb.hi[2] - vb.lo[2] + 1;
     const int nxh = (nx + 1) >> 1;
     const int n = nxh * ny * nz;
-    for (int c = T.tid; c < n; c += T.nth) {
+    auto gather = [&] (int c) {
+        CellIn<ABEC> in;
+        in.on = false;
+        if (c >= n) { return in; }
         const int ii = c % nxh, jk = c / nxh;
         const int j = vb.lo[1] + jk % ny, k = vb.lo[2] + jk / ny;
         const int i = vb.lo[0] + ((vb.lo[0] + j + k + redblack) & 1) + 2 * ii;
-        if (i > vb.hi[0]) { continue; }
-        double* pc = phi.ptr(i, j, k);
+        if (i > vb.hi[0]) { return in; }
+        in.on = true;
+        in.pc = phi.ptr(i, j, k);
+        in.q = load_nbrs(in.pc, i, j, k, vb, F, js, ks);
+        in.rhs = rhs(i, j, k);
+        if constexpr (ABEC) {
+            in.a = a(i, j, k); in.bxm = bx(i, j, k); in.bxp = bx(i + 1, j, k); in.bym = by(i, j, k); in.byp = by(i, j + 1, k);
+            in.bzm = bz(i, j, k); in.bzp = bz(i, j, k + 1);
+        }
+        in.i = i; in.j = j; in.k = k;
+        return in;
+    };
+    auto update = [&] (const CellIn<ABEC>& in) {
+        if (!in.on) { return; }
+        // relaxation coefficients of the boundary faces: surface cells only (rare), fetched here to keep the batch in registers
         FaceCoefs cf;
-        if (on_surface(i, j, k, vb)) { cf = face_coefs(i, j, k, vb, L.f, L.m); }
+        if (on_surface(in.i, in.j, in.k, vb)) { cf = face_coefs(in.i, in.j, in.k, vb, L.f, L.m); }
         else {
 #pragma unroll
             for (int q = 0; q < 6; ++q) { cf.c[q] = 0.0; }
         }
         if constexpr (ABEC) {
-            *pc = gsrb_abec_cell(*pc, pc[-1], pc[1], pc[-js], pc[js], pc[-ks], pc[ks], rhs(i, j, k), a(i, j, k),
-                                 bx(i, j, k), bx(i + 1, j, k), by(i, j, k), by(i, j + 1, k), bz(i, j, k), bz(i, j, k + 1),
-                                 cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], alpha, L.dh[0], L.dh[1], L.dh[2]);
+            *in.pc = gsrb_abec_cell(in.q.c, in.q.xm, in.q.xp, in.q.ym, in.q.yp, in.q.zm, in.q.zp, in.rhs, in.a,
+                                    in.bxm, in.bxp, in.bym, in.byp, in.bzm, in.bzp,
+                                    cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], alpha, L.dh[0], L.dh[1], L.dh[2]);
         } else {
-            *pc = gsrb_poisson_cell(*pc, pc[-1], pc[1], pc[-js], pc[js], pc[-ks], pc[ks], rhs(i, j, k),
-                                    cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], L.dh[0], L.dh[1], L.dh[2]);
+            *in.pc = gsrb_poisson_cell(in.q.c, in.q.xm, in.q.xp, in.q.ym, in.q.yp, in.q.zm, in.q.zp, in.rhs,
+                                       cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], L.dh[0], L.dh[1], L.dh[2]);
         }
+    };
+    // cells of one colour do not read each other: two per iteration, all loads ahead of the stores
+    for (int c = T.tid; c < n; c += 2 * T.nth) {
+        const CellIn<ABEC> A = gather(c);
+        const CellIn<ABEC> B = gather(c + T.nth);
+        update(A); update(B);
     }
 }
 
-// MLCellLinOpT::smooth (AMReX_MLCellLinOp.H:1206-1217): boundary fill + sweep, per colour
-template <bool ABEC, bool WIDE>
-__device__ __forceinline__ void smooth (const b200mg_leg_level& L, const BoxBC& bc, double alpha, const Team& T)
+// ---- lean versions for levels with at least 4 cells per direction (everything above the last two or three levels): plain
+// int index arithmetic on register copies of the descriptors, boundary values through FaceBC::w, no mask look-ups (a one-box
+// level has no covered ghost cells except across periodic faces).  Same per-cell arithmetic, same bits.
+struct Arr { const double* p; int js, ks; };                // p: element (lo0, lo1, lo2) of the array
+
+__device__ __forceinline__ Arr arr_of (const b200mg_fab& f, const b200mg_box& vb)
 {
-    const auto phi = view(L.cor);
-    for (int redblack = 0; redblack < 2; ++redblack) {
-        bc_fill(L.vb, bc, phi, T.tid, T.nth);
-        team_sync<WIDE>();
-        sweep<ABEC>(L, alpha, redblack, T);
-        team_sync<WIDE>();
+    const auto v = view(f);
+    return Arr{v.ptr(vb.lo[0], vb.lo[1], vb.lo[2]), int(v.js), int(v.ks)};
+}
+
+// ghost value beyond face o for the inside cell *pc (sst: stride towards the inside, n: box cells along the direction)
+__device__ __forceinline__ double ghost_w (const FaceBC& F, int o, const double* pc, int sst, int n)
+{
+    if (F.type[o] == kPeriodicFace) { return pc[(n - 1) * sst]; }
+    double tmp = 0.0;
+    tmp += pc[0] * F.w[o][0]; tmp += pc[sst] * F.w[o][1]; tmp += pc[2 * sst] * F.w[o][2];
+    return tmp;
+}
+
+struct FastBox { int nx, ny, nz, par0; };                   // par0: parity of lo0 + lo1 + lo2
+
+template <bool ABEC>
+struct FastIn { double* pc; double c, xm, xp, ym, yp, zm, zp, rhs, a, bxm, bxp, bym, byp, bzm, bzp; int i, j, k; bool on; };
+
+template <bool ABEC>
+__device__ __forceinline__ FastIn<ABEC> fast_gather (int i, int j, int k, bool on, const FastBox& B, const FaceBC& F, const Arr& P, const Arr& R,
+                                                     const Arr& A, const Arr& BX, const Arr& BY, const Arr& BZ)
+{
+    FastIn<ABEC> in;
+    in.on = on; in.i = i; in.j = j; in.k = k;
+    if (!on) { return in; }
+    double* pc = const_cast<double*>(P.p) + i + j * P.js + k * P.ks;
+    in.pc = pc;
+    in.c = *pc;
+    in.xm = (i > 0) ? pc[-1] : ghost_w(F, 0, pc, 1, B.nx);
+    in.xp = (i < B.nx - 1) ? pc[1] : ghost_w(F, 3, pc, -1, B.nx);
+    in.ym = (j > 0) ? pc[-P.js] : ghost_w(F, 1, pc, P.js, B.ny);
+    in.yp = (j < B.ny - 1) ? pc[P.js] : ghost_w(F, 4, pc, -P.js, B.ny);
+    in.zm = (k > 0) ? pc[-P.ks] : ghost_w(F, 2, pc, P.ks, B.nz);
+    in.zp = (k < B.nz - 1) ? pc[P.ks] : ghost_w(F, 5, pc, -P.ks, B.nz);
+    in.rhs = R.p[i + j * R.js + k * R.ks];
+    if constexpr (ABEC) {
+        in.a = A.p[i + j * A.js + k * A.ks];
+        const double* q = BX.p + i + j * BX.js + k * BX.ks; in.bxm = q[0]; in.bxp = q[1];
+        q = BY.p + i + j * BY.js + k * BY.ks; in.bym = q[0]; in.byp = q[BY.js];
+        q = BZ.p + i + j * BZ.js + k * BZ.ks; in.bzm = q[0]; in.bzp = q[BZ.ks];
+    }
+    return in;
+}
+
+// relaxation coefficient of face o at a surface cell (absolute indices): the slab value where the ghost cell beyond is a
+// boundary cell, i.e. everywhere except across periodic faces
+__device__ __forceinline__ double face_cf (const b200mg_leg_level& L, const FaceBC& F, int o, int i, int j, int k)
+{
+    return (F.type[o] == kPeriodicFace) ? 0.0 : view(L.f[o])(i, j, k);
+}
+
+template <bool ABEC>
+__device__ __noinline__ void sweep_fast (const b200mg_leg_level& L, const FaceBC& F, double alpha, int redblack, const Team& T)
+{
+    const b200mg_box vb = L.vb;
+    const FastBox B{vb.hi[0] - vb.lo[0] + 1, vb.hi[1] - vb.lo[1] + 1, vb.hi[2] - vb.lo[2] + 1, (vb.lo[0] + vb.lo[1] + vb.lo[2]) & 1};
+    const Arr P = arr_of(L.cor, vb), R = arr_of(L.res, vb);
+    Arr A = P, BX = P, BY = P, BZ = P;
+    if constexpr (ABEC) { A = arr_of(L.a, vb); BX = arr_of(L.bx, vb); BY = arr_of(L.by, vb); BZ = arr_of(L.bz, vb); }
+    const double dhx = L.dh[0], dhy = L.dh[1], dhz = L.dh[2];
+    const unsigned nxh = unsigned(B.nx + 1) >> 1, uny = unsigned(B.ny);
+    const unsigned n = nxh * uny * unsigned(B.nz);
+    auto locate = [&] (unsigned c, int& i, int& j, int& k) -> bool {
+        if (c >= n) { i = j = k = 0; return false; }
+        const unsigned ii = c % nxh, jk = c / nxh;
+        j = int(jk % uny); k = int(jk / uny);
+        i = ((B.par0 + j + k + redblack) & 1) + 2 * int(ii);
+        return i < B.nx;
+    };
+    auto update = [&] (const FastIn<ABEC>& in) {
+        if (!in.on) { return; }
+        double cf0 = 0.0, cf1 = 0.0, cf2 = 0.0, cf3 = 0.0, cf4 = 0.0, cf5 = 0.0;
+        if (in.i == 0) { cf0 = face_cf(L, F, 0, vb.lo[0], vb.lo[1] + in.j, vb.lo[2] + in.k); }
+        if (in.j == 0) { cf1 = face_cf(L, F, 1, vb.lo[0] + in.i, vb.lo[1], vb.lo[2] + in.k); }
+        if (in.k == 0) { cf2 = face_cf(L, F, 2, vb.lo[0] + in.i, vb.lo[1] + in.j, vb.lo[2]); }
+        if (in.i == B.nx - 1) { cf3 = face_cf(L, F, 3, vb.hi[0], vb.lo[1] + in.j, vb.lo[2] + in.k); }
+        if (in.j == B.ny - 1) { cf4 = face_cf(L, F, 4, vb.lo[0] + in.i, vb.hi[1], vb.lo[2] + in.k); }
+        if (in.k == B.nz - 1) { cf5 = face_cf(L, F, 5, vb.lo[0] + in.i, vb.lo[1] + in.j, vb.hi[2]); }
+        if constexpr (ABEC) {
+            *in.pc = gsrb_abec_cell(in.c, in.xm, in.xp, in.ym, in.yp, in.zm, in.zp, in.rhs, in.a, in.bxm, in.bxp, in.bym, in.byp, in.bzm, in.bzp,
+                                    cf0, cf1, cf2, cf3, cf4, cf5, alpha, dhx, dhy, dhz);
+        } else {
+            *in.pc = gsrb_poisson_cell(in.c, in.xm, in.xp, in.ym, in.yp, in.zm, in.zp, in.rhs, cf0, cf1, cf2, cf3, cf4, cf5, dhx, dhy, dhz);
+        }
+    };
+    // cells of one colour do not read each other: two per iteration, all loads ahead of the stores
+    for (unsigned c = unsigned(T.tid); c < n; c += 2u * unsigned(T.nth)) {
+        int i0, j0, k0, i1, j1, k1;
+        const bool on0 = locate(c, i0, j0, k0), on1 = locate(c + unsigned(T.nth), i1, j1, k1);
+        const FastIn<ABEC> X = fast_gather<ABEC>(i0, j0, k0, on0, B, F, P, R, A, BX, BY, BZ);
+        const FastIn<ABEC> Y = fast_gather<ABEC>(i1, j1, k1, on1, B, F, P, R, A, BX, BY, BZ);
+        update(X); update(Y);
     }
 }
 
-// rescor = res - L(cor) with homogeneous BCs (MLCellLinOpT::correctionResidual, AMReX_MLCellLinOp.H:1248-1270)
-template <bool ABEC, bool WIDE>
-__device__ __forceinline__ void residual (const b200mg_leg_level& L, const BoxBC& bc, double alpha, const Team& T)
+template <bool ABEC>
+__device__ __noinline__ void residual_fast (const b200mg_leg_level& L, const FaceBC& F, double alpha, const Team& T)
 {
-    const auto x = view(L.cor); const auto b = view(L.res); const auto y = view(L.rescor);
-    bc_fill(L.vb, bc, x, T.tid, T.nth);
-    team_sync<WIDE>();
-    const int js = int(x.js), ks = int(x.ks);
-    View<double> a = x, bx = x, by = x, bz = x;
-    if constexpr (ABEC) { a = view(L.a); bx = view(L.bx); by = view(L.by); bz = view(L.bz); }
-    for_box(L.vb, 0, T, [&] (int i, int j, int k) {
-        const double* xc = x.ptr(i, j, k);
+    const b200mg_box vb = L.vb;
+    const FastBox B{vb.hi[0] - vb.lo[0] + 1, vb.hi[1] - vb.lo[1] + 1, vb.hi[2] - vb.lo[2] + 1, 0};
+    const Arr P = arr_of(L.cor, vb), R = arr_of(L.res, vb), Y = arr_of(L.rescor, vb);
+    Arr A = P, BX = P, BY = P, BZ = P;
+    if constexpr (ABEC) { A = arr_of(L.a, vb); BX = arr_of(L.bx, vb); BY = arr_of(L.by, vb); BZ = arr_of(L.bz, vb); }
+    const double dhx = L.adh[0], dhy = L.adh[1], dhz = L.adh[2];
+    const unsigned unx = unsigned(B.nx), uny = unsigned(B.ny);
+    const unsigned n = unx * uny * unsigned(B.nz);
+    auto locate = [&] (unsigned c, int& i, int& j, int& k) -> bool {
+        if (c >= n) { i = j = k = 0; return false; }
+        const unsigned jk = c / unx;
+        i = int(c % unx); j = int(jk % uny); k = int(jk / uny);
+        return true;
+    };
+    auto finish = [&] (const FastIn<ABEC>& in) {
+        if (!in.on) { return; }
         double v;
         if constexpr (ABEC) {
-            v = adotx_abec_cell(*xc, xc[-1], xc[1], xc[-js], xc[js], xc[-ks], xc[ks], a(i, j, k), bx(i, j, k), bx(i + 1, j, k),
+            v = adotx_abec_cell(in.c, in.xm, in.xp, in.ym, in.yp, in.zm, in.zp, in.a, in.bxm, in.bxp, in.bym, in.byp, in.bzm, in.bzp, alpha, dhx, dhy, dhz);
+        } else {
+            v = adotx_poisson_cell(in.c, in.xm, in.xp, in.ym, in.yp, in.zm, in.zp, dhx, dhy, dhz);
+        }
+        const_cast<double*>(Y.p)[in.i + in.j * Y.js + in.k * Y.ks] = in.rhs + (-1.0) * v;      // Xpay(y,-1,b)
+    };
+    for (unsigned c = unsigned(T.tid); c < n; c += 2u * unsigned(T.nth)) {
+        int i0, j0, k0, i1, j1, k1;
+        const bool on0 = locate(c, i0, j0, k0), on1 = locate(c + unsigned(T.nth), i1, j1, k1);
+        const FastIn<ABEC> X = fast_gather<ABEC>(i0, j0, k0, on0, B, F, P, R, A, BX, BY, BZ);
+        const FastIn<ABEC> Z = fast_gather<ABEC>(i1, j1, k1, on1, B, F, P, R, A, BX, BY, BZ);
+        finish(X); finish(Z);
+    }
+}
+
+__device__ __forceinline__ bool fast_level (const b200mg_leg_level& L)
+{
+    return (L.vb.hi[0] - L.vb.lo[0] >= 3) && (L.vb.hi[1] - L.vb.lo[1] >= 3) && (L.vb.hi[2] - L.vb.lo[2] >= 3);
+}
+
+// MLCellLinOpT::smooth (AMReX_MLCellLinOp.H:1206-1217): per colour, boundary values (inline) + sweep
+template <bool ABEC, bool WIDE>
+__device__ __forceinline__ void smooth (const b200mg_leg_level& L, const FaceBC& F, double alpha, const Team& T, Stamps& st, int id)
+{
+    const bool fast = fast_level(L);
+    for (int redblack = 0; redblack < 2; ++redblack) {
+        if (fast) { sweep_fast<ABEC>(L, F, alpha, redblack, T); } else { sweep<ABEC>(L, F, alpha, redblack, T); }
+        team_sync<WIDE>();
+        st.mark(id + redblack);
+    }
+}
+
+// rescor = res - L(cor) with homogeneous BCs (MLCellLinOpT::correctionResidual, AMReX_MLCellLinOp.H:1248-1270); no barrier inside
+template <bool ABEC>
+__device__ __noinline__ void residual_generic (const b200mg_leg_level& L, const FaceBC& F, double alpha, const Team& T)
+{
+    const auto x = view(L.cor); const auto b = view(L.res); const auto y = view(L.rescor);
+    const long long js = x.js, ks = x.ks;
+    const b200mg_box vb = L.vb;
+    View<double> a = x, bx = x, by = x, bz = x;
+    if constexpr (ABEC) { a = view(L.a); bx = view(L.bx); by = view(L.by); bz = view(L.bz); }
+    for_box(vb, 0, T, [&] (int i, int j, int k) {
+        const Nbrs q = load_nbrs(x.ptr(i, j, k), i, j, k, vb, F, js, ks);
+        double v;
+        if constexpr (ABEC) {
+            v = adotx_abec_cell(q.c, q.xm, q.xp, q.ym, q.yp, q.zm, q.zp, a(i, j, k), bx(i, j, k), bx(i + 1, j, k),
                                 by(i, j, k), by(i, j + 1, k), bz(i, j, k), bz(i, j, k + 1), alpha, L.adh[0], L.adh[1], L.adh[2]);
         } else {
-            v = adotx_poisson_cell(*xc, xc[-1], xc[1], xc[-js], xc[js], xc[-ks], xc[ks], L.adh[0], L.adh[1], L.adh[2]);
+            v = adotx_poisson_cell(q.c, q.xm, q.xp, q.ym, q.yp, q.zm, q.zp, L.adh[0], L.adh[1], L.adh[2]);
         }
         y(i, j, k) = b(i, j, k) + (-1.0) * v;      // Xpay(y,-1,b)
     });
-    team_sync<WIDE>();
+}
+
+template <bool ABEC>
+__device__ __forceinline__ void residual (const b200mg_leg_level& L, const FaceBC& F, double alpha, const Team& T)
+{
+    if (fast_level(L)) { residual_fast<ABEC>(L, F, alpha, T); } else { residual_generic<ABEC>(L, F, alpha, T); }
 }
 
 // res(coarse) = average of rescor(fine) (amrex_avgdown, AMReX_MultiFabUtil_3D_C.H:381-394); also cor(coarse) = 0
@@ -169,6 +411,8 @@ k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out)
     __syncthreads();
     for (int l = 0; l < nl; ++l) { bc_prepare(sbc[l], S.maxorder, S.lev[l].dxi, tid); }
     __syncthreads();
+    __shared__ FaceBC fbc[B200MG_LEG_MAX_LEVELS];
+    if (tid < nl) { make_face_bc(fbc[tid], sbc[tid]); }
 
     __shared__ int wide[B200MG_LEG_MAX_LEVELS];
     if (tid < nl) {
@@ -181,6 +425,8 @@ k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out)
     const Team TW{cta * kLegThreads + tid, int(gridDim.x) * kLegThreads};
     const Team T0{tid, kLegThreads};
     const double alpha = S.alpha;
+    Stamps st{(cta == 0 && tid == 0) ? S.stamps : nullptr, 1};
+    st.mark(0);
 
     // ---- down: cor = 0, nu1 smooths, residual, restriction (mgVcycle, AMReX_MLMG.H:1318-1345)
     if (wide[0]) { zero_field(S.lev[0], TW); cg::this_grid().sync(); }
@@ -188,26 +434,32 @@ k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out)
     for (int l = 0; l < nl - 1; ++l) {
         const b200mg_leg_level& L = S.lev[l];
         if (wide[l]) {
-            for (int i = 0; i < S.nu1; ++i) { smooth<ABEC, true>(L, sbc[l], alpha, TW); }
-            residual<ABEC, true>(L, sbc[l], alpha, TW);
+            for (int i = 0; i < S.nu1; ++i) { smooth<ABEC, true>(L, fbc[l], alpha, TW, st, l * 16); }
+            residual<ABEC>(L, fbc[l], alpha, TW);
+            cg::this_grid().sync();
+            st.mark(l * 16 + 2);
             restrict_and_zero(L, S.lev[l + 1], TW);
             cg::this_grid().sync();
+            st.mark(l * 16 + 3);
         } else if (cta == 0) {
-            for (int i = 0; i < S.nu1; ++i) { smooth<ABEC, false>(L, sbc[l], alpha, T0); }
-            residual<ABEC, false>(L, sbc[l], alpha, T0);
+            for (int i = 0; i < S.nu1; ++i) { smooth<ABEC, false>(L, fbc[l], alpha, T0, st, l * 16); }
+            residual<ABEC>(L, fbc[l], alpha, T0);
+            __syncthreads();
+            st.mark(l * 16 + 2);
             restrict_and_zero(L, S.lev[l + 1], T0);
             __syncthreads();
+            st.mark(l * 16 + 3);
         }
     }
 
     // ---- bottom (bottomSolve, AMReX_MLMG.H:1460-1576): BiCGStab by CTA 0 alone, block barriers only
     const b200mg_leg_level& LB = S.lev[nl - 1];
     if (S.bottom_mode == 1 && wide[nl - 1]) {                       // BottomSolver::smoother on a big bottom level
-        for (int i = 0; i < S.nuf; ++i) { smooth<ABEC, true>(LB, sbc[nl - 1], alpha, TW); }
+        for (int i = 0; i < S.nuf; ++i) { smooth<ABEC, true>(LB, fbc[nl - 1], alpha, TW, st, (nl - 1) * 16 + 8); }
     } else if (cta == 0) {
         int ret = 0, iter = 0;
         if (S.bottom_mode == 1) {
-            for (int i = 0; i < S.nuf; ++i) { smooth<ABEC, false>(LB, sbc[nl - 1], alpha, T0); }
+            for (int i = 0; i < S.nuf; ++i) { smooth<ABEC, false>(LB, fbc[nl - 1], alpha, T0, st, (nl - 1) * 16 + 8); }
         } else {
             if (tid == 0) {
                 B.vb = LB.vb;
@@ -233,12 +485,13 @@ k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out)
                 __syncthreads();
             }
             bottom_bicgstab(B, sbc[nl - 1], C, ret, iter);
+            st.mark((nl - 1) * 16 + 7);
             if (ret != 0 && ret != 9) {                             // the solve failed: start the smooths from zero
                 zero_field(LB, T0);
                 __syncthreads();
             }
             const int n = (ret == 0) ? S.nub : S.nuf;
-            for (int i = 0; i < n; ++i) { smooth<ABEC, false>(LB, sbc[nl - 1], alpha, T0); }
+            for (int i = 0; i < n; ++i) { smooth<ABEC, false>(LB, fbc[nl - 1], alpha, T0, st, (nl - 1) * 16 + 8); }
         }
         if (tid == 0 && out != nullptr) { out[0] = double(ret); out[1] = double(iter); }
     }
@@ -251,11 +504,13 @@ k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out)
             if (!joined) { __threadfence(); cg::this_grid().sync(); joined = true; }
             prolong_add(L, S.lev[l + 1], TW);
             cg::this_grid().sync();
-            for (int i = 0; i < S.nu2; ++i) { smooth<ABEC, true>(L, sbc[l], alpha, TW); }
+            st.mark(l * 16 + 4);
+            for (int i = 0; i < S.nu2; ++i) { smooth<ABEC, true>(L, fbc[l], alpha, TW, st, l * 16 + 5); }
         } else if (cta == 0) {
             prolong_add(L, S.lev[l + 1], T0);
             __syncthreads();
-            for (int i = 0; i < S.nu2; ++i) { smooth<ABEC, false>(L, sbc[l], alpha, T0); }
+            st.mark(l * 16 + 4);
+            for (int i = 0; i < S.nu2; ++i) { smooth<ABEC, false>(L, fbc[l], alpha, T0, st, l * 16 + 5); }
         }
     }
 }

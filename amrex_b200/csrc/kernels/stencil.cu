@@ -336,6 +336,89 @@ k_adotx_pair (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restric
     }
 }
 
+// Residual fused with its restriction (MLMGT::mgVcycle, AMReX_MLMG.H:1332-1345: computeResOfCorrection followed by
+// restriction of rescor; kernels mlabeclap_adotx + Xpay + amrex_avgdown, AMReX_MultiFabUtil_3D_C.H:381-394): the fine residual
+// r - L(x) is never stored - the cycle does not read it again - only its 2x2x2 averages, so the pass moves 49 B/cell
+// instead of 56 + 9.  Thread map of k_adotx_pair; the thread of an even row collects the pair of the odd row above it
+// through shared memory (two plane buffers, one barrier per plane pair) and adds the eight values in amrex_avgdown's order
+// (x fastest, then y, then z), so the coarse field has the bits of the two-kernel sequence.  Requires even box corners and
+// extents (the boxes of a level that coarsens by 2) and an even tile depth.
+template <bool ABEC>
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y, 4)
+k_adotx_pair_restrict (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox,
+                       const b200mg_fab* cf, const b200mg_fab* xf, const b200mg_fab* rf, const b200mg_fab* af,
+                       const b200mg_fab* bxf, const b200mg_fab* byf, const b200mg_fab* bzf,
+                       double alpha, double dhx, double dhy, double dhz)
+{
+    __shared__ double2 sh[2][2][B200MG_TILE_Y / 2][kTileTX];      // [pair parity][plane of the pair][odd row][x pair]
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const int tx = int(threadIdx.x), ty = int(threadIdx.y);
+    const int i0 = vb.lo[0] + 2 * tx;
+    const int j = t.j0 + ty;
+    const bool idle = (i0 >= vb.hi[0] || j > vb.hi[1]);
+    const int k0 = t.k0, k1 = min(t.k0 + tile_nk(t) - 1, vb.hi[2]);
+    const auto x = view(xf[t.box]); const auto crse = view(cf[t.box]);
+    const int x_js = int(x.js), x_ks = int(x.ks);
+    const double* px = idle ? nullptr : x.ptr(i0, j, k0);
+    const double* pr = nullptr; int r_ks = 0;
+    { const auto r = view(rf[t.box]); if (!idle) { pr = r.ptr(i0, j, k0); } r_ks = int(r.ks); }
+    const double *pa = nullptr, *pbx = nullptr, *pby = nullptr, *pbz = nullptr;
+    int a_ks = 0, bx_ks = 0, by_ks = 0, by_js = 0, bz_ks = 0;
+    double2 bzlo = make_double2(0.0, 0.0);
+    if constexpr (ABEC) {
+        const auto a = view(af[t.box]); const auto bx = view(bxf[t.box]); const auto by = view(byf[t.box]); const auto bz = view(bzf[t.box]);
+        a_ks = int(a.ks); bx_ks = int(bx.ks); by_ks = int(by.ks); by_js = int(by.js); bz_ks = int(bz.ks);
+        if (!idle) {
+            pa = a.ptr(i0, j, k0); pbx = bx.ptr(i0, j, k0); pby = by.ptr(i0, j, k0); pbz = bz.ptr(i0, j, k0);
+            bzlo = __ldg(reinterpret_cast<const double2*>(pbz));
+        }
+    }
+    double2 xm = make_double2(0.0, 0.0), xc = xm;
+    if (!idle) { xm = *reinterpret_cast<const double2*>(px - x_ks); xc = *reinterpret_cast<const double2*>(px); }
+    double2 v0 = make_double2(0.0, 0.0);                          // this thread's residual pair of the first plane of the pair
+    for (int k = k0; k <= k1; ++k) {
+        double2 v = make_double2(0.0, 0.0);
+        if (!idle) {
+            const double2 xp = *reinterpret_cast<const double2*>(px + x_ks);
+            const double xl = px[-1], xr = px[2];
+            const double2 ylo = *reinterpret_cast<const double2*>(px - x_js);
+            const double2 yhi = *reinterpret_cast<const double2*>(px + x_js);
+            if constexpr (ABEC) {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(pa));
+                const double2 bx = __ldg(reinterpret_cast<const double2*>(pbx));
+                const double bx2 = __ldg(pbx + 2);
+                const double2 bylo = __ldg(reinterpret_cast<const double2*>(pby));
+                const double2 byhi = __ldg(reinterpret_cast<const double2*>(pby + by_js));
+                const double2 bzhi = __ldg(reinterpret_cast<const double2*>(pbz + bz_ks));
+                v.x = adotx_abec_cell(xc.x, xl, xc.y, ylo.x, yhi.x, xm.x, xp.x, a.x, bx.x, bx.y, bylo.x, byhi.x, bzlo.x, bzhi.x, alpha, dhx, dhy, dhz);
+                v.y = adotx_abec_cell(xc.y, xc.x, xr, ylo.y, yhi.y, xm.y, xp.y, a.y, bx.y, bx2, bylo.y, byhi.y, bzlo.y, bzhi.y, alpha, dhx, dhy, dhz);
+                bzlo = bzhi;
+                pa += a_ks; pbx += bx_ks; pby += by_ks; pbz += bz_ks;
+            } else {
+                v.x = adotx_poisson_cell(xc.x, xl, xc.y, ylo.x, yhi.x, xm.x, xp.x, dhx, dhy, dhz);
+                v.y = adotx_poisson_cell(xc.y, xc.x, xr, ylo.y, yhi.y, xm.y, xp.y, dhx, dhy, dhz);
+            }
+            const double2 r = __ldg(reinterpret_cast<const double2*>(pr));
+            v.x = r.x + (-1.0) * v.x; v.y = r.y + (-1.0) * v.y;       // Xpay(y,-1,b)
+            pr += r_ks;
+            xm = xc; xc = xp;
+            px += x_ks;
+        }
+        const int kk = k - k0;                                     // even: first plane of a pair
+        const int par = (kk >> 1) & 1;
+        if (ty & 1) { sh[par][kk & 1][ty >> 1][tx] = v; }
+        if ((kk & 1) == 0) { v0 = v; continue; }
+        __syncthreads();
+        if (!(ty & 1) && !idle) {
+            const double2 b0 = sh[par][0][ty >> 1][tx], b1 = sh[par][1][ty >> 1][tx];
+            double c = 0.0;
+            c += v0.x; c += v0.y; c += b0.x; c += b0.y; c += v.x; c += v.y; c += b1.x; c += b1.y;
+            crse(i0 >> 1, j >> 1, (k - 1) >> 1) = 0.125 * c;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
 k_normalize_abec (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox,
                   const b200mg_fab* xf, const b200mg_fab* af,
@@ -606,6 +689,25 @@ int b200mg_adotx_poisson_pairs (int ntiles, const b200mg_tile* tiles, const b200
     if (ntiles <= 0) { return 0; }
     if (norminf) { k_adotx_pair<false, true><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, nullptr, nullptr, nullptr, nullptr, 0.0, dhx, dhy, dhz, norminf); }
     else { k_adotx_pair<false, false><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, rhs, nullptr, nullptr, nullptr, nullptr, 0.0, dhx, dhy, dhz, nullptr); }
+    return last_error();
+}
+
+int b200mg_residual_restrict_abec (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                                   const b200mg_fab* crse, const b200mg_fab* x, const b200mg_fab* rhs, const b200mg_fab* a,
+                                   const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                                   double alpha, double dhx, double dhy, double dhz, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_adotx_pair_restrict<true><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, crse, x, rhs, a, bx, by, bz, alpha, dhx, dhy, dhz);
+    return last_error();
+}
+
+int b200mg_residual_restrict_poisson (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                                      const b200mg_fab* crse, const b200mg_fab* x, const b200mg_fab* rhs,
+                                      double dhx, double dhy, double dhz, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_adotx_pair_restrict<false><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, crse, x, rhs, nullptr, nullptr, nullptr, nullptr, 0.0, dhx, dhy, dhz);
     return last_error();
 }
 

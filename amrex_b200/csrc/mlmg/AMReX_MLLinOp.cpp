@@ -913,6 +913,35 @@ void MLLinOp::correctionResidual (int amrlev, int mglev, MultiFab& resid, MultiF
     Fapply(amrlev, mglev, resid, x, &b);
 }
 
+bool MLLinOp::correctionResidualRestrict (int amrlev, int mglev, MultiFab& crse, MultiFab& x, MultiFab const& b)
+{
+    if (!m_fuse_restrict || mglev + 1 >= H.num_mg_levels[amrlev] || Gpu::debugSync()) { return false; }
+    const int ratio = (amrlev > 0) ? 2 : H.mg_coarsen_ratio_vec[mglev][0];
+    if (ratio != 2 || (amrlev == 0 && H.mg_coarsen_ratio_vec[mglev] != IntVect(2))) { return false; }
+    LevelLayout const& FL = x.layout();               // (its tiles are 4, 8 or 16 planes deep: always whole plane pairs)
+    if (!FL.pairable()) { return false; }
+    LevelData const& LD = lev(amrlev, mglev);
+    if (LD.even_boxes < 0) {                          // every box of the level (all ranks decide alike)
+        LD.even_boxes = 1;
+        BoxArray const& ba = x.boxArray();
+        for (int i = 0, N = int(ba.size()); i < N && LD.even_boxes; ++i) {
+            for (int d = 0; d < 3; ++d) { if (ba[i].smallEnd(d) % 2 != 0 || ba[i].length(d) % 2 != 0) { LD.even_boxes = 0; } }
+        }
+    }
+    if (!LD.even_boxes) { return false; }
+    Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
+    applyBC(amrlev, mglev, x, BCMode::Homogeneous, StateMode::Correction, nullptr);
+    if (isMFIterSafe(amrlev, mglev, mglev + 1)) {
+        FresidualRestrict(amrlev, mglev, crse, x, b);
+    } else {   // the coarse level is re-gridded: through the coarsened-fine temporary + ParallelCopy, as restriction() does
+        LevelData const& L = lev(amrlev, mglev);
+        if (!L.restrict_tmp) { L.restrict_tmp = std::make_unique<MultiFab>(amrex::coarsen(x.boxArray(), ratio), x.DistributionMap(), 1, 0); }
+        FresidualRestrict(amrlev, mglev, *L.restrict_tmp, x, b);
+        crse.ParallelCopy(*L.restrict_tmp, 0, 0, 1);
+    }
+    return true;
+}
+
 // ---- post-solve API: face-centred gradient and flux of the solution
 void MLLinOp::compGrad (int amrlev, Array<MultiFab*, 3> const& grad, MultiFab& sol)
 {
@@ -1436,6 +1465,16 @@ bool MLABecLaplacian::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab con
 
 namespace { inline void gsrb_dh (Geometry const& g, Real b, Real dh[3]) { const Real* h = g.CellSize(); for (int d = 0; d < 3; ++d) { dh[d] = b / (h[d] * h[d]); } } }
 
+void MLABecLaplacian::FresidualRestrict (int amrlev, int mglev, MultiFab& crse, MultiFab const& x, MultiFab const& b) const
+{
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    auto const& T = x.layout().tiles(0);
+    B200_KCALL(b200mg_residual_restrict_abec(T.n, T.d.data(), x.layout().d_vbox(), crse.d_fabs(), x.d_fabs(), b.d_fabs(),
+                                             m_a_coeffs[amrlev][mglev].d_fabs(), m_b_coeffs[amrlev][mglev][0].d_fabs(),
+                                             m_b_coeffs[amrlev][mglev][1].d_fabs(), m_b_coeffs[amrlev][mglev][2].d_fabs(), m_a_scalar,
+                                             m_b_scalar * dxi[0] * dxi[0], m_b_scalar * dxi[1] * dxi[1], m_b_scalar * dxi[2] * dxi[2], Gpu::gpuStream()));
+}
+
 void MLABecLaplacian::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
 {
     LevelData const& L = lev(amrlev, mglev);
@@ -1531,6 +1570,14 @@ bool MLPoisson::Fapply (int amrlev, int mglev, MultiFab& out, MultiFab const& in
     B200_KCALL(b200mg_adotx_poisson(T.n, T.d.data(), out.layout().d_vbox(), out.d_fabs(), in.d_fabs(), rhs ? rhs->d_fabs() : nullptr,
                                     dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream()));
     return false;
+}
+
+void MLPoisson::FresidualRestrict (int amrlev, int mglev, MultiFab& crse, MultiFab const& x, MultiFab const& b) const
+{
+    const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
+    auto const& T = x.layout().tiles(0);
+    B200_KCALL(b200mg_residual_restrict_poisson(T.n, T.d.data(), x.layout().d_vbox(), crse.d_fabs(), x.d_fabs(), b.d_fabs(),
+                                                dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream()));
 }
 
 void MLPoisson::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const

@@ -159,6 +159,7 @@ MLMG::LegPlan::~LegPlan ()
 {
     for (auto& kv : args) { if (kv.second.first) { The_Arena()->free(kv.second.first); } }
     if (d_log) { The_Arena()->free(d_log); }
+    if (d_stamps) { The_Arena()->free(d_stamps); }
     if (h_log) { pinned_free(h_log); }
 }
 
@@ -425,8 +426,11 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
                 linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev], skip_fillboundary, i == 0);
                 skip_fillboundary = false;
             }
-            computeResOfCorrection(amrlev, mglev);
-            linop.restriction(amrlev, mglev + 1, res[amrlev][mglev + 1], rescor[amrlev][mglev]);
+            // residual + restriction in one pass when the level allows it (rescor of this level is then not formed)
+            if (!linop.correctionResidualRestrict(amrlev, mglev, res[amrlev][mglev + 1], cor[amrlev][mglev], res[amrlev][mglev])) {
+                computeResOfCorrection(amrlev, mglev);
+                linop.restriction(amrlev, mglev + 1, res[amrlev][mglev + 1], rescor[amrlev][mglev]);
+            }
         }
     };
     auto up = [&] (int m1, int m0) {                     // levels m1 down to m0: prolongation-add, post-smooth
@@ -572,6 +576,10 @@ void MLMG::runCoarseLeg (int leg0, int mglev_bottom, bool merged)
                 op.fillLegLevel(m - off, A.lev[l]);
                 A.lev[l].cor = Cor(m).desc(0); A.lev[l].res = Res(m).desc(0); A.lev[l].rescor = Rescor(m).desc(0);
             }
+            if (std::getenv("B200MG_LEG_STAMPS")) {               // tuning aid: per-phase SM clock stamps of the last launch
+                if (!m_leg.d_stamps) { m_leg.d_stamps = static_cast<unsigned long long*>(The_Arena()->alloc(B200MG_LEG_MAX_STAMPS * sizeof(unsigned long long))); }
+                A.stamps = m_leg.d_stamps;
+            }
             if (!plan.first) { plan.first = static_cast<b200mg_leg_args*>(The_Arena()->alloc(sizeof(b200mg_leg_args))); }
             Gpu::htod_memcpy_async(plan.first, &A, sizeof(A));
             Gpu::streamSynchronize();                          // A is reused by the next plan
@@ -599,6 +607,16 @@ void MLMG::runCoarseLeg (int leg0, int mglev_bottom, bool merged)
 // small all-reduce (only the rank that owns the coarse box knows the numbers) instead of a host round trip per V-cycle.
 void MLMG::collectLegLog ()
 {
+    if (m_leg.d_stamps && m_leg.launches > 0) {
+        std::vector<unsigned long long> h(B200MG_LEG_MAX_STAMPS);
+        Gpu::dtoh_memcpy_async(h.data(), m_leg.d_stamps, h.size() * sizeof(unsigned long long)); Gpu::streamSynchronize();
+        const int ns = int(std::min<unsigned long long>(h[0], B200MG_LEG_MAX_STAMPS));
+        std::fprintf(stderr, "[leg stamps] %d records (level*16+phase: cycles since the previous record)\n", ns - 1);
+        for (int i = 2; i < ns; ++i) {
+            std::fprintf(stderr, " %d:%lld", int(h[i] >> 48), (long long)((h[i] & 0xffffffffffffull) - (h[i - 1] & 0xffffffffffffull)));
+        }
+        std::fprintf(stderr, "\n");
+    }
     const int n = int(m_leg.slots.size());
     if (n == 0) { return; }
     std::vector<double> its(n, 0.0);

@@ -169,6 +169,17 @@ int b200mg_adotx_abec_pairs(int ntiles, const b200mg_tile* tiles, const b200mg_b
 int b200mg_adotx_poisson_pairs(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
                                const b200mg_fab* y, const b200mg_fab* x, const b200mg_fab* rhs,
                                double dhx, double dhy, double dhz, double* norminf, cudaStream_t s);
+/* residual fused with its restriction: crse = average_down(rhs - L(x)), the fine residual is not stored (MLMGT::mgVcycle
+ * AMReX_MLMG.H:1332-1345: computeResOfCorrection + restriction; amrex_avgdown AMReX_MultiFabUtil_3D_C.H:381-394).
+ * tiles / vbox: the FINE level's (ng = 0); crse: fab table on the coarsened fine layout (same local box order).  Requires
+ * the pair layout of b200mg_adotx_*_pairs, even box corners / extents and an even tile depth. */
+int b200mg_residual_restrict_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                                  const b200mg_fab* crse, const b200mg_fab* x, const b200mg_fab* rhs, const b200mg_fab* a,
+                                  const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                                  double alpha, double dhx, double dhy, double dhz, cudaStream_t s);
+int b200mg_residual_restrict_poisson(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
+                                     const b200mg_fab* crse, const b200mg_fab* x, const b200mg_fab* rhs,
+                                     double dhx, double dhy, double dhz, cudaStream_t s);
 /* K13 mlabeclap_normalize AMReX_MLABecLap_3D_K.H:60-75 */
 int b200mg_normalize_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
                           const b200mg_fab* x, const b200mg_fab* a,
@@ -315,8 +326,11 @@ typedef struct b200mg_leg_args {
     int maxiter, narrow_cells;
     double alpha, volinv, eps_rel, eps_abs;
     b200mg_fab r, p, v, t, rh, bb;  /* bottom-level scratch: r, p with one ghost cell */
+    unsigned long long* stamps;     /* NULL, or device array of B200MG_LEG_MAX_STAMPS words: CTA 0 records (id << 48 | SM clock) after
+                                       every phase (id = level * 16 + phase), entry 0 = number of records (tuning aid) */
     b200mg_leg_level lev[B200MG_LEG_MAX_LEVELS];
 } b200mg_leg_args;
+#define B200MG_LEG_MAX_STAMPS 2048
 /* d_args: the arguments in DEVICE memory; d_out (device, 2 doubles, may be NULL): return code and iteration count of the
  * BiCGStab bottom solve; ctas: CTAs of the cooperative grid (512 threads each; clamped to one per SM). */
 int b200mg_coarse_leg(int abec, const b200mg_leg_args* d_args, double* d_out, int ctas, cudaStream_t s);
