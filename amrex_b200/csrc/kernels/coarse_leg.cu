@@ -237,6 +237,50 @@ __device__ __forceinline__ double face_cf (const b200mg_leg_level& L, const Face
     return (F.type[o] == kPeriodicFace) ? 0.0 : view(L.f[o])(i, j, k);
 }
 
+// interior cell (no face of the box next to it): straight loads
+template <bool ABEC>
+__device__ __forceinline__ FastIn<ABEC> interior_gather (int i, int j, int k, bool on, const Arr& P, const Arr& R,
+                                                         const Arr& A, const Arr& BX, const Arr& BY, const Arr& BZ)
+{
+    FastIn<ABEC> in;
+    in.on = on; in.i = i; in.j = j; in.k = k;
+    if (!on) { return in; }
+    double* pc = const_cast<double*>(P.p) + i + j * P.js + k * P.ks;
+    in.pc = pc;
+    in.c = pc[0]; in.xm = pc[-1]; in.xp = pc[1]; in.ym = pc[-P.js]; in.yp = pc[P.js]; in.zm = pc[-P.ks]; in.zp = pc[P.ks];
+    in.rhs = R.p[i + j * R.js + k * R.ks];
+    if constexpr (ABEC) {
+        in.a = A.p[i + j * A.js + k * A.ks];
+        const double* q = BX.p + i + j * BX.js + k * BX.ks; in.bxm = q[0]; in.bxp = q[1];
+        q = BY.p + i + j * BY.js + k * BY.ks; in.bym = q[0]; in.byp = q[BY.js];
+        q = BZ.p + i + j * BZ.js + k * BZ.ks; in.bzm = q[0]; in.bzp = q[BZ.ks];
+    }
+    return in;
+}
+
+// the cells on the surface of an nx x ny x nz box, enumerated once each: x faces own their edges and corners, y faces
+// exclude the x extremes, z faces the x and y extremes (nx, ny, nz >= 3)
+struct SurfaceMap {
+    unsigned n_x, n_y, n_z, nx, ny, nz;          // cells of the two x / y / z faces
+    __device__ __forceinline__ SurfaceMap (int ax, int ay, int az)
+        : n_x(2u * unsigned(ay) * unsigned(az)), n_y(2u * unsigned(ax - 2) * unsigned(az)), n_z(2u * unsigned(ax - 2) * unsigned(ay - 2)),
+          nx(unsigned(ax)), ny(unsigned(ay)), nz(unsigned(az)) {}
+    __device__ __forceinline__ unsigned size () const { return n_x + n_y + n_z; }
+    __device__ __forceinline__ void locate (unsigned t, int& i, int& j, int& k) const
+    {
+        if (t < n_x) {
+            const unsigned side = t & 1u, q = t >> 1;
+            i = side ? int(nx) - 1 : 0; j = int(q % ny); k = int(q / ny);
+        } else if (t < n_x + n_y) {
+            const unsigned u = t - n_x, side = u & 1u, q = u >> 1;
+            j = side ? int(ny) - 1 : 0; i = 1 + int(q % (nx - 2u)); k = int(q / (nx - 2u));
+        } else {
+            const unsigned u = t - n_x - n_y, side = u & 1u, q = u >> 1;
+            k = side ? int(nz) - 1 : 0; i = 1 + int(q % (nx - 2u)); j = 1 + int(q / (nx - 2u));
+        }
+    }
+};
+
 template <bool ABEC>
 __device__ __noinline__ void sweep_fast (const b200mg_leg_level& L, const FaceBC& F, double alpha, int redblack, const Team& T)
 {
@@ -246,38 +290,59 @@ __device__ __noinline__ void sweep_fast (const b200mg_leg_level& L, const FaceBC
     Arr A = P, BX = P, BY = P, BZ = P;
     if constexpr (ABEC) { A = arr_of(L.a, vb); BX = arr_of(L.bx, vb); BY = arr_of(L.by, vb); BZ = arr_of(L.bz, vb); }
     const double dhx = L.dh[0], dhy = L.dh[1], dhz = L.dh[2];
-    const unsigned nxh = unsigned(B.nx + 1) >> 1, uny = unsigned(B.ny);
-    const unsigned n = nxh * uny * unsigned(B.nz);
-    auto locate = [&] (unsigned c, int& i, int& j, int& k) -> bool {
-        if (c >= n) { i = j = k = 0; return false; }
-        const unsigned ii = c % nxh, jk = c / nxh;
-        j = int(jk % uny); k = int(jk / uny);
-        i = ((B.par0 + j + k + redblack) & 1) + 2 * int(ii);
-        return i < B.nx;
-    };
-    auto update = [&] (const FastIn<ABEC>& in) {
-        if (!in.on) { return; }
-        double cf0 = 0.0, cf1 = 0.0, cf2 = 0.0, cf3 = 0.0, cf4 = 0.0, cf5 = 0.0;
-        if (in.i == 0) { cf0 = face_cf(L, F, 0, vb.lo[0], vb.lo[1] + in.j, vb.lo[2] + in.k); }
-        if (in.j == 0) { cf1 = face_cf(L, F, 1, vb.lo[0] + in.i, vb.lo[1], vb.lo[2] + in.k); }
-        if (in.k == 0) { cf2 = face_cf(L, F, 2, vb.lo[0] + in.i, vb.lo[1] + in.j, vb.lo[2]); }
-        if (in.i == B.nx - 1) { cf3 = face_cf(L, F, 3, vb.hi[0], vb.lo[1] + in.j, vb.lo[2] + in.k); }
-        if (in.j == B.ny - 1) { cf4 = face_cf(L, F, 4, vb.lo[0] + in.i, vb.hi[1], vb.lo[2] + in.k); }
-        if (in.k == B.nz - 1) { cf5 = face_cf(L, F, 5, vb.lo[0] + in.i, vb.lo[1] + in.j, vb.hi[2]); }
-        if constexpr (ABEC) {
-            *in.pc = gsrb_abec_cell(in.c, in.xm, in.xp, in.ym, in.yp, in.zm, in.zp, in.rhs, in.a, in.bxm, in.bxp, in.bym, in.byp, in.bzm, in.bzp,
-                                    cf0, cf1, cf2, cf3, cf4, cf5, alpha, dhx, dhy, dhz);
-        } else {
-            *in.pc = gsrb_poisson_cell(in.c, in.xm, in.xp, in.ym, in.yp, in.zm, in.zp, in.rhs, cf0, cf1, cf2, cf3, cf4, cf5, dhx, dhy, dhz);
+    const int par = (B.par0 + redblack) & 1;
+    // ---- interior cells of the colour: 1 <= i <= nx-2 etc.; row (j,k) holds them at i = 1 + ((par + 1 + j + k) & 1) + 2*ii
+    {
+        const unsigned mxh = unsigned(B.nx - 1) >> 1, my = unsigned(B.ny - 2);        // ceil((nx-2)/2) candidates per row
+        const unsigned n = mxh * my * unsigned(B.nz - 2);
+        auto locate = [&] (unsigned c, int& i, int& j, int& k) -> bool {
+            if (c >= n) { i = j = k = 1; return false; }
+            const unsigned ii = c % mxh, jk = c / mxh;
+            j = 1 + int(jk % my); k = 1 + int(jk / my);
+            i = 1 + ((par + 1 + j + k) & 1) + 2 * int(ii);
+            return i <= B.nx - 2;
+        };
+        auto update = [&] (const FastIn<ABEC>& in) {
+            if (!in.on) { return; }
+            if constexpr (ABEC) {
+                *in.pc = gsrb_abec_cell_interior(in.c, in.xm, in.xp, in.ym, in.yp, in.zm, in.zp, in.rhs, in.a, in.bxm, in.bxp, in.bym, in.byp,
+                                                 in.bzm, in.bzp, alpha, dhx, dhy, dhz);
+            } else {
+                *in.pc = gsrb_poisson_cell(in.c, in.xm, in.xp, in.ym, in.yp, in.zm, in.zp, in.rhs, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, dhx, dhy, dhz);
+            }
+        };
+        // cells of one colour do not read each other: two per iteration, all loads ahead of the stores
+        for (unsigned c = unsigned(T.tid); c < n; c += 2u * unsigned(T.nth)) {
+            int i0, j0, k0, i1, j1, k1;
+            const bool on0 = locate(c, i0, j0, k0), on1 = locate(c + unsigned(T.nth), i1, j1, k1);
+            const FastIn<ABEC> X = interior_gather<ABEC>(i0, j0, k0, on0, P, R, A, BX, BY, BZ);
+            const FastIn<ABEC> Y = interior_gather<ABEC>(i1, j1, k1, on1, P, R, A, BX, BY, BZ);
+            update(X); update(Y);
         }
-    };
-    // cells of one colour do not read each other: two per iteration, all loads ahead of the stores
-    for (unsigned c = unsigned(T.tid); c < n; c += 2u * unsigned(T.nth)) {
-        int i0, j0, k0, i1, j1, k1;
-        const bool on0 = locate(c, i0, j0, k0), on1 = locate(c + unsigned(T.nth), i1, j1, k1);
-        const FastIn<ABEC> X = fast_gather<ABEC>(i0, j0, k0, on0, B, F, P, R, A, BX, BY, BZ);
-        const FastIn<ABEC> Y = fast_gather<ABEC>(i1, j1, k1, on1, B, F, P, R, A, BX, BY, BZ);
-        update(X); update(Y);
+    }
+    // ---- surface cells of the colour: boundary values through FaceBC, relaxation coefficients from the face slabs
+    {
+        const SurfaceMap M(B.nx, B.ny, B.nz);
+        const unsigned n = M.size();
+        for (unsigned t = unsigned(T.tid); t < n; t += unsigned(T.nth)) {
+            int i, j, k;
+            M.locate(t, i, j, k);
+            if ((i + j + k + par) & 1) { continue; }
+            const FastIn<ABEC> in = fast_gather<ABEC>(i, j, k, true, B, F, P, R, A, BX, BY, BZ);
+            double cf0 = 0.0, cf1 = 0.0, cf2 = 0.0, cf3 = 0.0, cf4 = 0.0, cf5 = 0.0;
+            if (i == 0) { cf0 = face_cf(L, F, 0, vb.lo[0], vb.lo[1] + j, vb.lo[2] + k); }
+            if (j == 0) { cf1 = face_cf(L, F, 1, vb.lo[0] + i, vb.lo[1], vb.lo[2] + k); }
+            if (k == 0) { cf2 = face_cf(L, F, 2, vb.lo[0] + i, vb.lo[1] + j, vb.lo[2]); }
+            if (i == B.nx - 1) { cf3 = face_cf(L, F, 3, vb.hi[0], vb.lo[1] + j, vb.lo[2] + k); }
+            if (j == B.ny - 1) { cf4 = face_cf(L, F, 4, vb.lo[0] + i, vb.hi[1], vb.lo[2] + k); }
+            if (k == B.nz - 1) { cf5 = face_cf(L, F, 5, vb.lo[0] + i, vb.lo[1] + j, vb.hi[2]); }
+            if constexpr (ABEC) {
+                *in.pc = gsrb_abec_cell(in.c, in.xm, in.xp, in.ym, in.yp, in.zm, in.zp, in.rhs, in.a, in.bxm, in.bxp, in.bym, in.byp, in.bzm, in.bzp,
+                                        cf0, cf1, cf2, cf3, cf4, cf5, alpha, dhx, dhy, dhz);
+            } else {
+                *in.pc = gsrb_poisson_cell(in.c, in.xm, in.xp, in.ym, in.yp, in.zm, in.zp, in.rhs, cf0, cf1, cf2, cf3, cf4, cf5, dhx, dhy, dhz);
+            }
+        }
     }
 }
 
@@ -290,14 +355,6 @@ __device__ __noinline__ void residual_fast (const b200mg_leg_level& L, const Fac
     Arr A = P, BX = P, BY = P, BZ = P;
     if constexpr (ABEC) { A = arr_of(L.a, vb); BX = arr_of(L.bx, vb); BY = arr_of(L.by, vb); BZ = arr_of(L.bz, vb); }
     const double dhx = L.adh[0], dhy = L.adh[1], dhz = L.adh[2];
-    const unsigned unx = unsigned(B.nx), uny = unsigned(B.ny);
-    const unsigned n = unx * uny * unsigned(B.nz);
-    auto locate = [&] (unsigned c, int& i, int& j, int& k) -> bool {
-        if (c >= n) { i = j = k = 0; return false; }
-        const unsigned jk = c / unx;
-        i = int(c % unx); j = int(jk % uny); k = int(jk / uny);
-        return true;
-    };
     auto finish = [&] (const FastIn<ABEC>& in) {
         if (!in.on) { return; }
         double v;
@@ -308,12 +365,31 @@ __device__ __noinline__ void residual_fast (const b200mg_leg_level& L, const Fac
         }
         const_cast<double*>(Y.p)[in.i + in.j * Y.js + in.k * Y.ks] = in.rhs + (-1.0) * v;      // Xpay(y,-1,b)
     };
-    for (unsigned c = unsigned(T.tid); c < n; c += 2u * unsigned(T.nth)) {
-        int i0, j0, k0, i1, j1, k1;
-        const bool on0 = locate(c, i0, j0, k0), on1 = locate(c + unsigned(T.nth), i1, j1, k1);
-        const FastIn<ABEC> X = fast_gather<ABEC>(i0, j0, k0, on0, B, F, P, R, A, BX, BY, BZ);
-        const FastIn<ABEC> Z = fast_gather<ABEC>(i1, j1, k1, on1, B, F, P, R, A, BX, BY, BZ);
-        finish(X); finish(Z);
+    {   // interior
+        const unsigned mx = unsigned(B.nx - 2), my = unsigned(B.ny - 2);
+        const unsigned n = mx * my * unsigned(B.nz - 2);
+        auto locate = [&] (unsigned c, int& i, int& j, int& k) -> bool {
+            if (c >= n) { i = j = k = 1; return false; }
+            const unsigned jk = c / mx;
+            i = 1 + int(c % mx); j = 1 + int(jk % my); k = 1 + int(jk / my);
+            return true;
+        };
+        for (unsigned c = unsigned(T.tid); c < n; c += 2u * unsigned(T.nth)) {
+            int i0, j0, k0, i1, j1, k1;
+            const bool on0 = locate(c, i0, j0, k0), on1 = locate(c + unsigned(T.nth), i1, j1, k1);
+            const FastIn<ABEC> X = interior_gather<ABEC>(i0, j0, k0, on0, P, R, A, BX, BY, BZ);
+            const FastIn<ABEC> Z = interior_gather<ABEC>(i1, j1, k1, on1, P, R, A, BX, BY, BZ);
+            finish(X); finish(Z);
+        }
+    }
+    {   // surface
+        const SurfaceMap M(B.nx, B.ny, B.nz);
+        const unsigned n = M.size();
+        for (unsigned t = unsigned(T.tid); t < n; t += unsigned(T.nth)) {
+            int i, j, k;
+            M.locate(t, i, j, k);
+            finish(fast_gather<ABEC>(i, j, k, true, B, F, P, R, A, BX, BY, BZ));
+        }
     }
 }
 

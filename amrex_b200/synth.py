@@ -122,3 +122,109 @@ def synth_poisson(ab, n, mgs, maxorder=2, fusion=None):
         if fusion:
             op.setFusedMinBoxCells(32 ** 3)
     return dict(geom=geom, ba=ba, dm=dm, sol0=sol0, op=op, n=n)
+
+
+def synth_poisson_periodic(ab, ncell, mgs, maxorder=2, fusion=None, keep_host=False):
+    """Fully periodic MLPoisson (BASELINE config 5) on an ncell = (n0, n1, n2) domain of cubic cells of size 1 / min(ncell)
+    (so the physical box grows with the cell count: weak scaling keeps the per-cell problem), chopped into mgs^3 boxes.
+    rhs = the Laplacian of the analytic solution of the reference's Poisson test (initProb_K.H:7-38), which has period 1 and
+    zero mean.  The operator is singular: MLMG makes the right-hand side solvable and the solution is defined up to a
+    constant.  Returns dict with geom/ba/dm/sol/sol0/rhs/op and, with keep_host, per-local-box host arrays (rhs, exact)."""
+    nb = min(ncell)
+    ab.Geometry.setup((0., 0., 0.), tuple(float(n) / nb for n in ncell), (1, 1, 1))
+    geom = ab.Geometry((0, 0, 0), tuple(n - 1 for n in ncell))
+    ba = ab.BoxArray((0, 0, 0), tuple(n - 1 for n in ncell)).maxSize(mgs)
+    dm = ab.DistributionMapping(ba)
+    me = ab.lib.amrex_b200_myproc()
+    pmap = dm.pmap(ba.size())
+    sol = ab.MultiFab(ba, dm, 1, 1)
+    sol0 = ab.MultiFab(ba, dm, 1, 1)
+    rhs = ab.MultiFab(ba, dm, 1, 0)
+    sol0.setVal(0.0, ng=1)
+    sol.setVal(0.0, ng=1)
+    host = {}
+    h = 1.0 / nb
+    tpi, fpi = 2 * np.pi, 4 * np.pi
+    fac = tpi * tpi * 3.0
+    for g, box in enumerate(ba.boxes()):
+        if pmap[g] != me:
+            continue
+        x, y, z = np.meshgrid(*[(np.arange(box[d], box[d + 3] + 1) + 0.5) * h for d in range(3)], indexing="ij")
+        s2, s4 = np.sin(tpi * x) * np.sin(tpi * y) * np.sin(tpi * z), np.sin(fpi * x) * np.sin(fpi * y) * np.sin(fpi * z)
+        r = -fac * s2 - fac * s4
+        rhs.upload(r, box[:3])
+        if keep_host:
+            host[g] = dict(box=box, rhs=r, exact=s2 + .25 * s4)
+    P = ab.LinOpBCType.Periodic
+    op = ab.MLPoisson([geom], [ba], [dm])
+    op.setMaxOrder(maxorder)
+    op.setDomainBC((P, P, P), (P, P, P))
+    op.setLevelBC(0, sol0)
+    if fusion is not None:
+        op.setSmootherFusion(fusion)
+    return dict(geom=geom, ba=ba, dm=dm, sol=sol, sol0=sol0, rhs=rhs, op=op, keep=[], n=ncell, host=host, pmap=pmap, me=me,
+                ncells=int(np.prod(ncell)))
+
+
+def synth_abeclap_amr(ab, n, mgs, max_level=1, maxorder=3, fusion=None, a=1.e-3, b=1.0, keep_host=False):
+    """Two-level (max_level = 1) composite problem of BASELINE config 4: the variable-coefficient MLABecLaplacian of
+    synth_abeclap on an n^3 base level plus a refined patch (ratio 2) over the central half of the domain, i.e. (n/2)^3 coarse
+    cells refined to n^3 fine cells - the grids of the reference's test (Tests/LinearSolvers/ABecLaplacian_C/MyTest.cpp:612-619).
+    Returns dict with per-level lists geom/ba/dm/sol/sol0/rhs and op, host[level][g] = dict(box, rhs, exact)."""
+    ab.Geometry.setup((0., 0., 0.), (1., 1., 1.), (0, 0, 0))
+    geoms, bas, dms, sols, sol0s, rhss, keep, hosts = [], [], [], [], [], [], [], []
+    me = ab.lib.amrex_b200_myproc()
+    dlo, dhi = [0, 0, 0], [n - 1] * 3
+    glo, ghi = [0, 0, 0], [n - 1] * 3
+    acoefs, facess = [], []
+    for l in range(max_level + 1):
+        nl = n << l
+        geom = ab.Geometry(tuple(dlo), tuple(dhi))
+        ba = ab.BoxArray(tuple(glo), tuple(ghi)).maxSize(mgs)
+        dm = ab.DistributionMapping(ba)
+        pmap = dm.pmap(ba.size())
+        sol = ab.MultiFab(ba, dm, 1, 1)
+        sol0 = ab.MultiFab(ba, dm, 1, 1)
+        rhs = ab.MultiFab(ba, dm, 1, 0)
+        acoef = ab.MultiFab(ba, dm, 1, 0)
+        bcc = ab.MultiFab(ba, dm, 1, 1)
+        faces = []
+        for d in range(3):
+            nodal = [0, 0, 0]
+            nodal[d] = 1
+            faces.append(ab.MultiFab(ba, dm, 1, 0, nodal=nodal))
+        host = {}
+        for g, box in enumerate(ba.boxes()):
+            if pmap[g] != me:
+                continue
+            r, ex = abeclap_fields(box, nl, a, b)
+            beta, bc, glo_ = abeclap_beta_and_bc(box, nl)
+            rhs.upload(r, box[:3])
+            bcc.upload(beta, glo_, ng=1)
+            sol0.upload(bc, glo_, ng=1)
+            if keep_host:
+                host[g] = dict(box=box, rhs=r, exact=ex)
+        acoef.setVal(1.0)
+        ab.lib.amrex_b200_average_cellcenter_to_face(faces[0].ptr, faces[1].ptr, faces[2].ptr, bcc.ptr, geom.ptr)
+        ab.check()
+        sol.copy_from(sol0, ng=1)
+        geoms.append(geom); bas.append(ba); dms.append(dm); sols.append(sol); sol0s.append(sol0); rhss.append(rhs)
+        acoefs.append(acoef); facess.append(faces); keep += [acoef, bcc] + faces; hosts.append(host)
+        glo = [2 * (v + n // 4) for v in glo]
+        ghi = [2 * (v - n // 4) + 1 for v in ghi]
+        dlo = [2 * v for v in dlo]
+        dhi = [2 * v + 1 for v in dhi]
+    D, N = ab.LinOpBCType.Dirichlet, ab.LinOpBCType.Neumann
+    op = ab.MLABecLaplacian(geoms, bas, dms)
+    op.setMaxOrder(maxorder)
+    op.setDomainBC((D, N, N), (N, D, N))
+    for l in range(max_level + 1):
+        op.setLevelBC(l, sol0s[l])
+    op.setScalars(a, b)
+    for l in range(max_level + 1):
+        op.setACoeffs(l, acoefs[l])
+        op.setBCoeffs(l, facess[l])
+    if fusion is not None:
+        op.setSmootherFusion(fusion)
+    return dict(geom=geoms, ba=bas, dm=dms, sol=sols, sol0=sol0s, rhs=rhss, op=op, keep=keep, n=n, host=hosts, me=me,
+                ncells=int(sum(b_.numPts() for b_ in bas)))

@@ -31,6 +31,9 @@ TOL_REL = 1e-10
 GSRB_BYTES_PER_CELL = 56.0     # fused red+black ABecLap smooth: phi 8 + rhs 8 + a 8 + b 24 + phi_out 8
 
 
+WORKLOADS = ("abeclap", "periodic", "amr")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -40,6 +43,11 @@ def parse():
     ap.add_argument("--n-cell", type=int, default=512)
     ap.add_argument("--max-grid-size", type=int, default=128)
     ap.add_argument("--fusion", type=int, default=1, help="1: fused red+black pass (generation 4, bulk-async-copy staged) + surface shell; 0: one kernel per colour")
+    ap.add_argument("--workload", default="abeclap", choices=list(WORKLOADS),
+                    help="abeclap: BASELINE config 3 (headline: 512^3 MLABecLaplacian, strong scaling); periodic: config 5 (fully periodic "
+                         "Poisson, n-cell^3 per GPU, weak scaling: 1024^3 on 8 GPUs); amr: config 4 (two-level composite solve, (n-cell/2)^3 "
+                         "base + refined patch)")
+    ap.add_argument("--other-configs", type=int, default=1, help="1: after the headline workload also time configs 4 and 5 (light legs, 'other_configs')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-(kernel, MG level) device-time table of one solve to this file")
@@ -51,13 +59,25 @@ def workload_name(n, mgs):
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
-def run_reference_solve(n, mgs, nsolve, threads):
+def run_reference_solve(n, mgs, nsolve, threads, ref=None):
     from common import REF_DRIVER, have_ref, run_ref
     if not have_ref():
         raise RuntimeError(f"{REF_DRIVER} missing (built by __graft_entry__.build() where /root/reference is mounted)")
-    res, _ = run_ref(threads=threads, mode="solve", prob_type=2, n_cell=n, max_grid_size=mgs, linop_maxorder=2,
-                     agg_grid_size=32, nsolve=nsolve)
+    kw = dict(prob_type=2, linop_maxorder=2)
+    kw.update(ref or {})
+    kw.update(n_cell=n, max_grid_size=mgs)
+    res, _ = run_ref(threads=threads, mode="solve", agg_grid_size=32, nsolve=nsolve, **kw)
     return res
+
+
+def reference_kwargs(args):
+    """The reference's inputs for the workload: the same problem; for the periodic weak-scaling workload its one-GPU share
+    (n-cell^3), for the AMR workload the (n-cell/2)^3 base + refined patch."""
+    if args.workload == "periodic":
+        return args.n_cell, dict(prob_type=5, linop_maxorder=2)
+    if args.workload == "amr":
+        return args.n_cell // 2, dict(prob_type=2, linop_maxorder=3, max_level=1)
+    return args.n_cell, dict(prob_type=2, linop_maxorder=2)
 
 
 def reference_arm(args):
@@ -69,11 +89,11 @@ def reference_arm(args):
     # bounded sample: a full 512^3 solve costs 9.1 s on the 16 host threads of the GPU box (BENCH_r01.json; ~18 s on the
     # 8 cores of the build container); fall back to the 256^3 instance of the same problem (1/8 of the cells, same operator,
     # same tolerance) only when the requested steps would not finish within a few minutes
-    n = args.n_cell
-    per_solve_est = 9.2 * (n / 512.0) ** 3 * 16.0 / cores
+    n, refkw = reference_kwargs(args)
+    per_solve_est = 9.2 * (n / 512.0) ** 3 * 16.0 / cores * (2.0 if args.workload == "amr" else 1.0)
     if total * per_solve_est + 30.0 > 330.0 and n > 256:
         n = 256
-    res = run_reference_solve(n, min(args.max_grid_size, n), total, cores)
+    res = run_reference_solve(n, min(args.max_grid_size, n), total, cores, ref=refkw)
     times = res["solve_times"][args.warmup:]
     t = sum(times) / len(times)
     value = res["ncells"] / t
@@ -81,9 +101,11 @@ def reference_arm(args):
               f"reference AMReX 24.10 CPU OpenMP build (oracle/_ref/ref_driver), {res['omp_threads']} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.n_cell, args.max_grid_size), "timed_instance_n_cell": n, "iters": res["iters"]},
+        "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak" if args.workload == "periodic" else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.n_cell, args.max_grid_size) if args.workload == "abeclap" else
+                   f"{args.workload} (BASELINE config {5 if args.workload == 'periodic' else 4}), reference inputs: {refkw}",
+                   "timed_instance_n_cell": n, "iters": res["iters"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["omp_threads"], "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -91,7 +113,7 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample(n, mgs, cores=None):
+def cpu_baseline_sample(n, mgs, cores=None, ref=None):
     """The reference itself (oracle/_ref/ref_driver, all host cores) on a bounded sample of the workload: the second of two
     full solves (warm caches, as the reference's own scaling test times it) of the workload itself when one solve is
     expected to take <= ~20 s on this host (512^3: ~11 s on 16 threads), else of its 256^3 instance."""
@@ -99,7 +121,9 @@ def cpu_baseline_sample(n, mgs, cores=None):
     try:
         est = 9.2 * (n / 512.0) ** 3 * 16.0 / cores      # seconds per solve: 9.1 s measured on the 16 threads of the GPU box
         nb = n if est <= 20.0 else min(n, 256)
-        res = run_reference_solve(nb, min(mgs, nb), 2, cores)
+        if ref and "n_cell" in ref and est <= 20.0:
+            nb = ref["n_cell"]
+        res = run_reference_solve(nb, min(mgs, nb), 2, cores, ref=ref)
         t = res["solve_times"][-1]
         return {"value": res["ncells"] / t, "unit": UNIT, "cores": res["omp_threads"], "kind": "reference",
                 "sample": f"second of two full solves of the {nb}^3 instance of the workload ({res['iters']} V-cycles, {t:.2f} s), "
@@ -161,12 +185,60 @@ def measured_peak_gbs():
 
 
 # ------------------------------------------------------------------------------------------------- B200 arm
+WORKLOADS = ("abeclap", "periodic", "amr")
+
+
+def weak_dims(base, world):
+    """Domain of the periodic weak-scaling workload: base^3 cells per GPU, doubled direction by direction (8 GPUs: (2 base)^3)."""
+    d = [base, base, base]
+    w, k = world, 0
+    while w > 1:
+        d[k % 3] *= 2
+        w //= 2
+        k += 1
+    return tuple(d)
+
+
+def make_problem(ab, kind, args, world):
+    """Builds the workload on the library's ranks.  Returns a dict with per-AMR-level lists sols / sol0s / rhss / hosts, the
+    operator, the global cell count and the descriptive strings of the JSON line."""
+    from amrex_b200.synth import synth_abeclap, synth_abeclap_amr, synth_poisson_periodic
+    n, mgs = args.n_cell, args.max_grid_size
+    if kind == "abeclap":
+        P = synth_abeclap(ab, n, mgs, fusion=args.fusion, keep_host=True)
+        W = dict(sols=[P["sol"]], sol0s=[P["sol0"]], rhss=[P["rhs"]], hosts=[P["host"]], ncells=n ** 3, boxes=P["ba"].size(),
+                 name=workload_name(n, mgs), scaling="strong", gold=f"solve_p2_n{n}_g{mgs}.json", sample=f"sol_sample_p2_n{n}_g{mgs}.npz",
+                 bytes_per_cell=GSRB_BYTES_PER_CELL, kern="b200mg_gsrb4" if args.fusion else "b200mg_gsrb_abec_pairs_lean", scope=0,
+                 ref=dict(prob_type=2, n_cell=n, max_grid_size=mgs, linop_maxorder=2), singular=False)
+    elif kind == "periodic":
+        dims = weak_dims(n, world)
+        P = synth_poisson_periodic(ab, dims, mgs, fusion=args.fusion, keep_host=True)
+        W = dict(sols=[P["sol"]], sol0s=[P["sol0"]], rhss=[P["rhs"]], hosts=[P["host"]], ncells=P["ncells"], boxes=P["ba"].size(),
+                 name=(f"fully periodic MLPoisson, {dims[0]}x{dims[1]}x{dims[2]} cells ({n}^3 per GPU, weak scaling), max_grid_size={mgs}, "
+                       f"BiCGStab bottom solver, tol_rel=1e-10, V-cycles"),
+                 scaling="weak", gold=f"solve_p5_n{n}_g{mgs}.json" if world == 1 else None, sample=None,
+                 bytes_per_cell=24.0, kern="b200mg_gsrb4", scope=0,
+                 ref=dict(prob_type=5, n_cell=n, max_grid_size=mgs, linop_maxorder=2), singular=True)
+    else:
+        na = n // 2                      # 256^3 base + 256^3 refined patch when --n-cell is the default 512
+        P = synth_abeclap_amr(ab, na, mgs, max_level=1, maxorder=3, fusion=args.fusion, keep_host=True)
+        W = dict(sols=P["sol"], sol0s=P["sol0"], rhss=P["rhs"], hosts=P["host"], ncells=P["ncells"], boxes=sum(b.size() for b in P["ba"]),
+                 name=(f"2-level AMR composite solve (ref_ratio 2): {na}^3 base + {na}^3-cell refined patch over the central half, "
+                       f"variable-coefficient MLABecLaplacian, max_grid_size={mgs}, tol_rel=1e-10"),
+                 scaling="strong", gold=f"solve_p2_n{na}_g{mgs}_lev1_mo3.json", sample=None,
+                 bytes_per_cell=GSRB_BYTES_PER_CELL, kern="b200mg_gsrb4", scope=100,
+                 ref=dict(prob_type=2, n_cell=na, max_grid_size=mgs, linop_maxorder=3, max_level=1), singular=False)
+    W["op"] = P["op"]
+    W["keep"] = P
+    P["op"].setFusedMinBoxCells(0)     # the product default: the per-level cost model picks fused pass or colour sweeps (tests force fusion)
+    return W
+
+
 def b200_arm(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     import amrex_b200 as ab
-    from amrex_b200.synth import synth_abeclap
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -179,11 +251,6 @@ def b200_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         ab.comm_init_from_torch()
-    n, mgs = args.n_cell, args.max_grid_size
-    P = synth_abeclap(ab, n, mgs, fusion=args.fusion, keep_host=True)
-    P["op"].setFusedMinBoxCells(0)     # the product default: the per-level cost model picks fused pass or colour sweeps (tests force fusion)
-    mlmg = ab.MLMG(P["op"])
-    mlmg.setVerbose(0)
     stream = torch.cuda.ExternalStream(ab.lib.amrex_b200_stream(), device=torch.device("cuda", local))
 
     def barrier():
@@ -191,10 +258,6 @@ def b200_arm(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def step():
-        P["sol"].copy_from(P["sol0"], ng=1)
-        mlmg.solve([P["sol"]], [P["rhs"]], TOL_REL, 0.0)
 
     def timed(fn, k):
         barrier()
@@ -209,6 +272,106 @@ def b200_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def allsum(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    def boxshape(b):
+        return tuple(b[3 + d] - b[d] + 1 for d in range(3))
+
+    def check(W, mlmg):
+        """Error against the analytic solution (the norm the reference's test prints) and parity with the reference's own run
+        of the workload (committed fixtures: residual history, and for the headline workload the solution sampled at every
+        8th cell)."""
+        iters, hist = mlmg.numIters(), mlmg.residualHistory()
+        gold, sample = None, None
+        try:
+            if W["gold"]:
+                gold = json.load(open(os.path.join(ROOT, "tests", "golden", W["gold"])))
+            if W["sample"]:
+                sample = np.load(os.path.join(ROOT, "tests", "golden", W["sample"]))
+        except Exception:
+            pass
+        shift = 0.0
+        if W["singular"]:              # defined up to a constant: compare after removing the mean difference
+            acc = 0.0
+            for lev, host in enumerate(W["hosts"]):
+                for g, h in host.items():
+                    acc += float(np.sum(W["sols"][lev].download(h["box"][:3], boxshape(h["box"])) - h["exact"]))
+            shift = allsum([acc])[0] / float(W["ncells"])
+        err, sdiff = 0.0, -1.0
+        for lev, host in enumerate(W["hosts"]):
+            for g, h in host.items():
+                b = h["box"]
+                mine = W["sols"][lev].download(b[:3], boxshape(b))
+                err = max(err, float(np.max(np.abs(mine - shift - h["exact"]))))
+                if sample is not None and lev == 0:
+                    st, of = int(sample["stride"]), int(sample["offset"])
+                    first = [(of - b[d]) % st for d in range(3)]                  # first sampled cell inside the box, per direction
+                    mys = mine[first[0]::st, first[1]::st, first[2]::st]
+                    g0 = [(b[d] + first[d] - of) // st for d in range(3)]
+                    ref_s = sample["sol"][g0[0]:g0[0] + mys.shape[0], g0[1]:g0[1] + mys.shape[1], g0[2]:g0[2] + mys.shape[2]]
+                    sdiff = max(sdiff, float(np.max(np.abs(mys - ref_s))) / float(sample["solmax"]))
+        err, sdiff = allmax([err, sdiff])
+        parity = None
+        if gold is not None:
+            rh = gold["history"]
+            floor = 1e-13 * max(gold["rhsnorm0"], gold["resnorm0"])
+            hrel = max((abs(a - c) / max(abs(c), floor) for a, c in zip(hist, rh)), default=None)
+            err_ref = max(gold["err_inf"]) if gold.get("err_inf") else None
+            parity = {"fixture": "tests/golden/" + W["gold"] + (" + " + W["sample"] if W["sample"] else "") + " (the reference's own run of this workload)",
+                      "iters": iters, "iters_reference": gold["iters"], "history_max_rel_diff": hrel,
+                      "final_residual": hist[-1] if hist else None, "final_residual_reference": rh[-1],
+                      "solution_sample_rel_maxdiff": sdiff if sdiff >= 0 else None,
+                      "solution_sample_points": int(sample["sol"].size) if sample is not None else 0,
+                      "max_err_vs_analytic": err, "max_err_vs_analytic_reference": err_ref,
+                      "bar": "iters +-1, solution <= 1e-10 relative (north_star)",
+                      "ok": bool(abs(iters - gold["iters"]) <= 1 and (sdiff < 0 or sdiff <= 1e-10)
+                                 and (err_ref is None or abs(err - err_ref) <= 1e-9 * max(1.0, abs(err_ref)) + 1e-10))}
+        return iters, hist, err, parity
+
+    def run_light(kind):
+        """One of the other BASELINE configurations, timed the same way (device time, inputs resident), without the e2e /
+        roofline / CPU legs of the headline workload."""
+        W = make_problem(ab, kind, args, world)
+        mlmg = ab.MLMG(W["op"])
+        mlmg.setVerbose(0)
+
+        def step():
+            for s_, s0 in zip(W["sols"], W["sol0s"]):
+                s_.copy_from(s0, ng=1)
+            mlmg.solve(W["sols"], W["rhss"], TOL_REL, 0.0)
+
+        for _ in range(2):
+            step()
+        k = max(1, min(args.steps, 3))
+        ms = timed(step, k) / k
+        iters, hist, err, parity = check(W, mlmg)
+        out = {"workload": W["name"], "scaling": W["scaling"], "cells": W["ncells"], "boxes": W["boxes"], "ms_per_step": ms, "steps": k,
+               "value": W["ncells"] / (ms * 1e-3), "unit": UNIT, "iters": iters, "max_err_vs_analytic": err,
+               "bottom_iters": list(mlmg.cgIters())[:4], "parity_vs_reference": parity}
+        del mlmg, W
+        return out
+
+    kind = args.workload
+    n, mgs = args.n_cell, args.max_grid_size
+    W = make_problem(ab, kind, args, world)
+    mlmg = ab.MLMG(W["op"])
+    mlmg.setVerbose(0)
+
+    def step():
+        for s_, s0 in zip(W["sols"], W["sol0s"]):
+            s_.copy_from(s0, ng=1)
+        mlmg.solve(W["sols"], W["rhss"], TOL_REL, 0.0)
+
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
@@ -218,77 +381,38 @@ def b200_arm(args):
     ms = timed(step, args.steps)
     launches = int(ab.lib.amrex_b200_launch_count())
     clocks = sampler.stop() if rank == 0 else None
-    iters = mlmg.numIters()
-    hist = mlmg.residualHistory()
     ms_per_step = ms / args.steps
-    cells = n ** 3
+    cells = W["ncells"]
     value = cells / (ms_per_step * 1e-3)
-
-    # correctness of what was timed: error against the analytic solution (reference prints the same norm), and parity with
-    # the reference's own run of this workload (committed fixtures: residual history + the solution sampled at every 8th cell)
-    gold, sample = None, None
-    try:
-        gold = json.load(open(os.path.join(ROOT, "tests", "golden", f"solve_p2_n{n}_g{mgs}.json")))
-        sample = np.load(os.path.join(ROOT, "tests", "golden", f"sol_sample_p2_n{n}_g{mgs}.npz"))
-    except Exception:
-        pass
-    err, sdiff = 0.0, -1.0
-    for g, h in P["host"].items():
-        b = h["box"]
-        mine = P["sol"].download(b[:3], tuple(b[3 + d] - b[d] + 1 for d in range(3)))
-        err = max(err, float(np.max(np.abs(mine - h["exact"]))))
-        if sample is not None:
-            st, of = int(sample["stride"]), int(sample["offset"])
-            first = [(of - b[d]) % st for d in range(3)]                      # first sampled cell inside the box, per direction
-            mys = mine[first[0]::st, first[1]::st, first[2]::st]
-            g0 = [(b[d] + first[d] - of) // st for d in range(3)]
-            ref_s = sample["sol"][g0[0]:g0[0] + mys.shape[0], g0[1]:g0[1] + mys.shape[1], g0[2]:g0[2] + mys.shape[2]]
-            sdiff = max(sdiff, float(np.max(np.abs(mys - ref_s))) / float(sample["solmax"]))
-    errt = torch.tensor([err, sdiff], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(errt, op=dist.ReduceOp.MAX)
-    err, sdiff = float(errt[0].item()), float(errt[1].item())
-    parity = None
-    if gold is not None:
-        rh = gold["history"]
-        hrel = max((abs(a - c) / abs(c) for a, c in zip(hist, rh)), default=None)
-        parity = {"fixture": f"tests/golden/solve_p2_n{n}_g{mgs}.json + sol_sample_p2_n{n}_g{mgs}.npz (the reference's own run of this workload)",
-                  "iters": iters, "iters_reference": gold["iters"], "history_max_rel_diff": hrel,
-                  "final_residual": hist[-1] if hist else None, "final_residual_reference": rh[-1],
-                  "solution_sample_rel_maxdiff": sdiff if sdiff >= 0 else None, "solution_sample_points": int(sample["sol"].size) if sample is not None else 0,
-                  "bar": "iters +-1, solution <= 1e-10 relative (north_star)",
-                  "ok": bool(abs(iters - gold["iters"]) <= 1 and (sdiff < 0 or sdiff <= 1e-10))}
+    iters, hist, err, parity = check(W, mlmg)
 
     # ---- e2e: host buffers in, host buffer out, through the C ABI
     e2e = None
     if not args.no_e2e:
-        pin = {}
-        for g, h in P["host"].items():
-            r = torch.empty(h["rhs"].shape[::-1], dtype=torch.float64).pin_memory()      # Fortran order == reversed C shape
-            r.copy_(torch.from_numpy(np.ascontiguousarray(h["rhs"].transpose(2, 1, 0))))
-            s = torch.zeros_like(r).pin_memory()
-            o = torch.empty_like(r).pin_memory()
-            pin[g] = (r, s, o)
-        nbytes = sum(t[0].numel() * 8 for t in pin.values())
+        pin = []
+        for lev, host in enumerate(W["hosts"]):
+            for g, h in host.items():
+                r = torch.empty(h["rhs"].shape[::-1], dtype=torch.float64).pin_memory()      # Fortran order == reversed C shape
+                r.copy_(torch.from_numpy(np.ascontiguousarray(h["rhs"].transpose(2, 1, 0))))
+                s0 = torch.zeros_like(r).pin_memory()
+                o = torch.empty_like(r).pin_memory()
+                pin.append((lev, h["box"], r, s0, o))
+        nbytes = sum(t[2].numel() * 8 for t in pin)
 
         def e2e_step():
-            for g, (r, s, o) in pin.items():
-                b = P["host"][g]["box"]
-                P["rhs"].upload_ptr(r.data_ptr(), b[:3], b[3:])
-                P["sol"].upload_ptr(s.data_ptr(), b[:3], b[3:])
-            mlmg.solve([P["sol"]], [P["rhs"]], TOL_REL, 0.0)
-            for g, (r, s, o) in pin.items():
-                b = P["host"][g]["box"]
-                P["sol"].download_ptr(o.data_ptr(), b[:3], b[3:])
+            for lev, b, r, s0, o in pin:
+                W["rhss"][lev].upload_ptr(r.data_ptr(), b[:3], b[3:])
+                W["sols"][lev].upload_ptr(s0.data_ptr(), b[:3], b[3:])
+            mlmg.solve(W["sols"], W["rhss"], TOL_REL, 0.0)
+            for lev, b, r, s0, o in pin:
+                W["sols"][lev].download_ptr(o.data_ptr(), b[:3], b[3:])
 
         e2e_step()
         k = max(1, min(args.steps, 3))
         ems = timed(e2e_step, k) / k
-        h2d = torch.tensor([2.0 * nbytes, 1.0 * nbytes], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(h2d)
-        e2e = {"value": cells / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems, "h2d_bytes_per_step": int(h2d[0].item()),
-               "d2h_bytes_per_step": int(h2d[1].item()), "steps": k,
+        h2d = allsum([2.0 * nbytes, 1.0 * nbytes])
+        e2e = {"value": cells / (ems * 1e-3), "unit": UNIT, "ms_per_step": ems, "h2d_bytes_per_step": int(h2d[0]),
+               "d2h_bytes_per_step": int(h2d[1]), "steps": k,
                "what": "pinned host rhs + initial guess -> device, MLMG solve, solution -> pinned host; operator (coefficients, BCs) resident"}
 
     # ---- roofline of the dominant kernel (finest-level fused smoother), one extra solve with per-kernel CUDA events
@@ -299,27 +423,28 @@ def b200_arm(args):
     tot_ms = sum(r[3] for r in rep)
     if args.profile_out and rank == 0:
         with open(args.profile_out, "w") as fh:
-            fh.write(f"# one MLMG solve, {n}^3, {world} GPU(s), rank 0: kernel, scope (amrlev*100+mglev), launches, total ms, min ms, max ms\n")
+            fh.write(f"# one MLMG solve, {W['name']}, {world} GPU(s), rank 0: kernel, scope (amrlev*100+mglev), launches, total ms, min ms, max ms\n")
             for r in sorted(rep, key=lambda q: (q[1], -q[3])):
                 fh.write(f"{r[0]:36s} {r[1]:5d} {r[2]:6d} {r[3]:10.3f} {r[4]:9.4f} {r[5]:9.4f}\n")
-    kern = "b200mg_gsrb4" if args.fusion else "b200mg_gsrb_abec_pairs_lean"
-    top = [r for r in rep if r[0] == kern and r[1] == 0]
+    kern = W["kern"]
+    top = [r for r in rep if r[0] == kern and r[1] == W["scope"]]
     peak, peak_src = measured_peak_gbs()
     roofline = None
     if top:
         _, _, cnt, tms, mn, mx = top[0]
-        local_cells = sum(int(np.prod(h["rhs"].shape)) for h in P["host"].values())
-        bpc = GSRB_BYTES_PER_CELL if args.fusion else 44.0
+        finest = len(W["hosts"]) - 1
+        local_cells = sum(int(np.prod(h["rhs"].shape)) for h in W["hosts"][finest].values())
+        bpc = W["bytes_per_cell"] if args.fusion else 44.0
         avg_s = tms / cnt * 1e-3
         achieved = bpc * local_cells / avg_s / 1e9
         traffic, traffic_src = None, None
-        try:   # measured DRAM bytes per launch of this kernel from the committed ncu capture (same cell count only)
+        try:   # measured DRAM bytes per launch of this kernel from the committed ncu capture (same workload and cell count only)
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(kern)
-            if tj and tj["cells"] == local_cells:
+            if tj and tj["cells"] == local_cells and kind == "abeclap":
                 traffic, traffic_src = tj["bytes"], tj["source"]
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": kern + " (finest MG level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": kern + " (finest level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_cell": bpc,
                     "cells_per_launch": local_cells, "launches": cnt, "avg_launch_ms": tms / cnt,
                     "share_of_solve_kernel_time": tms / tot_ms if tot_ms > 0 else None}
@@ -327,23 +452,39 @@ def b200_arm(args):
     for r in rep:
         by_kernel[r[0]] = by_kernel.get(r[0], 0.0) + r[3]
     top5 = sorted(by_kernel.items(), key=lambda kv: -kv[1])[:8]
+    resid_over_norm = hist[-1] / max(mlmg.initRHS(), mlmg.initResidual()) if hist else None
+    bottom_iters = list(mlmg.cgIters())[:4]
 
     # ---- CPU baseline (rank 0, N = 1): the reference itself on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_sample(n, mgs)
+        cpu = cpu_baseline_sample(n, mgs, ref=W["ref"])
+
+    # ---- the other BASELINE configurations (4: two-level AMR composite solve, 5: periodic Poisson weak scaling), light legs
+    others = None
+    if args.other_configs and kind == "abeclap":
+        name, boxes, scaling = W["name"], W["boxes"], W["scaling"]
+        del mlmg, W
+        others = []
+        for k2 in ("periodic", "amr"):
+            try:
+                others.append(run_light(k2))
+            except Exception as e:      # the headline number stands on its own
+                others.append({"workload": k2, "error": str(e)[:300]})
+    else:
+        name, boxes, scaling = W["name"], W["boxes"], W["scaling"]
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(n, mgs), "n_cell": n, "max_grid_size": mgs, "boxes": P["ba"].size(),
+            "config": {"workload": name, "n_cell": n, "max_grid_size": mgs, "boxes": boxes, "cells": cells,
                        "l2": "inputs_exceed_l2 (every finest-level field is >= 1 GiB at 512^3)", "smoother_fusion": args.fusion,
-                       "iters": iters, "final_resid_over_norm": hist[-1] / max(mlmg.initRHS(), mlmg.initResidual()) if hist else None,
+                       "iters": iters, "final_resid_over_norm": resid_over_norm, "bottom_iters": bottom_iters,
                        "max_err_vs_analytic": err, "solve_time_s": ms_per_step * 1e-3},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "parity_vs_reference": parity,
+            "parity_vs_reference": parity, "other_configs": others,
             "kernel_time_top": [[k, round(v, 3)] for k, v in top5], "kernel_time_total_ms": round(tot_ms, 3),
         }
         print(json.dumps(line), flush=True)

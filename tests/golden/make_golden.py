@@ -58,7 +58,12 @@ SOLVE += [
     ("p2_n64_g32_lev1_levelsolve", dict(prob_type=2, n_cell=64, max_grid_size=32, linop_maxorder=2, max_level=1, composite_solve=0)),
     ("p1_n64_g32_lev1_levelsolve", dict(prob_type=1, n_cell=64, max_grid_size=32, linop_maxorder=2, max_level=1, composite_solve=0)),
 ]
-BIG = [("p2_n512_g128", dict(prob_type=2, n_cell=512, max_grid_size=128, linop_maxorder=2))]
+BIG = [("p2_n512_g128", dict(prob_type=2, n_cell=512, max_grid_size=128, linop_maxorder=2)),
+       # BASELINE configs 4 and 5 at the sizes bench.py runs on one GPU: two-level composite solve with a 256^3 base, and the
+       # fully periodic Poisson problem at 512^3 (one GPU's share of the 1024^3 weak-scaling run)
+       ("p2_n256_g128_lev1_mo3", dict(prob_type=2, n_cell=256, max_grid_size=128, linop_maxorder=3, max_level=1)),
+       ("p5_n512_g128", dict(prob_type=5, n_cell=512, max_grid_size=128, linop_maxorder=2)),
+       ("p5_n256_g64", dict(prob_type=5, n_cell=256, max_grid_size=64, linop_maxorder=2))]
 PRIM = [
     ("p2_n16_g8_m0", dict(prob_type=2, n_cell=16, max_grid_size=8, linop_maxorder=2, prim_mglev=0, agg_grid_size=4)),
     ("p1_n16_g8_m0", dict(prob_type=1, n_cell=16, max_grid_size=8, linop_maxorder=3, prim_mglev=0, agg_grid_size=4)),

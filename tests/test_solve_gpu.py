@@ -76,6 +76,17 @@ def test_periodic_poisson(ab):
     assert diff <= SOL_TOL
 
 
+def test_periodic_poisson_256_config5(ab):
+    """BASELINE config 5 (fully periodic Poisson, BiCGStab bottom solver on the made-solvable bottom level) at 256^3 with 64^3
+    boxes against the reference: V-cycle count, residual history, solution (up to the constant) within 1e-10."""
+    ref, mlmg, diff = solve_case(ab, 5, 256, 64)
+    assert abs(mlmg.numIters() - ref["iters"]) <= 1
+    floor = 1e-13 * max(ref["rhsnorm0"], ref["resnorm0"])
+    for a, b in zip(mlmg.residualHistory(), ref["history"]):
+        assert a == pytest.approx(b, rel=1e-5, abs=floor)
+    assert diff <= SOL_TOL
+
+
 @pytest.mark.parametrize("bottom", ["smoother", "cg"])
 def test_bottom_solvers(ab, bottom):
     ref, mlmg, diff = solve_case(ab, 1, 64, 32, bottom=bottom)
@@ -84,7 +95,8 @@ def test_bottom_solvers(ab, bottom):
 
 
 # ---- 2-level AMR composite solves (BASELINE config #4 at reduced size): coarse/fine interpolation, reflux
-@pytest.mark.parametrize("prob_type,n,mgs,maxorder", [(1, 64, 32, 3), (2, 64, 32, 3), (2, 64, 32, 2), (2, 128, 64, 3)])
+# (the last case is BASELINE config 4 at its named size: 256^3 base + 256^3-cell refined patch, max_grid_size 128)
+@pytest.mark.parametrize("prob_type,n,mgs,maxorder", [(1, 64, 32, 3), (2, 64, 32, 3), (2, 64, 32, 2), (2, 128, 64, 3), (2, 256, 128, 3)])
 def test_two_level_composite(ab, prob_type, n, mgs, maxorder):
     ref, dump = run_ref(dump=True, mode="solve", prob_type=prob_type, n_cell=n, max_grid_size=mgs, linop_maxorder=maxorder,
                         agg_grid_size=32, max_level=1)
