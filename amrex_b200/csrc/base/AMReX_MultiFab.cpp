@@ -447,6 +447,49 @@ Real MultiFab::sum (bool local) const
     return r;
 }
 
+Real MultiFab::min (int comp, int nghost, bool local) const
+{
+    auto const& T = layout().tiles(nghost);
+    B200_KCALL(b200mg_minmax(T.n, T.d.data(), layout().d_vbox(), d_fabs(comp), 0, nghost, reduce_result_slot(0), reduce_scratch(T.n), Gpu::gpuStream()));
+    double r = fetch_reduce_result(0);
+    if (!local) { ParallelDescriptor::ReduceRealMin(&r, 1); }
+    return r;
+}
+
+Real MultiFab::max (int comp, int nghost, bool local) const
+{
+    auto const& T = layout().tiles(nghost);
+    B200_KCALL(b200mg_minmax(T.n, T.d.data(), layout().d_vbox(), d_fabs(comp), 1, nghost, reduce_result_slot(0), reduce_scratch(T.n), Gpu::gpuStream()));
+    double r = fetch_reduce_result(0);
+    if (!local) { ParallelDescriptor::ReduceRealMax(&r, 1); }
+    return r;
+}
+
+void MultiFab::Multiply (MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, int ng)
+{
+    auto const& T = dst.layout().tiles(ng);
+    for (int n = 0; n < ncomp; ++n) {
+        B200_KCALL(b200mg_multiply(T.n, T.d.data(), dst.layout().d_vbox(), dst.d_fabs(dcomp + n), src.d_fabs(scomp + n), ng, Gpu::gpuStream()));
+    }
+}
+
+void MultiFab::Divide (MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, int ng)
+{
+    auto const& T = dst.layout().tiles(ng);
+    for (int n = 0; n < ncomp; ++n) {
+        B200_KCALL(b200mg_divide(T.n, T.d.data(), dst.layout().d_vbox(), dst.d_fabs(dcomp + n), src.d_fabs(scomp + n), ng, Gpu::gpuStream()));
+    }
+}
+
+void MultiFab::SumBoundary (int scomp, int ncomp, Periodicity const& period)
+{
+    if (m_ngrow == 0 && boxArray().ixType().cellCentered()) { return; }
+    MultiFab tmp(boxArray(), DistributionMap(), ncomp, m_ngrow);
+    MultiFab::Copy(tmp, *this, scomp, 0, ncomp, m_ngrow);
+    setVal(0.0, scomp, ncomp, 0);
+    ParallelCopy(tmp, 0, scomp, ncomp, m_ngrow, 0, period, CpOp::ADD);
+}
+
 Real MultiFab::Dot (MultiFab const& x, MultiFab const& y, bool local)
 {
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(x.nComp() == 1 && y.nComp() == 1, "MultiFab::Dot: single-component arrays only");
@@ -554,6 +597,7 @@ struct CommPlan {
     struct Peer { int rank; long long offset, count; };
     std::vector<Peer> snd_peers, rcv_peers;
     long long snd_total = 0, rcv_total = 0;
+    std::vector<int> remote_fabs;                        // local indices of the destination fabs that receive remote data (sorted)
     double *sndbuf = nullptr, *rcvbuf = nullptr;
     long long buf_ncomp = 0;
     cudaEvent_t ev_packed = nullptr, ev_arrived = nullptr;
@@ -575,11 +619,31 @@ b200mg_copytag make_tag (CopyComTag const& t, int dst_fab, int src_fab, long lon
     return r;
 }
 
-void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc)
+// cross_ng != nullptr: the plan serves a cross-stencil FillBoundary with that many ghost cells - local tags are clipped to the
+// face slabs of the destination box, as the reference does for its send / receive tags (AMReX_FabArrayBase.cpp:835-870); the
+// edge and corner pieces (which its local list keeps, and which a cross stencil never reads) are not copied
+void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc, const IntVect* cross_ng = nullptr)
 {
     std::vector<b200mg_copytag> h;
     auto npts = [] (CopyComTag const& t) { return int(std::min<Long>(t.dbox.numPts(), Long(1) << 30)); };
-    for (auto const& t : P.meta.LocTags) { h.push_back(make_tag(t, ldst.localIndex(t.dstIndex), lsrc.localIndex(t.srcIndex), 0)); P.maxloc = std::max(P.maxloc, npts(t)); }
+    for (auto const& t : P.meta.LocTags) {
+        const int ld = ldst.localIndex(t.dstIndex), ls = lsrc.localIndex(t.srcIndex);
+        if (cross_ng == nullptr) { h.push_back(make_tag(t, ld, ls, 0)); P.maxloc = std::max(P.maxloc, npts(t)); continue; }
+        Box const& vbx = ldst.box(ld);
+        const IntVect d2s = t.sbox.smallEnd() - t.dbox.smallEnd();
+        for (int dir = 0; dir < 3; ++dir) {
+            for (int side = 0; side < 2; ++side) {
+                Box slab = vbx;
+                if (side == 0) { slab.setSmall(dir, vbx.smallEnd(dir) - (*cross_ng)[dir]); slab.setBig(dir, vbx.smallEnd(dir) - 1); }
+                else { slab.setSmall(dir, vbx.bigEnd(dir) + 1); slab.setBig(dir, vbx.bigEnd(dir) + (*cross_ng)[dir]); }
+                slab &= t.dbox;
+                if (!slab.ok()) { continue; }
+                CopyComTag c = t;
+                c.dbox = slab; c.sbox = slab + d2s;
+                h.push_back(make_tag(c, ld, ls, 0)); P.maxloc = std::max(P.maxloc, npts(c));
+            }
+        }
+    }
     P.nloc = int(h.size()); P.d_loc.assign(h);
     h.clear();
     long long off = 0;
@@ -592,17 +656,23 @@ void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc)
     h.clear(); off = 0;
     for (auto const& kv : P.meta.RcvTags) {
         const long long start = off;
-        for (auto const& t : kv.second) { h.push_back(make_tag(t, ldst.localIndex(t.dstIndex), -1, off)); off += t.dbox.numPts(); P.maxrcv = std::max(P.maxrcv, npts(t)); }
+        for (auto const& t : kv.second) {
+            h.push_back(make_tag(t, ldst.localIndex(t.dstIndex), -1, off)); off += t.dbox.numPts(); P.maxrcv = std::max(P.maxrcv, npts(t));
+            P.remote_fabs.push_back(ldst.localIndex(t.dstIndex));
+        }
         P.rcv_peers.push_back({kv.first, start, off - start});
     }
+    std::sort(P.remote_fabs.begin(), P.remote_fabs.end());
+    P.remote_fabs.erase(std::unique(P.remote_fabs.begin(), P.remote_fabs.end()), P.remote_fabs.end());
     P.rcv_total = off; P.nrcv = int(h.size()); P.d_rcv.assign(h);
 }
 
-// Halo exchange of one plan.  The NVLink transfer (grouped ncclSend/ncclRecv on the communication stream) runs concurrently
-// with the intra-GPU copies on the compute stream: pack -> [event] -> send/recv on commStream, local copies meanwhile on
-// gpuStream, then gpuStream waits for the transfer and unpacks (FillBoundary_nowait / FillBoundary_finish of the
-// reference, AMReX_FabArrayCommI.H:8-247, with the local copies in between as in FBEP_nowait :118-135).
-void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op)
+// Halo exchange of one plan in two halves (FillBoundary_nowait / FillBoundary_finish of the reference,
+// AMReX_FabArrayCommI.H:8-247, with the local copies in between as in FBEP_nowait :118-135).  start: pack -> [event] ->
+// grouped ncclSend/ncclRecv on the communication stream (NVLink), and meanwhile the intra-GPU copies on the compute stream;
+// finish: the compute stream waits for the transfer and unpacks.  Whatever the caller launches on the compute stream between
+// the two halves (the smoother on the boxes without remote neighbours) overlaps the transfer.
+void start_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op)
 {
     cudaStream_t s = Gpu::gpuStream();
     const bool remote = (P.snd_total + P.rcv_total) > 0;
@@ -615,7 +685,6 @@ void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, i
             P.rcvbuf = static_cast<double*>(The_Arena()->alloc(std::max<long long>(1, P.rcv_total * ncomp) * sizeof(double)));
             P.buf_ncomp = ncomp;
         }
-        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(ncomp == 1, "remote halo exchange implemented for ncomp == 1");
         if (!P.ev_packed) {
             AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&P.ev_packed, cudaEventDisableTiming));
             AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&P.ev_arrived, cudaEventDisableTiming));
@@ -646,10 +715,23 @@ void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, i
         if (Gpu::debugSync()) { Gpu::check(Gpu::debugSyncNow(), "[B200MG_DEBUG_SYNC] ncclSend/ncclRecv group", __FILE__, __LINE__); }
     }
     B200_KCALL(b200mg_copy_tags(P.nloc, P.d_loc.data(), dst.d_fabs(), src.d_fabs(), nullptr, ncomp, scomp, dcomp, int(op), P.maxloc, s));
+}
+
+void finish_plan_exchange (CommPlan& P, MultiFab& dst, int scomp, int dcomp, int ncomp, CpOp op)
+{
+    cudaStream_t s = Gpu::gpuStream();
+    const bool remote = (P.snd_total + P.rcv_total) > 0;
+    static const bool overlap = std::getenv("B200MG_NO_COMM_OVERLAP") == nullptr;
     if (remote) {
         if (overlap) { AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(s, P.ev_arrived, 0)); }
         B200_KCALL(b200mg_copy_tags(P.nrcv, P.d_rcv.data(), dst.d_fabs(), nullptr, P.rcvbuf, ncomp, scomp, dcomp, int(op), P.maxrcv, s));
     }
+}
+
+void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op)
+{
+    start_plan(P, dst, src, scomp, dcomp, ncomp, op);
+    finish_plan_exchange(P, dst, scomp, dcomp, ncomp, op);
 }
 
 using FBKey = std::tuple<std::uint64_t, std::uint64_t, int, int, int, int, int, int, int>;
@@ -680,20 +762,50 @@ void evict_by_id (std::uint64_t id, int kind)
 void clear_comm_caches () { fb_cache().clear(); cpc_cache().clear(); }
 std::size_t comm_cache_size () { return fb_cache().size() + cpc_cache().size() + layouts().size(); }
 
-void MultiFab::FillBoundary (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross)
+namespace {
+CommPlan& fb_plan (MultiFab& mf, IntVect const& nghost, Periodicity const& period, bool cross)
 {
-    if (nghost.max() <= 0) { return; }
-    AMREX_ALWAYS_ASSERT(nghost.allLE(IntVect(m_ngrow)));
-    FBKey key{m_ba.id(), m_dm.id(), nghost[0], nghost[1], nghost[2], int(cross),
+    FBKey key{mf.boxArray().id(), mf.DistributionMap().id(), nghost[0], nghost[1], nghost[2], int(cross),
               period.intVect()[0], period.intVect()[1], period.intVect()[2]};
     auto it = fb_cache().find(key);
     if (it == fb_cache().end()) {
         auto P = std::make_unique<CommPlan>();
-        define_fb_metadata(P->meta, m_ba, m_dm, nghost, cross, period, ParallelDescriptor::MyProc());
-        finish_plan(*P, layout(), layout());
+        define_fb_metadata(P->meta, mf.boxArray(), mf.DistributionMap(), nghost, cross, period, ParallelDescriptor::MyProc());
+        finish_plan(*P, mf.layout(), mf.layout(), cross ? &nghost : nullptr);
         it = fb_cache().emplace(key, std::move(P)).first;
     }
-    execute_plan(*it->second, *this, *this, scomp, scomp, ncomp, CpOp::COPY);
+    return *it->second;
+}
+}
+
+void MultiFab::FillBoundary (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross)
+{
+    if (m_ngrow == 0 || nghost.max() == 0) { return; }
+    AMREX_ALWAYS_ASSERT(nghost.allLE(IntVect(m_ngrow)));
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_fb_pending == nullptr, "FillBoundary while a FillBoundary_nowait is pending on this MultiFab");
+    execute_plan(fb_plan(*this, nghost, period, cross), *this, *this, scomp, scomp, ncomp, CpOp::COPY);
+}
+
+void MultiFab::FillBoundary_nowait (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross)
+{
+    if (m_ngrow == 0 || nghost.max() == 0) { return; }
+    AMREX_ALWAYS_ASSERT(nghost.allLE(IntVect(m_ngrow)));
+    AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_fb_pending == nullptr, "FillBoundary_nowait: the previous one was not finished");
+    CommPlan& P = fb_plan(*this, nghost, period, cross);
+    start_plan(P, *this, *this, scomp, scomp, ncomp, CpOp::COPY);
+    m_fb_pending = &P; m_fb_scomp = scomp; m_fb_ncomp = ncomp;
+}
+
+void MultiFab::FillBoundary_finish ()
+{
+    if (m_fb_pending == nullptr) { return; }
+    finish_plan_exchange(*static_cast<CommPlan*>(m_fb_pending), *this, m_fb_scomp, m_fb_scomp, m_fb_ncomp, CpOp::COPY);
+    m_fb_pending = nullptr;
+}
+
+std::vector<int> const& MultiFab::FillBoundaryRemoteFabs (IntVect const& nghost, Periodicity const& period, bool cross)
+{
+    return fb_plan(*this, nghost, period, cross).remote_fabs;
 }
 
 void MultiFab::ParallelCopy (MultiFab const& src, int scomp, int dcomp, int ncomp, int src_ng, int dst_ng,

@@ -183,6 +183,7 @@ void reduce_small (T* v, int n, ncclDataType_t dt, ncclRedOp_t op)
 
 void ReduceRealSum (double* v, int n) { reduce_small(v, n, ncclDouble, ncclSum); }
 void ReduceRealMax (double* v, int n) { reduce_small(v, n, ncclDouble, ncclMax); }
+void ReduceRealMin (double* v, int n) { reduce_small(v, n, ncclDouble, ncclMin); }
 void ReduceLongSum (long long* v, int n) { reduce_small(v, n, ncclInt64, ncclSum); }
 void Barrier () { double z = 0; ReduceRealSum(&z, 1); }
 

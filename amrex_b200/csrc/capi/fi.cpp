@@ -5,6 +5,8 @@
 #include "amrex_b200_fi.h"
 
 #include <cstring>
+#include <iostream>
+#include <sstream>
 #include <limits>
 #include <string>
 
@@ -13,6 +15,7 @@ using namespace amrex;
 namespace amrex { void clear_comm_caches (); }
 
 namespace {
+void Print0 (std::string const& s) { if (ParallelDescriptor::IOProcessor()) { std::cout << s << std::flush; } }
 std::string g_err;
 bool g_has_err = false;
 void set_err (const char* where, const char* what) { g_err = std::string(where) + ": " + what; g_has_err = true; }
@@ -171,6 +174,158 @@ void amrex_fi_multifab_fill_boundary (MultiFab* mf, const Geometry* geom, int c,
 {
     FI_VOID( mf->FillBoundary(c, nc, geom->periodicity(), cross != 0); )
 }
+// ---- the rest of the reference's MultiFab / iMultiFab / MFIter / Geometry entries (Src/F_Interfaces/Base/AMReX_multifab_fi.cpp,
+//      AMReX_geometry_fi.cpp, AMReX_distromap_fi.cpp, AMReX_boxarray_fi.cpp): same names, same argument order.  Data pointers
+//      are DEVICE pointers (the fields live in HBM); the iteration helpers are host-side bookkeeping over the local boxes.
+namespace { inline int uniform_ng (const int* ng, const char* who) { if (!(ng[0] == ng[1] && ng[1] == ng[2])) { throw std::runtime_error(std::string(who) + ": uniform ghost width required"); } return ng[0]; } }
+Real amrex_fi_multifab_min (const MultiFab* mf, int comp, int nghost) { FI_TRY return mf->min(comp, nghost); FI_CATCH(return kNaN) }
+Real amrex_fi_multifab_max (const MultiFab* mf, int comp, int nghost) { FI_TRY return mf->max(comp, nghost); FI_CATCH(return kNaN) }
+Real amrex_fi_multifab_norm1 (const MultiFab* mf, int comp) { FI_TRY return mf->norm1(comp); FI_CATCH(return kNaN) }
+Real amrex_fi_multifab_norm2 (const MultiFab* mf, int comp) { FI_TRY return mf->norm2(comp); FI_CATCH(return kNaN) }
+void amrex_fi_multifab_multiply (MultiFab* d, const MultiFab* s, int sc, int dc, int nc, const int* ng) { FI_VOID( MultiFab::Multiply(*d, *s, sc, dc, nc, uniform_ng(ng, "multiply")); ) }
+void amrex_fi_multifab_divide (MultiFab* d, const MultiFab* s, int sc, int dc, int nc, const int* ng) { FI_VOID( MultiFab::Divide(*d, *s, sc, dc, nc, uniform_ng(ng, "divide")); ) }
+void amrex_fi_multifab_lincomb (MultiFab* d, Real a, const MultiFab* s1, int sc1, Real b, const MultiFab* s2, int sc2, int dc, int nc, const int* ng)
+{
+    // dst = a*src1 + b*src2 (MultiFab::LinComb, AMReX_MultiFab.cpp): copy src2, then dst = a*src1 + b*dst
+    FI_VOID( const int g = uniform_ng(ng, "lincomb");
+             if (d != s2) { MultiFab::Copy(*d, *s2, sc2, dc, nc, g); }
+             AMREX_ALWAYS_ASSERT_WITH_MESSAGE(d != s1 || d == s2, "lincomb: dst may alias src2 only");
+             MultiFab::LinComb(*d, a, *s1, b, sc1, dc, nc, g); )
+}
+void amrex_fi_multifab_parallelcopy_gv (MultiFab* d, const MultiFab* s, int sc, int dc, int nc, const int* srcng, const int* dstng, const Geometry* geom)
+{
+    FI_VOID( d->ParallelCopy(*s, sc, dc, nc, uniform_ng(srcng, "parallelcopy_gv"), uniform_ng(dstng, "parallelcopy_gv"), geom->periodicity()); )
+}
+void amrex_fi_multifab_sum_boundary (MultiFab* mf, const Geometry* geom, int icomp, int ncomp) { FI_VOID( mf->SumBoundary(icomp, ncomp, geom->periodicity()); ) }
+// node-centred synchronisation (OwnerMask / OverrideSync / AverageSync) belongs to the nodal solvers: outside the cell-centred path
+void amrex_fi_build_owner_imultifab (iMultiFab**, const BoxArray**, const DistributionMapping**, const MultiFab*, const Geometry*)
+{ set_err(__func__, "nodal owner masks are outside the cell-centred MLMG path of this library"); }
+void amrex_fi_multifab_override_sync (MultiFab*, const Geometry*) { set_err(__func__, "nodal OverrideSync is outside the cell-centred MLMG path of this library"); }
+void amrex_fi_multifab_override_sync_mask (MultiFab*, const Geometry*, const iMultiFab*) { set_err(__func__, "nodal OverrideSync is outside the cell-centred MLMG path of this library"); }
+void amrex_fi_multifab_average_sync (MultiFab*, const Geometry*) { set_err(__func__, "nodal AverageSync is outside the cell-centred MLMG path of this library"); }
+void amrex_fi_new_multifab_alias (MultiFab**, const MultiFab*, int, int) { set_err(__func__, "aliased MultiFabs are not supported: copy the components (amrex_fi_multifab_copy)"); }
+
+// iMultiFab
+void amrex_fi_new_imultifab (iMultiFab** imf, const BoxArray** ba, const DistributionMapping** dm, int nc, const int* ng, const int* nodal)
+{
+    FI_VOID( *imf = new iMultiFab(amrex::convert(**ba, IntVect(nodal[0], nodal[1], nodal[2])), **dm, nc, uniform_ng(ng, "new_imultifab"));
+             *ba = &((*imf)->boxArray()); *dm = &((*imf)->DistributionMap()); )
+}
+void amrex_fi_new_imultifab_alias (iMultiFab**, const iMultiFab*, int, int) { set_err(__func__, "aliased iMultiFabs are not supported"); }
+void amrex_fi_delete_imultifab (iMultiFab* imf) { delete imf; }
+void amrex_fi_imultifab_setval (iMultiFab* imf, int val, int ic, int nc, const int* ng)
+{
+    FI_VOID( const int g = uniform_ng(ng, "imultifab_setval");
+             AMREX_ALWAYS_ASSERT(g <= imf->nGrow() && ic >= 0 && ic + nc <= imf->nComp());
+             for (int li = 0; li < imf->local_size(); ++li) {      // device memset per row range: the whole grown fab when g == nGrow
+                 auto const& d = imf->desc(li);
+                 const Box b = amrex::grow(imf->layout().box(li), g);
+                 std::vector<int> row(std::size_t(b.length(0)), val);
+                 for (int n = ic; n < ic + nc; ++n) for (int k = b.smallEnd(2); k <= b.bigEnd(2); ++k) for (int j = b.smallEnd(1); j <= b.bigEnd(1); ++j) {
+                     int* p = d.p + (b.smallEnd(0) - d.lo[0]) + (j - d.lo[1]) * d.jstride + (k - d.lo[2]) * d.kstride + n * d.nstride;
+                     Gpu::htod_memcpy_async(p, row.data(), row.size() * sizeof(int));
+                 }
+                 Gpu::streamSynchronize();
+             } )
+}
+
+// MFIter: iteration over the local boxes (no tiling on the device: a tile is the whole box)
+int amrex_fi_mfiter_allow_multiple (int allow) { return allow; }
+void amrex_fi_new_mfiter_r (MFIter** mfi, MultiFab* mf, int, int) { FI_VOID( *mfi = new MFIter(*mf); ) }
+void amrex_fi_new_mfiter_i (MFIter** mfi, iMultiFab* imf, int, int) { FI_VOID( *mfi = new MFIter(*imf); ) }
+void amrex_fi_new_mfiter_rs (MFIter** mfi, MultiFab* mf, const int*, int) { FI_VOID( *mfi = new MFIter(*mf); ) }
+void amrex_fi_new_mfiter_is (MFIter** mfi, iMultiFab* imf, const int*, int) { FI_VOID( *mfi = new MFIter(*imf); ) }
+void amrex_fi_new_mfiter_badm (MFIter** mfi, BoxArray* ba, DistributionMapping* dm, int, int) { FI_VOID( *mfi = new MFIter(*ba, *dm); ) }
+void amrex_fi_new_mfiter_badm_s (MFIter** mfi, BoxArray* ba, DistributionMapping* dm, const int*, int) { FI_VOID( *mfi = new MFIter(*ba, *dm); ) }
+void amrex_fi_delete_mfiter (MFIter* mfi) { delete mfi; }
+void amrex_fi_increment_mfiter (MFIter* mfi, int* isvalid) { ++(*mfi); *isvalid = mfi->isValid() ? 1 : 0; }
+void amrex_fi_mfiter_is_valid (MFIter* mfi, int* isvalid) { *isvalid = mfi->isValid() ? 1 : 0; }
+int amrex_fi_mfiter_grid_index (MFIter* mfi) { return mfi->index(); }
+int amrex_fi_mfiter_local_tile_index (MFIter*) { return 0; }
+namespace {
+inline void box_out (Box const& bx, int lo[3], int hi[3], int* nodal)
+{
+    for (int d = 0; d < 3; ++d) { lo[d] = bx.smallEnd(d); hi[d] = bx.bigEnd(d); if (nodal) { nodal[d] = bx.ixType().test(d) ? 1 : 0; } }
+}
+}
+void amrex_fi_mfiter_tilebox (MFIter* mfi, int lo[3], int hi[3], int nodal[3]) { box_out(mfi->tilebox(), lo, hi, nodal); }
+void amrex_fi_mfiter_tilebox_iv (MFIter* mfi, int lo[3], int hi[3], const int nodal[3])
+{
+    box_out(amrex::convert(amrex::enclosedCells(mfi->tilebox()), IntVect(nodal[0], nodal[1], nodal[2])), lo, hi, nullptr);
+}
+void amrex_fi_mfiter_nodaltilebox (MFIter* mfi, int dir, int lo[3], int hi[3], int nodal[3])
+{
+    box_out(amrex::convert(amrex::enclosedCells(mfi->tilebox()), IntVect::TheDimensionVector(dir)), lo, hi, nodal);
+}
+void amrex_fi_mfiter_growntilebox (MFIter* mfi, int lo[3], int hi[3], int ng, int nodal[3]) { box_out(mfi->growntilebox(ng), lo, hi, nodal); }
+void amrex_fi_mfiter_grownnodaltilebox (MFIter* mfi, int lo[3], int hi[3], int dir, int ng, int nodal[3])
+{
+    box_out(amrex::grow(amrex::convert(amrex::enclosedCells(mfi->tilebox()), IntVect::TheDimensionVector(dir)), ng), lo, hi, nodal);
+}
+void amrex_fi_mfiter_validbox (MFIter* mfi, int lo[3], int hi[3], int nodal[3]) { box_out(mfi->validbox(), lo, hi, nodal); }
+void amrex_fi_mfiter_fabbox (MFIter* mfi, int lo[3], int hi[3], int nodal[3]) { box_out(mfi->fabbox(), lo, hi, nodal); }
+void amrex_fi_multifab_dataptr_iter (MultiFab* mf, MFIter* mfi, Real** dp, int lo[3], int hi[3])
+{
+    FI_VOID( auto const& d = mf->desc(mfi->LocalIndex()); *dp = d.p; for (int a = 0; a < 3; ++a) { lo[a] = d.lo[a]; hi[a] = d.hi[a]; } )
+}
+void amrex_fi_imultifab_dataptr (iMultiFab* imf, MFIter* mfi, int** dp, int lo[3], int hi[3])
+{
+    FI_VOID( auto const& d = imf->desc(mfi->LocalIndex()); *dp = d.p; for (int a = 0; a < 3; ++a) { lo[a] = d.lo[a]; hi[a] = d.hi[a]; } )
+}
+
+// Geometry / DistributionMapping / BoxArray leftovers
+void amrex_fi_geometry_get_pmask (const Geometry* geom, int is_per[3]) { for (int d = 0; d < 3; ++d) { is_per[d] = geom->isPeriodic(d) ? 1 : 0; } }
+void amrex_fi_geometry_get_probdomain (const Geometry* geom, Real problo[3], Real probhi[3])
+{
+    for (int d = 0; d < 3; ++d) { problo[d] = geom->ProbLo()[d]; probhi[d] = geom->ProbHi()[d]; }
+}
+void amrex_fi_clone_distromap (DistributionMapping** dmo, const DistributionMapping* dmi) { FI_VOID( *dmo = new DistributionMapping(*dmi); ) }
+int amrex_fi_distromap_issame (const DistributionMapping* a, const DistributionMapping* b) { return (*a == *b) ? 1 : 0; }
+void amrex_fi_print_distromap (const DistributionMapping* dm)
+{
+    std::string o = "(DistributionMapping"; for (int p : dm->ProcessorMap()) { o += " " + std::to_string(p); } Print0(o + ")\n");
+}
+int amrex_fi_boxarray_intersects_box (const BoxArray* ba, const int lo[3], const int hi[3])
+{
+    FI_TRY std::vector<std::pair<int, Box>> is; ba->intersections(Box(IntVect(lo[0], lo[1], lo[2]), IntVect(hi[0], hi[1], hi[2]), ba->ixType()), is);
+           return is.empty() ? 0 : 1; FI_CATCH(return 0)
+}
+void amrex_fi_print_boxarray (const BoxArray* ba)
+{
+    std::string o = "(BoxArray maxbox(" + std::to_string(ba->size()) + ")\n";
+    for (int i = 0, N = int(ba->size()); i < N; ++i) {
+        Box const& b = (*ba)[i];
+        o += "  ((" + std::to_string(b.smallEnd(0)) + "," + std::to_string(b.smallEnd(1)) + "," + std::to_string(b.smallEnd(2)) + ") ("
+           + std::to_string(b.bigEnd(0)) + "," + std::to_string(b.bigEnd(1)) + "," + std::to_string(b.bigEnd(2)) + "))\n";
+    }
+    Print0(o + ")\n");
+}
+void amrex_fi_print_box (const int lo[3], const int hi[3], const int nodal[3])
+{
+    std::ostringstream o;
+    o << "((" << lo[0] << "," << lo[1] << "," << lo[2] << ") (" << hi[0] << "," << hi[1] << "," << hi[2] << ") (" << nodal[0] << "," << nodal[1] << "," << nodal[2] << "))\n";
+    Print0(o.str());
+}
+// multi-level averaging (Src/F_Interfaces/Base/AMReX_multifabutil_fi.cpp)
+void amrex_fi_average_down (const MultiFab* S_fine, MultiFab* S_crse, const Geometry*, const Geometry*, int scomp, int ncomp, int rr)
+{
+    FI_VOID( amrex::average_down(*S_fine, *S_crse, scomp, ncomp, rr); )
+}
+void amrex_fi_average_down_faces (MultiFab const* fmf[], MultiFab* cmf[], const Geometry*, int scomp, int ncomp, int rr)
+{
+    FI_VOID( AMREX_ALWAYS_ASSERT_WITH_MESSAGE(scomp == 0 && ncomp == 1, "average_down_faces: one component");
+             for (int d = 0; d < 3; ++d) { amrex::average_down_faces(*fmf[d], *cmf[d], d, rr); } )
+}
+void amrex_fi_average_cellcenter_to_face (MultiFab* fc[], const MultiFab* cc, const Geometry* geom)
+{
+    FI_VOID( amrex::average_cellcenter_to_face({{fc[0], fc[1], fc[2]}}, *cc, *geom); )
+}
+void amrex_fi_average_down_cell_node (const MultiFab* S_fine, MultiFab* S_crse, int scomp, int ncomp, int rr)
+{
+    FI_VOID( AMREX_ALWAYS_ASSERT_WITH_MESSAGE(S_fine->ixType().cellCentered(), "average_down_cell_node: cell-centred data only (nodal averaging is outside this library's path)");
+             amrex::average_down(*S_fine, *S_crse, scomp, ncomp, rr); )
+}
+
 Real amrex_b200_multifab_dot (const MultiFab* x, const MultiFab* y) { FI_TRY return MultiFab::Dot(*x, *y); FI_CATCH(return kNaN) }
 void amrex_b200_multifab_upload (MultiFab* mf, const Real* h, const int lo[3], const int hi[3], int comp, int ng)
 {

@@ -14,6 +14,7 @@
 #include "bottom_solve.cuh"
 
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 using namespace b200mg;
@@ -33,10 +34,31 @@ struct Stamps {
     }
 };
 
-// WIDE: the team is the whole grid, else the calling CTA
-template <bool WIDE> __device__ __forceinline__ void team_sync ()
+// Grid barrier of the cooperative launch (all CTAs co-resident): one counter in global memory that only grows - CTA b's
+// thread 0 adds 1 and spins until the count reaches the barrier's target (epoch * CTAs), block barriers on both sides, the
+// fences make the CTA's writes visible to the grid and invalidate this SM's L1 before the CTA reads other CTAs' data.
+// Measured ~3x cheaper than cooperative_groups' grid.sync() here (B200MG_LEG_CG_SYNC=1 selects that one for comparison).
+struct GridBar { unsigned* counter; unsigned target; unsigned nctas; int use_cg; };
+
+__device__ __forceinline__ void grid_barrier (GridBar& B)
 {
-    if constexpr (WIDE) { cg::this_grid().sync(); } else { __syncthreads(); }
+    if (B.use_cg) { cg::this_grid().sync(); return; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        B.target += B.nctas;
+        __threadfence();
+        atomicAdd(B.counter, 1u);
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(B.counter) : "memory"); } while (v < B.target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// WIDE: the team is the whole grid, else the calling CTA
+template <bool WIDE> __device__ __forceinline__ void team_sync (GridBar& B)
+{
+    if constexpr (WIDE) { grid_barrier(B); } else { __syncthreads(); }
 }
 
 template <class F>
@@ -400,12 +422,12 @@ __device__ __forceinline__ bool fast_level (const b200mg_leg_level& L)
 
 // MLCellLinOpT::smooth (AMReX_MLCellLinOp.H:1206-1217): per colour, boundary values (inline) + sweep
 template <bool ABEC, bool WIDE>
-__device__ __forceinline__ void smooth (const b200mg_leg_level& L, const FaceBC& F, double alpha, const Team& T, Stamps& st, int id)
+__device__ __forceinline__ void smooth (const b200mg_leg_level& L, const FaceBC& F, double alpha, const Team& T, Stamps& st, int id, GridBar& bar)
 {
     const bool fast = fast_level(L);
     for (int redblack = 0; redblack < 2; ++redblack) {
         if (fast) { sweep_fast<ABEC>(L, F, alpha, redblack, T); } else { sweep<ABEC>(L, F, alpha, redblack, T); }
-        team_sync<WIDE>();
+        team_sync<WIDE>(bar);
         st.mark(id + redblack);
     }
 }
@@ -468,8 +490,10 @@ __device__ __forceinline__ void load_bc (BoxBC& bc, const b200mg_leg_level& L)
 
 template <bool ABEC>
 __global__ void __launch_bounds__(kLegThreads, 1)
-k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out)
+k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out, unsigned* __restrict__ bar_counter, int use_cg)
 {
+    __shared__ GridBar bar;
+    if (threadIdx.x == 0) { bar.counter = bar_counter; bar.target = 0u; bar.nctas = gridDim.x; bar.use_cg = use_cg; }
     __shared__ b200mg_leg_args S;
     __shared__ BoxBC sbc[B200MG_LEG_MAX_LEVELS];
     __shared__ BottomArgs B;
@@ -505,20 +529,20 @@ k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out)
     st.mark(0);
 
     // ---- down: cor = 0, nu1 smooths, residual, restriction (mgVcycle, AMReX_MLMG.H:1318-1345)
-    if (wide[0]) { zero_field(S.lev[0], TW); cg::this_grid().sync(); }
+    if (wide[0]) { zero_field(S.lev[0], TW); grid_barrier(bar); }
     else if (cta == 0) { zero_field(S.lev[0], T0); __syncthreads(); }
     for (int l = 0; l < nl - 1; ++l) {
         const b200mg_leg_level& L = S.lev[l];
         if (wide[l]) {
-            for (int i = 0; i < S.nu1; ++i) { smooth<ABEC, true>(L, fbc[l], alpha, TW, st, l * 16); }
+            for (int i = 0; i < S.nu1; ++i) { smooth<ABEC, true>(L, fbc[l], alpha, TW, st, l * 16, bar); }
             residual<ABEC>(L, fbc[l], alpha, TW);
-            cg::this_grid().sync();
+            grid_barrier(bar);
             st.mark(l * 16 + 2);
             restrict_and_zero(L, S.lev[l + 1], TW);
-            cg::this_grid().sync();
+            grid_barrier(bar);
             st.mark(l * 16 + 3);
         } else if (cta == 0) {
-            for (int i = 0; i < S.nu1; ++i) { smooth<ABEC, false>(L, fbc[l], alpha, T0, st, l * 16); }
+            for (int i = 0; i < S.nu1; ++i) { smooth<ABEC, false>(L, fbc[l], alpha, T0, st, l * 16, bar); }
             residual<ABEC>(L, fbc[l], alpha, T0);
             __syncthreads();
             st.mark(l * 16 + 2);
@@ -531,11 +555,11 @@ k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out)
     // ---- bottom (bottomSolve, AMReX_MLMG.H:1460-1576): BiCGStab by CTA 0 alone, block barriers only
     const b200mg_leg_level& LB = S.lev[nl - 1];
     if (S.bottom_mode == 1 && wide[nl - 1]) {                       // BottomSolver::smoother on a big bottom level
-        for (int i = 0; i < S.nuf; ++i) { smooth<ABEC, true>(LB, fbc[nl - 1], alpha, TW, st, (nl - 1) * 16 + 8); }
+        for (int i = 0; i < S.nuf; ++i) { smooth<ABEC, true>(LB, fbc[nl - 1], alpha, TW, st, (nl - 1) * 16 + 8, bar); }
     } else if (cta == 0) {
         int ret = 0, iter = 0;
         if (S.bottom_mode == 1) {
-            for (int i = 0; i < S.nuf; ++i) { smooth<ABEC, false>(LB, fbc[nl - 1], alpha, T0, st, (nl - 1) * 16 + 8); }
+            for (int i = 0; i < S.nuf; ++i) { smooth<ABEC, false>(LB, fbc[nl - 1], alpha, T0, st, (nl - 1) * 16 + 8, bar); }
         } else {
             if (tid == 0) {
                 B.vb = LB.vb;
@@ -567,7 +591,7 @@ k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out)
                 __syncthreads();
             }
             const int n = (ret == 0) ? S.nub : S.nuf;
-            for (int i = 0; i < n; ++i) { smooth<ABEC, false>(LB, fbc[nl - 1], alpha, T0, st, (nl - 1) * 16 + 8); }
+            for (int i = 0; i < n; ++i) { smooth<ABEC, false>(LB, fbc[nl - 1], alpha, T0, st, (nl - 1) * 16 + 8, bar); }
         }
         if (tid == 0 && out != nullptr) { out[0] = double(ret); out[1] = double(iter); }
     }
@@ -577,16 +601,16 @@ k_coarse_leg (const b200mg_leg_args* __restrict__ gA, double* __restrict__ out)
     for (int l = nl - 2; l >= 0; --l) {
         const b200mg_leg_level& L = S.lev[l];
         if (wide[l]) {
-            if (!joined) { __threadfence(); cg::this_grid().sync(); joined = true; }
+            if (!joined) { __threadfence(); grid_barrier(bar); joined = true; }
             prolong_add(L, S.lev[l + 1], TW);
-            cg::this_grid().sync();
+            grid_barrier(bar);
             st.mark(l * 16 + 4);
-            for (int i = 0; i < S.nu2; ++i) { smooth<ABEC, true>(L, fbc[l], alpha, TW, st, l * 16 + 5); }
+            for (int i = 0; i < S.nu2; ++i) { smooth<ABEC, true>(L, fbc[l], alpha, TW, st, l * 16 + 5, bar); }
         } else if (cta == 0) {
             prolong_add(L, S.lev[l + 1], T0);
             __syncthreads();
             st.mark(l * 16 + 4);
-            for (int i = 0; i < S.nu2; ++i) { smooth<ABEC, false>(L, fbc[l], alpha, T0, st, l * 16 + 5); }
+            for (int i = 0; i < S.nu2; ++i) { smooth<ABEC, false>(L, fbc[l], alpha, T0, st, l * 16 + 5, bar); }
         }
     }
 }
@@ -599,6 +623,12 @@ extern "C" {
 
 int b200mg_coarse_leg (int abec, const b200mg_leg_args* d_args, double* d_out, int ctas, cudaStream_t s)
 {
+    static unsigned* d_counter = nullptr;                 // the grid barrier's counter, zeroed ahead of every launch
+    static const int use_cg = std::getenv("B200MG_LEG_CG_SYNC") != nullptr;
+    if (!d_counter) {
+        const cudaError_t e = cudaMalloc(&d_counter, 64);
+        if (e != cudaSuccess) { return int(e); }
+    }
     auto kern = abec ? k_coarse_leg<true> : k_coarse_leg<false>;
     int& maxc = g_max_ctas[abec ? 1 : 0];
     if (maxc == 0) {
@@ -613,7 +643,12 @@ int b200mg_coarse_leg (int abec, const b200mg_leg_args* d_args, double* d_out, i
     }
     if (ctas < 1) { return int(cudaErrorInvalidValue); }
     if (ctas > maxc) { ctas = maxc; }
-    void* args[2] = {(void*)&d_args, (void*)&d_out};
+    {
+        const cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(unsigned), s);
+        if (e != cudaSuccess) { return int(e); }
+    }
+    int cgflag = use_cg;
+    void* args[4] = {(void*)&d_args, (void*)&d_out, (void*)&d_counter, (void*)&cgflag};
     const cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(unsigned(ctas), 1, 1), dim3(kLegThreads, 1, 1), args, 0, s);
     if (e != cudaSuccess) { return int(e); }
     return last_error();

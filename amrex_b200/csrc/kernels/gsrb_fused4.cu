@@ -535,25 +535,38 @@ int b200mg_gsrb4 (int abec, int nboxes, const b200mg_box* h_vbox,
                   const b200mg_fab* h_f, const b200mg_ifab* h_m,
                   double alpha, double dhx, double dhy, double dhz, int phi_zero, cudaStream_t s)
 {
+    return b200mg_gsrb4_subset(abec, nboxes, nullptr, h_vbox, h_phi_in, h_phi_out, h_rhs, h_a, h_bx, h_by, h_bz, h_f, h_m,
+                               alpha, dhx, dhy, dhz, phi_zero, s);
+}
+
+// the same pass over the listed local boxes only (ids == NULL: boxes 0 .. nboxes-1)
+int b200mg_gsrb4_subset (int abec, int nboxes, const int* ids, const b200mg_box* h_vbox,
+                         const b200mg_fab* h_phi_in, const b200mg_fab* h_phi_out, const b200mg_fab* h_rhs, const b200mg_fab* h_a,
+                         const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
+                         const b200mg_fab* h_f, const b200mg_ifab* h_m,
+                         double alpha, double dhx, double dhy, double dhz, int phi_zero, cudaStream_t s)
+{
     if (nboxes <= 0) { return 0; }
+    auto id = [&] (int n) { return ids ? ids[n] : n; };
     static FusedParams4 P;                              // kept off the stack; copied by value at every launch
     P.phi_zero = phi_zero ? 1 : 0;
     P.alpha = alpha; P.dhx = dhx; P.dhy = dhy; P.dhz = dhz;
     int nxmax = 0, nymax = 0;
-    for (int b = 0; b < nboxes; ++b) {
+    for (int q = 0; q < nboxes; ++q) {
+        const int b = id(q);
         const int nx = h_vbox[b].hi[0] - h_vbox[b].lo[0] + 1, ny = h_vbox[b].hi[1] - h_vbox[b].lo[1] + 1;
         if (nx % 2 != 0 || nx < 4 || nx > 128 || ny < 2) { return int(cudaErrorInvalidValue); }
         nxmax = nx > nxmax ? nx : nxmax; nymax = ny > nymax ? ny : nymax;
     }
     P.txp = ((nxmax / 2 + 31) / 32) * 32;
     P.nxs = nxmax;
-    P.ps = int(h_phi_in[0].jstride); P.cs = int(h_rhs[0].jstride); P.xs = abec ? int(h_bx[0].jstride) : 0;
+    P.ps = int(h_phi_in[id(0)].jstride); P.cs = int(h_rhs[id(0)].jstride); P.xs = abec ? int(h_bx[id(0)].jstride) : 0;
     const int ty = effective_tile_y(nxmax);
     P.nty = (nymax + ty - 1) / ty;
     for (int b0 = 0; b0 < nboxes; b0 += kMaxBoxes4) {
         const int nb = (nboxes - b0 < kMaxBoxes4) ? nboxes - b0 : kMaxBoxes4;
         for (int n = 0; n < nb; ++n) {
-            const int b = b0 + n;
+            const int b = id(b0 + n);
             FusedBox4& B = P.box[n];
             const int nx = h_vbox[b].hi[0] - h_vbox[b].lo[0] + 1;
             B.pin = farr4(h_phi_in[b]); B.pout = farr4(h_phi_out[b]); B.rhs = farr4(h_rhs[b]);

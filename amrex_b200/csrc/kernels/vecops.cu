@@ -54,13 +54,24 @@ k_plus (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vb
     tile_for(t, vb, ng, [&] (int i, int j, int k) { y(i, j, k) += v; });
 }
 
+// y = y * x (op 0) or y / x (op 1): MultiFab::Multiply / Divide (AMReX_MultiFab.H), one component per launch
+template <int OP>
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_binop (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* yf, const b200mg_fab* xf, int ng)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto y = view(yf[t.box]); const auto x = view(xf[t.box]);
+    tile_for(t, vb, ng, [&] (int i, int j, int k) { if (OP == 0) { y(i, j, k) *= x(i, j, k); } else { y(i, j, k) /= x(i, j, k); } });
+}
+
 // Two-stage deterministic reduction: per-block partials in scratch[0..n), the last block to finish
 // (ticket in scratch[n]) folds them in index order and resets the ticket.
 template <class Op, class F>
-__device__ __forceinline__ void reduce_tiles (const b200mg_tile t, const b200mg_box& vb, double* result, double* scratch, F&& f)
+__device__ __forceinline__ void reduce_tiles (const b200mg_tile t, const b200mg_box& vb, double* result, double* scratch, F&& f, int ng = 0)
 {
     double acc = Op::id();
-    tile_for(t, vb, 0, [&] (int i, int j, int k) { acc = Op::ap(acc, f(i, j, k)); });
+    tile_for(t, vb, ng, [&] (int i, int j, int k) { acc = Op::ap(acc, f(i, j, k)); });
     acc = block_reduce<Op>(acc);
     __shared__ bool is_last;
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
@@ -123,6 +134,21 @@ k_sum (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbo
     reduce_tiles<OpSum>(t, vb, result, scratch, [&] (int i, int j, int k) { return x(i, j, k); });
 }
 
+// signed extrema over the cells grown by ng (FabArray::min / max, AMReX_MultiFab.cpp)
+struct OpMinS { __device__ static double id () { return 1.7976931348623157e308; } __device__ static double ap (double a, double b) { return fmin(a, b); } };
+struct OpMaxS { __device__ static double id () { return -1.7976931348623157e308; } __device__ static double ap (double a, double b) { return fmax(a, b); } };
+
+template <class Op>
+__global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
+k_extremum (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* xf,
+            double* result, double* scratch, int ng)
+{
+    const b200mg_tile t = tiles[blockIdx.x];
+    const b200mg_box vb = vbox[t.box];
+    const auto x = view(xf[t.box]);
+    reduce_tiles<Op>(t, vb, result, scratch, [&] (int i, int j, int k) { return x(i, j, k); }, ng);
+}
+
 __global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
 k_asum (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox, const b200mg_fab* xf,
         double* result, double* scratch)
@@ -147,7 +173,9 @@ k_copy_tags (const b200mg_copytag* __restrict__ tags, const b200mg_fab* dstf, co
     if (t.src_fab >= 0) { src = view(srcf[t.src_fab]); }
     if (t.dst_fab >= 0) { dst = view(dstf[t.dst_fab]); }
     for (int n = 0; n < ncomp; ++n) {
-        double* b = buf ? buf + t.buf_offset + (long long)n * npts : nullptr;
+        // buffer layout: the tag's block starts at buf_offset * ncomp (offsets count points of one component), components follow
+        // each other inside the block (AMReX_FBI.H:765-771) - so the per-peer ranges [offset, offset + count) * ncomp are contiguous
+        double* b = buf ? buf + t.buf_offset * (long long)ncomp + (long long)n * npts : nullptr;
         for (unsigned r = threadIdx.x + blockIdx.y * blockDim.x; r < npts; r += blockDim.x * gridDim.y) {
             const unsigned k = r / n01, r2 = r - k * n01, j = r2 / n0, i = r2 - j * n0;
             const int ii = t.lo[0] + int(i), jj = t.lo[1] + int(j), kk = t.lo[2] + int(k);
@@ -202,6 +230,32 @@ int b200mg_plus (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, c
 {
     if (ntiles <= 0) { return 0; }
     k_plus<<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, v, ng);
+    return last_error();
+}
+
+int b200mg_multiply (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y, const b200mg_fab* x, int ng, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_binop<0><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, ng);
+    return last_error();
+}
+
+int b200mg_divide (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y, const b200mg_fab* x, int ng, cudaStream_t s)
+{
+    if (ntiles <= 0) { return 0; }
+    k_binop<1><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, y, x, ng);
+    return last_error();
+}
+
+int b200mg_minmax (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x, int want_max, int ng,
+                   double* result, double* scratch, cudaStream_t s)
+{
+    if (ntiles <= 0) {      // no local cells: the identity of the reduction
+        const double v = want_max ? -1.7976931348623157e308 : 1.7976931348623157e308;
+        return int(cudaMemcpyAsync(result, &v, sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    if (want_max) { k_extremum<OpMaxS><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, x, result, scratch, ng); }
+    else { k_extremum<OpMinS><<<ntiles, tile_block(), 0, s>>>(tiles, vbox, x, result, scratch, ng); }
     return last_error();
 }
 

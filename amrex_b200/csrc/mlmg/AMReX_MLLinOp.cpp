@@ -704,7 +704,7 @@ void MLLinOp::prepareForSolve ()
 
 // MLCellLinOpT::applyBC (AMReX_MLCellLinOp.H:684-893), cross stencil
 void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, StateMode, const BndrySlabs<double>* bndry,
-                       bool skip_fillboundary) const
+                       bool skip_fillboundary, bool nowait) const
 {
     Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     AMREX_ALWAYS_ASSERT(mglev == 0 || bc_mode == BCMode::Homogeneous);
@@ -733,11 +733,15 @@ void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, Stat
         B200_KCALL(b200mg_apply_bc(nf, L.bcfaces.data(), L.layout->d_vbox(), in.d_fabs(), L.mask.d_table(),
                                    bndry ? bndry->d_table() : nullptr, maxorder, dxi[0], dxi[1], dxi[2], flagbc, maxFaceCells(L), aux));
         AMREX_CUDA_SAFE_CALL(cudaEventRecord(ev_join, aux));
-        in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true);
+        if (nowait) { in.FillBoundary_nowait(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
+        else { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
         AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(s, ev_join, 0));
         return;
     }
-    if (!skip_fillboundary) { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
+    if (!skip_fillboundary) {
+        if (nowait) { in.FillBoundary_nowait(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
+        else { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
+    }
     if (nf == 0) { return; }
     B200_KCALL(b200mg_apply_bc(nf, L.bcfaces.data(), L.layout->d_vbox(), in.d_fabs(), L.mask.d_table(),
                                bndry ? bndry->d_table() : nullptr, maxorder, dxi[0], dxi[1], dxi[2], flagbc, maxFaceCells(L), Gpu::gpuStream()));
@@ -867,8 +871,58 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
     if (fuse) {
         if (!L.scratch) { L.scratch = std::make_unique<MultiFab>(sol.boxArray(), sol.DistributionMap(), 1, sol.nGrow()); }
         // (homogeneous BCs of a zero field are zero ghost cells: nothing to fill, and the pass does not read them)
+        // FillBoundary overlapped with interior work (FillBoundary_nowait / _finish of the reference, AMReX_FabArray.H:1023-1042):
+        // the pass over the boxes whose halo comes from this GPU only runs while the NVLink transfer is in flight, the pass
+        // over the boxes with remote neighbours after the unpack.  Out of place, so the two halves do not interact.
+        bool split = false;
+        if (!zero4 && !skip_fillboundary && m_halo_overlap && L.fused4_ok == 1 && ParallelDescriptor::NProcs() > 1 && !Gpu::debugSync()) {
+            if (L.halo_split < 0) {
+                auto const& rf = sol.FillBoundaryRemoteFabs(IntVect(1), H.geom[amrlev][mglev].periodicity(), true);
+                L.boxes_remote_halo = rf; L.boxes_local_halo.clear();
+                for (int li = 0, q = 0; li < L.layout->numLocal(); ++li) {
+                    if (q < int(rf.size()) && rf[q] == li) { ++q; } else { L.boxes_local_halo.push_back(li); }
+                }
+                L.halo_split = (!L.boxes_remote_halo.empty() && !L.boxes_local_halo.empty()) ? 1 : 0;
+            }
+            split = (L.halo_split == 1);
+        }
+        if (split) {
+            // main stream: physical-boundary fill, intra-GPU copies, then the pass over the boxes whose halo is complete;
+            // second stream: wait for the transfer, unpack, the pass over the other boxes - the two passes share the SMs, so
+            // there is no tail between them, and the first one hides the transfer
+            static cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+            if (!ev_ready) {
+                AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+                AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+            }
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, true);
+            cudaStream_t s = Gpu::gpuStream(), aux = Gpu::auxStream();
+            const bool side = !Gpu::profiling();                   // (the per-kernel profiler times launches on the main stream)
+            bool ok2 = true;
+            if (side) {
+                AMREX_CUDA_SAFE_CALL(cudaEventRecord(ev_ready, s));
+                AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(aux, ev_ready, 0));
+                Gpu::setStream(aux);
+                sol.FillBoundary_finish();
+                ok2 = Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs, false, &L.boxes_remote_halo);
+                Gpu::setStream(nullptr);
+                AMREX_CUDA_SAFE_CALL(cudaEventRecord(ev_done, aux));
+            }
+            const bool ok1 = Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs, false, &L.boxes_local_halo);
+            if (side) { AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(s, ev_done, 0)); }
+            else {
+                sol.FillBoundary_finish();
+                ok2 = Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs, false, &L.boxes_remote_halo);
+            }
+            AMREX_ALWAYS_ASSERT_WITH_MESSAGE(ok1 && ok2, "fused smoother: a level that took the pass before refused it");
+            sol.swap(*L.scratch);
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false);
+            FsmoothShell(amrlev, mglev, sol, rhs, 1);
+            return;
+        }
         if (!zero4) { applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary); }
         if (Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs, zero4)) {
+            L.fused4_ok = 1;
             sol.swap(*L.scratch);
             applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false);
             FsmoothShell(amrlev, mglev, sol, rhs, 1);
@@ -1497,7 +1551,8 @@ void MLABecLaplacian::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab co
                                 L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, Gpu::gpuStream()));
 }
 
-bool MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& sol_in, MultiFab const& rhs, bool zero_input) const
+bool MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& sol_in, MultiFab const& rhs, bool zero_input,
+                                const std::vector<int>* boxes) const
 {
     LevelData const& L = lev(amrlev, mglev);
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
@@ -1505,9 +1560,10 @@ bool MLABecLaplacian::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiF
     int e;
     {
         Gpu::KernelScope ks__("b200mg_gsrb4(abec)");
-        e = b200mg_gsrb4(1, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), &ac.desc(0),
-                         &bc[0].desc(0), &bc[1].desc(0), &bc[2].desc(0), L.undrrelxr.h_table(), L.mask.h_table(),
-                         m_a_scalar, dh[0], dh[1], dh[2], zero_input ? 1 : 0, Gpu::gpuStream());
+        e = b200mg_gsrb4_subset(1, boxes ? int(boxes->size()) : L.layout->numLocal(), boxes ? boxes->data() : nullptr, L.h_vbox.data(),
+                                &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), &ac.desc(0),
+                                &bc[0].desc(0), &bc[1].desc(0), &bc[2].desc(0), L.undrrelxr.h_table(), L.mask.h_table(),
+                                m_a_scalar, dh[0], dh[1], dh[2], zero_input ? 1 : 0, Gpu::gpuStream());
     }
     if (e == 0) { return true; }
     if (e != int(cudaErrorInvalidValue)) { Gpu::check(e, "b200mg_gsrb4", __FILE__, __LINE__); }
@@ -1599,16 +1655,18 @@ void MLPoisson::Fsmooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& r
                                    dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, Gpu::gpuStream()));
 }
 
-bool MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& sol_in, MultiFab const& rhs, bool zero_input) const
+bool MLPoisson::Fsmooth2 (int amrlev, int mglev, MultiFab& sol_out, MultiFab& sol_in, MultiFab const& rhs, bool zero_input,
+                          const std::vector<int>* boxes) const
 {
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
     int e;
     {
         Gpu::KernelScope ks__("b200mg_gsrb4(poisson)");
-        e = b200mg_gsrb4(0, L.layout->numLocal(), L.h_vbox.data(), &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), nullptr,
-                         nullptr, nullptr, nullptr, L.undrrelxr.h_table(), L.mask.h_table(),
-                         0.0, dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], zero_input ? 1 : 0, Gpu::gpuStream());
+        e = b200mg_gsrb4_subset(0, boxes ? int(boxes->size()) : L.layout->numLocal(), boxes ? boxes->data() : nullptr, L.h_vbox.data(),
+                                &sol_in.desc(0), &sol_out.desc(0), &rhs.desc(0), nullptr,
+                                nullptr, nullptr, nullptr, L.undrrelxr.h_table(), L.mask.h_table(),
+                                0.0, dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], zero_input ? 1 : 0, Gpu::gpuStream());
     }
     if (e == 0) { return true; }
     if (e != int(cudaErrorInvalidValue)) { Gpu::check(e, "b200mg_gsrb4", __FILE__, __LINE__); }

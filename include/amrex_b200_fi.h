@@ -19,15 +19,18 @@
 #define AMREX_B200_FI_H_
 
 #ifdef __cplusplus
+namespace amrex { template <class T> class FabArray; }
 extern "C" {
 #define B200_OPAQUE(T) namespace amrex { class T; } typedef amrex::T T
 B200_OPAQUE(BoxArray); B200_OPAQUE(DistributionMapping); B200_OPAQUE(Geometry); B200_OPAQUE(MultiFab);
-B200_OPAQUE(MLLinOp); B200_OPAQUE(MLMG); B200_OPAQUE(GMRESMLMG);
+B200_OPAQUE(MLLinOp); B200_OPAQUE(MLMG); B200_OPAQUE(GMRESMLMG); B200_OPAQUE(MFIter);
+typedef amrex::FabArray<int> iMultiFab;
 #undef B200_OPAQUE
 #else
 typedef struct BoxArray BoxArray; typedef struct DistributionMapping DistributionMapping;
 typedef struct Geometry Geometry; typedef struct MultiFab MultiFab;
 typedef struct MLLinOp MLLinOp; typedef struct MLMG MLMG; typedef struct GMRESMLMG GMRESMLMG;
+typedef struct MFIter MFIter; typedef struct iMultiFab iMultiFab;
 #endif
 typedef double Real;
 
@@ -105,6 +108,62 @@ void amrex_fi_multifab_saxpy(MultiFab* dstmf, Real a, const MultiFab* srcmf, int
 void amrex_fi_multifab_copy(MultiFab* dstmf, const MultiFab* srcmf, int srccomp, int dstcomp, int nc, const int* ng);
 void amrex_fi_multifab_parallelcopy(MultiFab* dstmf, const MultiFab* srcmf, int srccomp, int dstcomp, int nc, int srcng, int dstng, const Geometry* geom);
 void amrex_fi_multifab_fill_boundary(MultiFab* mf, const Geometry* geom, int c, int nc, int cross);
+/* ---- the rest of the reference's Base entries (Src/F_Interfaces/Base/AMReX_multifab_fi.cpp:96-300, AMReX_multifabutil_fi.cpp,
+ *      AMReX_geometry_fi.cpp:27-47, AMReX_distromap_fi.cpp, AMReX_boxarray_fi.cpp, AMReX_box_fi.cpp): same names and argument order,
+ *      so that the reference's Fortran modules (amrex_multifab_mod, amrex_multifabutil_mod, ...) link unchanged.  Data pointers
+ *      are device pointers.  The node-centred synchronisation entries (owner masks, override / average sync) and aliased
+ *      MultiFabs exist and report an error through amrex_b200_last_error: they belong to the nodal solvers, outside this path. */
+Real amrex_fi_multifab_min(const MultiFab* mf, int comp, int nghost);
+Real amrex_fi_multifab_max(const MultiFab* mf, int comp, int nghost);
+Real amrex_fi_multifab_norm1(const MultiFab* mf, int comp);
+Real amrex_fi_multifab_norm2(const MultiFab* mf, int comp);
+void amrex_fi_multifab_multiply(MultiFab* dstmf, const MultiFab* srcmf, int srccomp, int dstcomp, int nc, const int* ng);
+void amrex_fi_multifab_divide(MultiFab* dstmf, const MultiFab* srcmf, int srccomp, int dstcomp, int nc, const int* ng);
+void amrex_fi_multifab_lincomb(MultiFab* dstmf, Real a, const MultiFab* srcmf1, int srccomp1, Real b, const MultiFab* srcmf2, int srccomp2, int dstcomp, int nc, const int* ng);
+void amrex_fi_multifab_parallelcopy_gv(MultiFab* dstmf, const MultiFab* srcmf, int srccomp, int dstcomp, int nc, const int* srcng, const int* dstng, const Geometry* geom);
+void amrex_fi_multifab_sum_boundary(MultiFab* mf, const Geometry* geom, int icomp, int ncomp);
+void amrex_fi_build_owner_imultifab(iMultiFab** msk, const BoxArray** ba, const DistributionMapping** dm, const MultiFab* data, const Geometry* geom);
+void amrex_fi_multifab_override_sync(MultiFab* mf, const Geometry* geom);
+void amrex_fi_multifab_override_sync_mask(MultiFab* mf, const Geometry* geom, const iMultiFab* msk);
+void amrex_fi_multifab_average_sync(MultiFab* mf, const Geometry* geom);
+void amrex_fi_new_multifab_alias(MultiFab** mf, const MultiFab* srcmf, int comp, int ncomp);
+void amrex_fi_new_imultifab(iMultiFab** imf, const BoxArray** ba, const DistributionMapping** dm, int nc, const int* ng, const int* nodal);
+void amrex_fi_new_imultifab_alias(iMultiFab** mf, const iMultiFab* srcmf, int comp, int ncomp);
+void amrex_fi_delete_imultifab(iMultiFab* imf);
+void amrex_fi_imultifab_setval(iMultiFab* imf, int val, int ic, int nc, const int* ng);
+void amrex_fi_imultifab_dataptr(iMultiFab* imf, MFIter* mfi, int** dp, int lo[3], int hi[3]);
+void amrex_fi_multifab_dataptr_iter(MultiFab* mf, MFIter* mfi, Real** dp, int lo[3], int hi[3]);
+int  amrex_fi_mfiter_allow_multiple(int allow);
+void amrex_fi_new_mfiter_r(MFIter** mfi, MultiFab* mf, int tiling, int dynamic);
+void amrex_fi_new_mfiter_i(MFIter** mfi, iMultiFab* imf, int tiling, int dynamic);
+void amrex_fi_new_mfiter_rs(MFIter** mfi, MultiFab* mf, const int* tilesize, int dynamic);
+void amrex_fi_new_mfiter_is(MFIter** mfi, iMultiFab* imf, const int* tilesize, int dynamic);
+void amrex_fi_new_mfiter_badm(MFIter** mfi, BoxArray* ba, DistributionMapping* dm, int tiling, int dynamic);
+void amrex_fi_new_mfiter_badm_s(MFIter** mfi, BoxArray* ba, DistributionMapping* dm, const int* tilesize, int dynamic);
+void amrex_fi_delete_mfiter(MFIter* mfi);
+void amrex_fi_increment_mfiter(MFIter* mfi, int* isvalid);
+void amrex_fi_mfiter_is_valid(MFIter* mfi, int* isvalid);
+int  amrex_fi_mfiter_grid_index(MFIter* mfi);
+int  amrex_fi_mfiter_local_tile_index(MFIter* mfi);
+void amrex_fi_mfiter_tilebox(MFIter* mfi, int lo[3], int hi[3], int nodal[3]);
+void amrex_fi_mfiter_tilebox_iv(MFIter* mfi, int lo[3], int hi[3], const int nodal[3]);
+void amrex_fi_mfiter_nodaltilebox(MFIter* mfi, int dir, int lo[3], int hi[3], int nodal[3]);
+void amrex_fi_mfiter_growntilebox(MFIter* mfi, int lo[3], int hi[3], int ng, int nodal[3]);
+void amrex_fi_mfiter_grownnodaltilebox(MFIter* mfi, int lo[3], int hi[3], int dir, int ng, int nodal[3]);
+void amrex_fi_mfiter_validbox(MFIter* mfi, int lo[3], int hi[3], int nodal[3]);
+void amrex_fi_mfiter_fabbox(MFIter* mfi, int lo[3], int hi[3], int nodal[3]);
+void amrex_fi_geometry_get_pmask(const Geometry* geom, int is_per[3]);
+void amrex_fi_geometry_get_probdomain(const Geometry* geom, Real problo[3], Real probhi[3]);
+void amrex_fi_clone_distromap(DistributionMapping** dmo, const DistributionMapping* dmi);
+int  amrex_fi_distromap_issame(const DistributionMapping* dma, const DistributionMapping* dmb);
+void amrex_fi_print_distromap(const DistributionMapping* dm);
+int  amrex_fi_boxarray_intersects_box(const BoxArray* ba, const int lo[3], const int hi[3]);
+void amrex_fi_print_boxarray(const BoxArray* ba);
+void amrex_fi_print_box(const int lo[3], const int hi[3], const int nodal[3]);
+void amrex_fi_average_down(const MultiFab* S_fine, MultiFab* S_crse, const Geometry* fgeom, const Geometry* cgeom, int scomp, int ncomp, int rr);
+void amrex_fi_average_down_cell_node(const MultiFab* S_fine, MultiFab* S_crse, int scomp, int ncomp, int rr);
+void amrex_fi_average_down_faces(MultiFab const* fmf[], MultiFab* cmf[], const Geometry* cgeom, int scomp, int ncomp, int rr);
+void amrex_fi_average_cellcenter_to_face(MultiFab* fc[], const MultiFab* cc, const Geometry* geom);
 Real amrex_b200_multifab_dot(const MultiFab* x, const MultiFab* y);   /* amrex::Dot, AMReX_FabArrayUtility.H:1554 */
 /* host <-> device: `h` is a Fortran-order array covering exactly the index box [lo,hi] (of the MultiFab's index
  * type); cells of every local fab inside grow(validbox,ng) are transferred.  Host memory may be pinned. */

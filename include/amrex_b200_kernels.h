@@ -119,6 +119,13 @@ int b200mg_gsrb4(int abec, int nboxes, const b200mg_box* h_vbox,
                  const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
                  const b200mg_fab* h_f, const b200mg_ifab* h_m,
                  double alpha, double dhx, double dhy, double dhz, int phi_zero, cudaStream_t s);
+/* the same pass over the nboxes local boxes listed in ids (host array; NULL: boxes 0 .. nboxes-1); the tables stay indexed
+ * by local box.  Used to run the boxes whose halo is complete while the remote part of a FillBoundary is in flight. */
+int b200mg_gsrb4_subset(int abec, int nboxes, const int* ids, const b200mg_box* h_vbox,
+                        const b200mg_fab* h_phi_in, const b200mg_fab* h_phi_out, const b200mg_fab* h_rhs, const b200mg_fab* h_a,
+                        const b200mg_fab* h_bx, const b200mg_fab* h_by, const b200mg_fab* h_bz,
+                        const b200mg_fab* h_f, const b200mg_ifab* h_m,
+                        double alpha, double dhx, double dhy, double dhz, int phi_zero, cudaStream_t s);
 /* launch plan of b200mg_gsrb4: rows per CTA tile and ring depths; (8,4,2) default, (8,4,3), (6,5,3), (6,4,2), (4,4,4) */
 int b200mg_set_gsrb4_plan(int tile_y, int early_stages, int late_stages);
 /* synchronisation inside a CTA of b200mg_gsrb4: 0 = one CTA barrier per plane, 1 = decoupled warps (mbarrier arrive / wait) */
@@ -261,6 +268,12 @@ int b200mg_lincomb(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
                    double a, const b200mg_fab* x, double b, int ng, cudaStream_t s);
 int b200mg_plus(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y,
                 double v, int ng, cudaStream_t s);
+/* y *= x / y /= x on the cells grown by ng (MultiFab::Multiply / Divide, Src/Base/AMReX_MultiFab.H) */
+int b200mg_multiply(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y, const b200mg_fab* x, int ng, cudaStream_t s);
+int b200mg_divide(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y, const b200mg_fab* x, int ng, cudaStream_t s);
+/* signed minimum (want_max == 0) / maximum over the cells grown by ng (FabArray min / max); tiles built for that ng */
+int b200mg_minmax(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* x, int want_max, int ng,
+                  double* result, double* scratch, cudaStream_t s);
 /* ghost cells only (setBndry) */
 int b200mg_setbndry(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, const b200mg_fab* y,
                     double v, int ng, cudaStream_t s);

@@ -53,7 +53,8 @@ def main():
         sols, rhss = P["sol"], P["rhs"]
         bas, dms = P["ba"], P["dm"]
     else:
-        P = build_problem(ab, prob_type, n, mgs, dump, maxorder=maxorder)
+        fusion = int(os.environ["WORKER_FUSION"]) if "WORKER_FUSION" in os.environ else None    # 1: fused pass on boxes >= 32^3
+        P = build_problem(ab, prob_type, n, mgs, dump, maxorder=maxorder, fusion=fusion)
         sols, rhss = [P["sol"]], [P["rhs"]]
         bas, dms = [P["ba"]], [P["dm"]]
     mlmg = ab.MLMG(P["op"])

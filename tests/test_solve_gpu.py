@@ -81,7 +81,9 @@ def test_periodic_poisson_256_config5(ab):
     boxes against the reference: V-cycle count, residual history, solution (up to the constant) within 1e-10."""
     ref, mlmg, diff = solve_case(ab, 5, 256, 64)
     assert abs(mlmg.numIters() - ref["iters"]) <= 1
-    floor = 1e-13 * max(ref["rhsnorm0"], ref["resnorm0"])
+    # singular operator: the solvability offsets (sums over the level, in another order than the reference's) put a rounding
+    # floor of ~1e-12 of the initial norm under every residual
+    floor = 1e-12 * max(ref["rhsnorm0"], ref["resnorm0"])
     for a, b in zip(mlmg.residualHistory(), ref["history"]):
         assert a == pytest.approx(b, rel=1e-5, abs=floor)
     assert diff <= SOL_TOL
