@@ -9,6 +9,6 @@ is visible when a device operation is requested, calls raise.
 from .capi import (  # noqa: F401
     lib, load_library, LIB_PATH, AmrexError, check,
     init, finalize, comm_init_from_torch, profile_enable, profile_report,
-    Geometry, BoxArray, DistributionMapping, MultiFab, MLLinOp, MLABecLaplacian, MLPoisson, MLMG, GMRESMLMG,
+    Geometry, BoxArray, DistributionMapping, MultiFab, MLLinOp, MLABecLaplacian, MLALaplacian, MLPoisson, MLMG, GMRESMLMG,
     hierarchy, fb_tags, cpc_tags, make_sfc, LinOpBCType, write_plotfile,
 )

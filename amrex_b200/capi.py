@@ -66,6 +66,7 @@ _SIGS = {
     "amrex_fi_new_poisson": (None, [_PP, _I, _PP, _PP, _PP, _I, _I, _I, _I]),
     "amrex_fi_delete_linop": (None, [_P]), "amrex_fi_linop_set_maxorder": (None, [_P, _I]),
     "amrex_fi_linop_set_domain_bc": (None, [_P, _IP, _IP]), "amrex_fi_linop_set_level_bc": (None, [_P, _I, _P]),
+    "amrex_b200_linop_set_level_bc_robin": (None, [_P, _I, _P, _P, _P, _P]),
     "amrex_fi_linop_set_coarse_fine_bc": (None, [_P, _P, _I]),
     "amrex_fi_abeclap_set_scalars": (None, [_P, _D, _D]), "amrex_fi_abeclap_set_acoeffs": (None, [_P, _I, _P]),
     "amrex_fi_abeclap_set_bcoeffs": (None, [_P, _I, _PP]),
@@ -412,8 +413,12 @@ class MLLinOp(_Obj):
         lib.amrex_fi_linop_set_domain_bc(self.ptr, _i3(lo), _i3(hi))
         check()
 
-    def setLevelBC(self, amrlev, mf):
-        lib.amrex_fi_linop_set_level_bc(self.ptr, amrlev, mf.ptr if mf is not None else None)
+    def setLevelBC(self, amrlev, mf, robin=None):
+        """robin: (a, b, f) MultiFabs with the Robin data a*phi + b*dphi/dn = f in their ghost cells"""
+        if robin is not None:
+            lib.amrex_b200_linop_set_level_bc_robin(self.ptr, amrlev, mf.ptr if mf is not None else None, robin[0].ptr, robin[1].ptr, robin[2].ptr)
+        else:
+            lib.amrex_fi_linop_set_level_bc(self.ptr, amrlev, mf.ptr if mf is not None else None)
         check()
 
     def setCoarseFineBC(self, crse, ratio):
@@ -493,6 +498,11 @@ class MLABecLaplacian(MLLinOp):
 
 class MLPoisson(MLLinOp):
     _kind = 1
+
+
+class MLALaplacian(MLABecLaplacian):
+    """(alpha a - beta Laplacian): the reference's MLALaplacian (kind 2 of amrex_b200_new_linop)"""
+    _kind = 2
 
 
 class MLMG(_Obj):

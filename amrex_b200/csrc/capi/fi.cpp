@@ -365,6 +365,7 @@ MLLinOp* make_linop (int kind, int nlevels, const Geometry* geom[], const BoxArr
     Vector<Geometry> g; Vector<BoxArray> b; Vector<DistributionMapping> d;
     for (int i = 0; i < nlevels; ++i) { g.push_back(*geom[i]); b.push_back(*ba[i]); d.push_back(*dm[i]); }
     if (kind == 0) { return new MLABecLaplacian(g, b, d, info); }
+    if (kind == 2) { return new MLALaplacian(g, b, d, info); }
     return new MLPoisson(g, b, d, info);
 }
 LPInfo make_info (int agglomeration, int consolidation, int max_coarsening_level)
@@ -403,6 +404,11 @@ void amrex_fi_linop_set_domain_bc (MLLinOp* linop, const int* ilobc, const int* 
 }
 void amrex_fi_linop_set_coarse_fine_bc (MLLinOp* linop, const MultiFab* crse, int crse_ratio) { FI_VOID( linop->setCoarseFineBC(crse, crse_ratio); ) }
 void amrex_fi_linop_set_level_bc (MLLinOp* linop, int amrlev, const MultiFab* levelbcdata) { FI_VOID( linop->setLevelBC(amrlev, levelbcdata); ) }
+void amrex_b200_linop_set_level_bc_robin (MLLinOp* linop, int amrlev, const MultiFab* levelbcdata, const MultiFab* robinbc_a,
+                                          const MultiFab* robinbc_b, const MultiFab* robinbc_f)
+{
+    FI_VOID( linop->setLevelBC(amrlev, levelbcdata, robinbc_a, robinbc_b, robinbc_f); )
+}
 void amrex_fi_abeclap_set_scalars (MLLinOp* linop, Real a, Real b) { FI_VOID( dynamic_cast<MLABecLaplacian&>(*linop).setScalars(a, b); ) }
 void amrex_fi_abeclap_set_acoeffs (MLLinOp* linop, int amrlev, const MultiFab* alpha) { FI_VOID( dynamic_cast<MLABecLaplacian&>(*linop).setACoeffs(amrlev, *alpha); ) }
 void amrex_fi_abeclap_set_bcoeffs (MLLinOp* linop, int amrlev, const MultiFab* beta[])

@@ -526,6 +526,55 @@ k_apply_innu (const b200mg_bcface* __restrict__ faces, const b200mg_box* __restr
     });
 }
 
+// Robin boundary condition a*phi + b*dphi/dn = f on flagged domain faces; the data sits in the ghost cells of the face slabs
+// ra / rb / rf.  With u_ghost = A + B*u_in, A = f/(b/h + a/2), B = (b/h - a/2)/(b/h + a/2), the face acts as a homogeneous
+// Neumann face with a modified diagonal and right-hand side (AMReX_MLABecLaplacian.H:459-600, AMReX_MLCellABecLap.H:448-510):
+//   mode 0: acoef(cell inside) += fac[d]*bcoef(face)*(1-B)      fac = (b_scalar/a_scalar)*dxinv^2   (applyRobinBCTermsCoeffs)
+//   mode 1: rhs(cell inside)   += fac[d]*bcoef(face)*A          fac = b_scalar*dxinv^2             (applyInhomogNeumannTerm)
+//   mode 2: face value of out3[d] := fac[d]*bcoef*dxinv*((1-B)*phi_in - A) on low faces, fac*b*dxinv*(A + (B-1)*phi_in) on high
+//           faces                                               (addInhomogNeumannFlux, AMReX_MLCellABecLap.H:579-612)
+// Modes 0 / 1 are read-modify-writes of cells that may belong to several faces: one face orientation per launch.
+struct Robin { const b200mg_fab* out[3]; const b200mg_fab* b[3]; const b200mg_fab* phi; double fac[3]; double dxi[3]; int on_face[6]; int mode; };
+
+__global__ void __launch_bounds__(128)
+k_robin (const b200mg_bcface* __restrict__ faces, const b200mg_box* __restrict__ vbox, const b200mg_ifab* mf,
+         const b200mg_fab* raf, const b200mg_fab* rbf, const b200mg_fab* rff, Robin P)
+{
+    const b200mg_bcface fc = faces[blockIdx.x];
+    if (!P.on_face[fc.face]) { return; }
+    const b200mg_box vb = vbox[fc.box];
+    const int d = fc.face % 3;
+    const bool low = fc.face < 3;
+    const auto mask = view(mf[fc.box * 6 + fc.face]);
+    const auto ra = view(raf[fc.box * 6 + fc.face]); const auto rb = view(rbf[fc.box * 6 + fc.face]); const auto rf = view(rff[fc.box * 6 + fc.face]);
+    const auto out = view(P.out[d][fc.box]);
+    const bool has_b = (P.b[d] != nullptr);
+    View<double> bc = out, phi = out;
+    if (has_b) { bc = view(P.b[d][fc.box]); }
+    if (P.mode == 2) { phi = view(P.phi[fc.box]); }
+    const double fac = P.fac[d], dxi = P.dxi[d];
+    face_loop(vb, fc.face, [&] (int i, int j, int k) {
+        if (mask(i, j, k) != 2) { return; }
+        const int ci = i + (d == 0 ? (low ? 1 : -1) : 0), cj = j + (d == 1 ? (low ? 1 : -1) : 0), ck = k + (d == 2 ? (low ? 1 : -1) : 0);   // cell inside
+        const int fi = low ? ci : i, fj = low ? cj : j, fk = low ? ck : k;                                                          // the domain face
+        const double b = has_b ? bc(fi, fj, fk) : 1.0;
+        const double a_ = ra(i, j, k), b_ = rb(i, j, k);
+        if (P.mode == 0) {
+            const double B = (b_ * dxi - a_ * 0.5) / (b_ * dxi + a_ * 0.5);
+            out(ci, cj, ck) += fac * b * (1.0 - B);
+        } else if (P.mode == 1) {
+            const double A = rf(i, j, k) / (b_ * dxi + a_ * 0.5);
+            out(ci, cj, ck) += fac * b * A;
+        } else {
+            const double tmp = 1.0 / (b_ * dxi + a_ * 0.5);
+            const double RA = rf(i, j, k) * tmp;
+            const double RB = (b_ * dxi - a_ * 0.5) * tmp;
+            if (low) { out(fi, fj, fk) = fac * b * dxi * ((1.0 - RB) * phi(ci, cj, ck) - RA); }
+            else { out(fi, fj, fk) = fac * b * dxi * (RA + (RB - 1.0) * phi(ci, cj, ck)); }
+        }
+    });
+}
+
 __global__ void __launch_bounds__(128)
 k_comp_interp_coef0 (const b200mg_bcface* __restrict__ faces, const b200mg_box* __restrict__ vbox,
                      const b200mg_fab* ff, const b200mg_ifab* mf,
@@ -657,6 +706,20 @@ int b200mg_apply_innu (int nfaces, const b200mg_bcface* faces, const b200mg_box*
     for (int f = 0; f < 6; ++f) { P.on_face[f] = on_face[f]; }
     P.mode = mode;
     k_apply_innu<<<dim3(nfaces, 8), 128, 0, s>>>(faces, vbox, m, bcval, P);
+    return last_error();
+}
+
+int b200mg_robin (int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
+                  const b200mg_fab* const out3[3], const b200mg_fab* const b3[3], const b200mg_fab* phi,
+                  const b200mg_ifab* m, const b200mg_fab* ra, const b200mg_fab* rb, const b200mg_fab* rf,
+                  const double fac[3], const double dxinv[3], const int on_face[6], int mode, cudaStream_t s)
+{
+    if (nfaces <= 0) { return 0; }
+    Robin P;
+    for (int d = 0; d < 3; ++d) { P.out[d] = out3[d]; P.b[d] = b3 ? b3[d] : nullptr; P.fac[d] = fac[d]; P.dxi[d] = dxinv[d]; }
+    for (int f = 0; f < 6; ++f) { P.on_face[f] = on_face[f]; }
+    P.phi = phi; P.mode = mode;
+    k_robin<<<dim3(nfaces, 8), 128, 0, s>>>(faces, vbox, m, ra, rb, rf, P);
     return last_error();
 }
 

@@ -350,11 +350,13 @@ void MLLinOp::setDomainBC (Array<BCType, 3> const& a_lobc, Array<BCType, 3> cons
         } else {
             AMREX_ALWAYS_ASSERT(m_lobc[d] != BCType::Periodic && m_hibc[d] != BCType::Periodic);
         }
-        if (m_lobc[d] == BCType::Robin || m_hibc[d] == BCType::Robin) { Abort("Robin BC not supported"); }
-        // inhomogeneous Neumann acts as Neumann inside the cycle; its data moves into the right-hand side
-        // (MLLinOpT::setDomainBC, AMReX_MLLinOp.H:1211-1221)
-        if (m_lobc[d] == BCType::inhomogNeumann) { m_lobc[d] = BCType::Neumann; }
-        if (m_hibc[d] == BCType::inhomogNeumann) { m_hibc[d] = BCType::Neumann; }
+        if (m_lobc[d] == BCType::Robin || m_hibc[d] == BCType::Robin) {
+            AMREX_ALWAYS_ASSERT_WITH_MESSAGE(supportRobinBC(), "Robin BC not supported");
+        }
+        // inhomogeneous Neumann and Robin act as Neumann inside the cycle; their data moves into the right-hand side
+        // (and, for Robin, the diagonal): MLLinOpT::setDomainBC, AMReX_MLLinOp.H:1211-1221
+        if (m_lobc[d] == BCType::inhomogNeumann || m_lobc[d] == BCType::Robin) { m_lobc[d] = BCType::Neumann; }
+        if (m_hibc[d] == BCType::inhomogNeumann || m_hibc[d] == BCType::Robin) { m_hibc[d] = BCType::Neumann; }
     }
 }
 
@@ -364,18 +366,43 @@ bool MLLinOp::hasInhomogNeumannBC () const noexcept
     return false;
 }
 
-namespace {
-void innu_faces (Array<LinOpBCType, 3> const& lo, Array<LinOpBCType, 3> const& hi, int on_face[6])
+bool MLLinOp::hasRobinBC () const noexcept
 {
-    for (int d = 0; d < 3; ++d) {
-        on_face[d] = (lo[d] == LinOpBCType::inhomogNeumann); on_face[d + 3] = (hi[d] == LinOpBCType::inhomogNeumann);
-    }
+    for (int d = 0; d < 3; ++d) { if (m_lobc_orig[d] == BCType::Robin || m_hibc_orig[d] == BCType::Robin) { return true; } }
+    return false;
+}
+
+namespace {
+void innu_faces (Array<LinOpBCType, 3> const& lo, Array<LinOpBCType, 3> const& hi, int on_face[6], LinOpBCType which = LinOpBCType::inhomogNeumann)
+{
+    for (int d = 0; d < 3; ++d) { on_face[d] = (lo[d] == which); on_face[d + 3] = (hi[d] == which); }
 }
 }
 
 // MLCellABecLapT::applyInhomogNeumannTerm (AMReX_MLCellABecLap.H:295-513)
 void MLLinOp::applyInhomogNeumannTerm (int amrlev, MultiFab& rhs) const
 {
+    if (hasRobinBC()) {       // rhs += beta*dxinv^2*b*A next to Robin faces (AMReX_MLCellABecLap.H:448-510)
+        LevelData const& L = lev(amrlev, 0);
+        const int nf = int(L.bcfaces_h.size());
+        if (nf > 0) {
+            AMREX_ALWAYS_ASSERT_WITH_MESSAGE(int(m_robin.size()) > amrlev && m_robin[amrlev][0], "Robin BC: setLevelBC must supply robinbc_a / _b / _f");
+            Array<MultiFab const*, 3> b; Real bscalar;
+            getFluxCoeffs(amrlev, b, bscalar);
+            const Real* dxi = H.geom[amrlev][0].InvCellSize();
+            const b200mg_fab* out3[3] = {rhs.d_fabs(), rhs.d_fabs(), rhs.d_fabs()};
+            const b200mg_fab* b3[3] = {b[0] ? b[0]->d_fabs() : nullptr, b[1] ? b[1]->d_fabs() : nullptr, b[2] ? b[2]->d_fabs() : nullptr};
+            const double fac[3] = {bscalar * dxi[0] * dxi[0], bscalar * dxi[1] * dxi[1], bscalar * dxi[2] * dxi[2]};
+            const double dx3[3] = {dxi[0], dxi[1], dxi[2]};
+            int on_face[6]; innu_faces(m_lobc_orig, m_hibc_orig, on_face, LinOpBCType::Robin);
+            for (int f = 0; f < 6; ++f) {
+                if (!on_face[f]) { continue; }
+                int only[6] = {0, 0, 0, 0, 0, 0}; only[f] = 1;
+                B200_KCALL(b200mg_robin(nf, L.bcfaces.data(), L.layout->d_vbox(), out3, b3, nullptr, L.mask.d_table(), m_robin[amrlev][0]->d_table(),
+                                        m_robin[amrlev][1]->d_table(), m_robin[amrlev][2]->d_table(), fac, dx3, only, 1, Gpu::gpuStream()));
+            }
+        }
+    }
     if (!hasInhomogNeumannBC()) { return; }
     LevelData const& L = lev(amrlev, 0);
     const int nf = int(L.bcfaces_h.size());
@@ -402,9 +429,10 @@ void MLLinOp::applyInhomogNeumannTerm (int amrlev, MultiFab& rhs) const
 }
 
 // MLCellABecLapT::addInhomogNeumannFlux (AMReX_MLCellABecLap.H:517-620): mult_bcoef: grad holds -b grad(phi), else grad(phi)
-void MLLinOp::addInhomogNeumannFlux (int amrlev, Array<MultiFab*, 3> const& grad, bool mult_bcoef) const
+void MLLinOp::addInhomogNeumannFlux (int amrlev, Array<MultiFab*, 3> const& grad, MultiFab const& sol, bool mult_bcoef) const
 {
-    if (!hasInhomogNeumannBC()) { return; }
+    const bool has_innu = hasInhomogNeumannBC(), has_robin = hasRobinBC();
+    if (!has_innu && !has_robin) { return; }
     LevelData const& L = lev(amrlev, 0);
     const int nf = int(L.bcfaces_h.size());
     if (nf == 0) { return; }
@@ -414,9 +442,20 @@ void MLLinOp::addInhomogNeumannFlux (int amrlev, Array<MultiFab*, 3> const& grad
     const b200mg_fab* b3[3] = {b[0] ? b[0]->d_fabs() : nullptr, b[1] ? b[1]->d_fabs() : nullptr, b[2] ? b[2]->d_fabs() : nullptr};
     const double f = mult_bcoef ? -1.0 : 1.0;
     const double fac[3] = {f, f, f};
-    int on_face[6]; innu_faces(m_lobc_orig, m_hibc_orig, on_face);
-    B200_KCALL(b200mg_apply_innu(nf, L.bcfaces.data(), L.layout->d_vbox(), out3, b3, L.mask.d_table(), m_bndry_sol[amrlev]->d_table(),
-                                 fac, on_face, 1, Gpu::gpuStream()));
+    int on_face[6];
+    if (has_innu) {
+        innu_faces(m_lobc_orig, m_hibc_orig, on_face);
+        B200_KCALL(b200mg_apply_innu(nf, L.bcfaces.data(), L.layout->d_vbox(), out3, b3, L.mask.d_table(), m_bndry_sol[amrlev]->d_table(),
+                                     fac, on_face, 1, Gpu::gpuStream()));
+    }
+    if (has_robin) {
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(int(m_robin.size()) > amrlev && m_robin[amrlev][0], "Robin BC: setLevelBC must supply robinbc_a / _b / _f");
+        const Real* dxi = H.geom[amrlev][0].InvCellSize();
+        const double dx3[3] = {dxi[0], dxi[1], dxi[2]};
+        innu_faces(m_lobc_orig, m_hibc_orig, on_face, LinOpBCType::Robin);
+        B200_KCALL(b200mg_robin(nf, L.bcfaces.data(), L.layout->d_vbox(), out3, b3, sol.d_fabs(), L.mask.d_table(), m_robin[amrlev][0]->d_table(),
+                                m_robin[amrlev][1]->d_table(), m_robin[amrlev][2]->d_table(), fac, dx3, on_face, 2, Gpu::gpuStream()));
+    }
 }
 
 void MLLinOp::setCoarseFineBC (const MultiFab* crse, int crse_ratio, LinOpBCType bc_type)
@@ -460,7 +499,8 @@ void MLLinOp::buildBCFaces (int a, int m)
 
 // MLCellLinOpT::setLevelBC (AMReX_MLCellLinOp.H:513-642): physical-boundary ghost values of levelbcdata are copied
 // into the level's boundary slabs (InterpBndryData::setPhysBndryValues, AMReX_InterpBndryData.H:128-156).
-void MLLinOp::setLevelBC (int amrlev, const MultiFab* levelbcdata)
+void MLLinOp::setLevelBC (int amrlev, const MultiFab* levelbcdata, const MultiFab* robinbc_a, const MultiFab* robinbc_b,
+                          const MultiFab* robinbc_f)
 {
     AMREX_ALWAYS_ASSERT(amrlev >= 0 && amrlev < H.num_amr_levels);
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_lobc[0] != BCType::bogus, "setDomainBC must be called before setLevelBC");
@@ -513,6 +553,44 @@ void MLLinOp::setLevelBC (int amrlev, const MultiFab* levelbcdata)
         }
     }
     for (int m = 0; m < H.num_mg_levels[amrlev]; ++m) { buildBCFaces(amrlev, m); }
+    if (hasRobinBC()) {
+        // m_robin_bcval (AMReX_MLCellLinOp.H:596-640): a, b, f of the ghost cells outside the Robin faces of the domain
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(robinbc_a != nullptr && robinbc_b != nullptr && robinbc_f != nullptr,
+                                         "MLLinOp::setLevelBC: Robin BC needs robinbc_a, robinbc_b and robinbc_f");
+        if (int(m_robin.size()) < H.num_amr_levels) { m_robin.resize(H.num_amr_levels); }
+        Geometry const& geom = H.geom[amrlev][0];
+        const Box domain = geom.Domain();
+        const MultiFab* src[3] = {robinbc_a, robinbc_b, robinbc_f};
+        for (int q = 0; q < 3; ++q) {
+            AMREX_ALWAYS_ASSERT_WITH_MESSAGE(src[q]->nGrow() >= 1 && src[q]->boxArray() == H.grids[amrlev][0] && src[q]->DistributionMap() == H.dmap[amrlev][0],
+                                             "MLLinOp::setLevelBC: Robin data must live on the level's grids with one ghost cell");
+            m_robin[amrlev][q] = std::make_unique<BndrySlabs<double>>();
+            BndrySlabs<double>& B = *m_robin[amrlev][q];
+            B.define(*L.layout, false);
+            std::vector<b200mg_copytag> tags;
+            for (int li = 0; li < L.layout->numLocal(); ++li) {
+                Box const& bx = L.layout->box(li);
+                for (int f = 0; f < 6; ++f) {
+                    const int d = f % 3; const bool low = f < 3;
+                    const bool robin = (low ? m_lobc_orig[d] : m_hibc_orig[d]) == BCType::Robin;
+                    const int dface = low ? domain.smallEnd(d) : domain.bigEnd(d);
+                    const int bface = low ? bx.smallEnd(d) : bx.bigEnd(d);
+                    if (robin && dface == bface && !geom.isPeriodic(d)) {
+                        Box const& sb = B.box(li, f);
+                        b200mg_copytag t;
+                        for (int x = 0; x < 3; ++x) { t.lo[x] = sb.smallEnd(x); t.hi[x] = sb.bigEnd(x); t.shift[x] = 0; }
+                        t.dst_fab = li * 6 + f; t.src_fab = li; t.pad = 0; t.buf_offset = 0;
+                        tags.push_back(t);
+                    }
+                }
+            }
+            if (!tags.empty()) {
+                DeviceTable<b200mg_copytag> dt(tags);
+                B200_KCALL(b200mg_copy_tags(int(tags.size()), dt.data(), B.d_table(), src[q]->d_fabs(), nullptr, 1, 0, 0, 0, 0, Gpu::gpuStream()));
+                Gpu::streamSynchronize();
+            }
+        }
+    }
 }
 
 // ---- single-kernel BiCGStab bottom solve (kernels/bottom.cu)
@@ -1010,7 +1088,7 @@ void MLLinOp::compGrad (int amrlev, Array<MultiFab*, 3> const& grad, MultiFab& s
         auto const& T = g.layout().tiles(0);
         B200_KCALL(b200mg_face_flux(T.n, T.d.data(), g.layout().d_vbox(), g.d_fabs(), sol.d_fabs(), nullptr, dxi[d], 1.0, d, 0, Gpu::gpuStream()));
     }
-    addInhomogNeumannFlux(amrlev, grad, false);              // AMReX_MLCellLinOp.H:1441
+    addInhomogNeumannFlux(amrlev, grad, sol, false);         // AMReX_MLCellLinOp.H:1441
 }
 
 void MLLinOp::compFlux (int amrlev, Array<MultiFab*, 3> const& fluxes, MultiFab& sol)
@@ -1041,7 +1119,7 @@ void MLLinOp::getFluxes (Vector<Array<MultiFab*, 3>> const& a_flux, Vector<Multi
 {
     for (int alev = 0; alev < H.num_amr_levels; ++alev) {
         compFlux(alev, a_flux[alev], *a_sol[alev]);
-        addInhomogNeumannFlux(alev, a_flux[alev], true);     // AMReX_MLCellABecLap.H:289
+        addInhomogNeumannFlux(alev, a_flux[alev], *a_sol[alev], true);     // AMReX_MLCellABecLap.H:289
     }
 }
 
@@ -1398,6 +1476,7 @@ void MLABecLaplacian::define (Vector<Geometry> const& a_geom, Vector<BoxArray> c
 
 void MLABecLaplacian::setScalars (Real a, Real b) noexcept
 {
+    m_scalars_set = true;
     m_a_scalar = a; m_b_scalar = b;
     if (a == 0.0) { for (int l = 0; l < H.num_amr_levels; ++l) { m_a_coeffs[l][0].setVal(0.0); } }
 }
@@ -1406,10 +1485,10 @@ void MLABecLaplacian::setACoeffs (int amrlev, MultiFab const& alpha)
 {
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(alpha.nComp() == 1, "MLABecLaplacian::setACoeffs: alpha is supposed to be single component.");
     m_a_coeffs[amrlev][0].ParallelCopy(alpha, 0, 0, 1);   // LocalCopy when layouts agree
-    m_needs_update = true;
+    m_needs_update = true; m_acoef_set = true;
 }
 
-void MLABecLaplacian::setACoeffs (int amrlev, Real alpha) { m_a_coeffs[amrlev][0].setVal(alpha); m_needs_update = true; }
+void MLABecLaplacian::setACoeffs (int amrlev, Real alpha) { m_a_coeffs[amrlev][0].setVal(alpha); m_needs_update = true; m_acoef_set = true; }
 
 void MLABecLaplacian::setBCoeffs (int amrlev, Array<MultiFab const*, 3> const& beta)
 {
@@ -1459,9 +1538,45 @@ void MLABecLaplacian::update_singular_flags ()
     }
 }
 
+// MLABecLaplacianT::applyRobinBCTermsCoeffs (AMReX_MLABecLaplacian.H:459-609): a Robin face acts as a homogeneous Neumann face
+// with a larger diagonal: acoef(cell inside) += (b_scalar / a_scalar) * dxinv^2 * bcoef(face) * (1 - B)
+void MLABecLaplacian::applyRobinBCTermsCoeffs ()
+{
+    if (!hasRobinBC()) { return; }
+    bool reset_alpha = false;
+    if (m_a_scalar == Real(0.0)) { m_a_scalar = Real(1.0); reset_alpha = true; }
+    const Real bovera = m_b_scalar / m_a_scalar;
+    if (!reset_alpha) {
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_scalars_set && m_acoef_set,
+                                         "To reuse solver With Robin BC, one must re-call setScalars (and setACoeffs if the scalar is not zero)");
+    }
+    m_scalars_set = false; m_acoef_set = false;
+    for (int amrlev = 0; amrlev < H.num_amr_levels; ++amrlev) {
+        if (reset_alpha) { m_a_coeffs[amrlev][0].setVal(0.0); }
+        LevelData const& L = lev(amrlev, 0);
+        const int nf = int(L.bcfaces_h.size());
+        if (nf == 0) { continue; }
+        AMREX_ALWAYS_ASSERT_WITH_MESSAGE(int(m_robin.size()) > amrlev && m_robin[amrlev][0], "Robin BC: setLevelBC must supply robinbc_a / _b / _f");
+        const Real* dxi = H.geom[amrlev][0].InvCellSize();
+        MultiFab& ac = m_a_coeffs[amrlev][0];
+        const b200mg_fab* out3[3] = {ac.d_fabs(), ac.d_fabs(), ac.d_fabs()};
+        const b200mg_fab* b3[3] = {m_b_coeffs[amrlev][0][0].d_fabs(), m_b_coeffs[amrlev][0][1].d_fabs(), m_b_coeffs[amrlev][0][2].d_fabs()};
+        const double fac[3] = {bovera * dxi[0] * dxi[0], bovera * dxi[1] * dxi[1], bovera * dxi[2] * dxi[2]};
+        const double dx3[3] = {dxi[0], dxi[1], dxi[2]};
+        for (int f = 0; f < 6; ++f) {
+            const int d = f % 3;
+            if ((f < 3 ? m_lobc_orig[d] : m_hibc_orig[d]) != BCType::Robin) { continue; }
+            int only[6] = {0, 0, 0, 0, 0, 0}; only[f] = 1;
+            B200_KCALL(b200mg_robin(nf, L.bcfaces.data(), L.layout->d_vbox(), out3, b3, nullptr, L.mask.d_table(), m_robin[amrlev][0]->d_table(),
+                                    m_robin[amrlev][1]->d_table(), m_robin[amrlev][2]->d_table(), fac, dx3, only, 0, Gpu::gpuStream()));
+        }
+    }
+}
+
 void MLABecLaplacian::prepareForSolve ()
 {
     MLLinOp::prepareForSolve();
+    applyRobinBCTermsCoeffs();
     averageDownCoeffs();
     update_singular_flags();
     m_needs_update = false;
@@ -1470,6 +1585,7 @@ void MLABecLaplacian::prepareForSolve ()
 
 void MLABecLaplacian::update ()
 {
+    applyRobinBCTermsCoeffs();
     averageDownCoeffs();
     update_singular_flags();
     m_needs_update = false;

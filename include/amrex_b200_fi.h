@@ -192,6 +192,10 @@ void amrex_fi_linop_set_maxorder(MLLinOp* linop, int ord);
 void amrex_fi_linop_set_domain_bc(MLLinOp* linop, const int* ilobc, const int* ihibc);   /* LinOpBCType values */
 void amrex_fi_linop_set_coarse_fine_bc(MLLinOp* linop, const MultiFab* crse, int crse_ratio);
 void amrex_fi_linop_set_level_bc(MLLinOp* linop, int amrlev, const MultiFab* levelbcdata);
+/* MLLinOpT::setLevelBC with Robin data a*phi + b*dphi/dn = f in the ghost cells outside the Robin faces (AMReX_MLLinOp.H:220-241,
+ * AMReX_MLCellLinOp.H:513-642); the reference's Fortran interface has no such entry */
+void amrex_b200_linop_set_level_bc_robin(MLLinOp* linop, int amrlev, const MultiFab* levelbcdata, const MultiFab* robinbc_a,
+                                         const MultiFab* robinbc_b, const MultiFab* robinbc_f);
 void amrex_fi_abeclap_set_scalars(MLLinOp* linop, Real a, Real b);
 void amrex_fi_abeclap_set_acoeffs(MLLinOp* linop, int amrlev, const MultiFab* alpha);
 void amrex_fi_abeclap_set_bcoeffs(MLLinOp* linop, int amrlev, const MultiFab* beta[]);

@@ -210,6 +210,15 @@ int b200mg_apply_bc(int nfaces, const b200mg_bcface* faces, const b200mg_box* vb
 int b200mg_apply_innu(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
                       const b200mg_fab* const out3[3], const b200mg_fab* const b3[3],
                       const b200mg_ifab* m, const b200mg_fab* bcval, const double fac[3], const int on_face[6], int mode, cudaStream_t s);
+/* Robin boundary condition a*phi + b*dphi/dn = f on the flagged domain faces (data in the ghost cells of the slabs ra / rb / rf,
+ * [box*6+face]): mode 0 adds the diagonal term to the a coefficient (MLABecLaplacian applyRobinBCTermsCoeffs,
+ * AMReX_MLABecLaplacian.H:459-600; fac = (b_scalar/a_scalar)*dxinv^2), mode 1 the right-hand-side term
+ * (AMReX_MLCellABecLap.H:448-510; fac = b_scalar*dxinv^2), mode 2 writes the domain-face flux (:579-612; phi: the solution).
+ * Modes 0 / 1: flag ONE face orientation per launch. */
+int b200mg_robin(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
+                 const b200mg_fab* const out3[3], const b200mg_fab* const b3[3], const b200mg_fab* phi,
+                 const b200mg_ifab* m, const b200mg_fab* ra, const b200mg_fab* rb, const b200mg_fab* rf,
+                 const double fac[3], const double dxinv[3], const int on_face[6], int mode, cudaStream_t s);
 int b200mg_comp_interp_coef0(int nfaces, const b200mg_bcface* faces, const b200mg_box* vbox,
                              const b200mg_fab* f, const b200mg_ifab* m,
                              int maxorder, double dxinv0, double dxinv1, double dxinv2, cudaStream_t s);

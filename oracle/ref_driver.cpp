@@ -19,6 +19,7 @@
 #include <AMReX_MLMG.H>
 #include <AMReX_MLABecLaplacian.H>
 #include <AMReX_MLPoisson.H>
+#include <AMReX_MLALaplacian.H>
 #include <AMReX_GMRES_MLMG.H>
 #include <AMReX_PlotFileUtil.H>
 #include <AMReX_Print.H>
@@ -73,7 +74,11 @@ struct Problem {
     Vector<Geometry> geom; Vector<BoxArray> grids; Vector<DistributionMapping> dmap;
     Vector<MultiFab> sol, rhs, exact, acoef, bcoef;
     Vector<Array<MultiFab,3>> bface;
+    Vector<MultiFab> robin_a, robin_b, robin_f;      // prob_type 6: Robin data a*phi + b*dphi/dn = f in the ghost cells
 };
+
+// 2: variable-coefficient ABecLap; 3: its fields with inhomogeneous Neumann data on every face; 6: with Robin data on the x and z faces
+inline bool is_abec (Params const& p) { return p.prob_type == 2 || p.prob_type == 3 || p.prob_type == 6; }
 
 constexpr double kPi = 3.1415926535897932;
 
@@ -89,8 +94,9 @@ void build_problem (Params const& p, Problem& P)
     const int nlev = p.max_level+1;
     P.geom.resize(nlev); P.grids.resize(nlev); P.dmap.resize(nlev);
     P.sol.resize(nlev); P.rhs.resize(nlev); P.exact.resize(nlev);
-    const bool abec = (p.prob_type == 2 || p.prob_type == 3);   // 3: the fields of 2 with inhomogeneous Neumann data on every face
+    const bool abec = is_abec(p);
     if (abec) { P.acoef.resize(nlev); P.bcoef.resize(nlev); P.bface.resize(nlev); }
+    if (p.prob_type == 6) { P.robin_a.resize(nlev); P.robin_b.resize(nlev); P.robin_f.resize(nlev); }
 
     RealBox rb({0.,0.,0.},{1.,1.,1.});
     const int per = (p.prob_type == 5) ? 1 : 0;
@@ -112,6 +118,29 @@ void build_problem (Params const& p, Problem& P)
         if (abec) {
             P.acoef[l].define(P.grids[l], P.dmap[l], 1, 0);
             P.bcoef[l].define(P.grids[l], P.dmap[l], 1, 1);
+        }
+        if (p.prob_type == 7) {      // MLALaplacian: alpha*a(x)*phi - beta*Lap(phi), a = the bubble field of problem 2, fields of problem 1
+            if (int(P.acoef.size()) < nlev) { P.acoef.resize(nlev); }
+            P.acoef[l].define(P.grids[l], P.dmap[l], 1, 0);
+            const auto dxa = P.geom[l].CellSizeArray();
+            for (MFIter mfi(P.acoef[l]); mfi.isValid(); ++mfi) {
+                auto al = P.acoef[l].array(mfi);
+                amrex::LoopOnCpu(mfi.validbox(), [&] (int i, int j, int k) { al(i,j,k) = beta_bubble(dxa[0]*(i+0.5), dxa[1]*(j+0.5), dxa[2]*(k+0.5)); });
+            }
+        }
+        if (p.prob_type == 6) {
+            // smooth positive a, b and a smooth f everywhere (only the ghost cells outside the Robin faces are read)
+            P.robin_a[l].define(P.grids[l], P.dmap[l], 1, 1); P.robin_b[l].define(P.grids[l], P.dmap[l], 1, 1); P.robin_f[l].define(P.grids[l], P.dmap[l], 1, 1);
+            const auto dxr = P.geom[l].CellSizeArray();
+            for (MFIter mfi(P.robin_a[l]); mfi.isValid(); ++mfi) {
+                auto ra = P.robin_a[l].array(mfi); auto rb = P.robin_b[l].array(mfi); auto rf = P.robin_f[l].array(mfi);
+                amrex::LoopOnCpu(amrex::grow(mfi.validbox(),1), [&] (int i, int j, int k) {
+                    const double x = dxr[0]*(i+0.5), y = dxr[1]*(j+0.5), z = dxr[2]*(k+0.5);
+                    ra(i,j,k) = 1.0 + 0.5*std::cos(2.*kPi*y)*std::cos(2.*kPi*z);
+                    rb(i,j,k) = 1.0 + 0.25*std::sin(2.*kPi*(x+z));
+                    rf(i,j,k) = std::sin(2.*kPi*(x+y)) + 0.3;
+                });
+            }
         }
         const auto dx = P.geom[l].CellSizeArray();
         const double a = p.ascalar, b = p.bscalar;
@@ -248,11 +277,17 @@ void setup_abec (Params const& p, Problem& P, MLABecLaplacian& op)
     if (p.prob_type == 3) {
         const auto t = LinOpBCType::inhomogNeumann;
         op.setDomainBC({t,t,t},{t,t,t});
+    } else if (p.prob_type == 6) {
+        op.setDomainBC({LinOpBCType::Robin, LinOpBCType::Dirichlet, LinOpBCType::Robin},
+                       {LinOpBCType::Robin, LinOpBCType::Neumann, LinOpBCType::Robin});
     } else {
         op.setDomainBC({LinOpBCType::Dirichlet, LinOpBCType::Neumann, LinOpBCType::Neumann},
                        {LinOpBCType::Neumann, LinOpBCType::Dirichlet, LinOpBCType::Neumann});
     }
-    for (int l = 0; l <= p.max_level; ++l) { op.setLevelBC(l, &P.sol[l]); }
+    for (int l = 0; l <= p.max_level; ++l) {
+        if (p.prob_type == 6) { op.setLevelBC(l, &P.sol[l], &P.robin_a[l], &P.robin_b[l], &P.robin_f[l]); }
+        else { op.setLevelBC(l, &P.sol[l]); }
+    }
     op.setScalars(p.ascalar, p.bscalar);
     for (int l = 0; l <= p.max_level; ++l) {
         op.setACoeffs(l, P.acoef[l]);
@@ -283,11 +318,17 @@ void dump_inputs (Params const& p, Problem& P, std::ostream& man)
         dump_mf(p.dump_dir, "sol0"+s, P.sol[l], 1, man);
         dump_mf(p.dump_dir, "rhs"+s, P.rhs[l], 0, man);
         dump_mf(p.dump_dir, "exact"+s, P.exact[l], 0, man);
-        if (p.prob_type == 2 || p.prob_type == 3) {
+        if (is_abec(p)) {
             dump_mf(p.dump_dir, "acoef"+s, P.acoef[l], 0, man);
             dump_mf(p.dump_dir, "bx"+s, P.bface[l][0], 0, man);
             dump_mf(p.dump_dir, "by"+s, P.bface[l][1], 0, man);
             dump_mf(p.dump_dir, "bz"+s, P.bface[l][2], 0, man);
+        }
+        if (p.prob_type == 7) { dump_mf(p.dump_dir, "acoef"+s, P.acoef[l], 0, man); }
+        if (p.prob_type == 6) {
+            dump_mf(p.dump_dir, "robin_a"+s, P.robin_a[l], 1, man);
+            dump_mf(p.dump_dir, "robin_b"+s, P.robin_b[l], 1, man);
+            dump_mf(p.dump_dir, "robin_f"+s, P.robin_f[l], 1, man);
         }
     }
 }
@@ -301,8 +342,16 @@ int run_solve (Params const& p)
 
     std::unique_ptr<MLLinOp> op;
     LPInfo info = make_info(p);
-    if (p.prob_type == 2 || p.prob_type == 3) {
+    if (is_abec(p)) {
         auto o = std::make_unique<MLABecLaplacian>(P.geom, P.grids, P.dmap, info); setup_abec(p, P, *o); op = std::move(o);
+    } else if (p.prob_type == 7) {
+        auto o = std::make_unique<MLALaplacian>(P.geom, P.grids, P.dmap, info);
+        o->setMaxOrder(p.maxorder);
+        o->setDomainBC({LinOpBCType::Dirichlet,LinOpBCType::Dirichlet,LinOpBCType::Dirichlet},{LinOpBCType::Dirichlet,LinOpBCType::Dirichlet,LinOpBCType::Dirichlet});
+        for (int l = 0; l <= p.max_level; ++l) { o->setLevelBC(l, &P.sol[l]); }
+        o->setScalars(1.0, 1.0);
+        for (int l = 0; l <= p.max_level; ++l) { o->setACoeffs(l, P.acoef[l]); }
+        op = std::move(o);
     } else {
         auto o = std::make_unique<MLPoisson>(P.geom, P.grids, P.dmap, info); setup_poisson(p, P, *o); op = std::move(o);
     }
@@ -317,7 +366,7 @@ int run_solve (Params const& p)
         auto t0 = std::chrono::steady_clock::now();
         for (int l = 0; l <= p.max_level; ++l) {
             std::unique_ptr<MLLinOp> lop;
-            if (p.prob_type == 2 || p.prob_type == 3) {
+            if (is_abec(p)) {
                 auto o = std::make_unique<MLABecLaplacian>(Vector<Geometry>{P.geom[l]}, Vector<BoxArray>{P.grids[l]}, Vector<DistributionMapping>{P.dmap[l]}, info);
                 o->setMaxOrder(p.maxorder); o->setGaussSeidel(p.gauss_seidel != 0);
                 o->setDomainBC({LinOpBCType::Dirichlet, LinOpBCType::Neumann, LinOpBCType::Neumann},
@@ -510,7 +559,7 @@ int run_amr (Params const& p)
     dump_inputs(p, P, man);
     std::unique_ptr<MLLinOp> op;
     LPInfo info = make_info(p);
-    if (p.prob_type == 2 || p.prob_type == 3) {
+    if (is_abec(p)) {
         auto o = std::make_unique<MLABecLaplacian>(P.geom, P.grids, P.dmap, info); setup_abec(p, P, *o); op = std::move(o);
     } else {
         auto o = std::make_unique<MLPoisson>(P.geom, P.grids, P.dmap, info); setup_poisson(p, P, *o); op = std::move(o);

@@ -72,16 +72,29 @@ def build_problem(ab, prob_type, n_cell, max_grid_size, dump, maxorder=2, agg_gr
     rhs.upload(a, lo)
     D, N, P = ab.LinOpBCType.Dirichlet, ab.LinOpBCType.Neumann, ab.LinOpBCType.Periodic
     keep = []
-    if prob_type in (2, 3):
+    if prob_type in (2, 3, 6):
         op = ab.MLABecLaplacian([geom], [ba], [dm], agg_grid_size=agg_grid_size, con_grid_size=agg_grid_size,
                                 max_coarsening_level=max_coarsening_level)
         op.setMaxOrder(maxorder)
         if prob_type == 3:     # the fields of problem 2 with inhomogeneous Neumann data (ghost cells of sol0) on every face
             IN = ab.LinOpBCType.inhomogNeumann
             op.setDomainBC((IN, IN, IN), (IN, IN, IN))
+        elif prob_type == 6:   # the fields of problem 2 with Robin data on the x and z faces (reference driver prob_type 6)
+            R = ab.LinOpBCType.Robin
+            op.setDomainBC((R, D, R), (R, N, R))
         else:
             op.setDomainBC((D, N, N), (N, D, N))
-        op.setLevelBC(0, sol)
+        if prob_type == 6:
+            robin = []
+            for nm in ("robin_a", "robin_b", "robin_f"):
+                f = ab.MultiFab(ba, dm, 1, 1)
+                lo, a = dump[nm + "_lev0"]
+                f.upload(a, lo, ng=1)
+                robin.append(f)
+            keep += robin
+            op.setLevelBC(0, sol, robin=robin)
+        else:
+            op.setLevelBC(0, sol)
         op.setScalars(1.e-3, 1.0)
         acoef = ab.MultiFab(ba, dm, 1, 0)
         lo, a = dump["acoef_lev0"]
@@ -97,6 +110,18 @@ def build_problem(ab, prob_type, n_cell, max_grid_size, dump, maxorder=2, agg_gr
             faces.append(f)
         op.setBCoeffs(0, faces)
         keep += [acoef] + faces
+    elif prob_type == 7:      # MLALaplacian: alpha*a(x) - beta*Laplacian, homogeneous Dirichlet (reference driver prob_type 7)
+        op = ab.MLALaplacian([geom], [ba], [dm], agg_grid_size=agg_grid_size, con_grid_size=agg_grid_size,
+                             max_coarsening_level=max_coarsening_level)
+        op.setMaxOrder(maxorder)
+        op.setDomainBC((D, D, D), (D, D, D))
+        op.setLevelBC(0, sol)
+        op.setScalars(1.0, 1.0)
+        acoef = ab.MultiFab(ba, dm, 1, 0)
+        lo, a = dump["acoef_lev0"]
+        acoef.upload(a, lo)
+        op.setACoeffs(0, acoef)
+        keep += [acoef]
     else:
         op = ab.MLPoisson([geom], [ba], [dm], agg_grid_size=agg_grid_size, con_grid_size=agg_grid_size,
                           max_coarsening_level=max_coarsening_level)

@@ -213,3 +213,92 @@ def test_fused4_vs_pairs_reference_problems(ab, prob, n, mgs):
         res[fusion] = _two_smooths(ab, op, n, 0, 3)
     assert "b200mg_gsrb4" in res[1][1]
     assert np.array_equal(res[0][0], res[1][0])
+
+
+def test_base_fi_entries(ab):
+    """The Base amrex_fi_* entries the reference's Fortran modules bind beyond the solver path (MFIter family, reductions,
+    element-wise products, lincomb, SumBoundary, iMultiFab, geometry / distromap getters), against numpy on small data."""
+    import ctypes as C
+    lib = ab.lib
+    n, mgs = 32, 16
+    ab.Geometry.setup((0., 0., 0.), (1., 2., 4.), (1, 0, 1))
+    geom = ab.Geometry((0, 0, 0), (n - 1,) * 3)
+    ba = ab.BoxArray((0, 0, 0), (n - 1,) * 3).maxSize(mgs)
+    dm = ab.DistributionMapping(ba)
+    rng = np.random.default_rng(7)
+    A, B = rng.standard_normal((n, n, n)), rng.standard_normal((n, n, n)) + 3.0
+    x, y, z = ab.MultiFab(ba, dm, 1, 1), ab.MultiFab(ba, dm, 1, 1), ab.MultiFab(ba, dm, 1, 1)
+    x.setVal(0.0, ng=1); y.setVal(0.0, ng=1); z.setVal(0.0, ng=1)
+    x.upload(A, (0, 0, 0)); y.upload(B, (0, 0, 0))
+    for f, rt in (("amrex_fi_multifab_min", C.c_double), ("amrex_fi_multifab_max", C.c_double), ("amrex_fi_multifab_norm1", C.c_double),
+                  ("amrex_fi_multifab_norm2", C.c_double), ("amrex_fi_distromap_issame", C.c_int), ("amrex_fi_mfiter_grid_index", C.c_int),
+                  ("amrex_fi_boxarray_intersects_box", C.c_int)):
+        getattr(lib, f).restype = rt
+    P, I = C.c_void_p, C.c_int
+    i3 = lambda v: (C.c_int * 3)(*v)
+    assert lib.amrex_fi_multifab_min(P(x.ptr.value), 0, 0) == pytest.approx(A.min(), rel=0, abs=0)
+    assert lib.amrex_fi_multifab_max(P(x.ptr.value), 0, 0) == pytest.approx(A.max(), rel=0, abs=0)
+    assert lib.amrex_fi_multifab_norm1(P(x.ptr.value), 0) == pytest.approx(np.abs(A).sum(), rel=1e-13)
+    assert lib.amrex_fi_multifab_norm2(P(x.ptr.value), 0) == pytest.approx(np.sqrt((A * A).sum()), rel=1e-13)
+    ng0 = i3((0, 0, 0))
+    lib.amrex_fi_multifab_copy(P(z.ptr.value), P(x.ptr.value), 0, 0, 1, ng0)
+    lib.amrex_fi_multifab_multiply(P(z.ptr.value), P(y.ptr.value), 0, 0, 1, ng0)
+    assert np.array_equal(z.download((0, 0, 0), (n, n, n)), A * B)
+    lib.amrex_fi_multifab_divide(P(z.ptr.value), P(y.ptr.value), 0, 0, 1, ng0)
+    assert np.array_equal(z.download((0, 0, 0), (n, n, n)), (A * B) / B)
+    lib.amrex_fi_multifab_lincomb(P(z.ptr.value), C.c_double(2.0), P(x.ptr.value), 0, C.c_double(-0.5), P(y.ptr.value), 0, 0, 1, ng0)
+    assert np.array_equal(z.download((0, 0, 0), (n, n, n)), 2.0 * A + (-0.5) * B)
+    ab.check()
+    # MFIter over the local boxes: grid indices, valid / grown boxes, data pointer bounds
+    it = P()
+    lib.amrex_fi_new_mfiter_r(C.byref(it), P(x.ptr.value), 0, 0)
+    valid, seen = C.c_int(0), []
+    lib.amrex_fi_mfiter_is_valid(it, C.byref(valid))
+    while valid.value:
+        lo, hi, nod = i3((0, 0, 0)), i3((0, 0, 0)), i3((9, 9, 9))
+        lib.amrex_fi_mfiter_validbox(it, lo, hi, nod)
+        g = lib.amrex_fi_mfiter_grid_index(it)
+        assert tuple(lo) + tuple(hi) == ba.boxes()[g] and tuple(nod) == (0, 0, 0)
+        glo, ghi = i3((0, 0, 0)), i3((0, 0, 0))
+        lib.amrex_fi_mfiter_growntilebox(it, glo, ghi, 1, nod)
+        assert tuple(glo) == tuple(v - 1 for v in lo) and tuple(ghi) == tuple(v + 1 for v in hi)
+        dp, dlo, dhi = P(), i3((0, 0, 0)), i3((0, 0, 0))
+        lib.amrex_fi_multifab_dataptr_iter(P(x.ptr.value), it, C.byref(dp), dlo, dhi)
+        assert dp.value and tuple(dlo) == tuple(glo) and tuple(dhi) == tuple(ghi)
+        seen.append(g)
+        lib.amrex_fi_increment_mfiter(it, C.byref(valid))
+    lib.amrex_fi_delete_mfiter(it)
+    assert sorted(seen) == list(range(ba.size()))
+    # SumBoundary: ghost cells are added to the valid cells they overlap (periodic in x and z)
+    w = ab.MultiFab(ba, dm, 1, 1)
+    w.setVal(1.0, ng=1)
+    lib.amrex_fi_multifab_sum_boundary(P(w.ptr.value), P(geom.ptr.value), 0, 1)
+    ab.check()
+    got = w.download((0, 0, 0), (n, n, n))
+    cnt = np.ones((n, n, n))
+    for d, per in enumerate((1, 0, 1)):       # every cell collects one extra contribution per box face it touches (domain faces only when periodic)
+        for c in range(n):
+            k = (1 if c % mgs == 0 and (c > 0 or per) else 0) + (1 if c % mgs == mgs - 1 and (c < n - 1 or per) else 0)
+            sl = [slice(None)] * 3
+            sl[d] = c
+            cnt[tuple(sl)] *= (1 + k)
+    # contributions multiply along the three directions (a corner ghost cell of a box overlaps the diagonal neighbour)
+    assert np.array_equal(got, cnt)
+    # iMultiFab, geometry / distromap getters
+    imf, pba, pdm = P(), P(ba.ptr.value), P(dm.ptr.value)
+    lib.amrex_fi_new_imultifab(C.byref(imf), C.byref(pba), C.byref(pdm), 1, i3((1, 1, 1)), i3((0, 0, 0)))
+    lib.amrex_fi_imultifab_setval(imf, 7, 0, 1, i3((1, 1, 1)))
+    lib.amrex_fi_delete_imultifab(imf)
+    ab.check()
+    pm = i3((0, 0, 0))
+    lib.amrex_fi_geometry_get_pmask(P(geom.ptr.value), pm)
+    assert tuple(pm) == (1, 0, 1)
+    plo, phi = (C.c_double * 3)(), (C.c_double * 3)()
+    lib.amrex_fi_geometry_get_probdomain(P(geom.ptr.value), plo, phi)
+    assert tuple(plo) == (0., 0., 0.) and tuple(phi) == (1., 2., 4.)
+    dm2 = P()
+    lib.amrex_fi_clone_distromap(C.byref(dm2), P(dm.ptr.value))
+    assert lib.amrex_fi_distromap_issame(dm2, P(dm.ptr.value)) == 1
+    lib.amrex_fi_delete_distromap(dm2)
+    assert lib.amrex_fi_boxarray_intersects_box(P(ba.ptr.value), i3((5, 5, 5)), i3((6, 6, 6))) == 1
+    assert lib.amrex_fi_boxarray_intersects_box(P(ba.ptr.value), i3((n, n, n)), i3((n + 2, n + 2, n + 2))) == 0

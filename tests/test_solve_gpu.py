@@ -89,6 +89,41 @@ def test_periodic_poisson_256_config5(ab):
     assert diff <= SOL_TOL
 
 
+def test_alaplacian(ab):
+    """MLALaplacian (alpha*a(x) - beta*Laplacian) against the reference's own operator class: same V-cycle count, history to
+    1e-5, solution to 1e-10 (the kernels are the variable-coefficient ones with b = 1: equal to rounding)."""
+    ref, mlmg, diff = solve_case(ab, 7, 64, 32)
+    assert abs(mlmg.numIters() - ref["iters"]) <= 1
+    for a, b in zip(mlmg.residualHistory(), ref["history"]):
+        assert a == pytest.approx(b, rel=1e-5)
+    assert diff <= SOL_TOL
+
+
+@pytest.mark.parametrize("n,mgs", [(64, 32), (128, 64)])
+def test_robin_bc(ab, n, mgs):
+    """Robin boundary condition a*phi + b*dphi/dn = f on the x and z faces (Dirichlet / Neumann on y): the diagonal and
+    right-hand-side terms of MLABecLaplacian (applyRobinBCTermsCoeffs, applyInhomogNeumannTerm) against the reference, and
+    the post-solve face fluxes, whose Robin faces take a value of their own (addInhomogNeumannFlux)."""
+    ref, dump = run_ref(dump=True, mode="solve", prob_type=6, n_cell=n, max_grid_size=mgs, linop_maxorder=2, agg_grid_size=32)
+    P = build_problem(ab, 6, n, mgs, dump, maxorder=2)
+    mlmg = ab.MLMG(P["op"])
+    mlmg.setVerbose(0)
+    mlmg.solve([P["sol"]], [P["rhs"]], 1e-10, 0.0)
+    assert abs(mlmg.numIters() - ref["iters"]) <= 1
+    assert mlmg.initResidual() == pytest.approx(ref["resnorm0"], rel=1e-12)
+    for a, b in zip(mlmg.residualHistory(), ref["history"]):
+        assert a == pytest.approx(b, rel=1e-5)
+    refsol = dump["sol_lev0"][1][1:-1, 1:-1, 1:-1]
+    assert rel_maxdiff(P["sol"].download((0, 0, 0), (n, n, n)), refsol) <= SOL_TOL
+    faces = [ab.MultiFab(P["ba"], P["dm"], 1, 0, nodal=[1 if a == d else 0 for a in range(3)]) for d in range(3)]
+    for kind, call in (("flux", mlmg.getFluxes), ("grad", mlmg.getGradSolution)):
+        call([faces])
+        for d in range(3):
+            shape = tuple(n + (1 if a == d else 0) for a in range(3))
+            lo, want = dump[f"{kind}{d}_lev0"]
+            assert rel_maxdiff(faces[d].download((0, 0, 0), shape), want) <= 1e-7, (kind, d)
+
+
 @pytest.mark.parametrize("bottom", ["smoother", "cg"])
 def test_bottom_solvers(ab, bottom):
     ref, mlmg, diff = solve_case(ab, 1, 64, 32, bottom=bottom)
