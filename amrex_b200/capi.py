@@ -56,6 +56,8 @@ _SIGS = {
     "amrex_fi_multifab_fill_boundary": (None, [_P, _P, _I, _I, _I]),
     "amrex_b200_multifab_dot": (_D, [_P, _P]),
     "amrex_b200_multifab_upload": (None, [_P, _P, _IP, _IP, _I, _I]),
+    "amrex_b200_multifab_upload_async": (None, [_P, _P, _IP, _IP, _I, _I, _P]),
+    "amrex_b200_multifab_download_async": (None, [_P, _P, _IP, _IP, _I, _I, _P]),
     "amrex_b200_multifab_download": (None, [_P, _P, _IP, _IP, _I, _I]),
     "amrex_b200_average_cellcenter_to_face": (None, [_P, _P, _P, _P, _P]),
     "amrex_fi_write_plotfile": (None, [C.c_char_p, _I, _PP, C.POINTER(C.c_char_p), _PP, _D, _IP, _IP]),
@@ -383,6 +385,15 @@ class MultiFab(_Obj):
         lib.amrex_b200_multifab_download(self.ptr, a.ctypes.data_as(C.c_void_p), _i3(lo), _i3(hi), 0, ng)
         check()
         return a
+
+    def upload_ptr_async(self, host_ptr, lo, hi, stream, ng=0):
+        """enqueue on the CUDA stream `stream` (a cudaStream_t as int), no synchronisation; pinned host memory"""
+        lib.amrex_b200_multifab_upload_async(self.ptr, C.c_void_p(host_ptr), _i3(lo), _i3(hi), 0, ng, C.c_void_p(stream))
+        check()
+
+    def download_ptr_async(self, host_ptr, lo, hi, stream, ng=0):
+        lib.amrex_b200_multifab_download_async(self.ptr, C.c_void_p(host_ptr), _i3(lo), _i3(hi), 0, ng, C.c_void_p(stream))
+        check()
 
     def download_ptr(self, host_ptr, lo, hi, ng=0):
         lib.amrex_b200_multifab_download(self.ptr, C.c_void_p(host_ptr), _i3(lo), _i3(hi), 0, ng)

@@ -287,18 +287,18 @@ void copy3d (DESC const& d, T* h, Box const& region, Box const& isect, int comp,
 }
 
 template <class T>
-void FabArray<T>::copyFromHost (const T* h, Box const& region, int comp, int ng)
+void FabArray<T>::copyFromHost (const T* h, Box const& region, int comp, int ng, bool sync)
 {
     AMREX_ALWAYS_ASSERT(ng <= m_ngrow && region.ixType() == ixType());
     for (int li = 0; li < local_size(); ++li) {
         Box isect = amrex::grow(validbox(li), ng) & region;
         if (isect.ok()) { copy3d(m_hdesc[li], const_cast<T*>(h), region, isect, comp, false); }
     }
-    Gpu::streamSynchronize();
+    if (sync) { Gpu::streamSynchronize(); }
 }
 
 template <class T>
-void FabArray<T>::copyToHost (T* h, Box const& region, int comp, int ng, bool valid_wins) const
+void FabArray<T>::copyToHost (T* h, Box const& region, int comp, int ng, bool valid_wins, bool sync) const
 {
     AMREX_ALWAYS_ASSERT(ng <= m_ngrow && region.ixType() == ixType());
     const int npass = (ng > 0 && valid_wins) ? 2 : 1;
@@ -308,7 +308,7 @@ void FabArray<T>::copyToHost (T* h, Box const& region, int comp, int ng, bool va
             if (isect.ok()) { copy3d(m_hdesc[li], h, region, isect, comp, true); }
         }
     }
-    Gpu::streamSynchronize();
+    if (sync) { Gpu::streamSynchronize(); }
 }
 
 // one local fab (its own valid + ng ghost cells, nothing from its neighbours), Fortran order over the grown box

@@ -335,6 +335,22 @@ void amrex_b200_multifab_download (const MultiFab* mf, Real* h, const int lo[3],
 {
     FI_VOID( mf->copyToHost(h, Box(IntVect(lo[0], lo[1], lo[2]), IntVect(hi[0], hi[1], hi[2]), mf->ixType()), comp, ng); )
 }
+// the same transfers enqueued on a stream of the caller's (pinned host memory), without synchronisation: a streaming
+// application uploads the inputs of the next solve and downloads the previous solution while the current solve runs
+void amrex_b200_multifab_upload_async (MultiFab* mf, const Real* h, const int lo[3], const int hi[3], int comp, int ng, void* stream)
+{
+    FI_TRY Gpu::setStream(static_cast<cudaStream_t>(stream));
+           mf->copyFromHost(h, Box(IntVect(lo[0], lo[1], lo[2]), IntVect(hi[0], hi[1], hi[2]), mf->ixType()), comp, ng, false);
+           Gpu::setStream(nullptr);
+    FI_CATCH(Gpu::setStream(nullptr); return)
+}
+void amrex_b200_multifab_download_async (const MultiFab* mf, Real* h, const int lo[3], const int hi[3], int comp, int ng, void* stream)
+{
+    FI_TRY Gpu::setStream(static_cast<cudaStream_t>(stream));
+           mf->copyToHost(h, Box(IntVect(lo[0], lo[1], lo[2]), IntVect(hi[0], hi[1], hi[2]), mf->ixType()), comp, ng, true, false);
+           Gpu::setStream(nullptr);
+    FI_CATCH(Gpu::setStream(nullptr); return)
+}
 void amrex_b200_average_cellcenter_to_face (MultiFab* fx, MultiFab* fy, MultiFab* fz, const MultiFab* cc, const Geometry* geom)
 {
     FI_VOID( average_cellcenter_to_face({fx, fy, fz}, *cc, *geom); )
