@@ -57,6 +57,7 @@ _SIGS = {
     "amrex_b200_multifab_dot": (_D, [_P, _P]),
     "amrex_b200_multifab_upload": (None, [_P, _P, _IP, _IP, _I, _I]),
     "amrex_b200_multifab_upload_async": (None, [_P, _P, _IP, _IP, _I, _I, _P]),
+    "amrex_b200_multifab_download_fab": (None, [_P, _I, _P, _I, _I]),
     "amrex_b200_multifab_download_async": (None, [_P, _P, _IP, _IP, _I, _I, _P]),
     "amrex_b200_multifab_download": (None, [_P, _P, _IP, _IP, _I, _I]),
     "amrex_b200_average_cellcenter_to_face": (None, [_P, _P, _P, _P, _P]),
@@ -360,29 +361,37 @@ class MultiFab(_Obj):
         lib.amrex_fi_multifab_subtract(self.ptr, src.ptr, scomp, dcomp, ncomp, _i3((ng,) * 3))
         check()
 
-    def fill_boundary(self, geom, cross=False):
-        lib.amrex_fi_multifab_fill_boundary(self.ptr, geom.ptr, 0, 1, int(cross))
+    def fill_boundary(self, geom, cross=False, comp=0, ncomp=1):
+        lib.amrex_fi_multifab_fill_boundary(self.ptr, geom.ptr, comp, ncomp, int(cross))
         check()
 
-    def parallel_copy(self, src, geom, srcng=0, dstng=0):
-        lib.amrex_fi_multifab_parallelcopy(self.ptr, src.ptr, 0, 0, 1, srcng, dstng, geom.ptr)
+    def parallel_copy(self, src, geom, srcng=0, dstng=0, scomp=0, dcomp=0, ncomp=1):
+        lib.amrex_fi_multifab_parallelcopy(self.ptr, src.ptr, scomp, dcomp, ncomp, srcng, dstng, geom.ptr)
         check()
 
-    def upload(self, arr, lo, ng=0):
+    def upload(self, arr, lo, ng=0, comp=0):
         """arr: numpy float64 array indexed [i,j,k] (any memory order) whose [0,0,0] element is index `lo`."""
         a = np.asfortranarray(arr, dtype=np.float64)
         hi = [lo[d] + a.shape[d] - 1 for d in range(3)]
-        lib.amrex_b200_multifab_upload(self.ptr, a.ctypes.data_as(C.c_void_p), _i3(lo), _i3(hi), 0, ng)
+        lib.amrex_b200_multifab_upload(self.ptr, a.ctypes.data_as(C.c_void_p), _i3(lo), _i3(hi), comp, ng)
         check()
 
     def upload_ptr(self, host_ptr, lo, hi, ng=0):
         lib.amrex_b200_multifab_upload(self.ptr, C.c_void_p(host_ptr), _i3(lo), _i3(hi), 0, ng)
         check()
 
-    def download(self, lo, shape, ng=0):
+    def download(self, lo, shape, ng=0, comp=0):
         a = np.zeros(shape, dtype=np.float64, order="F")
         hi = [lo[d] + shape[d] - 1 for d in range(3)]
-        lib.amrex_b200_multifab_download(self.ptr, a.ctypes.data_as(C.c_void_p), _i3(lo), _i3(hi), 0, ng)
+        lib.amrex_b200_multifab_download(self.ptr, a.ctypes.data_as(C.c_void_p), _i3(lo), _i3(hi), comp, ng)
+        check()
+        return a
+
+    def download_fab(self, igrd, box, ng=0, comp=0):
+        """local grid igrd alone (its own ghost cells, nothing from its neighbours); box = (lo0,lo1,lo2,hi0,hi1,hi2) of the grid"""
+        shape = tuple(box[d + 3] - box[d] + 1 + 2 * ng for d in range(3))
+        a = np.zeros(shape, dtype=np.float64, order="F")
+        lib.amrex_b200_multifab_download_fab(self.ptr, igrd, a.ctypes.data_as(C.c_void_p), comp, ng)
         check()
         return a
 
@@ -533,7 +542,7 @@ class MLMG(_Obj):
     def setFixedIter(self, n): lib.amrex_fi_multigrid_set_fixed_iter(self.ptr, n)
 
     def setBottomSolver(self, s):
-        lib.amrex_fi_multigrid_set_bottom_solver(self.ptr, {"smoother": 0, "bicgstab": 1, "cg": 2}[s])
+        lib.amrex_fi_multigrid_set_bottom_solver(self.ptr, {"smoother": 0, "bicgstab": 1, "cg": 2, "bicgcg": 5, "cgbicg": 6}[s])
         check()
 
     def solve(self, sol, rhs, tol_rel, tol_abs):

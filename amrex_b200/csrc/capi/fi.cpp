@@ -335,6 +335,13 @@ void amrex_b200_multifab_download (const MultiFab* mf, Real* h, const int lo[3],
 {
     FI_VOID( mf->copyToHost(h, Box(IntVect(lo[0], lo[1], lo[2]), IntVect(hi[0], hi[1], hi[2]), mf->ixType()), comp, ng); )
 }
+// local grid igrd (global box index) alone: its valid cells and ng ghost layers, Fortran order over the grown box
+void amrex_b200_multifab_download_fab (const MultiFab* mf, int igrd, Real* h, int comp, int ng)
+{
+    FI_VOID( const int li = mf->layout().localIndex(igrd);
+             AMREX_ALWAYS_ASSERT_WITH_MESSAGE(li >= 0, "amrex_b200_multifab_download_fab: the grid is not local");
+             mf->copyFabToHost(li, h, comp, ng); )
+}
 // the same transfers enqueued on a stream of the caller's (pinned host memory), without synchronisation: a streaming
 // application uploads the inputs of the next solve and downloads the previous solution while the current solve runs
 void amrex_b200_multifab_upload_async (MultiFab* mf, const Real* h, const int lo[3], const int hi[3], int comp, int ng, void* stream)
@@ -530,6 +537,8 @@ void amrex_fi_multigrid_set_bottom_solver (MLMG* mlmg, int s)
         if (s == 0) { mlmg->setBottomSolver(BottomSolver::smoother); }
         else if (s == 1) { mlmg->setBottomSolver(BottomSolver::bicgstab); }
         else if (s == 2) { mlmg->setBottomSolver(BottomSolver::cg); }
+        else if (s == 5) { mlmg->setBottomSolver(BottomSolver::bicgcg); }     // 5 / 6: the two-stage solvers (C++ only in the reference;
+        else if (s == 6) { mlmg->setBottomSolver(BottomSolver::cgbicg); }     //        its codes 3 / 4 are hypre / petsc: not available)
         else { Abort("amrex_fi_multigrid_set_bottom_solver: unknown or unavailable bottom solver"); } )
 }
 void amrex_fi_multigrid_set_bottom_verbose (MLMG* mlmg, int n) { mlmg->setBottomVerbose(n); }

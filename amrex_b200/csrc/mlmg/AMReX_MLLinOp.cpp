@@ -953,7 +953,9 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
         // the pass over the boxes whose halo comes from this GPU only runs while the NVLink transfer is in flight, the pass
         // over the boxes with remote neighbours after the unpack.  Out of place, so the two halves do not interact.
         bool split = false;
-        if (!zero4 && !skip_fillboundary && m_halo_overlap && L.fused4_ok == 1 && ParallelDescriptor::NProcs() > 1 && !Gpu::debugSync()) {
+        // (not under the per-kernel profiler: it times whole-level launches on the main stream)
+        if (!zero4 && !skip_fillboundary && m_halo_overlap && L.fused4_ok == 1 && ParallelDescriptor::NProcs() > 1 && !Gpu::debugSync()
+            && !Gpu::profiling()) {
             if (L.halo_split < 0) {
                 auto const& rf = sol.FillBoundaryRemoteFabs(IntVect(1), H.geom[amrlev][mglev].periodicity(), true);
                 L.boxes_remote_halo = rf; L.boxes_local_halo.clear();
@@ -975,7 +977,7 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
             }
             applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, true);
             cudaStream_t s = Gpu::gpuStream(), aux = Gpu::auxStream();
-            const bool side = !Gpu::profiling();                   // (the per-kernel profiler times launches on the main stream)
+            const bool side = true;
             bool ok2 = true;
             if (side) {
                 AMREX_CUDA_SAFE_CALL(cudaEventRecord(ev_ready, s));

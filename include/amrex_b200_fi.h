@@ -169,6 +169,8 @@ Real amrex_b200_multifab_dot(const MultiFab* x, const MultiFab* y);   /* amrex::
  * type); cells of every local fab inside grow(validbox,ng) are transferred.  Host memory may be pinned. */
 void amrex_b200_multifab_upload(MultiFab* mf, const Real* h, const int lo[3], const int hi[3], int comp, int ng);
 void amrex_b200_multifab_download(const MultiFab* mf, Real* h, const int lo[3], const int hi[3], int comp, int ng);
+/* one local grid alone (global box index igrd): valid cells + ng ghost layers of THAT fab, Fortran order over the grown box */
+void amrex_b200_multifab_download_fab(const MultiFab* mf, int igrd, Real* h, int comp, int ng);
 /* the same, enqueued on the caller's cudaStream_t without synchronisation (pinned host memory): lets an application overlap the
  * upload of the next solve's inputs and the download of the previous solution with the running solve */
 void amrex_b200_multifab_upload_async(MultiFab* mf, const Real* h, const int lo[3], const int hi[3], int comp, int ng, void* stream);

@@ -309,6 +309,8 @@ void set_bottom (Params const& p, MLMG& mlmg)
     if (p.bottom == "smoother") mlmg.setBottomSolver(BottomSolver::smoother);
     else if (p.bottom == "bicgstab") mlmg.setBottomSolver(BottomSolver::bicgstab);
     else if (p.bottom == "cg") mlmg.setBottomSolver(BottomSolver::cg);
+    else if (p.bottom == "bicgcg") mlmg.setBottomSolver(BottomSolver::bicgcg);
+    else if (p.bottom == "cgbicg") mlmg.setBottomSolver(BottomSolver::cgbicg);
 }
 
 void dump_inputs (Params const& p, Problem& P, std::ostream& man)

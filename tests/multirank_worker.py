@@ -27,8 +27,92 @@ CASES = {
 }
 
 
+def exchange_case(ab, world, rank, out_path):
+    """Two-component halo exchange and ParallelCopy across ranks against the known answer (the reference's
+    Tests/MultiPeriod/main.cpp:33-69: every ghost cell holds the value of its periodic image): pack -> ncclSend/Recv ->
+    unpack with the components of a tag back to back in the buffer (AMReX_FBI.H:765-771)."""
+    import torch
+    import torch.distributed as dist
+    n, mgs = 64, 16
+    ab.Geometry.setup((0., 0., 0.), (1., 1., 1.), (1, 1, 0))
+    geom = ab.Geometry((0, 0, 0), (n - 1,) * 3)
+    ba = ab.BoxArray((0, 0, 0), (n - 1,) * 3).maxSize(mgs)
+    dm = ab.DistributionMapping(ba)
+    pmap = dm.pmap(ba.size())
+    me = ab.lib.amrex_b200_myproc()
+    f = lambda i, j, k, c: (i % n) + n * ((j % n) + n * k) + 0.5 * c * n ** 3      # periodic in x and y
+    bad = 0
+    for cross in (False, True):
+        mf = ab.MultiFab(ba, dm, 2, 1)
+        mf.setVal(-1.0, ng=1)
+        boxes = ba.boxes()
+        for g, b in enumerate(boxes):
+            if pmap[g] != me:
+                continue
+            I, J, K = np.meshgrid(*[np.arange(b[d], b[d + 3] + 1) for d in range(3)], indexing="ij")
+            for c in range(2):
+                mf.upload(f(I, J, K, c), b[:3], comp=c)
+        mf.fill_boundary(geom, cross=cross, comp=0, ncomp=2)
+        for g, b in enumerate(boxes):
+            if pmap[g] != me:
+                continue
+            glo = [v - 1 for v in b[:3]]
+            shp = tuple(b[d + 3] - b[d] + 3 for d in range(3))
+            I, J, K = np.meshgrid(*[np.arange(glo[d], glo[d] + shp[d]) for d in range(3)], indexing="ij")
+            inside_z = (K >= 0) & (K <= n - 1)
+            nout = (I < b[0]).astype(int) + (I > b[3]) + (J < b[1]) + (J > b[4]) + (K < b[2]) + (K > b[5])
+            check = inside_z & ((nout <= 1) if cross else (nout >= 0))          # cross: faces only
+            for c in range(2):
+                # a region that is this box grown by one: only this fab's own ghost cells are read where it covers them last
+                got = mf.download_fab(g, b, ng=1, comp=c)          # this fab's own ghost cells
+                bad += int(np.count_nonzero(check & (got != f(I, J, K, c))))
+    # ParallelCopy of both components onto another layout (boxes of 32^3, other owners)
+    ba2 = ab.BoxArray((0, 0, 0), (n - 1,) * 3).maxSize(32)
+    dm2 = ab.DistributionMapping(ba2)
+    src = ab.MultiFab(ba, dm, 2, 0)
+    for g, b in enumerate(ba.boxes()):
+        if pmap[g] != me:
+            continue
+        I, J, K = np.meshgrid(*[np.arange(b[d], b[d + 3] + 1) for d in range(3)], indexing="ij")
+        for c in range(2):
+            src.upload(f(I, J, K, c), b[:3], comp=c)
+    dst = ab.MultiFab(ba2, dm2, 2, 0)
+    dst.setVal(-1.0)
+    dst.parallel_copy(src, geom, scomp=0, dcomp=0, ncomp=2)
+    pmap2 = dm2.pmap(ba2.size())
+    for g, b in enumerate(ba2.boxes()):
+        if pmap2[g] != me:
+            continue
+        I, J, K = np.meshgrid(*[np.arange(b[d], b[d + 3] + 1) for d in range(3)], indexing="ij")
+        for c in range(2):
+            bad += int(np.count_nonzero(dst.download(b[:3], tuple(b[d + 3] - b[d] + 1 for d in range(3)), comp=c) != f(I, J, K, c)))
+    t = torch.tensor([float(bad)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t)
+    if rank == 0:
+        with open(out_path, "w") as fh:
+            fh.write(json.dumps(dict(case="exchange2", world=world, mismatches=int(t.item()), comm_nranks=int(ab.lib.amrex_b200_nprocs()))) + "\n")
+
+
 def main():
     case, out_path = sys.argv[1], sys.argv[2]
+    if case == "exchange2":
+        import torch
+        import torch.distributed as dist
+        import amrex_b200 as ab
+        world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        ab.init(local)
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            ab.comm_init_from_torch()
+        exchange_case(ab, world, rank, out_path)
+        if world > 1:
+            dist.barrier()
+            ab.lib.amrex_b200_comm_finalize()
+            dist.destroy_process_group()
+        return
     prob_type, n, mgs, max_level, maxorder = CASES[case]
     import torch
     import torch.distributed as dist

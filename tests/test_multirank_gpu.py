@@ -90,3 +90,10 @@ def test_multirank_halo_overlap_is_bit_neutral(tmp_path):
     assert "b200mg_gsrb4" in a["kernels"] and "b200mg_gsrb4" in b["kernels"]
     assert a["history"] == b["history"] and a["cg_iters"] == b["cg_iters"]
     assert a["sol_rel_maxdiff"] <= 1e-10 and abs(a["iters"] - a["ref_iters"]) <= 1
+
+
+def test_multirank_two_component_exchange(tmp_path):
+    """FillBoundary (full and cross stencil, periodic in x and y) and ParallelCopy of a TWO-component MultiFab over 2 ranks:
+    every ghost cell must hold the value of its periodic image, every copied cell its source value."""
+    r = _run("exchange2", 2, tmp_path)
+    assert r["comm_nranks"] == 2 and r["mismatches"] == 0, r

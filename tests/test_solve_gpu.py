@@ -124,7 +124,7 @@ def test_robin_bc(ab, n, mgs):
             assert rel_maxdiff(faces[d].download((0, 0, 0), shape), want) <= 1e-7, (kind, d)
 
 
-@pytest.mark.parametrize("bottom", ["smoother", "cg"])
+@pytest.mark.parametrize("bottom", ["smoother", "cg", "bicgcg", "cgbicg"])
 def test_bottom_solvers(ab, bottom):
     ref, mlmg, diff = solve_case(ab, 1, 64, 32, bottom=bottom)
     assert abs(mlmg.numIters() - ref["iters"]) <= 1
@@ -153,6 +153,36 @@ def test_two_level_composite(ab, prob_type, n, mgs, maxorder):
         refv = refsol[1:-1, 1:-1, 1:-1]
         mine = P["sol"][lev].download(tuple(v + 1 for v in lo), refv.shape)
         assert rel_maxdiff(mine, refv) <= SOL_TOL
+
+
+def test_level_solve_with_coarse_fine_bc(ab):
+    """A single-level operator on the FINE AMR level whose faces inside the domain take Dirichlet data interpolated from the
+    coarse solution (MLLinOp::setCoarseFineBC + setLevelBC, AMReX_MLCellLinOp.H:536-566) - the second solve of the reference's
+    level-by-level mode (Tests/LinearSolvers/ABecLaplacian_C/MyTest.cpp:104-141) - driven directly through the C ABI with
+    the reference's coarse solution as the coarse data, against the reference's fine-level solution."""
+    ref, dump = run_ref(dump=True, mode="solve", prob_type=2, n_cell=64, max_grid_size=32, linop_maxorder=2, agg_grid_size=32,
+                        max_level=1, composite_solve=0)
+    P = build_problem_amr(ab, 2, 64, 32, dump, max_level=1, maxorder=2)
+    crse = ab.MultiFab(P["ba"][0], P["dm"][0], 1, 1)
+    lo, a = dump["sol_lev0"]                       # the reference's coarse-level solution, ghost cells included
+    crse.upload(a, lo, ng=1)
+    D, N = ab.LinOpBCType.Dirichlet, ab.LinOpBCType.Neumann
+    op = ab.MLABecLaplacian([P["geom"][1]], [P["ba"][1]], [P["dm"][1]])
+    op.setMaxOrder(2)
+    op.setDomainBC((D, N, N), (N, D, N))
+    op.setCoarseFineBC(crse, 2)
+    op.setLevelBC(0, P["sol"][1])
+    op.setScalars(1.e-3, 1.0)
+    acoef, faces = P["keep"][4], P["keep"][5:8]    # level-1 coefficients uploaded by build_problem_amr
+    op.setACoeffs(0, acoef)
+    op.setBCoeffs(0, faces)
+    mlmg = ab.MLMG(op)
+    mlmg.setVerbose(0)
+    mlmg.solve([P["sol"][1]], [P["rhs"][1]], 1e-10, 0.0)
+    lo, refsol = dump["sol_lev1"]
+    refv = refsol[1:-1, 1:-1, 1:-1]
+    mine = P["sol"][1].download(tuple(v + 1 for v in lo), refv.shape)
+    assert rel_maxdiff(mine, refv) <= SOL_TOL
 
 
 @pytest.mark.parametrize("prob_type,n,mgs", [(2, 64, 32), (1, 64, 32), (3, 64, 32)])
