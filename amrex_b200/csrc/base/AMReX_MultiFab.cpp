@@ -672,7 +672,7 @@ void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc,
 // grouped ncclSend/ncclRecv on the communication stream (NVLink), and meanwhile the intra-GPU copies on the compute stream;
 // finish: the compute stream waits for the transfer and unpacks.  Whatever the caller launches on the compute stream between
 // the two halves (the smoother on the boxes without remote neighbours) overlaps the transfer.
-void start_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op)
+void start_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op, int parity = -1)
 {
     cudaStream_t s = Gpu::gpuStream();
     const bool remote = (P.snd_total + P.rcv_total) > 0;
@@ -689,7 +689,7 @@ void start_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int
             AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&P.ev_packed, cudaEventDisableTiming));
             AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&P.ev_arrived, cudaEventDisableTiming));
         }
-        B200_KCALL(b200mg_copy_tags(P.nsnd, P.d_snd.data(), nullptr, src.d_fabs(), P.sndbuf, ncomp, scomp, dcomp, 0, P.maxsnd, s));
+        B200_KCALL(b200mg_copy_tags_colour(P.nsnd, P.d_snd.data(), nullptr, src.d_fabs(), P.sndbuf, ncomp, scomp, dcomp, 0, P.maxsnd, parity, s));
         ncclComm_t comm = static_cast<ncclComm_t>(ParallelDescriptor::Comm());
         AMREX_ALWAYS_ASSERT_WITH_MESSAGE(comm != nullptr, "multi-rank exchange without an NCCL communicator");
         cudaStream_t cs = overlap ? Gpu::commStream() : s;
@@ -714,24 +714,24 @@ void start_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int
         if (overlap) { AMREX_CUDA_SAFE_CALL(cudaEventRecord(P.ev_arrived, cs)); }
         if (Gpu::debugSync()) { Gpu::check(Gpu::debugSyncNow(), "[B200MG_DEBUG_SYNC] ncclSend/ncclRecv group", __FILE__, __LINE__); }
     }
-    B200_KCALL(b200mg_copy_tags(P.nloc, P.d_loc.data(), dst.d_fabs(), src.d_fabs(), nullptr, ncomp, scomp, dcomp, int(op), P.maxloc, s));
+    B200_KCALL(b200mg_copy_tags_colour(P.nloc, P.d_loc.data(), dst.d_fabs(), src.d_fabs(), nullptr, ncomp, scomp, dcomp, int(op), P.maxloc, parity, s));
 }
 
-void finish_plan_exchange (CommPlan& P, MultiFab& dst, int scomp, int dcomp, int ncomp, CpOp op)
+void finish_plan_exchange (CommPlan& P, MultiFab& dst, int scomp, int dcomp, int ncomp, CpOp op, int parity = -1)
 {
     cudaStream_t s = Gpu::gpuStream();
     const bool remote = (P.snd_total + P.rcv_total) > 0;
     static const bool overlap = std::getenv("B200MG_NO_COMM_OVERLAP") == nullptr;
     if (remote) {
         if (overlap) { AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(s, P.ev_arrived, 0)); }
-        B200_KCALL(b200mg_copy_tags(P.nrcv, P.d_rcv.data(), dst.d_fabs(), nullptr, P.rcvbuf, ncomp, scomp, dcomp, int(op), P.maxrcv, s));
+        B200_KCALL(b200mg_copy_tags_colour(P.nrcv, P.d_rcv.data(), dst.d_fabs(), nullptr, P.rcvbuf, ncomp, scomp, dcomp, int(op), P.maxrcv, parity, s));
     }
 }
 
-void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op)
+void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op, int parity = -1)
 {
-    start_plan(P, dst, src, scomp, dcomp, ncomp, op);
-    finish_plan_exchange(P, dst, scomp, dcomp, ncomp, op);
+    start_plan(P, dst, src, scomp, dcomp, ncomp, op, parity);
+    finish_plan_exchange(P, dst, scomp, dcomp, ncomp, op, parity);
 }
 
 using FBKey = std::tuple<std::uint64_t, std::uint64_t, int, int, int, int, int, int, int>;
@@ -778,28 +778,28 @@ CommPlan& fb_plan (MultiFab& mf, IntVect const& nghost, Periodicity const& perio
 }
 }
 
-void MultiFab::FillBoundary (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross)
+void MultiFab::FillBoundary (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross, int parity)
 {
     if (m_ngrow == 0 || nghost.max() == 0) { return; }
     AMREX_ALWAYS_ASSERT(nghost.allLE(IntVect(m_ngrow)));
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_fb_pending == nullptr, "FillBoundary while a FillBoundary_nowait is pending on this MultiFab");
-    execute_plan(fb_plan(*this, nghost, period, cross), *this, *this, scomp, scomp, ncomp, CpOp::COPY);
+    execute_plan(fb_plan(*this, nghost, period, cross), *this, *this, scomp, scomp, ncomp, CpOp::COPY, parity);
 }
 
-void MultiFab::FillBoundary_nowait (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross)
+void MultiFab::FillBoundary_nowait (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross, int parity)
 {
     if (m_ngrow == 0 || nghost.max() == 0) { return; }
     AMREX_ALWAYS_ASSERT(nghost.allLE(IntVect(m_ngrow)));
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_fb_pending == nullptr, "FillBoundary_nowait: the previous one was not finished");
     CommPlan& P = fb_plan(*this, nghost, period, cross);
-    start_plan(P, *this, *this, scomp, scomp, ncomp, CpOp::COPY);
-    m_fb_pending = &P; m_fb_scomp = scomp; m_fb_ncomp = ncomp;
+    start_plan(P, *this, *this, scomp, scomp, ncomp, CpOp::COPY, parity);
+    m_fb_pending = &P; m_fb_scomp = scomp; m_fb_ncomp = ncomp; m_fb_parity = parity;
 }
 
 void MultiFab::FillBoundary_finish ()
 {
     if (m_fb_pending == nullptr) { return; }
-    finish_plan_exchange(*static_cast<CommPlan*>(m_fb_pending), *this, m_fb_scomp, m_fb_scomp, m_fb_ncomp, CpOp::COPY);
+    finish_plan_exchange(*static_cast<CommPlan*>(m_fb_pending), *this, m_fb_scomp, m_fb_scomp, m_fb_ncomp, CpOp::COPY, m_fb_parity);
     m_fb_pending = nullptr;
 }
 

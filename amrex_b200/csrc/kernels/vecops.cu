@@ -163,7 +163,7 @@ k_asum (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vb
 // x fastest, then y, z, component -- the order that also defines the linear buffer layout (AMReX_FBI.H:765-771).
 __global__ void __launch_bounds__(256)
 k_copy_tags (const b200mg_copytag* __restrict__ tags, const b200mg_fab* dstf, const b200mg_fab* srcf,
-             double* __restrict__ buf, int ncomp, int scomp, int dcomp, int op)
+             double* __restrict__ buf, int ncomp, int scomp, int dcomp, int op, int parity)
 {
     const b200mg_copytag t = tags[blockIdx.x];
     const unsigned n0 = unsigned(t.hi[0] - t.lo[0] + 1), n1 = unsigned(t.hi[1] - t.lo[1] + 1), n2 = unsigned(t.hi[2] - t.lo[2] + 1);
@@ -179,6 +179,8 @@ k_copy_tags (const b200mg_copytag* __restrict__ tags, const b200mg_fab* dstf, co
         for (unsigned r = threadIdx.x + blockIdx.y * blockDim.x; r < npts; r += blockDim.x * gridDim.y) {
             const unsigned k = r / n01, r2 = r - k * n01, j = r2 / n0, i = r2 - j * n0;
             const int ii = t.lo[0] + int(i), jj = t.lo[1] + int(j), kk = t.lo[2] + int(k);
+            // one colour of the red-black lattice only (destination indices: the same cells on the packing and the unpacking side)
+            if (parity >= 0 && ((ii + jj + kk) & 1) != parity) { continue; }
             double v;
             if (t.src_fab >= 0) { v = src(ii + t.shift[0], jj + t.shift[1], kk + t.shift[2], n + scomp); }
             else { v = b[r]; }
@@ -293,16 +295,22 @@ int b200mg_asum (int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox, c
     return last_error();
 }
 
-int b200mg_copy_tags (int ntags, const b200mg_copytag* tags, const b200mg_fab* dst, const b200mg_fab* src,
-                      double* buf, int ncomp, int scomp, int dcomp, int op, int max_pts, cudaStream_t s)
+int b200mg_copy_tags_colour (int ntags, const b200mg_copytag* tags, const b200mg_fab* dst, const b200mg_fab* src,
+                             double* buf, int ncomp, int scomp, int dcomp, int op, int max_pts, int parity, cudaStream_t s)
 {
     if (ntags <= 0) { return 0; }
     // blockIdx.y chunks: ~2 points per thread on the largest tag (these launches are latency bound: few tags on a GPU that
     // owns few boxes), one chunk for the small tags of coarse levels; max_pts <= 0: unknown, 4 chunks
     int chunks = 4;
     if (max_pts > 0) { chunks = (max_pts + 511) / 512; chunks = chunks < 1 ? 1 : (chunks > 32 ? 32 : chunks); }
-    k_copy_tags<<<dim3(ntags, chunks), 256, 0, s>>>(tags, dst, src, buf, ncomp, scomp, dcomp, op);
+    k_copy_tags<<<dim3(ntags, chunks), 256, 0, s>>>(tags, dst, src, buf, ncomp, scomp, dcomp, op, parity);
     return last_error();
+}
+
+int b200mg_copy_tags (int ntags, const b200mg_copytag* tags, const b200mg_fab* dst, const b200mg_fab* src,
+                      double* buf, int ncomp, int scomp, int dcomp, int op, int max_pts, cudaStream_t s)
+{
+    return b200mg_copy_tags_colour(ntags, tags, dst, src, buf, ncomp, scomp, dcomp, op, max_pts, -1, s);
 }
 
 } // extern "C"

@@ -782,8 +782,9 @@ void MLLinOp::prepareForSolve ()
 
 // MLCellLinOpT::applyBC (AMReX_MLCellLinOp.H:684-893), cross stencil
 void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, StateMode, const BndrySlabs<double>* bndry,
-                       bool skip_fillboundary, bool nowait) const
+                       bool skip_fillboundary, bool nowait, int halo_parity) const
 {
+    if (!m_colour_halo) { halo_parity = -1; }
     Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     AMREX_ALWAYS_ASSERT(mglev == 0 || bc_mode == BCMode::Homogeneous);
     AMREX_ALWAYS_ASSERT(bndry != nullptr || bc_mode == BCMode::Homogeneous);
@@ -811,14 +812,14 @@ void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, Stat
         B200_KCALL(b200mg_apply_bc(nf, L.bcfaces.data(), L.layout->d_vbox(), in.d_fabs(), L.mask.d_table(),
                                    bndry ? bndry->d_table() : nullptr, maxorder, dxi[0], dxi[1], dxi[2], flagbc, maxFaceCells(L), aux));
         AMREX_CUDA_SAFE_CALL(cudaEventRecord(ev_join, aux));
-        if (nowait) { in.FillBoundary_nowait(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
-        else { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
+        if (nowait) { in.FillBoundary_nowait(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity); }
+        else { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity); }
         AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(s, ev_join, 0));
         return;
     }
     if (!skip_fillboundary) {
-        if (nowait) { in.FillBoundary_nowait(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
-        else { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true); }
+        if (nowait) { in.FillBoundary_nowait(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity); }
+        else { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity); }
     }
     if (nf == 0) { return; }
     B200_KCALL(b200mg_apply_bc(nf, L.bcfaces.data(), L.layout->d_vbox(), in.d_fabs(), L.mask.d_table(),
@@ -975,7 +976,7 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
                 AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
                 AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
             }
-            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, true);
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, true, 1);
             cudaStream_t s = Gpu::gpuStream(), aux = Gpu::auxStream();
             const bool side = true;
             bool ok2 = true;
@@ -996,15 +997,17 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
             }
             AMREX_ALWAYS_ASSERT_WITH_MESSAGE(ok1 && ok2, "fused smoother: a level that took the pass before refused it");
             sol.swap(*L.scratch);
-            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false);
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, false, 0);
             FsmoothShell(amrlev, mglev, sol, rhs, 1);
             return;
         }
-        if (!zero4) { applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary); }
+        // the pass updates the red cells everywhere (they read black ghost cells: parity 1) and the black cells off the box
+        // surface (no ghost cells); the black shell afterwards reads red ghost cells (parity 0)
+        if (!zero4) { applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary, false, 1); }
         if (Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs, zero4)) {
             L.fused4_ok = 1;
             sol.swap(*L.scratch);
-            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false);
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, false, 0);
             FsmoothShell(amrlev, mglev, sol, rhs, 1);
             return;
         }
@@ -1013,7 +1016,8 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
         if (zero4) { sol.setVal(0.0); skip_fillboundary = true; }
     }
     for (int redblack = 0; redblack < 2; ++redblack) {
-        applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary);
+        // the sweep of colour redblack updates cells with (i+j+k+redblack) even and reads their neighbours: the other colour
+        applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary, false, 1 - redblack);
         Fsmooth(amrlev, mglev, sol, rhs, redblack);
         skip_fillboundary = false;
     }

@@ -218,7 +218,8 @@ def test_post_solve_fluxes_and_gradients(ab, prob_type, n, mgs):
 def test_b200_schedule_switches_are_bit_neutral(ab, kind, monkeypatch):
     """The B200-only schedule changes - residual + inf-norm in one kernel, first pre-smooth without zeroing / reading the
     correction, BC fill on a second stream next to the halo copies, residual + restriction in one kernel (the fine residual
-    is never stored) - must not change a single bit of the solve: same
+    is never stored), smoother halo exchanges that move only the colour the next sweep reads - must not change a single bit
+    of the solve: same
     residual history and same solution as with all three switched off (environment read when the operator is built)."""
     import os
     from common import synth_abeclap, synth_poisson
@@ -226,7 +227,7 @@ def test_b200_schedule_switches_are_bit_neutral(ab, kind, monkeypatch):
     out = {}
     monkeypatch.setenv("B200MG_NO_MERGED_LEG", "1")       # keep the 128^3 / 64^3 levels on the launch-per-operation path under test
     for off in (True, False):
-        for v in ("B200MG_NO_FUSED_RESNORM", "B200MG_NO_ZERO_INPUT", "B200MG_NO_BC_OVERLAP", "B200MG_NO_FUSED_RESTRICT"):
+        for v in ("B200MG_NO_FUSED_RESNORM", "B200MG_NO_ZERO_INPUT", "B200MG_NO_BC_OVERLAP", "B200MG_NO_FUSED_RESTRICT", "B200MG_NO_COLOUR_HALO"):
             if off:
                 monkeypatch.setenv(v, "1")
             else:
