@@ -4,7 +4,8 @@ import os
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libamrex_b200.so")
+# (AMREX_B200_LIB: another build of the same library, for A/B timing of kernel variants on the GPU box)
+LIB_PATH = os.environ.get("AMREX_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libamrex_b200.so")
 
 _lib = None
 

@@ -26,136 +26,18 @@
 // all boxes of the launch share the row pitches, and rhs / a / by / bz share one pitch.
 #include "common.cuh"
 #include "stencil_math.cuh"
-
-#include <cstdint>
+#include "gsrb_fused_stage.cuh"
 
 using namespace b200mg;
+using namespace b200mg::fused;
 
 namespace {
 
-struct FArr4 { double* p; int js, ks; };                // fab base (element (lo) of the fab's own box), strides in elements
 
-struct FusedBox4 {
-    FArr4 pin, pout, rhs, a, bx, by, bz;
-    const int* m[6];                                    // mask slabs (one cell outside each face), [face]
-    const double* f[6];                                 // relaxation-coefficient slabs (one cell inside each face)
-    int lo[3], hi[3];                                   // valid box
-    int glo_in[3], glo_out[3];                          // lower corner of the grown boxes of pin / pout
-    int glo_b[3][3];                                    // lower corners of bx, by, bz
-};
-
-constexpr int kMaxBoxes4 = 64;
-
-struct FusedParams4 {
-    FusedBox4 box[kMaxBoxes4];
-    double alpha, dhx, dhy, dhz;
-    int nty;                                            // y tiles per box
-    int txp;                                            // compute threads per row (multiple of 32)
-    int nxs;                                            // longest row (max nx, even)
-    int ps, cs, xs;                                     // row pitches (elements) of phi, of rhs / a / by / bz, and of bx
-    int phi_zero;                                       // 1: the input is identically zero (first smooth of a V-cycle): it is
-                                                        // not read from HBM, the shared-memory planes are zero-filled instead
-};
-
-// ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32 (const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init (uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx (uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait (uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s (uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive (uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async () { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// CTA-wide barrier reached from two different code paths (compute warps inside step4, the producer warp in its loop)
-__device__ __forceinline__ void cta_sync () { asm volatile("bar.sync 1, %0;" :: "r"(int(blockDim.x)) : "memory"); }
-
-// ---------------------------------------------------------------------------------------------- shared-memory layout
-template <bool ABEC, int TY>
-struct Lay {
-    int PS, XS, NX;                                     // row pitches: phi, bx, the others (NX: rhs / a / by / bz)
-    int e_phi, e_bz, e_size;                            // element offsets inside an EARLY stage
-    int l_rhs, l_a, l_bx, l_by, l_size;                 // ... inside a LATE stage
-    __host__ __device__ Lay (int nxs, int ps, int cs, int xs)
-    {
-        NX = cs; PS = ps; XS = xs;
-        const int cc = (TY + 1) * cs + nxs;             // TY+2 rows of a cell-centred array, last row without its padding
-        e_phi = 0; e_bz = (TY + 3) * ps + nxs + 4; e_size = e_bz + (ABEC ? cc : 0);
-        l_rhs = 0; l_a = cc;
-        l_bx = l_a + (ABEC ? cc : 0);
-        l_by = l_bx + (ABEC ? (TY + 1) * xs + nxs + 2 : 0);
-        l_size = l_by + (ABEC ? (TY + 2) * cs + nxs : 0);
-    }
-};
-
-constexpr int kBarBytes = 128;                           // mbarriers live in the first 128 bytes of dynamic shared memory
-constexpr int kHdrBytes = 384;                           // ... followed by the copy descriptors; the rings start here
-
-// one bulk copy per array and plane: global range of plane q = g + q*gstep (bytes), `bytes` into slot offset soff
-struct CopyDesc { const char* g; long long gstep; uint32_t soff; uint32_t bytes; int qmin, qmax; };   // 32 bytes
-struct Header {                                          // shared memory behind the mbarriers
-    CopyDesc d[6];                                       // EARLY: phi, bz; LATE: rhs, a, bx, by
-    uint32_t bytesE0, bytesE, bytesL;                    // transaction bytes of EARLY[0], EARLY[q >= 1], LATE[q]
-};
-static_assert(kBarBytes + sizeof(Header) <= kHdrBytes, "header does not fit");
-
-// Ring positions of step t: EARLY slots of planes t, t+1, t+2 (+ phase parity of t+2); LATE slot of plane t+1 (+ parity).
-// Power-of-two depths are computed from t (no state); other depths keep counters.
-template <int SE, int SL>
-struct Ring {
-    static constexpr bool pe = (SE & (SE - 1)) == 0, pl = (SL & (SL - 1)) == 0;
-    uint32_t c2 = 2u, cp2 = 0u, cl = 0u, cpl = 0u;
-    __device__ __forceinline__ uint32_t sm1 (int t) const { return pe ? uint32_t(t - 1) & (SE - 1) : (c2 >= 3u ? c2 - 3u : c2 + SE - 3u); }
-    __device__ __forceinline__ uint32_t s0 (int t) const { return pe ? uint32_t(t) & (SE - 1) : (c2 >= 2u ? c2 - 2u : c2 + SE - 2u); }
-    __device__ __forceinline__ uint32_t s1 (int t) const { return pe ? uint32_t(t + 1) & (SE - 1) : (c2 >= 1u ? c2 - 1u : c2 + SE - 1u); }
-    __device__ __forceinline__ uint32_t s2 (int t) const { return pe ? uint32_t(t + 2) & (SE - 1) : c2; }
-    __device__ __forceinline__ uint32_t par2 (int t) const { return pe ? (uint32_t(t + 2) / SE) & 1u : cp2; }
-    __device__ __forceinline__ uint32_t l (int t) const { return pl ? uint32_t(t) & (SL - 1) : cl; }
-    __device__ __forceinline__ uint32_t parl (int t) const { return pl ? (uint32_t(t) / SL) & 1u : cpl; }
-    __device__ __forceinline__ void advance ()
-    {
-        if (!pe) { if (++c2 == uint32_t(SE)) { c2 = 0u; cp2 ^= 1u; } }
-        if (!pl) { if (++cl == uint32_t(SL)) { cl = 0u; cpl ^= 1u; } }
-    }
-};
-
-struct Carry { double rhs, a, bxm, bxp, bym, byp; };     // coefficients of the black cell of the pair, read one step ahead
-
-// ---------------------------------------------------------------------------------------------- one z step (compute threads)
-// thread 0: arm the slot's mbarrier with the plane's byte count, then issue the plane's copies (descriptors d0 .. d1-1)
-__device__ __forceinline__ void
-produce (const Header* H, int d0, int d1, uint32_t bar, uint32_t stage_base, int q, uint32_t total_bytes)
-{
-    mbar_arrive_expect_tx(bar, total_bytes);
-    for (int d = d0; d < d1; ++d) {
-        const CopyDesc c = H->d[d];
-        if (c.bytes != 0u && q >= c.qmin && q <= c.qmax) { bulk_g2s(stage_base + c.soff, c.g + q * c.gstep, c.bytes, bar); }
-    }
-}
-
-template <bool ABEC, int TY, int SE, int SL, bool DEC, int C>
+template <bool ABEC, int TY, int SE, int SL, int C>
 __device__ __forceinline__ void
 step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double* __restrict__ smE, double* __restrict__ smL,
-       const Header* H, uint32_t barE, uint32_t barL, uint32_t barS, Ring<SE, SL>& R, int t, int nz,
+       const Header* H, uint32_t barE, uint32_t barL, Ring<SE, SL>& R, int t, int nz,
        bool row_load, bool row_red, bool row_black, bool first, bool last, bool jlo, bool jhi, int tx2, int jrel,
        int prow, int crow, int xrow, int& out_cur,
        double& zlo_b, double2& pk, double2& pp1, double& bzm_b, double2& bz1, Carry& cb, int& xmk, double& xf)
@@ -204,9 +86,6 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
     // zero input: the red value this thread left in plane t-1 two steps ago (last read during step t-1) is cleared before
     // the slot is used again - the copy engine does not touch the phi part of the planes in this mode
     if (P.phi_zero && t >= 2) { smE[R.sm1(t) * Y.e_size + Y.e_phi + prow + C] = 0.0; }
-
-    // decoupled warps: the red x / y neighbours in EARLY[t].phi were written by other warps during THEIR step t-1
-    if constexpr (DEC) { if (t >= 1) { mbar_wait(barS + 8u * uint32_t((t - 1) & 1), uint32_t(((t - 1) >> 1) & 1)); } }
 
     // ---- black cell of plane t, part 1: everything that does not need the red value above it (computed below).
     //      New red values on five sides: EARLY[t].phi in x / y (written during step t-1), zlo_b below.
@@ -283,11 +162,6 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
         if (C) { pp1.y = vr; } else { pp1.x = vr; }
         sr[0] = vr;
     }
-    if constexpr (DEC) {                                 // this warp's red cells of plane t+1 are in shared memory
-        __syncwarp();
-        if ((threadIdx.x & 31u) == 0u) { mbar_arrive(barS + 8u * uint32_t(t & 1)); }
-    }
-
     // ---- black cell of plane t, part 2 (needs the red value above: pp1); box-surface cells pass through unchanged and
     //      are finished by the shell kernel after the second halo refresh
     if (do_black) {
@@ -319,15 +193,7 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
         if constexpr (ABEC) { if (row_red) { bz1 = *reinterpret_cast<const double2*>(e2 + Y.e_bz + crow); } }
     }
     fence_proxy_async();
-    if constexpr (DEC) {
-        // No CTA barrier: warps drift by up to a step.  Every warp reports the end of its step; only the issuing thread
-        // waits for all of them before it hands the freed slots back to the copy engine.
-        __syncwarp();
-        if ((threadIdx.x & 31u) == 0u) { mbar_arrive(barS + 16u + 8u * uint32_t(t & 1)); }
-        if (threadIdx.x == 0) { mbar_wait(barS + 16u + 8u * uint32_t(t & 1), uint32_t((t >> 1) & 1)); }
-    } else {
-        cta_sync();
-    }
+    cta_sync();
     // ---- EARLY[t] and LATE[t+1] are free: refill them with planes t+SE and t+1+SL, then rotate the ring
     if (threadIdx.x == 0) {
         if (t + SE <= nz + 1) {
@@ -340,7 +206,7 @@ step4 (const FusedParams4& P, const FusedBox4& B, const Lay<ABEC, TY>& Y, double
     R.advance();
 }
 
-template <bool ABEC, int TY, int SE, int SL, bool DEC, int MAXT>
+template <bool ABEC, int TY, int SE, int SL, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 k_gsrb4 (const __grid_constant__ FusedParams4 P)
 {
@@ -355,8 +221,7 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
     double* smE = reinterpret_cast<double*>(sm_raw + kHdrBytes);
     double* smL = smE + SE * Y.e_size;
     const uint32_t barE = smem_u32(sm_raw), barL = barE + 8u * SE;
-    const uint32_t barS = barL + 8u * SL;                           // red-done [2], step-done [2] (decoupled warps)
-    static_assert(8 * (SE + SL + 4) <= kBarBytes, "too many stages for the mbarrier block");
+    static_assert(8 * (SE + SL) <= kBarBytes, "too many stages for the mbarrier block");
     static_assert(SE >= 4 && SL >= 2, "ring depths: EARLY planes live three steps, LATE planes one");
 
     const int tid = int(threadIdx.x);
@@ -366,7 +231,6 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
     }
     if (tid == 0) {
         for (int s = 0; s < SE + SL; ++s) { mbar_init(barE + 8u * s, 1u); }
-        for (int s = 0; s < 4; ++s) { mbar_init(barS + 8u * s, blockDim.x / 32u); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // rows this tile needs (clipped to what exists); one contiguous range per array and plane
         const int pj_lo = max(j0 - 2, B.lo[1] - 1), pj_hi = min(j1 + 2, B.hi[1] + 1);    // phi rows (ghost rows exist)
@@ -439,7 +303,7 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
     const int c_first = (i0 + j + B.lo[2]) & 1;                    // pair position of the red cell of plane lo_z (step 0)
     int xmk = 0; double xf = 0.0;                                  // x-face slab values of step 0 (see step4)
     if ((c_first ? last : first) && row_red) { xmk = B.m[c_first ? 3 : 0][jrel]; xf = B.f[c_first ? 3 : 0][jrel]; }
-#define B200MG_STEP4(CC, TT) step4<ABEC, TY, SE, SL, DEC, CC>(P, B, Y, smE, smL, H, barE, barL, barS, R, TT, nz, row_load, row_red, row_black, first, last, \
+#define B200MG_STEP4(CC, TT) step4<ABEC, TY, SE, SL, CC>(P, B, Y, smE, smL, H, barE, barL, R, TT, nz, row_load, row_red, row_black, first, last, \
                                                          jlo, jhi, tx2, jrel, prow, crow, xrow, out_cur, zlo_b, pk, pp1, bzm_b, bz1, cb, xmk, xf)
     int t = 0;
     if (c_first) {
@@ -453,9 +317,9 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
 }
 
 int g_plan_ty = 8, g_plan_se = 4, g_plan_sl = 2;                   // launch plan (b200mg_set_gsrb4_plan)
-int g_plan_dec = 0;                                                 // 1: decoupled warps (mbarrier arrive / wait instead of the CTA barrier)
+int g_plan_one_pair = 0;                                            // 1: one cell pair per thread also on rows of more than 64 cells
 
-template <bool ABEC, int TY, int SE, int SL, bool DEC>
+template <bool ABEC, int TY, int SE, int SL>
 int launch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
 {
     const Lay<ABEC, TY> Y(P.nxs, P.ps, P.cs, P.xs);
@@ -465,17 +329,17 @@ int launch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
     const dim3 grid(P.nty, nboxes, 1);
     cudaError_t e = cudaSuccess;
     if (nthreads <= 384) {
-        auto kern = k_gsrb4<ABEC, TY, SE, SL, DEC, 384>;
+        auto kern = k_gsrb4<ABEC, TY, SE, SL, 384>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) { return int(e); }
         kern<<<grid, nthreads, smem, s>>>(P);
     } else if (nthreads <= 512) {
-        auto kern = k_gsrb4<ABEC, TY, SE, SL, DEC, 512>;
+        auto kern = k_gsrb4<ABEC, TY, SE, SL, 512>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) { return int(e); }
         kern<<<grid, nthreads, smem, s>>>(P);
     } else {
-        auto kern = k_gsrb4<ABEC, TY, SE, SL, DEC, 640>;
+        auto kern = k_gsrb4<ABEC, TY, SE, SL, 640>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) { return int(e); }
         kern<<<grid, nthreads, smem, s>>>(P);
@@ -488,12 +352,14 @@ int launch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
 // overheads twice
 int effective_tile_y (int nxmax) { return (g_plan_ty == 8 && nxmax <= 64) ? 16 : g_plan_ty; }
 
+// cell pairs per thread: two on rows of 65 .. 128 cells (one warp per row, the kernel of gsrb_fused5.cu)
+int pairs_per_thread (int nxmax) { return (nxmax > 64 && !g_plan_one_pair) ? 2 : 1; }
+
 template <bool ABEC>
 int dispatch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
 {
     const int key = effective_tile_y(P.nxs) * 100 + g_plan_se * 10 + g_plan_sl;
-    // (the zero-input mode clears consumed red values behind the CTA barrier of the previous step: lock-step kernel only)
-#define B200MG_PLAN4(K, TYv, SEv, SLv) case K: return (g_plan_dec && !P.phi_zero) ? launch4<ABEC, TYv, SEv, SLv, true>(P, nboxes, s) : launch4<ABEC, TYv, SEv, SLv, false>(P, nboxes, s)
+#define B200MG_PLAN4(K, TYv, SEv, SLv) case K: return launch4<ABEC, TYv, SEv, SLv>(P, nboxes, s)
     switch (key) {
         B200MG_PLAN4(842, 8, 4, 2);
         B200MG_PLAN4(843, 8, 4, 3);
@@ -525,8 +391,8 @@ int b200mg_set_gsrb4_plan (int tile_y, int early_stages, int late_stages)
     return 0;
 }
 
-// synchronisation inside the CTA: 0 = one CTA barrier per plane, 1 = decoupled warps (mbarrier arrive / wait)
-void b200mg_set_gsrb4_sync (int decoupled) { g_plan_dec = decoupled ? 1 : 0; }
+// cell pairs per thread on rows of more than 64 cells: 0 = two (default, gsrb_fused5.cu), 1 = one (this file)
+void b200mg_set_gsrb4_sync (int one_pair) { g_plan_one_pair = one_pair ? 1 : 0; }
 
 // HOST descriptor tables as in b200mg_gsrb3.  abec == 0: Poisson (a, bx, by, bz ignored).
 int b200mg_gsrb4 (int abec, int nboxes, const b200mg_box* h_vbox,
@@ -558,7 +424,8 @@ int b200mg_gsrb4_subset (int abec, int nboxes, const int* ids, const b200mg_box*
         if (nx % 2 != 0 || nx < 4 || nx > 128 || ny < 2) { return int(cudaErrorInvalidValue); }
         nxmax = nx > nxmax ? nx : nxmax; nymax = ny > nymax ? ny : nymax;
     }
-    P.txp = ((nxmax / 2 + 31) / 32) * 32;
+    const bool two_pairs = pairs_per_thread(nxmax) == 2;
+    P.txp = two_pairs ? 32 : ((nxmax / 2 + 31) / 32) * 32;
     P.nxs = nxmax;
     P.ps = int(h_phi_in[id(0)].jstride); P.cs = int(h_rhs[id(0)].jstride); P.xs = abec ? int(h_bx[id(0)].jstride) : 0;
     const int ty = effective_tile_y(nxmax);
@@ -593,7 +460,11 @@ int b200mg_gsrb4_subset (int abec, int nboxes, const int* ids, const b200mg_box*
             }
             for (int f = 0; f < 6; ++f) { B.m[f] = h_m[b * 6 + f].p; B.f[f] = h_f[b * 6 + f].p; }
         }
-        const int e = abec ? dispatch4<true>(P, nb, s) : dispatch4<false>(P, nb, s);
+        // the default (8,4,2) plan runs its rows of 65 .. 128 cells with three LATE stages: two pairs per thread make the step
+        // short enough that one step of prefetch distance no longer covers the HBM latency (profiles/r02_s24_tune_gsrb5.txt)
+        const int sl5 = (g_plan_ty == 8 && g_plan_se == 4 && g_plan_sl == 2) ? 3 : g_plan_sl;
+        const int e = two_pairs ? dispatch5(abec != 0, P, nb, effective_tile_y(nxmax), g_plan_se, sl5, s)
+                                : (abec ? dispatch4<true>(P, nb, s) : dispatch4<false>(P, nb, s));
         if (e != 0) { return e; }
     }
     return 0;

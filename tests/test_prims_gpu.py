@@ -115,7 +115,10 @@ def test_prims_vs_live_reference(ab, kw, fusion):
 
 # ---- fused smoother, generation 4 (bulk-async-copy staged pass): every compiled launch plan must reproduce the
 #      reference schedule (one kernel per colour) BIT FOR BIT, on both MG levels that are eligible (64^3 and 32^3 boxes)
-FUSED4_PLANS = [(8, 4, 2, 0), (8, 4, 3, 0), (6, 5, 3, 0), (6, 4, 2, 0), (4, 4, 4, 0), (8, 4, 2, 1), (6, 5, 3, 1)]   # (tile_y, EARLY, LATE, decoupled warps)
+# (tile_y, EARLY, LATE, one cell pair per thread also on rows of > 64 cells, box size): 64^3 / 32^3 boxes run one pair per
+# thread, 128^3 / 64^3 boxes two pairs per thread on the finer level unless the switch forces one
+FUSED4_PLANS = [(8, 4, 2, 0, 64), (8, 4, 3, 0, 64), (6, 5, 3, 0, 64), (6, 4, 2, 0, 64), (4, 4, 4, 0, 64),
+                (8, 4, 2, 0, 128), (8, 4, 2, 1, 128), (8, 4, 3, 0, 128), (6, 5, 3, 0, 128), (6, 4, 2, 0, 128), (4, 4, 4, 0, 128)]
 
 
 def _two_smooths(ab, op, n, mglev, seed):
@@ -137,7 +140,7 @@ def _two_smooths(ab, op, n, mglev, seed):
 @pytest.mark.parametrize("plan", FUSED4_PLANS)
 def test_fused4_abeclap_bitwise(ab, plan):
     from common import synth_abeclap
-    n, mgs = 128, 64
+    n, mgs = 128, plan[4]
     want = {}
     P = synth_abeclap(ab, n, mgs, fusion=0)
     P["op"].prepareForSolve()
@@ -159,16 +162,16 @@ def test_fused4_abeclap_bitwise(ab, plan):
         ab.lib.b200mg_set_gsrb4_sync(0)
 
 
-@pytest.mark.parametrize("plan", [(8, 4, 2), (6, 5, 3), (4, 4, 4)])
+@pytest.mark.parametrize("plan", [(8, 4, 2), (6, 5, 3), (4, 4, 4), (8, 4, 2, 128)])
 @pytest.mark.parametrize("kind", ["abeclap", "poisson"])
 def test_fused4_zero_input_bitwise(ab, kind, plan):
     """smooth(zero_input) - MLMG's cor.setVal(0) + first pre-smooth as ONE pass that never reads cor - must give the bits
     of setVal(0) followed by the ordinary smooth, also when cor holds garbage (NaN) on entry; a second smooth follows to
     show that the ghost cells the pass leaves behind are handled."""
     from common import synth_abeclap, synth_poisson
-    n, mgs = 128, 64
+    n, mgs = 128, (plan[3] if len(plan) > 3 else 64)      # 128: two cell pairs per thread on the finer level
     synth = synth_abeclap if kind == "abeclap" else synth_poisson
-    assert ab.lib.amrex_b200_set_fused4_plan(*plan) == 0
+    assert ab.lib.amrex_b200_set_fused4_plan(*plan[:3]) == 0
     try:
         out = {}
         for zero_input in (False, True):
