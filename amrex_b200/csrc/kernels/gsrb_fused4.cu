@@ -317,7 +317,7 @@ k_gsrb4 (const __grid_constant__ FusedParams4 P)
 }
 
 int g_plan_ty = 8, g_plan_se = 4, g_plan_sl = 2;                   // launch plan (b200mg_set_gsrb4_plan)
-int g_plan_one_pair = 0;                                            // 1: one cell pair per thread also on rows of more than 64 cells
+int g_plan_pairs = 0;                                               // cell pairs per thread on rows of > 64 cells: 0 auto, 1 one, 2 two
 
 template <bool ABEC, int TY, int SE, int SL>
 int launch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
@@ -352,8 +352,24 @@ int launch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
 // overheads twice
 int effective_tile_y (int nxmax) { return (g_plan_ty == 8 && nxmax <= 64) ? 16 : g_plan_ty; }
 
-// cell pairs per thread: two on rows of 65 .. 128 cells (one warp per row, the kernel of gsrb_fused5.cu)
-int pairs_per_thread (int nxmax) { return (nxmax > 64 && !g_plan_one_pair) ? 2 : 1; }
+// cell pairs per thread: two on rows of 65 .. 128 cells (one warp per row, the kernel of gsrb_fused5.cu) when the launch
+// runs several waves of CTAs.  The tiles that hold the first / last row of a box look up their y-face coefficients in
+// global memory in every step; with two pairs per thread that load sits on the step's critical path (0.33 ms for such a
+// tile against 0.20 ms for the others), which the average over waves hides (1.52 against 1.60 ms at 6.9 waves) but a launch
+// of one or two waves shows in full: 0.329 against 0.246 ms for the 8 boxes of 128^3 a GPU owns in the 8-GPU run
+// (profiles/r02_s30_single_wave.txt).  Fetching those coefficients a step ahead, or pulling them into L1, cured the edge
+// tiles and cost the others more than it gained (r02_s32 .. s34 in the same file).
+int g_num_sms = 0;
+int pairs_per_thread (int nxmax, long long nctas)
+{
+    if (g_num_sms == 0) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) { g_num_sms = 148; }
+    }
+    if (nxmax <= 64 || g_plan_pairs == 1) { return 1; }
+    return (g_plan_pairs == 2 || nctas > 3LL * g_num_sms) ? 2 : 1;
+}
 
 template <bool ABEC>
 int dispatch4 (const FusedParams4& P, int nboxes, cudaStream_t s)
@@ -391,8 +407,9 @@ int b200mg_set_gsrb4_plan (int tile_y, int early_stages, int late_stages)
     return 0;
 }
 
-// cell pairs per thread on rows of more than 64 cells: 0 = two (default, gsrb_fused5.cu), 1 = one (this file)
-void b200mg_set_gsrb4_sync (int one_pair) { g_plan_one_pair = one_pair ? 1 : 0; }
+// cell pairs per thread on rows of more than 64 cells: 0 = by the size of the launch (default, see pairs_per_thread),
+// 1 = one (this file), 2 = two (gsrb_fused5.cu)
+void b200mg_set_gsrb4_sync (int pairs) { g_plan_pairs = (pairs == 1 || pairs == 2) ? pairs : 0; }
 
 // HOST descriptor tables as in b200mg_gsrb3.  abec == 0: Poisson (a, bx, by, bz ignored).
 int b200mg_gsrb4 (int abec, int nboxes, const b200mg_box* h_vbox,
@@ -424,12 +441,12 @@ int b200mg_gsrb4_subset (int abec, int nboxes, const int* ids, const b200mg_box*
         if (nx % 2 != 0 || nx < 4 || nx > 128 || ny < 2) { return int(cudaErrorInvalidValue); }
         nxmax = nx > nxmax ? nx : nxmax; nymax = ny > nymax ? ny : nymax;
     }
-    const bool two_pairs = pairs_per_thread(nxmax) == 2;
+    const int ty = effective_tile_y(nxmax);
+    P.nty = (nymax + ty - 1) / ty;
+    const bool two_pairs = pairs_per_thread(nxmax, (long long)P.nty * nboxes) == 2;
     P.txp = two_pairs ? 32 : ((nxmax / 2 + 31) / 32) * 32;
     P.nxs = nxmax;
     P.ps = int(h_phi_in[id(0)].jstride); P.cs = int(h_rhs[id(0)].jstride); P.xs = abec ? int(h_bx[id(0)].jstride) : 0;
-    const int ty = effective_tile_y(nxmax);
-    P.nty = (nymax + ty - 1) / ty;
     for (int b0 = 0; b0 < nboxes; b0 += kMaxBoxes4) {
         const int nb = (nboxes - b0 < kMaxBoxes4) ? nboxes - b0 : kMaxBoxes4;
         for (int n = 0; n < nb; ++n) {

@@ -128,9 +128,9 @@ int b200mg_gsrb4_subset(int abec, int nboxes, const int* ids, const b200mg_box* 
                         double alpha, double dhx, double dhy, double dhz, int phi_zero, cudaStream_t s);
 /* launch plan of b200mg_gsrb4: rows per CTA tile and ring depths; (8,4,2) default, (8,4,3), (6,5,3), (6,4,2), (4,4,4) */
 int b200mg_set_gsrb4_plan(int tile_y, int early_stages, int late_stages);
-/* cell pairs per thread of b200mg_gsrb4 on rows of more than 64 cells: 0 = two (default, one warp per 128-cell row),
- * 1 = one pair per thread */
-void b200mg_set_gsrb4_sync(int one_pair);
+/* cell pairs per thread of b200mg_gsrb4 on rows of more than 64 cells: 0 = chosen by the size of the launch (two when it runs
+ * more than three waves of CTAs), 1 = one pair per thread, 2 = two (one warp per 128-cell row + a producer warp) */
+void b200mg_set_gsrb4_sync(int pairs);
 /* black (redblack=1) or red sweep restricted to the 1-cell surface shell of every box; max_face_cells = cells of the
  * largest box face of the level (sizes the grid: one thread per swept cell) */
 int b200mg_gsrb_shell_abec(int nboxes, const b200mg_box* vbox,

@@ -1,6 +1,7 @@
 """A/B timing of the finest-level smoother variants on the benchmark workload (run on the GPU box):
     python scripts/tune_smoother.py [n_cell] [reps] [variant ...]
-variant = "ty,early,late,producer_warp" (default: the compiled plans).  Prints one JSON line per variant: time of one
+variant = "ty,early,late,pairs" (cell pairs per thread on rows of more than 64 cells: 0 by launch size, 1 = generation 4,
+2 = generation 5; default: a few of the compiled plans).  Prints one JSON line per variant: time of one
 smooth and of its kernels (CUDA events around every launch, amrex_b200 profile report), and whether the smoothed field has
 the bits of the first variant."""
 import json
@@ -16,7 +17,7 @@ from common import synth_abeclap  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-variants = [tuple(int(v) for v in a.split(",")) for a in sys.argv[3:]] or [(8, 4, 2, 1), (8, 4, 2, 0), (8, 4, 3, 1), (6, 4, 2, 1)]
+variants = [tuple(int(v) for v in a.split(",")) for a in sys.argv[3:]] or [(8, 4, 2, 2), (8, 4, 2, 1), (8, 4, 2, 0)]
 mgs = 128 if n >= 128 else n
 ab.init(0)
 first = None
@@ -43,7 +44,7 @@ for var in variants:
         kern[name] = kern.get(name, 0.0) + total / reps
     cells = float(n) ** 3
     k = kern.get("b200mg_gsrb4", 0.0)
-    line = {"variant": "ty=%d early=%d late=%d producer_warp=%d" % var, "n": n, "ms_per_smooth": round(sum(kern.values()), 4),
+    line = {"variant": "ty=%d early=%d late=%d pairs=%d" % var, "n": n, "ms_per_smooth": round(sum(kern.values()), 4),
             "gsrb4_ms": round(k, 4), "gsrb4_gbs_56": round(56.0 * cells / (k * 1e-3) / 1e9, 1) if k > 0 else None,
             "kernels": {q: round(v, 4) for q, v in sorted(kern.items())}}
     if n <= 256:

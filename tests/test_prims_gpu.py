@@ -115,10 +115,10 @@ def test_prims_vs_live_reference(ab, kw, fusion):
 
 # ---- fused smoother, generation 4 (bulk-async-copy staged pass): every compiled launch plan must reproduce the
 #      reference schedule (one kernel per colour) BIT FOR BIT, on both MG levels that are eligible (64^3 and 32^3 boxes)
-# (tile_y, EARLY, LATE, one cell pair per thread also on rows of > 64 cells, box size): 64^3 / 32^3 boxes run one pair per
-# thread, 128^3 / 64^3 boxes two pairs per thread on the finer level unless the switch forces one
+# (tile_y, EARLY, LATE, cell pairs per thread on rows of > 64 cells [0: by launch size, 1, 2], box size): 64^3 / 32^3 boxes
+# always run one pair per thread (generation 4), a 128^3 box the kernel the switch names (2: generation 5)
 FUSED4_PLANS = [(8, 4, 2, 0, 64), (8, 4, 3, 0, 64), (6, 5, 3, 0, 64), (6, 4, 2, 0, 64), (4, 4, 4, 0, 64),
-                (8, 4, 2, 0, 128), (8, 4, 2, 1, 128), (8, 4, 3, 0, 128), (6, 5, 3, 0, 128), (6, 4, 2, 0, 128), (4, 4, 4, 0, 128)]
+                (8, 4, 2, 2, 128), (8, 4, 2, 1, 128), (8, 4, 2, 0, 128), (8, 4, 3, 2, 128), (6, 5, 3, 2, 128), (6, 4, 2, 2, 128), (4, 4, 4, 2, 128)]
 
 
 def _two_smooths(ab, op, n, mglev, seed):
@@ -169,9 +169,10 @@ def test_fused4_zero_input_bitwise(ab, kind, plan):
     of setVal(0) followed by the ordinary smooth, also when cor holds garbage (NaN) on entry; a second smooth follows to
     show that the ghost cells the pass leaves behind are handled."""
     from common import synth_abeclap, synth_poisson
-    n, mgs = 128, (plan[3] if len(plan) > 3 else 64)      # 128: two cell pairs per thread on the finer level
+    n, mgs = 128, (plan[3] if len(plan) > 3 else 64)      # 128: two cell pairs per thread on the finer level (forced)
     synth = synth_abeclap if kind == "abeclap" else synth_poisson
     assert ab.lib.amrex_b200_set_fused4_plan(*plan[:3]) == 0
+    ab.lib.b200mg_set_gsrb4_sync(2 if mgs == 128 else 0)
     try:
         out = {}
         for zero_input in (False, True):
@@ -201,6 +202,7 @@ def test_fused4_zero_input_bitwise(ab, kind, plan):
             assert np.array_equal(out[(False, mglev)], out[(True, mglev)]), f"mglev {mglev}"
     finally:
         ab.lib.amrex_b200_set_fused4_plan(8, 4, 2)
+        ab.lib.b200mg_set_gsrb4_sync(0)
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref/ref_driver not built")
