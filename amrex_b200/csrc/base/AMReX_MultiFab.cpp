@@ -598,6 +598,11 @@ struct CommPlan {
     std::vector<Peer> snd_peers, rcv_peers;
     long long snd_total = 0, rcv_total = 0;
     std::vector<int> remote_fabs;                        // local indices of the destination fabs that receive remote data (sorted)
+    // cross-stencil FillBoundary with one ghost cell whose every LOCAL tag is a whole box face copied from one local fab: the
+    // local part of the exchange as a table of face links [local fab * 6 + face] (b200mg_facelink); faces fed by other ranks
+    // (receive tags) have no link
+    DeviceTable<b200mg_facelink> d_links;
+    bool links_ok = false;
     double *sndbuf = nullptr, *rcvbuf = nullptr;
     long long buf_ncomp = 0;
     cudaEvent_t ev_packed = nullptr, ev_arrived = nullptr;
@@ -626,6 +631,9 @@ void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc,
 {
     std::vector<b200mg_copytag> h;
     auto npts = [] (CopyComTag const& t) { return int(std::min<Long>(t.dbox.numPts(), Long(1) << 30)); };
+    const bool want_links = cross_ng != nullptr && *cross_ng == IntVect(1) && &ldst == &lsrc;
+    std::vector<b200mg_facelink> links(want_links ? 6 * std::size_t(ldst.numLocal()) : 0, b200mg_facelink{-1, {0, 0, 0}});
+    bool links_ok = want_links;
     for (auto const& t : P.meta.LocTags) {
         const int ld = ldst.localIndex(t.dstIndex), ls = lsrc.localIndex(t.srcIndex);
         if (cross_ng == nullptr) { h.push_back(make_tag(t, ld, ls, 0)); P.maxloc = std::max(P.maxloc, npts(t)); continue; }
@@ -633,18 +641,25 @@ void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc,
         const IntVect d2s = t.sbox.smallEnd() - t.dbox.smallEnd();
         for (int dir = 0; dir < 3; ++dir) {
             for (int side = 0; side < 2; ++side) {
-                Box slab = vbx;
-                if (side == 0) { slab.setSmall(dir, vbx.smallEnd(dir) - (*cross_ng)[dir]); slab.setBig(dir, vbx.smallEnd(dir) - 1); }
-                else { slab.setSmall(dir, vbx.bigEnd(dir) + 1); slab.setBig(dir, vbx.bigEnd(dir) + (*cross_ng)[dir]); }
-                slab &= t.dbox;
+                Box face = vbx;
+                if (side == 0) { face.setSmall(dir, vbx.smallEnd(dir) - (*cross_ng)[dir]); face.setBig(dir, vbx.smallEnd(dir) - 1); }
+                else { face.setSmall(dir, vbx.bigEnd(dir) + 1); face.setBig(dir, vbx.bigEnd(dir) + (*cross_ng)[dir]); }
+                Box slab = face; slab &= t.dbox;
                 if (!slab.ok()) { continue; }
                 CopyComTag c = t;
                 c.dbox = slab; c.sbox = slab + d2s;
                 h.push_back(make_tag(c, ld, ls, 0)); P.maxloc = std::max(P.maxloc, npts(c));
+                if (want_links) {
+                    b200mg_facelink& l = links[std::size_t(ld) * 6 + dir + 3 * side];
+                    if (slab == face && l.fab < 0) { l.fab = ls; for (int d = 0; d < 3; ++d) { l.shift[d] = d2s[d]; } }
+                    else { links_ok = false; }       // a face fed by several boxes, or in part
+                }
             }
         }
     }
     P.nloc = int(h.size()); P.d_loc.assign(h);
+    P.links_ok = links_ok && P.nloc > 0;
+    if (P.links_ok) { P.d_links.assign(links); }
     h.clear();
     long long off = 0;
     for (auto const& kv : P.meta.SndTags) {
@@ -672,7 +687,8 @@ void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc,
 // grouped ncclSend/ncclRecv on the communication stream (NVLink), and meanwhile the intra-GPU copies on the compute stream;
 // finish: the compute stream waits for the transfer and unpacks.  Whatever the caller launches on the compute stream between
 // the two halves (the smoother on the boxes without remote neighbours) overlaps the transfer.
-void start_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op, int parity = -1)
+void start_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op, int parity = -1,
+                 bool remote_only = false)
 {
     cudaStream_t s = Gpu::gpuStream();
     const bool remote = (P.snd_total + P.rcv_total) > 0;
@@ -714,7 +730,9 @@ void start_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int
         if (overlap) { AMREX_CUDA_SAFE_CALL(cudaEventRecord(P.ev_arrived, cs)); }
         if (Gpu::debugSync()) { Gpu::check(Gpu::debugSyncNow(), "[B200MG_DEBUG_SYNC] ncclSend/ncclRecv group", __FILE__, __LINE__); }
     }
-    B200_KCALL(b200mg_copy_tags_colour(P.nloc, P.d_loc.data(), dst.d_fabs(), src.d_fabs(), nullptr, ncomp, scomp, dcomp, int(op), P.maxloc, parity, s));
+    if (!remote_only) {
+        B200_KCALL(b200mg_copy_tags_colour(P.nloc, P.d_loc.data(), dst.d_fabs(), src.d_fabs(), nullptr, ncomp, scomp, dcomp, int(op), P.maxloc, parity, s));
+    }
 }
 
 void finish_plan_exchange (CommPlan& P, MultiFab& dst, int scomp, int dcomp, int ncomp, CpOp op, int parity = -1)
@@ -728,9 +746,10 @@ void finish_plan_exchange (CommPlan& P, MultiFab& dst, int scomp, int dcomp, int
     }
 }
 
-void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op, int parity = -1)
+void execute_plan (CommPlan& P, MultiFab& dst, MultiFab const& src, int scomp, int dcomp, int ncomp, CpOp op, int parity = -1,
+                   bool remote_only = false)
 {
-    start_plan(P, dst, src, scomp, dcomp, ncomp, op, parity);
+    start_plan(P, dst, src, scomp, dcomp, ncomp, op, parity, remote_only);
     finish_plan_exchange(P, dst, scomp, dcomp, ncomp, op, parity);
 }
 
@@ -778,21 +797,23 @@ CommPlan& fb_plan (MultiFab& mf, IntVect const& nghost, Periodicity const& perio
 }
 }
 
-void MultiFab::FillBoundary (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross, int parity)
+void MultiFab::FillBoundary (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross, int parity,
+                             bool remote_only)
 {
     if (m_ngrow == 0 || nghost.max() == 0) { return; }
     AMREX_ALWAYS_ASSERT(nghost.allLE(IntVect(m_ngrow)));
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_fb_pending == nullptr, "FillBoundary while a FillBoundary_nowait is pending on this MultiFab");
-    execute_plan(fb_plan(*this, nghost, period, cross), *this, *this, scomp, scomp, ncomp, CpOp::COPY, parity);
+    execute_plan(fb_plan(*this, nghost, period, cross), *this, *this, scomp, scomp, ncomp, CpOp::COPY, parity, remote_only);
 }
 
-void MultiFab::FillBoundary_nowait (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross, int parity)
+void MultiFab::FillBoundary_nowait (int scomp, int ncomp, IntVect const& nghost, Periodicity const& period, bool cross, int parity,
+                                    bool remote_only)
 {
     if (m_ngrow == 0 || nghost.max() == 0) { return; }
     AMREX_ALWAYS_ASSERT(nghost.allLE(IntVect(m_ngrow)));
     AMREX_ALWAYS_ASSERT_WITH_MESSAGE(m_fb_pending == nullptr, "FillBoundary_nowait: the previous one was not finished");
     CommPlan& P = fb_plan(*this, nghost, period, cross);
-    start_plan(P, *this, *this, scomp, scomp, ncomp, CpOp::COPY, parity);
+    start_plan(P, *this, *this, scomp, scomp, ncomp, CpOp::COPY, parity, remote_only);
     m_fb_pending = &P; m_fb_scomp = scomp; m_fb_ncomp = ncomp; m_fb_parity = parity;
 }
 
@@ -806,6 +827,12 @@ void MultiFab::FillBoundary_finish ()
 std::vector<int> const& MultiFab::FillBoundaryRemoteFabs (IntVect const& nghost, Periodicity const& period, bool cross)
 {
     return fb_plan(*this, nghost, period, cross).remote_fabs;
+}
+
+const b200mg_facelink* MultiFab::FillBoundaryFaceLinks (IntVect const& nghost, Periodicity const& period, bool cross)
+{
+    CommPlan& P = fb_plan(*this, nghost, period, cross);
+    return P.links_ok ? P.d_links.data() : nullptr;
 }
 
 void MultiFab::ParallelCopy (MultiFab const& src, int scomp, int dcomp, int ncomp, int src_ng, int dst_ng,

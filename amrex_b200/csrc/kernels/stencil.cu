@@ -215,6 +215,86 @@ k_gsrb_shell_poisson (const b200mg_box* __restrict__ vbox, PoisArgs A, int redbl
     shell_loop(vb, face, redblack, [&] (int i, int j, int k) { gsrb_at(i, j, k, vb, V); });
 }
 
+// Shell sweep with face links (b200mg_facelink): the six neighbours of a shell cell, the one(s) beyond a linked face taken
+// from the neighbouring fab's valid cell - the value a halo exchange would have copied into the ghost cell, so the bits do
+// not change - and, with push, the new value stored into the ghost cell(s) that fab keeps for this cell.  A cell on an edge
+// or a corner of its box lies on two or three faces.  No races within one colour: a cell of the swept colour reads cells of
+// the other colour only, and the pushed ghost cells (swept colour) are read by nobody during the sweep.
+struct Nbr6 { double xm, xp, ym, yp, zm, zp; };
+
+__device__ __forceinline__ Nbr6
+linked_neighbours (int i, int j, int k, const b200mg_box& vb, const double* pc, int js, int ks,
+                   const b200mg_fab* phif, const b200mg_facelink* __restrict__ L6)
+{
+    Nbr6 n;
+    auto beyond = [&] (int face, int ii, int jj, int kk, const double* own) {
+        const b200mg_facelink l = L6[face];
+        return (l.fab >= 0) ? view(phif[l.fab])(ii + l.shift[0], jj + l.shift[1], kk + l.shift[2]) : *own;
+    };
+    n.xm = (i == vb.lo[0]) ? beyond(0, i - 1, j, k, pc - 1) : pc[-1];
+    n.xp = (i == vb.hi[0]) ? beyond(3, i + 1, j, k, pc + 1) : pc[1];
+    n.ym = (j == vb.lo[1]) ? beyond(1, i, j - 1, k, pc - js) : pc[-js];
+    n.yp = (j == vb.hi[1]) ? beyond(4, i, j + 1, k, pc + js) : pc[js];
+    n.zm = (k == vb.lo[2]) ? beyond(2, i, j, k - 1, pc - ks) : pc[-ks];
+    n.zp = (k == vb.hi[2]) ? beyond(5, i, j, k + 1, pc + ks) : pc[ks];
+    return n;
+}
+
+__device__ __forceinline__ void
+push_to_links (int i, int j, int k, const b200mg_box& vb, double v, const b200mg_fab* phif, const b200mg_facelink* __restrict__ L6)
+{
+    // this cell is the ghost cell (i,j,k) + shift of the fab behind every linked face it lies on
+    auto put = [&] (int face) {
+        const b200mg_facelink l = L6[face];
+        if (l.fab >= 0) { view(phif[l.fab])(i + l.shift[0], j + l.shift[1], k + l.shift[2]) = v; }
+    };
+    if (i == vb.lo[0]) { put(0); }
+    if (i == vb.hi[0]) { put(3); }
+    if (j == vb.lo[1]) { put(1); }
+    if (j == vb.hi[1]) { put(4); }
+    if (k == vb.lo[2]) { put(2); }
+    if (k == vb.hi[2]) { put(5); }
+}
+
+__global__ void __launch_bounds__(256)
+k_gsrb_shell_abec_linked (const b200mg_box* __restrict__ vbox, AbecArgs A, int redblack, const b200mg_facelink* __restrict__ links, int push)
+{
+    const int box = blockIdx.x / 6, face = blockIdx.x % 6;
+    const b200mg_box vb = vbox[box];
+    const AbecViews V(A, box);
+    const b200mg_facelink* L6 = links + 6 * box;
+    shell_loop(vb, face, redblack, [&] (int i, int j, int k) {
+        double* pc = V.phi.ptr(i, j, k);
+        const double p = *pc;
+        const Nbr6 n = linked_neighbours(i, j, k, vb, pc, int(V.phi.js), int(V.phi.ks), A.phi, L6);
+        const double* pbx = V.bx.ptr(i, j, k); const double* pby = V.by.ptr(i, j, k); const double* pbz = V.bz.ptr(i, j, k);
+        const FaceCoefs cf = face_coefs(i, j, k, vb, V.f6, V.m6);      // (every shell cell is a surface cell)
+        const double r = gsrb_abec_cell(p, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp,
+                                        V.rhs(i, j, k), V.a(i, j, k), pbx[0], pbx[1], pby[0], pby[V.by.js], pbz[0], pbz[V.bz.ks],
+                                        cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], V.alpha, V.dhx, V.dhy, V.dhz);
+        *pc = r;
+        if (push) { push_to_links(i, j, k, vb, r, A.phi, L6); }
+    });
+}
+
+__global__ void __launch_bounds__(256)
+k_gsrb_shell_poisson_linked (const b200mg_box* __restrict__ vbox, PoisArgs A, int redblack, const b200mg_facelink* __restrict__ links, int push)
+{
+    const int box = blockIdx.x / 6, face = blockIdx.x % 6;
+    const b200mg_box vb = vbox[box];
+    const PoisViews V(A, box);
+    const b200mg_facelink* L6 = links + 6 * box;
+    shell_loop(vb, face, redblack, [&] (int i, int j, int k) {
+        double* pc = V.phi.ptr(i, j, k);
+        const Nbr6 n = linked_neighbours(i, j, k, vb, pc, int(V.phi.js), int(V.phi.ks), A.phi, L6);
+        const FaceCoefs cf = face_coefs(i, j, k, vb, V.f6, V.m6);
+        const double r = gsrb_poisson_cell(*pc, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp, V.rhs(i, j, k),
+                                           cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], V.dhx, V.dhy, V.dhz);
+        *pc = r;
+        if (push) { push_to_links(i, j, k, vb, r, A.phi, L6); }
+    });
+}
+
 // ---------------------------------------------------------------------------------------- adotx
 __global__ void __launch_bounds__(kTileTX * B200MG_TILE_Y)
 k_adotx_abec (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restrict__ vbox,
@@ -652,6 +732,33 @@ int b200mg_gsrb_shell_poisson (int nboxes, const b200mg_box* vbox,
     if (nboxes <= 0) { return 0; }
     PoisArgs A{phi, rhs, f, m, dhx, dhy, dhz};
     k_gsrb_shell_poisson<<<dim3(nboxes * 6, shell_chunks(max_face_cells)), kShellThreads, 0, s>>>(vbox, A, redblack);
+    return last_error();
+}
+
+int b200mg_gsrb_shell_abec_linked (int nboxes, const b200mg_box* vbox,
+                                   const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,
+                                   const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                                   const b200mg_fab* f, const b200mg_ifab* m,
+                                   double alpha, double dhx, double dhy, double dhz, int redblack, int max_face_cells,
+                                   const b200mg_facelink* links, int push, cudaStream_t s)
+{
+    if (links == nullptr) { return b200mg_gsrb_shell_abec(nboxes, vbox, phi, rhs, a, bx, by, bz, f, m, alpha, dhx, dhy, dhz, redblack, max_face_cells, s); }
+    if (nboxes <= 0) { return 0; }
+    AbecArgs A{phi, rhs, a, bx, by, bz, f, m, alpha, dhx, dhy, dhz};
+    k_gsrb_shell_abec_linked<<<dim3(nboxes * 6, shell_chunks(max_face_cells)), kShellThreads, 0, s>>>(vbox, A, redblack, links, push);
+    return last_error();
+}
+
+int b200mg_gsrb_shell_poisson_linked (int nboxes, const b200mg_box* vbox,
+                                      const b200mg_fab* phi, const b200mg_fab* rhs,
+                                      const b200mg_fab* f, const b200mg_ifab* m,
+                                      double dhx, double dhy, double dhz, int redblack, int max_face_cells,
+                                      const b200mg_facelink* links, int push, cudaStream_t s)
+{
+    if (links == nullptr) { return b200mg_gsrb_shell_poisson(nboxes, vbox, phi, rhs, f, m, dhx, dhy, dhz, redblack, max_face_cells, s); }
+    if (nboxes <= 0) { return 0; }
+    PoisArgs A{phi, rhs, f, m, dhx, dhy, dhz};
+    k_gsrb_shell_poisson_linked<<<dim3(nboxes * 6, shell_chunks(max_face_cells)), kShellThreads, 0, s>>>(vbox, A, redblack, links, push);
     return last_error();
 }
 

@@ -782,7 +782,7 @@ void MLLinOp::prepareForSolve ()
 
 // MLCellLinOpT::applyBC (AMReX_MLCellLinOp.H:684-893), cross stencil
 void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, StateMode, const BndrySlabs<double>* bndry,
-                       bool skip_fillboundary, bool nowait, int halo_parity) const
+                       bool skip_fillboundary, bool nowait, int halo_parity, bool halo_remote_only) const
 {
     if (!m_colour_halo) { halo_parity = -1; }
     Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
@@ -812,14 +812,14 @@ void MLLinOp::applyBC (int amrlev, int mglev, MultiFab& in, BCMode bc_mode, Stat
         B200_KCALL(b200mg_apply_bc(nf, L.bcfaces.data(), L.layout->d_vbox(), in.d_fabs(), L.mask.d_table(),
                                    bndry ? bndry->d_table() : nullptr, maxorder, dxi[0], dxi[1], dxi[2], flagbc, maxFaceCells(L), aux));
         AMREX_CUDA_SAFE_CALL(cudaEventRecord(ev_join, aux));
-        if (nowait) { in.FillBoundary_nowait(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity); }
-        else { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity); }
+        if (nowait) { in.FillBoundary_nowait(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity, halo_remote_only); }
+        else { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity, halo_remote_only); }
         AMREX_CUDA_SAFE_CALL(cudaStreamWaitEvent(s, ev_join, 0));
         return;
     }
     if (!skip_fillboundary) {
-        if (nowait) { in.FillBoundary_nowait(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity); }
-        else { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity); }
+        if (nowait) { in.FillBoundary_nowait(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity, halo_remote_only); }
+        else { in.FillBoundary(0, 1, IntVect(1), H.geom[amrlev][mglev].periodicity(), true, halo_parity, halo_remote_only); }
     }
     if (nf == 0) { return; }
     B200_KCALL(b200mg_apply_bc(nf, L.bcfaces.data(), L.layout->d_vbox(), in.d_fabs(), L.mask.d_table(),
@@ -927,11 +927,15 @@ std::size_t MLABecLaplacian::graphKey (int amrlev, int mglev) const
     return h;
 }
 
-void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, bool skip_fillboundary, bool zero_input) const
+void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, bool skip_fillboundary, bool zero_input,
+                      bool consecutive) const
 {
     Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
     LevelData const& L = lev(amrlev, mglev);
     const bool fuse = m_fuse_colors && m_use_gauss_seidel && planFused(L) && L.fused4_ok != 0;
+    // did the previous smooth of this loop leave the black surface values in the neighbours' ghost cells (face links)?
+    const bool ghosts_pushed = consecutive && L.shell_pushed;
+    L.shell_pushed = false;
     // zero input without a prior setVal: the fused pass can do without reading sol
     const bool zero4 = zero_input && fuse && m_zero_input_opt;
     if (zero_input && !zero4) { sol.setVal(0.0); skip_fillboundary = true; }
@@ -953,6 +957,15 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
         // FillBoundary overlapped with interior work (FillBoundary_nowait / _finish of the reference, AMReX_FabArray.H:1023-1042):
         // the pass over the boxes whose halo comes from this GPU only runs while the NVLink transfer is in flight, the pass
         // over the boxes with remote neighbours after the unpack.  Out of place, so the two halves do not interact.
+        // Face links (a level whose exchange between boxes of this GPU is nothing but whole faces): the shell reads the red
+        // cells behind a linked face from the neighbouring box itself, so the exchange ahead of it only has to bring the
+        // faces other GPUs feed, and it stores its black results into the neighbours' ghost cells as well, so the same holds
+        // for the exchange ahead of the NEXT pass when that follows at once (consecutive).  Same values, same bits.
+        if (L.face_links_state < 0) {
+            L.face_links = (m_face_links && L.fused4_ok != 0) ? sol.FillBoundaryFaceLinks(IntVect(1), H.geom[amrlev][mglev].periodicity(), true) : nullptr;
+            L.face_links_state = (L.face_links != nullptr) ? 1 : 0;
+        }
+        const b200mg_facelink* links = (L.face_links_state == 1 && L.fused4_ok == 1) ? L.face_links : nullptr;
         bool split = false;
         // (not under the per-kernel profiler: it times whole-level launches on the main stream)
         if (!zero4 && !skip_fillboundary && m_halo_overlap && L.fused4_ok == 1 && ParallelDescriptor::NProcs() > 1 && !Gpu::debugSync()
@@ -976,7 +989,7 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
                 AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
                 AMREX_CUDA_SAFE_CALL(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
             }
-            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, true, 1);
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, true, 1, links && ghosts_pushed);
             cudaStream_t s = Gpu::gpuStream(), aux = Gpu::auxStream();
             const bool side = true;
             bool ok2 = true;
@@ -997,18 +1010,22 @@ void MLLinOp::smooth (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs,
             }
             AMREX_ALWAYS_ASSERT_WITH_MESSAGE(ok1 && ok2, "fused smoother: a level that took the pass before refused it");
             sol.swap(*L.scratch);
-            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, false, 0);
-            FsmoothShell(amrlev, mglev, sol, rhs, 1);
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, false, 0, links != nullptr);
+            FsmoothShell(amrlev, mglev, sol, rhs, 1, links, links != nullptr);
+            L.shell_pushed = (links != nullptr);
             return;
         }
         // the pass updates the red cells everywhere (they read black ghost cells: parity 1) and the black cells off the box
         // surface (no ghost cells); the black shell afterwards reads red ghost cells (parity 0)
-        if (!zero4) { applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary, false, 1); }
+        if (!zero4) {
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, skip_fillboundary, false, 1, links && ghosts_pushed);
+        }
         if (Fsmooth2(amrlev, mglev, *L.scratch, sol, rhs, zero4)) {
             L.fused4_ok = 1;
             sol.swap(*L.scratch);
-            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, false, 0);
-            FsmoothShell(amrlev, mglev, sol, rhs, 1);
+            applyBC(amrlev, mglev, sol, BCMode::Homogeneous, StateMode::Solution, nullptr, false, false, 0, links != nullptr);
+            FsmoothShell(amrlev, mglev, sol, rhs, 1, links, links != nullptr);
+            L.shell_pushed = (links != nullptr);
             return;
         }
         // the layout cannot take the bulk copies (L.fused4_ok is 0 from now on): colour sweeps; the boundary fill above is
@@ -1705,13 +1722,15 @@ void MLABecLaplacian::Fjacobi (int amrlev, int mglev, MultiFab& sol_out, MultiFa
                                   m_b_scalar * dxi[0] * dxi[0], m_b_scalar * dxi[1] * dxi[1], m_b_scalar * dxi[2] * dxi[2], Gpu::gpuStream()));
 }
 
-void MLABecLaplacian::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
+void MLABecLaplacian::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack,
+                                    const b200mg_facelink* links, bool push) const
 {
     LevelData const& L = lev(amrlev, mglev);
     Real dh[3]; gsrb_dh(H.geom[amrlev][mglev], m_b_scalar, dh);
-    B200_KCALL(b200mg_gsrb_shell_abec(L.layout->numLocal(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), m_a_coeffs[amrlev][mglev].d_fabs(),
-                                      m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(), m_b_coeffs[amrlev][mglev][2].d_fabs(),
-                                      L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, maxFaceCells(L), Gpu::gpuStream()));
+    B200_KCALL(b200mg_gsrb_shell_abec_linked(L.layout->numLocal(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), m_a_coeffs[amrlev][mglev].d_fabs(),
+                                             m_b_coeffs[amrlev][mglev][0].d_fabs(), m_b_coeffs[amrlev][mglev][1].d_fabs(), m_b_coeffs[amrlev][mglev][2].d_fabs(),
+                                             L.undrrelxr.d_table(), L.mask.d_table(), m_a_scalar, dh[0], dh[1], dh[2], redblack, maxFaceCells(L),
+                                             links, push ? 1 : 0, Gpu::gpuStream()));
 }
 
 // ============================================================================================ MLPoisson
@@ -1805,12 +1824,14 @@ void MLPoisson::Fjacobi (int amrlev, int mglev, MultiFab& sol_out, MultiFab cons
                                      L.undrrelxr.d_table(), L.mask.d_table(), dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], Gpu::gpuStream()));
 }
 
-void MLPoisson::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack) const
+void MLPoisson::FsmoothShell (int amrlev, int mglev, MultiFab& sol, MultiFab const& rhs, int redblack,
+                              const b200mg_facelink* links, bool push) const
 {
     LevelData const& L = lev(amrlev, mglev);
     const Real* dxi = H.geom[amrlev][mglev].InvCellSize();
-    B200_KCALL(b200mg_gsrb_shell_poisson(L.layout->numLocal(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
-                                         dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, maxFaceCells(L), Gpu::gpuStream()));
+    B200_KCALL(b200mg_gsrb_shell_poisson_linked(L.layout->numLocal(), L.layout->d_vbox(), sol.d_fabs(), rhs.d_fabs(), L.undrrelxr.d_table(), L.mask.d_table(),
+                                                dxi[0] * dxi[0], dxi[1] * dxi[1], dxi[2] * dxi[2], redblack, maxFaceCells(L),
+                                                links, push ? 1 : 0, Gpu::gpuStream()));
 }
 
 } // namespace amrex

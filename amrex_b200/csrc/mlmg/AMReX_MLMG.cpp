@@ -423,7 +423,7 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
             if (nu1 <= 0) { cor[amrlev][mglev].setVal(0.0); }
             bool skip_fillboundary = true;
             for (int i = 0; i < nu1; ++i) {
-                linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev], skip_fillboundary, i == 0);
+                linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev], skip_fillboundary, i == 0, i > 0);
                 skip_fillboundary = false;
             }
             // residual + restriction in one pass when the level allows it (rescor of this level is then not formed)
@@ -437,7 +437,7 @@ void MLMG::mgVcycle (int amrlev, int mglev_top)
         for (int mglev = m1; mglev >= m0; --mglev) {
             Gpu::ProfScope prof_scope__(amrlev * 100 + mglev);
             addInterpCorrection(amrlev, mglev);
-            for (int i = 0; i < nu2; ++i) { linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev]); }
+            for (int i = 0; i < nu2; ++i) { linop.smooth(amrlev, mglev, cor[amrlev][mglev], res[amrlev][mglev], false, false, i > 0); }
         }
     };
     // B200: every level from the first single-box level down to the bottom solve and back up is ONE kernel
@@ -672,7 +672,7 @@ void MLMG::bottomSolve ()
     x.setVal(0.0);
     if (bottom_solver == BottomSolver::smoother) {
         bool skip_fillboundary = true;
-        for (int i = 0; i < nuf; ++i) { linop.smooth(amrlev, mglev, x, b, skip_fillboundary); skip_fillboundary = false; }
+        for (int i = 0; i < nuf; ++i) { linop.smooth(amrlev, mglev, x, b, skip_fillboundary, false, i > 0); skip_fillboundary = false; }
     } else {
         MultiFab* pb = &b;
         if (linop.isBottomSingular() && linop.getEnforceSingularSolvable()) {
@@ -692,7 +692,7 @@ void MLMG::bottomSolve ()
         }
         if (ret != 0 && ret != 9) { cor[amrlev][mglev].setVal(0.0); }
         const int n = (ret == 0) ? nub : nuf;
-        for (int i = 0; i < n; ++i) { linop.smooth(amrlev, mglev, x, b); }
+        for (int i = 0; i < n; ++i) { linop.smooth(amrlev, mglev, x, b, false, false, i > 0); }
     }
     timer[2] += ParallelDescriptor::second() - t0;
 }

@@ -65,6 +65,15 @@ typedef struct b200mg_copytag {
     long long buf_offset;
 } b200mg_copytag;
 
+/* Face link of a local box: the one local fab whose valid cells lie behind the whole face (fab < 0: none - physical boundary,
+ * coarse/fine boundary, another rank, or several neighbours), and the index shift from this box's ghost cell to the cell of
+ * that fab that holds its value (non-zero across a periodic boundary).  Table layout [box * 6 + face], faces 0,1,2 = x,y,z low,
+ * 3,4,5 = high. */
+typedef struct b200mg_facelink {
+    int fab;
+    int shift[3];
+} b200mg_facelink;
+
 /* ---- smoother: one red or black sweep (K1 abec_gsrb AMReX_MLABecLap_3D_K.H:210-264,
  *      K2 mlpoisson_gsrb AMReX_MLPoisson_3D_K.H:155-196).  f / m: tables of 6*nboxes slabs, [box*6+face]. */
 int b200mg_gsrb_abec(int ntiles, const b200mg_tile* tiles, const b200mg_box* vbox,
@@ -142,6 +151,21 @@ int b200mg_gsrb_shell_poisson(int nboxes, const b200mg_box* vbox,
                               const b200mg_fab* phi, const b200mg_fab* rhs,
                               const b200mg_fab* f, const b200mg_ifab* m,
                               double dhx, double dhy, double dhz, int redblack, int max_face_cells, cudaStream_t s);
+/* the same with face links: a shell cell reads the value beyond a linked face from the neighbouring fab's valid cell instead
+ * of its own ghost cell (so the halo exchange ahead of the shell sweep has nothing to copy between local boxes), and with
+ * push != 0 it stores its new value into that fab's ghost cell as well (so the exchange ahead of the NEXT sweep of the other
+ * colour has nothing to copy either).  links == NULL: the plain shell sweep. */
+int b200mg_gsrb_shell_abec_linked(int nboxes, const b200mg_box* vbox,
+                                  const b200mg_fab* phi, const b200mg_fab* rhs, const b200mg_fab* a,
+                                  const b200mg_fab* bx, const b200mg_fab* by, const b200mg_fab* bz,
+                                  const b200mg_fab* f, const b200mg_ifab* m,
+                                  double alpha, double dhx, double dhy, double dhz, int redblack, int max_face_cells,
+                                  const b200mg_facelink* links, int push, cudaStream_t s);
+int b200mg_gsrb_shell_poisson_linked(int nboxes, const b200mg_box* vbox,
+                                     const b200mg_fab* phi, const b200mg_fab* rhs,
+                                     const b200mg_fab* f, const b200mg_ifab* m,
+                                     double dhx, double dhy, double dhz, int redblack, int max_face_cells,
+                                     const b200mg_facelink* links, int push, cudaStream_t s);
 
 /* ---- damped Jacobi sweep (abec_jacobi AMReX_MLABecLap_3D_K.H:332-375, mlpoisson_jacobi AMReX_MLPoisson_3D_K.H:250-281):
  *      phi_out = phi_in + 2/3 * (rhs - L(phi_in)) / (gamma - face terms) on every valid cell, out of place, with L(phi_in)

@@ -83,14 +83,19 @@ def test_multirank_halo_overlap_is_bit_neutral(tmp_path):
     """2 ranks x 32 boxes of 32^3 with the fused smoother forced on and the merged leg capped at 16^3, so that the 128^3 and
     64^3 levels run the launch-per-operation path: the pass over the boxes without remote neighbours is launched while the
     NVLink transfer of the halo is in flight (FillBoundary_nowait / _finish), the other boxes after the unpack, and every
-    smoother exchange packs / unpacks only the colour the next sweep reads.  Same bits as the sequential full exchanges
-    (B200MG_NO_HALO_OVERLAP=1, B200MG_NO_COLOUR_HALO=1), and the reference's answer."""
+    smoother exchange packs / unpacks only the colour the next sweep reads, and the copies between the boxes of a rank are
+    replaced by face links.  Same bits as the sequential full exchanges (B200MG_NO_HALO_OVERLAP=1, B200MG_NO_COLOUR_HALO=1,
+    B200MG_NO_FACE_LINKS=1), and the reference's answer."""
     env = {"B200MG_MERGED_MAX_CELLS": "4096", "WORKER_FUSION": "1"}
     a = _run("abeclap128", 2, tmp_path, env=env)
-    b = _run("abeclap128", 2, tmp_path, env=dict(env, B200MG_NO_HALO_OVERLAP="1", B200MG_NO_COLOUR_HALO="1"))
+    b = _run("abeclap128", 2, tmp_path, env=dict(env, B200MG_NO_HALO_OVERLAP="1", B200MG_NO_COLOUR_HALO="1", B200MG_NO_FACE_LINKS="1"))
     assert "b200mg_gsrb4" in a["kernels"] and "b200mg_gsrb4" in b["kernels"]
     assert a["history"] == b["history"] and a["cg_iters"] == b["cg_iters"]
     assert a["sol_rel_maxdiff"] <= 1e-10 and abs(a["iters"] - a["ref_iters"]) <= 1
+    # face links alone (the shell sweep follows them between the boxes of a rank, the exchanges around it carry the faces the
+    # other rank feeds only), with the overlap on
+    c = _run("abeclap128", 2, tmp_path, env=dict(env, B200MG_NO_FACE_LINKS="1"))
+    assert a["history"] == c["history"] and a["cg_iters"] == c["cg_iters"]
 
 
 def test_multirank_two_component_exchange(tmp_path):

@@ -218,8 +218,9 @@ def test_post_solve_fluxes_and_gradients(ab, prob_type, n, mgs):
 def test_b200_schedule_switches_are_bit_neutral(ab, kind, monkeypatch):
     """The B200-only schedule changes - residual + inf-norm in one kernel, first pre-smooth without zeroing / reading the
     correction, BC fill on a second stream next to the halo copies, residual + restriction in one kernel (the fine residual
-    is never stored), smoother halo exchanges that move only the colour the next sweep reads - must not change a single bit
-    of the solve: same
+    is never stored), smoother halo exchanges that move only the colour the next sweep reads, the shell sweep that reads /
+    writes the neighbouring boxes through face links instead of two of the three halo exchanges of a smooth - must not change
+    a single bit of the solve: same
     residual history and same solution as with all three switched off (environment read when the operator is built)."""
     import os
     from common import synth_abeclap, synth_poisson
@@ -227,7 +228,8 @@ def test_b200_schedule_switches_are_bit_neutral(ab, kind, monkeypatch):
     out = {}
     monkeypatch.setenv("B200MG_NO_MERGED_LEG", "1")       # keep the 128^3 / 64^3 levels on the launch-per-operation path under test
     for off in (True, False):
-        for v in ("B200MG_NO_FUSED_RESNORM", "B200MG_NO_ZERO_INPUT", "B200MG_NO_BC_OVERLAP", "B200MG_NO_FUSED_RESTRICT", "B200MG_NO_COLOUR_HALO"):
+        for v in ("B200MG_NO_FUSED_RESNORM", "B200MG_NO_ZERO_INPUT", "B200MG_NO_BC_OVERLAP", "B200MG_NO_FUSED_RESTRICT", "B200MG_NO_COLOUR_HALO",
+                  "B200MG_NO_FACE_LINKS"):
             if off:
                 monkeypatch.setenv(v, "1")
             else:
@@ -248,6 +250,48 @@ def test_b200_schedule_switches_are_bit_neutral(ab, kind, monkeypatch):
     assert out[True][0] == out[False][0]
     assert out[True][1] == out[False][1]
     assert np.array_equal(out[True][2], out[False][2])
+
+
+@pytest.mark.parametrize("kind,periodic,n,mgs", [("abeclap", False, 128, 64), ("poisson", False, 128, 64), ("poisson", True, 128, 64),
+                                                 ("poisson", True, (128, 64, 64), 64)])
+def test_face_links_are_bit_neutral(ab, kind, periodic, n, mgs, monkeypatch):
+    """Face links alone (B200MG_NO_FACE_LINKS): a level whose halo exchange is whole faces between local boxes runs its shell
+    sweep on the neighbouring boxes' cells (exchange ahead of the shell dropped) and pushes the shell's results into their
+    ghost cells (exchange ahead of the next consecutive pass dropped) - incl. across a periodic boundary, where a box can be
+    its own neighbour (the 128 x 64 x 64 case: two boxes, each its own neighbour in y and z).  Same V-cycle count, bit-identical residual history and solution; fewer halo launches."""
+    from amrex_b200.synth import synth_poisson_periodic
+    from common import synth_abeclap, synth_poisson
+    out = {}
+    monkeypatch.setenv("B200MG_NO_MERGED_LEG", "1")       # keep the 128^3 / 64^3 levels on the launch-per-operation path under test
+    for off in (True, False):
+        if off:
+            monkeypatch.setenv("B200MG_NO_FACE_LINKS", "1")
+        else:
+            monkeypatch.delenv("B200MG_NO_FACE_LINKS", raising=False)
+        if kind == "abeclap":
+            P = synth_abeclap(ab, n, mgs, fusion=1)
+            sol, rhs = P["sol"], P["rhs"]
+        elif periodic:
+            P = synth_poisson_periodic(ab, n if isinstance(n, tuple) else (n, n, n), mgs, fusion=1)
+            P["op"].setFusedMinBoxCells(32 ** 3)           # fused pass (and with it the shell sweep) on the 64^3 and 32^3 boxes
+            sol, rhs = P["sol"], P["rhs"]
+        else:
+            P = synth_poisson(ab, n, mgs, fusion=1)
+            sol = ab.MultiFab(P["ba"], P["dm"], 1, 1)
+            rhs = ab.MultiFab(P["ba"], P["dm"], 1, 0)
+            sol.setVal(0.0, ng=1)
+            rhs.upload(np.random.default_rng(3).standard_normal((n, n, n)), (0, 0, 0))
+        mlmg = ab.MLMG(P["op"])
+        mlmg.setVerbose(0)
+        ab.profile_enable(True)
+        mlmg.solve([sol], [rhs], 1e-10, 0.0)
+        copies = sum(q[2] for q in ab.profile_report() if q[0].startswith("b200mg_copy_tags"))
+        ab.profile_enable(False)
+        out[off] = (mlmg.numIters(), list(mlmg.residualHistory()), sol.download((0, 0, 0), n if isinstance(n, tuple) else (n, n, n)), copies)
+    assert out[True][0] == out[False][0]
+    assert out[True][1] == out[False][1]
+    assert np.array_equal(out[True][2], out[False][2])
+    assert out[False][3] < out[True][3], (out[False][3], out[True][3])        # the links really replaced exchanges
 
 
 @pytest.mark.parametrize("kind,n,mgs,bottom", [("abeclap", 128, 64, None), ("poisson", 128, 64, None), ("abeclap", 64, 32, None),
