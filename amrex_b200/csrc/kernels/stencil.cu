@@ -222,13 +222,28 @@ k_gsrb_shell_poisson (const b200mg_box* __restrict__ vbox, PoisArgs A, int redbl
 // the other colour only, and the pushed ghost cells (swept colour) are read by nobody during the sweep.
 struct Nbr6 { double xm, xp, ym, yp, zm, zp; };
 
+// the link of the face a block sweeps, resolved once per block: every cell of the block lies on that face
+struct OwnLink { int face; bool linked; View<double> nbr; int s0, s1, s2; };
+
+__device__ __forceinline__ OwnLink
+own_link (int face, const b200mg_fab* phif, const b200mg_facelink* __restrict__ L6)
+{
+    OwnLink o;
+    const b200mg_facelink l = L6[face];
+    o.face = face; o.linked = (l.fab >= 0);
+    o.nbr = view(phif[o.linked ? l.fab : 0]);
+    o.s0 = l.shift[0]; o.s1 = l.shift[1]; o.s2 = l.shift[2];
+    return o;
+}
+
 __device__ __forceinline__ Nbr6
 linked_neighbours (int i, int j, int k, const b200mg_box& vb, const double* pc, int js, int ks,
-                   const b200mg_fab* phif, const b200mg_facelink* __restrict__ L6)
+                   const b200mg_fab* phif, const b200mg_facelink* __restrict__ L6, const OwnLink& O)
 {
     Nbr6 n;
     auto beyond = [&] (int face, int ii, int jj, int kk, const double* own) {
-        const b200mg_facelink l = L6[face];
+        if (face == O.face) { return O.linked ? O.nbr(ii + O.s0, jj + O.s1, kk + O.s2) : *own; }
+        const b200mg_facelink l = L6[face];              // a cell on an edge or a corner of the box: its other face(s)
         return (l.fab >= 0) ? view(phif[l.fab])(ii + l.shift[0], jj + l.shift[1], kk + l.shift[2]) : *own;
     };
     n.xm = (i == vb.lo[0]) ? beyond(0, i - 1, j, k, pc - 1) : pc[-1];
@@ -241,10 +256,12 @@ linked_neighbours (int i, int j, int k, const b200mg_box& vb, const double* pc, 
 }
 
 __device__ __forceinline__ void
-push_to_links (int i, int j, int k, const b200mg_box& vb, double v, const b200mg_fab* phif, const b200mg_facelink* __restrict__ L6)
+push_to_links (int i, int j, int k, const b200mg_box& vb, double v, const b200mg_fab* phif, const b200mg_facelink* __restrict__ L6,
+               const OwnLink& O)
 {
     // this cell is the ghost cell (i,j,k) + shift of the fab behind every linked face it lies on
     auto put = [&] (int face) {
+        if (face == O.face) { if (O.linked) { O.nbr(i + O.s0, j + O.s1, k + O.s2) = v; } return; }
         const b200mg_facelink l = L6[face];
         if (l.fab >= 0) { view(phif[l.fab])(i + l.shift[0], j + l.shift[1], k + l.shift[2]) = v; }
     };
@@ -263,17 +280,18 @@ k_gsrb_shell_abec_linked (const b200mg_box* __restrict__ vbox, AbecArgs A, int r
     const b200mg_box vb = vbox[box];
     const AbecViews V(A, box);
     const b200mg_facelink* L6 = links + 6 * box;
+    const OwnLink O = own_link(face, A.phi, L6);
     shell_loop(vb, face, redblack, [&] (int i, int j, int k) {
         double* pc = V.phi.ptr(i, j, k);
         const double p = *pc;
-        const Nbr6 n = linked_neighbours(i, j, k, vb, pc, int(V.phi.js), int(V.phi.ks), A.phi, L6);
+        const Nbr6 n = linked_neighbours(i, j, k, vb, pc, int(V.phi.js), int(V.phi.ks), A.phi, L6, O);
         const double* pbx = V.bx.ptr(i, j, k); const double* pby = V.by.ptr(i, j, k); const double* pbz = V.bz.ptr(i, j, k);
         const FaceCoefs cf = face_coefs(i, j, k, vb, V.f6, V.m6);      // (every shell cell is a surface cell)
         const double r = gsrb_abec_cell(p, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp,
                                         V.rhs(i, j, k), V.a(i, j, k), pbx[0], pbx[1], pby[0], pby[V.by.js], pbz[0], pbz[V.bz.ks],
                                         cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], V.alpha, V.dhx, V.dhy, V.dhz);
         *pc = r;
-        if (push) { push_to_links(i, j, k, vb, r, A.phi, L6); }
+        if (push) { push_to_links(i, j, k, vb, r, A.phi, L6, O); }
     });
 }
 
@@ -284,14 +302,15 @@ k_gsrb_shell_poisson_linked (const b200mg_box* __restrict__ vbox, PoisArgs A, in
     const b200mg_box vb = vbox[box];
     const PoisViews V(A, box);
     const b200mg_facelink* L6 = links + 6 * box;
+    const OwnLink O = own_link(face, A.phi, L6);
     shell_loop(vb, face, redblack, [&] (int i, int j, int k) {
         double* pc = V.phi.ptr(i, j, k);
-        const Nbr6 n = linked_neighbours(i, j, k, vb, pc, int(V.phi.js), int(V.phi.ks), A.phi, L6);
+        const Nbr6 n = linked_neighbours(i, j, k, vb, pc, int(V.phi.js), int(V.phi.ks), A.phi, L6, O);
         const FaceCoefs cf = face_coefs(i, j, k, vb, V.f6, V.m6);
         const double r = gsrb_poisson_cell(*pc, n.xm, n.xp, n.ym, n.yp, n.zm, n.zp, V.rhs(i, j, k),
                                            cf.c[0], cf.c[1], cf.c[2], cf.c[3], cf.c[4], cf.c[5], V.dhx, V.dhy, V.dhz);
         *pc = r;
-        if (push) { push_to_links(i, j, k, vb, r, A.phi, L6); }
+        if (push) { push_to_links(i, j, k, vb, r, A.phi, L6, O); }
     });
 }
 
