@@ -83,6 +83,28 @@ k_prolong_add (const b200mg_tile* __restrict__ tiles, const b200mg_box* __restri
     const b200mg_tile t = tiles[blockIdx.x];
     const b200mg_box fb = fbox[t.box];
     const auto fine = view(ff[t.box]); const auto crse = view(cf[t.box]);
+    // rows that start on an even cell and hold an even number of cells (16-byte aligned, as the FabArray allocator lays them
+    // out): a thread adds ONE coarse value to a cell pair, 16-byte read-modify-write (17 B/cell at 0.67 -> 0.9 of the HBM peak)
+    const int nx = fb.hi[0] - fb.lo[0] + 1;
+    const bool pairs = ((fb.lo[0] | nx) & 1) == 0 && ((fine.js | fine.ks) & 1) == 0
+        && (reinterpret_cast<unsigned long long>(fine.ptr(fb.lo[0], fb.lo[1], fb.lo[2])) & 15ull) == 0ull;
+    if (pairs) {
+        const int j = t.j0 + int(threadIdx.y);
+        if (j > fb.hi[1]) { return; }
+        const int khi = min(t.k0 + tile_nk(t) - 1, fb.hi[2]);
+        const int ic0 = floor_half(fb.lo[0]), jc = floor_half(j);
+        for (int k = t.k0; k <= khi; ++k) {
+            double2* frow = reinterpret_cast<double2*>(fine.ptr(fb.lo[0], j, k));
+            const double* crow = crse.ptr(ic0, jc, floor_half(k));
+            for (int ip = int(threadIdx.x); 2 * ip < nx; ip += int(blockDim.x)) {
+                double2 v = frow[ip];
+                const double c = crow[ip];
+                v.x += c; v.y += c;
+                frow[ip] = v;
+            }
+        }
+        return;
+    }
     tile_for(t, fb, 0, [&] (int i, int j, int k) {
         fine(i, j, k) += crse(floor_half(i), floor_half(j), floor_half(k));
     });
