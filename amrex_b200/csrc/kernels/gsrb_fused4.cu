@@ -354,11 +354,10 @@ int effective_tile_y (int nxmax) { return (g_plan_ty == 8 && nxmax <= 64) ? 16 :
 
 // cell pairs per thread: two on rows of 65 .. 128 cells (one warp per row, the kernel of gsrb_fused5.cu) when the launch
 // runs several waves of CTAs.  The tiles that hold the first / last row of a box look up their y-face coefficients in
-// global memory in every step; with two pairs per thread that load sits on the step's critical path (0.33 ms for such a
-// tile against 0.20 ms for the others), which the average over waves hides (1.52 against 1.60 ms at 6.9 waves) but a launch
-// of one or two waves shows in full: 0.329 against 0.246 ms for the 8 boxes of 128^3 a GPU owns in the 8-GPU run
-// (profiles/r02_s30_single_wave.txt).  Fetching those coefficients a step ahead, or pulling them into L1, cured the edge
-// tiles and cost the others more than it gained (r02_s32 .. s34 in the same file).
+// global memory in every step; with two pairs per thread that load sits on the step's critical path (0.26 ms for such a
+// tile against 0.20 ms for the others, with the producer warp's L1 prefetch; 0.33 ms without), which the average over waves
+// hides (1.47 against 1.60 ms at 6.9 waves) but a launch of one or two waves shows in full: 0.260 against 0.247 ms for the
+// 8 boxes of 128^3 a GPU owns in the 8-GPU run (profiles/r02_s30_single_wave.txt).
 int g_num_sms = 0;
 int pairs_per_thread (int nxmax, long long nctas)
 {
