@@ -162,6 +162,29 @@ def test_fused4_abeclap_bitwise(ab, plan):
         ab.lib.b200mg_set_gsrb4_sync(0)
 
 
+@pytest.mark.parametrize("kind,n,mgs", [("abeclap", 96, 96), ("abeclap", 72, 72), ("poisson", 96, 96), ("abeclap", 192, 96), ("abeclap", 104, 104)])
+def test_fused5_partial_rows_bitwise(ab, kind, n, mgs):
+    """Generation 5 of the fused pass (two cell pairs per thread, the second 64 cells to the right of the first) on rows
+    shorter than 128 cells, where only some lanes own a second pair and the last cell of the row sits in a second pair of a
+    lane other than 31: 96-, 72- and 104-cell rows (32, 4 and 20 second pairs), one box and eight boxes.  Bit for bit the
+    colour sweeps, two smooths in a row."""
+    from common import synth_abeclap, synth_poisson
+    synth = synth_abeclap if kind == "abeclap" else synth_poisson
+    P = synth(ab, n, mgs, fusion=0)
+    P["op"].prepareForSolve()
+    want, names = _two_smooths(ab, P["op"], n, 0, 7)
+    assert "b200mg_gsrb4" not in names
+    P = synth(ab, n, mgs, fusion=1)
+    ab.lib.b200mg_set_gsrb4_sync(2)
+    try:
+        P["op"].prepareForSolve()
+        got, names = _two_smooths(ab, P["op"], n, 0, 7)
+        assert "b200mg_gsrb4" in names, names
+        assert np.array_equal(got, want), f"max|diff| {np.abs(got - want).max():.3e}"
+    finally:
+        ab.lib.b200mg_set_gsrb4_sync(0)
+
+
 @pytest.mark.parametrize("plan", [(8, 4, 2), (6, 5, 3), (4, 4, 4), (8, 4, 2, 128)])
 @pytest.mark.parametrize("kind", ["abeclap", "poisson"])
 def test_fused4_zero_input_bitwise(ab, kind, plan):
