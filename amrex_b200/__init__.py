@@ -10,5 +10,5 @@ from .capi import (  # noqa: F401
     lib, load_library, LIB_PATH, AmrexError, check,
     init, finalize, comm_init_from_torch, profile_enable, profile_report,
     Geometry, BoxArray, DistributionMapping, MultiFab, MLLinOp, MLABecLaplacian, MLALaplacian, MLPoisson, MLMG, GMRESMLMG,
-    hierarchy, fb_tags, cpc_tags, make_sfc, LinOpBCType, write_plotfile,
+    hierarchy, fb_tags, fb_face_links, cpc_tags, make_sfc, LinOpBCType, write_plotfile,
 )

@@ -113,6 +113,7 @@ _SIGS = {
     "amrex_b200_hierarchy_shares_box_list": (_I, [_P, _I, _I, _I]),
     "amrex_b200_fb_tags": (_I, [_P, _P, _I, _I, _IP, _I, _I, _IP, _I]),
     "amrex_b200_cpc_tags": (_I, [_P, _P, _I, _P, _P, _I, _IP, _I, _I, _IP, _I]),
+    "amrex_b200_fb_face_links": (_I, [_P, _P, _IP, _I, _IP, _I]),
 }
 
 
@@ -631,6 +632,18 @@ def fb_tags(ba, dm, ng, cross, period, myproc, kind):
     buf = (C.c_int * (15 * max(n, 1)))()
     lib.amrex_b200_fb_tags(ba.ptr, dm.ptr, ng, int(cross), _i3(period), myproc, kind, buf, n)
     return _tags(n, buf)
+
+
+def fb_face_links(ba, dm, period, myproc):
+    """Face links of the cross-stencil one-ghost-cell FillBoundary as rank myproc sees it: list over its boxes (ascending
+    global index) of 6 (linked local box or -1, shift) pairs, or None when the pattern has no face-link form."""
+    n = lib.amrex_b200_fb_face_links(ba.ptr, dm.ptr, _i3(period), myproc, None, 0)
+    check()
+    if n < 0:
+        return None
+    buf = (C.c_int * (24 * max(n, 1)))()
+    lib.amrex_b200_fb_face_links(ba.ptr, dm.ptr, _i3(period), myproc, buf, 6 * n)
+    return [[(buf[4 * (6 * b + f)], tuple(buf[4 * (6 * b + f) + 1: 4 * (6 * b + f) + 4])) for f in range(6)] for b in range(n)]
 
 
 def cpc_tags(ba_dst, dm_dst, ng_dst, ba_src, dm_src, ng_src, period, myproc, kind):

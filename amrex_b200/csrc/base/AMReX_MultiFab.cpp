@@ -587,6 +587,44 @@ void MultiFab::Xpay (MultiFab& dst, Real a, MultiFab const& src, int scomp, int 
 { LinComb(dst, 1.0, src, a, scomp, dcomp, ncomp, ng); }
 
 // ================================================================================== halo exchange plans
+bool define_fb_face_links (std::vector<b200mg_facelink>& links, CommMetaData const& cmd, std::vector<int> const& local_index,
+                           std::vector<Box> const& local_boxes)
+{
+    links.assign(6 * local_index.size(), b200mg_facelink{-1, {0, 0, 0}});
+    auto local_of = [&] (int g) {
+        auto it = std::lower_bound(local_index.begin(), local_index.end(), g);
+        return (it != local_index.end() && *it == g) ? int(it - local_index.begin()) : -1;
+    };
+    bool ok = true;
+    for (auto const& t : cmd.LocTags) {
+        const int ld = local_of(t.dstIndex), ls = local_of(t.srcIndex);
+        if (ld < 0 || ls < 0) { return false; }
+        Box const& vbx = local_boxes[ld];
+        const IntVect d2s = t.sbox.smallEnd() - t.dbox.smallEnd();
+        for (int dir = 0; dir < 3; ++dir) {
+            for (int side = 0; side < 2; ++side) {
+                Box face = vbx;                          // the one-cell slab of ghost cells behind this face
+                if (side == 0) { face.setSmall(dir, vbx.smallEnd(dir) - 1); face.setBig(dir, vbx.smallEnd(dir) - 1); }
+                else { face.setSmall(dir, vbx.bigEnd(dir) + 1); face.setBig(dir, vbx.bigEnd(dir) + 1); }
+                Box slab = face; slab &= t.dbox;
+                if (!slab.ok()) { continue; }            // (edge / corner pieces of a tag: a cross stencil never reads them)
+                b200mg_facelink& l = links[std::size_t(ld) * 6 + dir + 3 * side];
+                if (slab == face && l.fab < 0) { l.fab = ls; for (int d = 0; d < 3; ++d) { l.shift[d] = d2s[d]; } }
+                else { ok = false; }                     // a face fed by several boxes, or in part
+            }
+        }
+    }
+    return ok;
+}
+
+bool define_fb_face_links (std::vector<b200mg_facelink>& links, CommMetaData const& cmd, BoxArray const& ba,
+                           DistributionMapping const& dm, int myproc)
+{
+    std::vector<int> idx; std::vector<Box> boxes;
+    for (int g = 0; g < int(ba.size()); ++g) { if (dm[g] == myproc) { idx.push_back(g); boxes.push_back(ba[g]); } }
+    return define_fb_face_links(links, cmd, idx, boxes);
+}
+
 namespace {
 
 struct CommPlan {
@@ -631,9 +669,6 @@ void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc,
 {
     std::vector<b200mg_copytag> h;
     auto npts = [] (CopyComTag const& t) { return int(std::min<Long>(t.dbox.numPts(), Long(1) << 30)); };
-    const bool want_links = cross_ng != nullptr && *cross_ng == IntVect(1) && &ldst == &lsrc;
-    std::vector<b200mg_facelink> links(want_links ? 6 * std::size_t(ldst.numLocal()) : 0, b200mg_facelink{-1, {0, 0, 0}});
-    bool links_ok = want_links;
     for (auto const& t : P.meta.LocTags) {
         const int ld = ldst.localIndex(t.dstIndex), ls = lsrc.localIndex(t.srcIndex);
         if (cross_ng == nullptr) { h.push_back(make_tag(t, ld, ls, 0)); P.maxloc = std::max(P.maxloc, npts(t)); continue; }
@@ -649,17 +684,17 @@ void finish_plan (CommPlan& P, LevelLayout const& ldst, LevelLayout const& lsrc,
                 CopyComTag c = t;
                 c.dbox = slab; c.sbox = slab + d2s;
                 h.push_back(make_tag(c, ld, ls, 0)); P.maxloc = std::max(P.maxloc, npts(c));
-                if (want_links) {
-                    b200mg_facelink& l = links[std::size_t(ld) * 6 + dir + 3 * side];
-                    if (slab == face && l.fab < 0) { l.fab = ls; for (int d = 0; d < 3; ++d) { l.shift[d] = d2s[d]; } }
-                    else { links_ok = false; }       // a face fed by several boxes, or in part
-                }
             }
         }
     }
     P.nloc = int(h.size()); P.d_loc.assign(h);
-    P.links_ok = links_ok && P.nloc > 0;
-    if (P.links_ok) { P.d_links.assign(links); }
+    if (cross_ng != nullptr && *cross_ng == IntVect(1) && &ldst == &lsrc && P.nloc > 0) {
+        std::vector<b200mg_facelink> links;
+        std::vector<Box> boxes;
+        for (int li = 0; li < ldst.numLocal(); ++li) { boxes.push_back(ldst.box(li)); }
+        P.links_ok = define_fb_face_links(links, P.meta, ldst.indexArray(), boxes);
+        if (P.links_ok) { P.d_links.assign(links); }
+    }
     h.clear();
     long long off = 0;
     for (auto const& kv : P.meta.SndTags) {

@@ -631,6 +631,21 @@ int amrex_b200_fb_tags (const BoxArray* ba, const DistributionMapping* dm, int n
         return write_tags(cmd, kind, out, capacity);
     FI_CATCH(return -1)
 }
+int amrex_b200_fb_face_links (const BoxArray* ba, const DistributionMapping* dm, const int period[3], int myproc, int* out, int capacity)
+{
+    FI_TRY
+        CommMetaData cmd;
+        define_fb_metadata(cmd, *ba, *dm, IntVect(1), true, Periodicity(IntVect(period[0], period[1], period[2])), myproc);
+        std::vector<b200mg_facelink> links;
+        if (!define_fb_face_links(links, cmd, *ba, *dm, myproc)) { return -2; }
+        if (out != nullptr) {
+            for (std::size_t q = 0; q < links.size() && int(q) < capacity; ++q) {
+                out[4 * q] = links[q].fab; out[4 * q + 1] = links[q].shift[0]; out[4 * q + 2] = links[q].shift[1]; out[4 * q + 3] = links[q].shift[2];
+            }
+        }
+        return int(links.size() / 6);
+    FI_CATCH(return -1)
+}
 int amrex_b200_cpc_tags (const BoxArray* ba_dst, const DistributionMapping* dm_dst, int ng_dst, const BoxArray* ba_src, const DistributionMapping* dm_src,
                          int ng_src, const int period[3], int myproc, int kind, int* out, int capacity)
 {

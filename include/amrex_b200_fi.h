@@ -295,6 +295,13 @@ int  amrex_b200_fb_tags(const BoxArray* ba, const DistributionMapping* dm, int n
 int  amrex_b200_cpc_tags(const BoxArray* ba_dst, const DistributionMapping* dm_dst, int ng_dst,
                          const BoxArray* ba_src, const DistributionMapping* dm_src, int ng_src,
                          const int period[3], int myproc, int kind, int* out, int capacity);
+/* Face links of the cross-stencil, one-ghost-cell FillBoundary as rank `myproc` sees it (the form in which the shell sweep
+ * of the fused smoother replaces the copies between boxes of one GPU): 4 ints per (local box, face) in
+ * out - linked local box index (-1: none) and the index shift[3]; local boxes in ascending global index, faces 0,1,2 = x,y,z
+ * low, 3,4,5 = high.  Returns the number of local boxes when every local tag is one whole face from one box, -2 when the
+ * pattern has no such form, -1 on error (out == NULL: only the return value).  Host only. */
+int  amrex_b200_fb_face_links(const BoxArray* ba, const DistributionMapping* dm, const int period[3], int myproc,
+                              int* out, int capacity);
 
 #ifdef __cplusplus
 }

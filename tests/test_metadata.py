@@ -162,3 +162,85 @@ def test_cpc_face_symmetry_across_agglomeration(d, nprocs):
     assert snd == rcv          # what rank a packs for rank b is exactly what b expects from a
     if d == 2:   # the SFC split of 2/4/8 ranks always cuts across z: the shared face plane must be exchanged
         assert any(v > 0 for v in snd.values())
+
+
+# ---- face links: the form in which the fused smoother's shell sweep replaces the copies between the boxes of one GPU
+def _links_case(ab, ba, nprocs, period):
+    dm = ab.DistributionMapping(ba, nprocs=nprocs)
+    boxes = ba.boxes()
+    pmap = dm.pmap(ba.size())
+    out = {}
+    for me in range(nprocs):
+        out[me] = (ab.fb_face_links(ba, dm, period, me), [g for g in range(len(boxes)) if pmap[g] == me])
+    return boxes, out
+
+
+@pytest.mark.parametrize("n,mgs,nprocs,period", [(128, 64, 1, (0, 0, 0)), (128, 64, 1, (128, 128, 128)), (128, 64, 2, (0, 0, 0)),
+                                                 (128, 32, 4, (128, 0, 128)), (64, 64, 1, (64, 64, 64)), ((128, 64, 64), 64, 1, (128, 64, 64)),
+                                                 (96, 40, 3, (0, 96, 0))])
+def test_face_links_geometry_and_symmetry(n, mgs, nprocs, period):
+    """Every link (box b, face f) -> (box c, shift s) of amrex_b200_fb_face_links: the slab of ghost cells behind face f of b,
+    shifted by s, lies inside c's valid box; c is on the same rank; c's opposite face links back to b with shift -s; a face
+    without link has no same-rank box behind it (it is a domain face, or another rank's).  Uniform tilings always have the
+    face-link form."""
+    import amrex_b200 as ab
+    ab.load_library()
+    hi = tuple(x - 1 for x in n) if isinstance(n, tuple) else (n - 1,) * 3
+    ba = ab.BoxArray((0, 0, 0), hi).maxSize(mgs)
+    boxes, per_rank = _links_case(ab, ba, nprocs, period)
+    dom = (0, 0, 0) + hi
+    nlinks = 0
+    for me, (links, mine) in per_rank.items():
+        assert links is not None and len(links) == len(mine)
+        for lb, g in enumerate(mine):
+            b = boxes[g]
+            for f in range(6):
+                d, side = f % 3, f // 3
+                slab = list(b)
+                slab[d] = slab[d + 3] = (b[d] - 1) if side == 0 else (b[d + 3] + 1)
+                c_local, s = links[lb][f]
+                # the box (any rank) that holds the cells behind the face, through the periodic image if there is one
+                img = list(slab)
+                for q in range(3):
+                    if period[q] and img[q] < dom[q]:
+                        img[q] += period[q]; img[q + 3] += period[q]
+                    elif period[q] and img[q + 3] > dom[q + 3]:
+                        img[q] -= period[q]; img[q + 3] -= period[q]
+                owners = [h for h, c in enumerate(boxes) if all(c[q] <= img[q] and img[q + 3] <= c[q + 3] for q in range(3))]
+                inside = all(dom[q] <= img[q] and img[q + 3] <= dom[q + 3] for q in range(3))
+                if c_local < 0:
+                    assert s == (0, 0, 0)
+                    assert (not inside) or (owners and owners[0] not in mine), (me, g, f)
+                    continue
+                nlinks += 1
+                c = boxes[mine[c_local]]
+                assert all(c[q] <= slab[q] + s[q] and slab[q + 3] + s[q] <= c[q + 3] for q in range(3)), (me, g, f, s)
+                assert owners == [mine[c_local]], (me, g, f, owners)
+                back = links[c_local][(d + 3) if side == 0 else d]
+                assert back == (lb, tuple(-x for x in s)), (me, g, f, back)
+    assert nlinks > 0 or (len(boxes) == 1 and not any(period))
+
+
+def test_face_links_refuse_partial_faces():
+    """A face fed by two smaller boxes, or covered in part (box lists that are not a tensor-product tiling - AMR patches):
+    no face-link form; the exchange keeps its copy kernel."""
+    import amrex_b200 as ab
+    ab.load_library()
+    # one 64x64x64 box next to two 64x32x64 boxes
+    ba = ab.BoxArray(boxes=[(0, 0, 0, 63, 63, 63), (64, 0, 0, 127, 31, 63), (64, 32, 0, 127, 63, 63)])
+    dm = ab.DistributionMapping(ba, nprocs=1)
+    assert ab.fb_face_links(ba, dm, (0, 0, 0), 0) is None
+    # a face covered in part: the neighbour is shorter than the face
+    ba = ab.BoxArray(boxes=[(0, 0, 0, 63, 63, 63), (64, 0, 0, 127, 31, 63)])
+    dm = ab.DistributionMapping(ba, nprocs=1)
+    assert ab.fb_face_links(ba, dm, (0, 0, 0), 0) is None
+    # the two halves on different ranks: the big box's face is another rank's business on rank 0 ... but rank 1 holds both
+    # small boxes, whose faces towards the big box are remote and whose common face is a whole-face link
+    ba = ab.BoxArray(boxes=[(0, 0, 0, 63, 63, 63), (64, 0, 0, 127, 31, 63), (64, 32, 0, 127, 63, 63)])
+    dm = ab.DistributionMapping(ba, nprocs=2)
+    pm = dm.pmap(3)
+    for me in (0, 1):
+        mine = [g for g in range(3) if pm[g] == me]
+        links = ab.fb_face_links(ba, dm, (0, 0, 0), me)
+        if set(mine) == {1, 2}:
+            assert links is not None and links[0][4] == (1, (0, 0, 0)) and links[1][1] == (0, (0, 0, 0))
