@@ -98,6 +98,18 @@ def test_multirank_halo_overlap_is_bit_neutral(tmp_path):
     assert a["history"] == c["history"] and a["cg_iters"] == c["cg_iters"]
 
 
+def test_multirank_face_links_when_every_box_has_a_remote_face(tmp_path):
+    """2 ranks x 4 boxes of 64^3 (each rank one z layer of the 2 x 2 x 2 boxes): every box has two linked faces and one face
+    the other rank feeds, so the smooth takes the unsplit path with remote-only exchanges around a linked shell sweep - the
+    situation of every rank of the 8-GPU benchmark.  Same bits with and without the links, and the reference's answer."""
+    env = {"B200MG_MERGED_MAX_CELLS": "4096", "WORKER_FUSION": "1"}
+    a = _run("abeclap128_g64", 2, tmp_path, env=env)
+    b = _run("abeclap128_g64", 2, tmp_path, env=dict(env, B200MG_NO_FACE_LINKS="1"))
+    assert "b200mg_gsrb4" in a["kernels"] and "b200mg_gsrb_shell_abec_linked" in a["kernels"], a["kernels"]   # (the entry point's name with or without links)
+    assert a["history"] == b["history"] and a["cg_iters"] == b["cg_iters"]
+    assert a["sol_rel_maxdiff"] <= 1e-10 and abs(a["iters"] - a["ref_iters"]) <= 1
+
+
 def test_multirank_two_component_exchange(tmp_path):
     """FillBoundary (full and cross stencil, periodic in x and y) and ParallelCopy of a TWO-component MultiFab over 2 ranks:
     every ghost cell must hold the value of its periodic image, every copied cell its source value."""
