@@ -479,8 +479,14 @@ int b200mg_gsrb4_subset (int abec, int nboxes, const int* ids, const b200mg_box*
         // the default (8,4,2) plan runs its rows of 65 .. 128 cells with three LATE stages: two pairs per thread make the step
         // short enough that one step of prefetch distance no longer covers the HBM latency (profiles/r02_s24_tune_gsrb5.txt)
         const int sl5 = (g_plan_ty == 8 && g_plan_se == 4 && g_plan_sl == 2) ? 3 : g_plan_sl;
-        const int e = two_pairs ? dispatch5(abec != 0, P, nb, effective_tile_y(nxmax), g_plan_se, sl5, s)
-                                : (abec ? dispatch4<true>(P, nb, s) : dispatch4<false>(P, nb, s));
+        int e = two_pairs ? dispatch5(abec != 0, P, nb, effective_tile_y(nxmax), g_plan_se, sl5, s)
+                          : (abec ? dispatch4<true>(P, nb, s) : dispatch4<false>(P, nb, s));
+        if (two_pairs && e == int(cudaErrorInvalidValue)) {
+            // (row pitches under which the deeper rings of generation 5 exceed the shared memory, or a plan it does not
+            //  compile: nothing was launched - the one-pair kernel takes the launch)
+            P.txp = ((nxmax / 2 + 31) / 32) * 32;
+            e = abec ? dispatch4<true>(P, nb, s) : dispatch4<false>(P, nb, s);
+        }
         if (e != 0) { return e; }
     }
     return 0;
